@@ -1,0 +1,264 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle ("port") for the Krylov + preconditioner half of the path.
+//
+// PARITY UNPINNED: the arithmetic restated here lives in Trilinos (Belos / Ifpack / Epetra), which is neither
+// vendored in /root/reference nor pinned to a version (README:11-13 "git clone ... Trilinos.git").  What is
+// restated is the published behaviour of those packages for the parameter set the reference hard-codes
+// (solver_lin_belos.h:224-264, precond_ifpack.h:28-48), anchored on the reference's own call sites:
+//   solver_lin_belos.h:130-222  (solveProblem: null-space projection, right preconditioning, solver choice)
+//   solver_lin.h:130-140        (PoissonProjection::Apply  y = A x ; y -= (y.n) n)
+//   solver_lin.cpp:59-77        (createNullVector: mask / ||mask||_2)
+//   precond_ifpack.h:50-75      (Ifpack::Create(type, A, overlap) -> SetParameters -> Initialize -> Compute; ApplyInverse)
+// Belos semantics restated: BlockGmresSolMgr/Block(F)GmresIter with block size 1 — right-preconditioned (flexible)
+// Arnoldi, DGKS orthogonalisation (classical Gram-Schmidt, a 2nd pass when ||w||^2 drops below dep_tol=1/sqrt(2) of
+// its pre-projection value), Givens least squares, implicit residual |g_{j+1}| scaled by the norm of the FIRST
+// initial residual, test `<= tol`, restart every `Num Blocks`, stop at Maximum Iterations / Maximum Restarts.
+// BlockCGSolMgr with block size 1 — standard PCG, test ||r||_2 / ||r_0||_2 before every iteration.
+// Ifpack semantics restated: point relaxation (Jacobi, zero start), Ifpack_Chebyshev (ApplyInverse recurrence with
+// alpha = lmax/ratio, beta = 1.1 lmax; lmax from a 10-step power method on D^-1 A), Ifpack_ILU level 0 on the local
+// block (overlap 0: off-block columns dropped), row-wise IKJ, L unit-lower, D stored inverted, U unit-upper scaled.
+// Deviation (documented in DESIGN.md): Epetra's Random() start vector of the power method is replaced by a
+// deterministic per-row hash, identically here and in the CUDA path.
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include "krylov_oracle.h"
+
+namespace {
+
+struct Csr { int n; const int *rp, *ci; const double *v; };
+
+double dot(int n, const double *a, const double *b) {
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+void axpy(int n, double a, const double *x, double *y) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) y[i] += a * x[i];
+}
+void spmv(const Csr &A, const double *x, double *y) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < A.n; ++i) { double s = 0.0; for (int p = A.rp[i]; p < A.rp[i + 1]; ++p) if (A.ci[p] >= 0) s += A.v[p] * x[A.ci[p]]; y[i] = s; }
+}
+
+double hash01(unsigned long long t, int salt) {   // same generator as implicit-sph_b200/lattice.py::_hash01 and the CUDA path
+  unsigned long long z = t + 0x9E3779B97F4A7C15ULL * (unsigned long long)(salt + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct Precond {
+  int type; const Csr *A; const orc_krylov_params *prm;
+  std::vector<double> invdiag;
+  double lmax;
+  // ILU(0): factors stored on A's pattern restricted to the row's block
+  std::vector<double> fv, dinv; std::vector<int> diagpos; const int *blk;
+  std::vector<double> V, W;
+
+  void setup(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
+    A = &A_; prm = p; type = p->precond; blk = block_of_row; const int n = A_.n;
+    if (type == ORC_PREC_JACOBI || type == ORC_PREC_CHEBYSHEV) {
+      invdiag.assign(n, 0.0);
+      for (int i = 0; i < n; ++i) { double d = 0.0; for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] == i) d += A_.v[q];
+        if (fabs(d) < p->min_diag) d = p->min_diag; if (d != 0.0) invdiag[i] = 1.0 / d; }
+      V.assign(n, 0.0);
+    }
+    if (type == ORC_PREC_CHEBYSHEV) {
+      lmax = p->cheb_lambda_max;
+      if (lmax <= 0.0) {                                  // Ifpack_Chebyshev::PowerMethod
+        std::vector<double> x(n), y(n);
+        for (int i = 0; i < n; ++i) x[i] = 2.0 * hash01((unsigned long long)(p->row_gid ? p->row_gid[i] : i + 1), 7) - 1.0;
+        double nrm = sqrt(dot(n, x.data(), x.data()));
+        for (int i = 0; i < n; ++i) x[i] *= 1.0 / nrm;
+        for (int it = 0; it < p->cheb_eig_iters; ++it) {
+          spmv(A_, x.data(), y.data());
+          for (int i = 0; i < n; ++i) y[i] *= invdiag[i];
+          const double top = dot(n, y.data(), x.data()), bot = dot(n, x.data(), x.data());
+          lmax = top / bot;
+          nrm = sqrt(dot(n, y.data(), y.data()));
+          for (int i = 0; i < n; ++i) x[i] = y[i] * (1.0 / nrm);
+        }
+      }
+      V.assign(n, 0.0); W.assign(n, 0.0);
+    }
+    if (type == ORC_PREC_ILU0) {                           // Ifpack_ILU::Compute, level-of-fill 0, relax 0, athresh 0, rthresh 1
+      fv.assign(A_.v, A_.v + A_.rp[n]); dinv.assign(n, 0.0); diagpos.assign(n, -1);
+      std::vector<int> colflag(n, -1);
+      auto inblk = [&](int i, int c) { return c >= 0 && (!blk || blk[c] == blk[i]); };
+      for (int i = 0; i < n; ++i) for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] == i) diagpos[i] = q;
+      for (int i = 0; i < n; ++i) {
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (inblk(i, A_.ci[q])) colflag[A_.ci[q]] = q;
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) {     // columns ascending => strictly-lower part first
+          const int j = A_.ci[q]; if (!inblk(i, j) || j >= i) continue;
+          const double multiplier = fv[q];
+          fv[q] *= dinv[j];
+          for (int u = A_.rp[j]; u < A_.rp[j + 1]; ++u) { const int k = A_.ci[u]; if (!inblk(j, k) || k <= j) continue;
+            const int kk = colflag[k]; if (kk > -1) fv[kk] -= multiplier * fv[u]; }
+        }
+        double d = fv[diagpos[i]];
+        d = 1.0 / d;
+        dinv[i] = d;
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) { const int k = A_.ci[q]; if (inblk(i, k) && k > i) fv[q] *= d; }
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] >= 0) colflag[A_.ci[q]] = -1;
+      }
+    }
+  }
+
+  // z = M^-1 r   (Epetra_Operator::ApplyInverse of the Ifpack object, as wrapped by Belos::EpetraPrecOp)
+  void apply(const double *r, double *z) {
+    const int n = A->n;
+    switch (type) {
+    case ORC_PREC_NONE: memcpy(z, r, sizeof(double) * n); break;
+    case ORC_PREC_JACOBI:                                   // Ifpack_PointRelaxation, Jacobi, zero starting solution
+      for (int i = 0; i < n; ++i) z[i] = 0.0;
+      for (int s = 0; s < prm->jacobi_sweeps; ++s) {
+        if (s == 0) { for (int i = 0; i < n; ++i) z[i] = prm->jacobi_damping * invdiag[i] * r[i]; }
+        else { spmv(*A, z, V.data()); for (int i = 0; i < n; ++i) z[i] += prm->jacobi_damping * invdiag[i] * (r[i] - V[i]); }
+      }
+      break;
+    case ORC_PREC_CHEBYSHEV: {                              // Ifpack_Chebyshev::ApplyInverse
+      const double alpha = lmax / prm->cheb_ratio, beta = 1.1 * lmax, delta = 2.0 / (beta - alpha), theta = 0.5 * (beta + alpha), s1 = theta * delta;
+      const double oneOverTheta = 1.0 / theta;
+      for (int i = 0; i < n; ++i) { W[i] = invdiag[i] * r[i] * oneOverTheta; z[i] = W[i]; }
+      double rhok = 1.0 / s1;
+      for (int deg = 0; deg < prm->cheb_degree - 1; ++deg) {
+        spmv(*A, z, V.data());
+        const double rhokp1 = 1.0 / (2.0 * s1 - rhok), dtemp1 = rhokp1 * rhok, dtemp2 = 2.0 * rhokp1 * delta; rhok = rhokp1;
+        for (int i = 0; i < n; ++i) { W[i] *= dtemp1; W[i] += dtemp2 * invdiag[i] * (r[i] - V[i]); z[i] += W[i]; }
+      }
+      break; }
+    case ORC_PREC_ILU0: {                                   // Ifpack_ILU::ApplyInverse: L (unit) solve, D^-1 scale, U (unit) solve
+      auto inblk = [&](int i, int c) { return c >= 0 && (!blk || blk[c] == blk[i]); };
+      for (int i = 0; i < n; ++i) { double s = r[i]; for (int q = A->rp[i]; q < A->rp[i + 1]; ++q) { const int j = A->ci[q]; if (inblk(i, j) && j < i) s -= fv[q] * z[j]; } z[i] = s; }
+      for (int i = 0; i < n; ++i) z[i] *= dinv[i];
+      for (int i = n - 1; i >= 0; --i) { double s = z[i]; for (int q = A->rp[i]; q < A->rp[i + 1]; ++q) { const int j = A->ci[q]; if (inblk(i, j) && j > i) s -= fv[q] * z[j]; } z[i] = s; }
+      break; }
+    }
+  }
+};
+
+struct Op {   // A, or PoissonProjection (I - n n^T) A   (solver_lin.h:130-140)
+  const Csr *A; const double *nv;
+  void apply(const double *x, double *y) const {
+    spmv(*A, x, y);
+    if (nv) { const double val = dot(A->n, y, nv); axpy(A->n, -val, nv, y); }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void orc_krylov_default_params(orc_krylov_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->solver = ORC_SOLVER_GMRES; p->flexible = 1; p->num_blocks = 50; p->max_iters = 500; p->max_restarts = 15; p->tol = 1.0e-8;   // solver_lin_belos.h:231-240
+  p->precond = ORC_PREC_NONE; p->jacobi_sweeps = 1; p->jacobi_damping = 1.0; p->min_diag = 0.0;
+  p->cheb_degree = 1; p->cheb_ratio = 30.0; p->cheb_lambda_max = -1.0; p->cheb_eig_iters = 10; p->row_gid = 0;
+}
+
+int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
+                     const int *block_of_row, const int *null_mask, int use_null, double *b, double *x,
+                     int *iters_out, double *relres_out, double *history, int history_cap) {
+  Csr A{n, rowptr, col, val};
+  std::vector<double> nvec;
+  if (use_null) {                                           // solver_lin.cpp:59-77 ; solver_lin_belos.h:138-144
+    nvec.assign(n, 1.0);
+    if (null_mask) for (int i = 0; i < n; ++i) nvec[i] = null_mask[i];
+    const double nrm = sqrt(dot(n, nvec.data(), nvec.data()));
+    for (auto &v : nvec) v *= 1.0 / nrm;
+    const double bn = dot(n, b, nvec.data()); axpy(n, -bn, nvec.data(), b);
+  }
+  Op op{&A, use_null ? nvec.data() : nullptr};
+  Precond M; M.setup(A, prm, block_of_row);                 // prec->create(), solver_lin_belos.h:153
+  int iters = 0, nhist = 0; bool converged = false; double scale = 0.0, res = 0.0;
+  std::vector<double> r(n), w(n);
+
+  if (prm->solver == ORC_SOLVER_CG) {                       // Belos CGIter (block size 1)
+    std::vector<double> z(n), p(n), Ap(n);
+    op.apply(x, w.data()); for (int i = 0; i < n; ++i) r[i] = b[i] - w[i];
+    M.apply(r.data(), z.data()); p = z;
+    double rHz = dot(n, r.data(), z.data());
+    scale = sqrt(dot(n, r.data(), r.data())); res = scale;
+    if (history && nhist < history_cap) history[nhist++] = res;
+    while (true) {
+      if (scale == 0.0 || res / scale <= prm->tol) { converged = true; break; }
+      if (iters >= prm->max_iters) break;
+      ++iters;
+      op.apply(p.data(), Ap.data());
+      const double pAp = dot(n, p.data(), Ap.data()), alpha = rHz / pAp;
+      axpy(n, alpha, p.data(), x); axpy(n, -alpha, Ap.data(), r.data());
+      res = sqrt(dot(n, r.data(), r.data()));
+      if (history && nhist < history_cap) history[nhist++] = res;
+      if (res / scale <= prm->tol) { converged = true; break; }
+      if (iters >= prm->max_iters) break;
+      M.apply(r.data(), z.data());
+      const double rHz_old = rHz; rHz = dot(n, r.data(), z.data());
+      const double beta = rHz / rHz_old;
+      for (int i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    }
+  } else {                                                  // Belos Block(F)GmresIter, block size 1
+    const int m = prm->num_blocks;
+    std::vector<double> V((size_t)(m + 1) * n), Z(prm->flexible ? (size_t)m * n : (size_t)n);
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), y(m);
+    int restarts = 0; bool first = true;
+    while (true) {
+      op.apply(x, w.data()); for (int i = 0; i < n; ++i) r[i] = b[i] - w[i];
+      const double beta = sqrt(dot(n, r.data(), r.data()));
+      if (first) { scale = beta; first = false; if (history && nhist < history_cap) history[nhist++] = beta; }
+      res = beta;
+      if (scale == 0.0 || res / scale <= prm->tol) { converged = true; break; }
+      for (int i = 0; i < n; ++i) V[i] = r[i] / beta;
+      std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
+      int j = 0; bool stop = false;
+      for (; j < m; ++j) {
+        double *vj = &V[(size_t)j * n], *zj = prm->flexible ? &Z[(size_t)j * n] : Z.data(), *vn = &V[(size_t)(j + 1) * n];
+        M.apply(vj, zj); op.apply(zj, vn);
+        // DGKS (DGKSOrthoManager::blkOrtho1 + normalisation)
+        const double oldDot = dot(n, vn, vn);
+        for (int k = 0; k <= j; ++k) h[k] = dot(n, &V[(size_t)k * n], vn);
+        for (int k = 0; k <= j; ++k) axpy(n, -h[k], &V[(size_t)k * n], vn);
+        double newDot = dot(n, vn, vn);
+        if (newDot < 0.70710678118654752440 * oldDot) {
+          for (int k = 0; k <= j; ++k) h2[k] = dot(n, &V[(size_t)k * n], vn);
+          for (int k = 0; k <= j; ++k) axpy(n, -h2[k], &V[(size_t)k * n], vn);
+          for (int k = 0; k <= j; ++k) h[k] += h2[k];
+          newDot = dot(n, vn, vn);
+        }
+        const double hn = sqrt(newDot); h[j + 1] = hn;
+        if (hn > 0.0) for (int i = 0; i < n; ++i) vn[i] *= 1.0 / hn;
+        // Givens update of column j (BlockGmresIter::updateLSQR)
+        for (int k = 0; k < j; ++k) { const double t = cs[k] * h[k] + sn[k] * h[k + 1]; h[k + 1] = -sn[k] * h[k] + cs[k] * h[k + 1]; h[k] = t; }
+        { const double a = h[j], bb = h[j + 1], rr = hypot(a, bb); cs[j] = rr == 0.0 ? 1.0 : a / rr; sn[j] = rr == 0.0 ? 0.0 : bb / rr; h[j] = rr; h[j + 1] = 0.0;
+          g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j]; }
+        for (int k = 0; k <= j; ++k) H[(size_t)k * m + j] = h[k];
+        ++iters; res = fabs(g[j + 1]);
+        if (history && nhist < history_cap) history[nhist++] = res;
+        if (res / scale <= prm->tol) { converged = true; stop = true; ++j; break; }
+        if (iters >= prm->max_iters) { stop = true; ++j; break; }
+      }
+      // y = H^-1 g ; x += Z y  (flexible)  or  x += M^-1 (V y)
+      for (int k = j - 1; k >= 0; --k) { double s = g[k]; for (int l = k + 1; l < j; ++l) s -= H[(size_t)k * m + l] * y[l]; y[k] = s / H[(size_t)k * m + k]; }
+      if (prm->flexible) { for (int k = 0; k < j; ++k) axpy(n, y[k], &Z[(size_t)k * n], x); }
+      else { std::fill(w.begin(), w.end(), 0.0); for (int k = 0; k < j; ++k) axpy(n, y[k], &V[(size_t)k * n], w.data()); M.apply(w.data(), r.data()); axpy(n, 1.0, r.data(), x); }
+      if (stop) break;
+      if (restarts >= prm->max_restarts) break;
+      ++restarts;
+    }
+  }
+  if (use_null) { const double xn = dot(n, x, nvec.data()); axpy(n, -xn, nvec.data(), x); }   // solver_lin_belos.h:215-219
+  if (iters_out) *iters_out = iters;
+  if (relres_out) *relres_out = scale > 0.0 ? res / scale : 0.0;
+  return converged ? 0 : 1;
+}
+
+int orc_precond_apply(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
+                      const int *block_of_row, const double *r, double *z, double *lambda_max_out) {
+  Csr A{n, rowptr, col, val}; Precond M; M.setup(A, prm, block_of_row); M.apply(r, z);
+  if (lambda_max_out) *lambda_max_out = M.lmax;
+  return 0;
+}
+
+}  // extern "C"

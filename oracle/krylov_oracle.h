@@ -1,0 +1,39 @@
+/* TEST INFRASTRUCTURE ONLY — CPU oracle for the Krylov/preconditioner half (see krylov_oracle.cpp header:
+ * "parity unpinned": Belos/Ifpack are un-vendored, un-pinned third-party code). */
+#ifndef ISPH_KRYLOV_ORACLE_H
+#define ISPH_KRYLOV_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+enum { ORC_SOLVER_GMRES = 0, ORC_SOLVER_CG = 1 };
+enum { ORC_PREC_NONE = 0, ORC_PREC_JACOBI = 1, ORC_PREC_CHEBYSHEV = 2, ORC_PREC_ILU0 = 3 };
+typedef struct {
+  int solver;            /* "Solver Type": Block GMRES | Block CG   (solver_lin_belos.h:173-182) */
+  int flexible;          /* "Flexible Gmres" */
+  int num_blocks;        /* "Num Blocks" (restart length) */
+  int max_iters;         /* "Maximum Iterations" */
+  int max_restarts;      /* "Maximum Restarts" */
+  double tol;            /* "Convergence Tolerance" */
+  int precond;           /* Ifpack "Precond Type": none | point relaxation (Jacobi) | Chebyshev | ILU (fill 0, overlap 0) */
+  int jacobi_sweeps;     /* "relaxation: sweeps" */
+  double jacobi_damping; /* "relaxation: damping factor" */
+  double min_diag;       /* "relaxation: min diagonal value" / "chebyshev: min diagonal value" */
+  int cheb_degree;       /* "chebyshev: degree" */
+  double cheb_ratio;     /* "chebyshev: ratio eigenvalue" */
+  double cheb_lambda_max;/* "chebyshev: max eigenvalue" (<=0: power method) */
+  int cheb_eig_iters;    /* "chebyshev: eigenvalue max iterations" */
+  const int *row_gid;    /* global id per row for the power-method start vector (NULL: row+1) */
+} orc_krylov_params;
+
+void orc_krylov_default_params(orc_krylov_params *p);
+/* col = local row index of each column, -1 for a column that is not in this process' rows.  b is modified in place
+ * when use_null (as solver_lin_belos.h:141-143 does).  returns 0 converged, 1 not converged. */
+int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
+                     const int *block_of_row, const int *null_mask, int use_null, double *b, double *x,
+                     int *iters_out, double *relres_out, double *history, int history_cap);
+int orc_precond_apply(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
+                      const int *block_of_row, const double *r, double *z, double *lambda_max_out);
+#ifdef __cplusplus
+}
+#endif
+#endif

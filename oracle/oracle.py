@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front-end to the CPU oracles (see oracle_api.h).
+
+`Oracle(kind="port")` loads oracle/libisph_oracle.so (our restatement), `kind="ref"` loads
+oracle/_ref/libisph_ref.so (the reference's own functor headers).  Both export the same symbols.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libisph_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libisph_ref.so")
+
+FLUID, SOLID, BOUNDARY, BUFFER_DIRICHLET, BUFFER_NEUMANN, ALL = 99, 12, 16, 32, 64, 127
+NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
+WENDLAND, CUBIC, QUINTIC = 0, 1, 2
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI = range(13)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_longlong)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def build(which=("port", "ref")):
+    """(Re)build the oracle libraries with oracle/Makefile; `ref` is skipped when /root/reference is absent."""
+    for w in which:
+        subprocess.run(["make", "-s", "-C", HERE, w], check=True)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_libs = {}
+
+
+def _load(kind):
+    if kind in _libs:
+        return _libs[kind]
+    path = PORT_SO if kind == "port" else REF_SO
+    if not os.path.exists(path):
+        build((kind,))
+    L = C.CDLL(path)
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _ip, _ip, C.c_int, _ip, _lp, _ip, C.c_int, _ip,
+                             C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_name.restype = C.c_char_p
+    L.orc_graph.restype = C.c_longlong
+    for f in ("orc_set_field", "orc_get_field"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_int, _dp]
+    for f in ("orc_compute_volumes", "orc_compute_gradient_correction", "orc_compute_laplacian_correction",
+              "orc_compute_normals", "orc_graph", "orc_graph_max_row", "orc_invalidate_matrix"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.orc_graph_get.argtypes = [C.c_void_p, _ip, _ip]
+    L.orc_ns_poisson.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, _dp]
+    L.orc_ns_helmholtz.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]
+    L.orc_pb_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
+    L.orc_diag_get.argtypes = [C.c_void_p, _dp, _dp]
+    L.orc_spmv.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+    _libs[kind] = L
+    return L
+
+
+class Oracle:
+    """One particle configuration (= one LAMMPS time step's worth of inputs) on the CPU oracle."""
+
+    def __init__(self, P, kinds=(0, FLUID), h_over_dx=1.5, h=None, h_min=None, cut_over_h=2.0, kernel=WENDLAND,
+                 morris_safe=0.43301, kind="port"):
+        self.L = _load(kind)
+        self.kind = kind
+        self.P = P
+        self.dim = P["dim"]; self.nlocal = P["nlocal"]; self.nghost = P["nghost"]; self.nall = self.nlocal + self.nghost
+        h = P["dx"] * h_over_dx if h is None else h
+        h_min = h if h_min is None else h_min
+        self.h = h
+        kinds = np.asarray(kinds, dtype=np.int32)
+        x = np.ascontiguousarray(P["x"], dtype=np.float64)
+        self._keep = (x, P["type"], P["tag"], P["ilist"], P["noff"], P["neigh"], kinds)
+        self.p = self.L.orc_create(self.dim, self.nlocal, self.nghost, _d(x), _i(P["type"]), _i(P["tag"]),
+                                   len(P["ilist"]), _i(P["ilist"]), P["noff"].ctypes.data_as(_lp), _i(P["neigh"]),
+                                   len(kinds) - 1, _i(kinds), h, h_min, cut_over_h, kernel, morris_safe)
+        self.nnz = None
+
+    def close(self):
+        if self.p:
+            self.L.orc_destroy(self.p); self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"oracle[{self.kind}] {what} failed rc={rc}")
+
+    def set_field(self, f, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size == self.nall * self.L.orc_field_ncomp(f), (a.shape, f)
+        self._ck(self.L.orc_set_field(self.p, f, _d(a)), "set_field")
+
+    def get_field(self, f):
+        nc = self.L.orc_field_ncomp(f)
+        a = np.empty((self.nall, nc) if nc > 1 else (self.nall,), dtype=np.float64)
+        self._ck(self.L.orc_get_field(self.p, f, _d(a)), "get_field")
+        return a
+
+    def compute_pre(self, normals=False):
+        self._ck(self.L.orc_compute_volumes(self.p), "volumes")
+        self._ck(self.L.orc_compute_gradient_correction(self.p), "gradient_correction")
+        self._ck(self.L.orc_compute_laplacian_correction(self.p), "laplacian_correction")
+        if normals:
+            self._ck(self.L.orc_compute_normals(self.p), "normals")
+
+    def graph(self):
+        nnz = self.L.orc_graph(self.p)
+        if nnz < 0:
+            raise RuntimeError("oracle graph failed")
+        self.nnz = int(nnz)
+        rowptr = np.empty(self.nlocal + 1, dtype=np.int32); col = np.empty(self.nnz, dtype=np.int32)
+        self._ck(self.L.orc_graph_get(self.p, _i(rowptr), _i(col)), "graph_get")
+        return rowptr, col
+
+    def ns_poisson(self, dt, anti=True, singular=NULLSPACE, morris_holmes=False):
+        b = np.zeros(self.nlocal)
+        self._ck(self.L.orc_ns_poisson(self.p, dt, int(anti), singular, int(morris_holmes), _d(b)), "ns_poisson")
+        return b
+
+    def ns_helmholtz(self, dt, theta, b, anti=True, morris_holmes=False, incremental_pressure=True, g=(0.0, 0.0, 0.0)):
+        b = np.asfortranarray(np.array(b, dtype=np.float64).reshape(self.nlocal, self.dim, order="F"))
+        gg = np.asarray(g, dtype=np.float64)
+        self._ck(self.L.orc_ns_helmholtz(self.p, dt, theta, int(anti), int(morris_holmes), int(incremental_pressure), _d(gg), _d(b)), "ns_helmholtz")
+        return b
+
+    def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
+        self._ck(self.L.orc_pb_jacobian(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma), "pb_jacobian")
+
+    def invalidate_matrix(self):
+        self.L.orc_invalidate_matrix(self.p)
+
+    def matrix(self):
+        v = np.empty(self.nnz)
+        self._ck(self.L.orc_matrix_get(self.p, _d(v)), "matrix_get")
+        return v
+
+    def diagonals(self):
+        d = np.empty(self.nlocal); s = np.empty(self.nlocal)
+        self._ck(self.L.orc_diag_get(self.p, _d(d), _d(s)), "diag_get")
+        return d, s
+
+    def spmv(self, x):
+        x = np.asfortranarray(np.asarray(x, dtype=np.float64).reshape(self.nlocal, -1, order="F"))
+        y = np.zeros_like(x, order="F")
+        self._ck(self.L.orc_spmv(self.p, _d(x), _d(y), x.shape[1]), "spmv")
+        return y
