@@ -1,0 +1,161 @@
+// Internal state of the B200 linear-solve path (host C++ side).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/isph_b200.h"
+
+#define ISPH_NEIGHMASK 0x3FFFFFFF        /* LAMMPS NEIGHMASK, functor_graph.h:72 */
+#define ISPH_EPS_R 1.0e-24               /* ISPH_EPSILON, macrodef.h:6 */
+#define ISPH_MAXT 8                      /* particle types 1..7 */
+#define ISPH_SLICE 32                    /* SELL-C slice height = warp size */
+
+#define CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+  throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
+#define ISPH_REQUIRE(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string(msg)); } while (0)
+
+namespace isph {
+
+// grow-only device buffer (the matrix is rebuilt every step, pair_isph.cpp:1351-1372: never free/realloc on the hot path)
+template <class T> struct DevBuf {
+  T *p = nullptr; size_t cap = 0;
+  void ensure(size_t n, bool keep = false) {
+    if (n <= cap) return;
+    size_t ncap = n + n / 8 + 64; T *q = nullptr;
+    CUDA_CHECK(cudaMalloc(&q, ncap * sizeof(T)));
+    if (keep && p && cap) CUDA_CHECK(cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (p) cudaFree(p);
+    p = q; cap = ncap;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct PinBuf {
+  T *p = nullptr; size_t cap = 0;
+  void ensure(size_t n) { if (n <= cap) return; if (p) cudaFreeHost(p); cap = n + n / 8 + 64; CUDA_CHECK(cudaMallocHost(&p, cap * sizeof(T))); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// pair tables (PairISPH_Corrected::coeff, pair_isph_corrected.cpp:1302-1337); kC/kCh are the kernel's cached
+// normalisation `_C` and `_C/_h` per type pair, computed on the host with the reference's expressions
+struct PairTab {
+  double cutsq[ISPH_MAXT][ISPH_MAXT], h[ISPH_MAXT][ISPH_MAXT], kC[ISPH_MAXT][ISPH_MAXT], kCh[ISPH_MAXT][ISPH_MAXT];
+  double cut[ISPH_MAXT][ISPH_MAXT];      // sqrt(cutsq), the argument the functors pass to computeMirrorCoefficient
+  int kind[ISPH_MAXT];
+  int kernel, ntypes, dim;
+  double morris_safe;
+};
+
+// SELL-32 matrix with slack: slice s holds rows 32s..32s+31 column-major; entry k of row r at slice_off[s] + 32k + (r&31).
+// Columns ascend within a row (local column id: owned rows first, then halo slots); `atom` = the neighbor atom that
+// produced the entry (-1 for padding / external matrices); row r's self entry has atom == ilist[r].
+struct Matrix {
+  int n = 0, ncols = 0, nslices = 0; long long total = 0, nnz = 0; int max_row = 0, ndup = 0;
+  DevBuf<long long> slice_off; DevBuf<int> slice_len, row_len, diag_k, col, atom; DevBuf<double> val;
+  DevBuf<double> diagonal, sld;          // A.diagonal, A.scaled_laplace_diagonal (pair_isph.h:385-392)
+  std::vector<long long> h_slice_off;
+  int is_filled = 0; bool built = false; bool external = false;
+};
+
+struct Timer { cudaEvent_t a = nullptr, b = nullptr; double ms = 0.0; bool open = false, pending = false; };
+
+struct SolverParams {              // SolverLin_Belos::setParameters defaults, solver_lin_belos.h:224-264
+  std::string solver_type = "Block GMRES", ortho = "DGKS";
+  bool flexible = true; int num_blocks = 50, block_size = 1, max_iters = 500, max_restarts = 15; double tol = 1.0e-8;
+};
+struct PrecondParams {             // names of precond_ifpack.h:28-48 + Ifpack's own lists; defaults differ where BASELINE says so
+  std::string type = "ILU", relax_type = "Jacobi";
+  int overlap = 0, fill = 0, sweeps = 1, cheb_degree = 1, cheb_eig_iters = 10;
+  double damping = 1.0, min_diag = 0.0, cheb_ratio = 30.0, cheb_lmax = -1.0;
+};
+
+struct Halo;      // halo.cu
+struct IluData;   // precond.cu
+
+struct Ctx {
+  int device = 0, nranks = 1, rank = 0;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  std::string err;
+  long long launches = 0;
+  // pair
+  bool have_pair = false; PairTab tab; DevBuf<PairTab> d_tab;
+  // atoms
+  int nlocal = 0, nghost = 0, nall = 0, first_fluid_row = -1, max_tag = 0; bool have_atoms = false;
+  DevBuf<double> x; DevBuf<int> type, tag, kind, col_of_atom, tag2own; std::vector<int> h_type, h_tag;
+  DevBuf<double> field[ISPH_F_COUNT];
+  // neighbors
+  int inum = 0, max_jnum = 0; long long nneigh = 0; bool have_neigh = false;
+  DevBuf<int> ilist, neigh; DevBuf<long long> noff; std::vector<long long> h_noff;
+  PinBuf<int> pin_neigh;
+  // matrix
+  Matrix A;
+  // solver state (SolverLin members, solver_lin.h:70-97)
+  SolverParams sp; PrecondParams pp;
+  double *x_host = nullptr, *b_host = nullptr; int x_lda = 0, b_lda = 0, x_nvec = 0, b_nvec = 0; bool x_owned = true, b_owned = true;
+  DevBuf<double> xs, bs;           // device solution / load multivectors, column-major, leading dimension ld
+  int ld = 0;                      // padded length of every Krylov vector (>= ncols)
+  bool is_singular = false, have_mask = false; DevBuf<double> nullvec; DevBuf<int> mask;
+  int init_type = -1; double init_val = 0.0;
+  DevBuf<double> V, Z, wk, red, hbuf; DevBuf<int> flag;      // Krylov workspace
+  PinBuf<double> h_scal;
+  int last_iters = 0, last_converged = 0; double last_relres = 0.0, last_lmax = 0.0;
+  // preconditioner
+  bool prec_ready = false; int prec_kind = 0; DevBuf<double> invdiag, cw, cv; DevBuf<int> block_of_row; bool have_blocks = false;
+  IluData *ilu = nullptr;
+  // multi-GPU
+  Halo *halo = nullptr;
+  unsigned char nccl_id[128]; bool have_nccl_id = false;
+  // timers
+  std::map<std::string, Timer> timers;
+
+  void tic(const char *name);
+  void toc(const char *name);
+};
+
+inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels / drivers implemented across the .cu files ---------------------------------------------------------
+void build_column_map(Ctx *c);                               // graph.cu
+void graph_build(Ctx *c);
+void graph_export(Ctx *c, int *rowptr, int *col_tags, double *val);
+void matrix_from_csr(Ctx *c, int n, const int *rowptr, const int *col, const double *val);
+void matrix_put_scalar(Ctx *c, double a);
+void matrix_scale(Ctx *c, double a);
+void matrix_left_scale_dev(Ctx *c, const double *d_s, bool reciprocal);
+void matrix_extract_diag_dev(Ctx *c, double *d_out);
+void matrix_replace_diag_dev(Ctx *c, const double *d_in);
+void matrix_merge_duplicates(Ctx *c);
+
+void compute_volumes(Ctx *c);                                // assemble.cu
+void compute_gradient_correction(Ctx *c);
+void compute_laplacian_correction(Ctx *c);
+void compute_normals(Ctx *c);
+void forward_comm(Ctx *c, int field);
+void assemble_laplacian(Ctx *c, double alpha, const double *d_material, bool anti, bool mh, int f0, int f1);
+void assemble_gradient_dot(Ctx *c, double alpha, const double *d_vec, int f0, int f1);
+void ns_poisson(Ctx *c, double dt, bool anti, int singular, bool mh);
+void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp, const double *g);
+void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma);
+
+void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy);   // spmv.cu (does the halo exchange when nranks > 1)
+
+void precond_create(Ctx *c);                                 // precond.cu
+void precond_free(Ctx *c);
+void precond_apply(Ctx *c, const double *d_r, double *d_z);  // z = M^-1 r
+
+void solver_prepare_vectors(Ctx *c);                         // krylov.cu
+void solver_solve(Ctx *c, bool use_prec, const char *label);
+
+void halo_setup(Ctx *c);                                     // halo.cu
+void halo_exchange(Ctx *c, double *d_x, int nvec, int ldx);
+void halo_allreduce(Ctx *c, double *d_buf, int count);
+void halo_forward_field(Ctx *c, int field, int ncomp);
+void halo_destroy(Ctx *c);
+int halo_ncols(Ctx *c);
+
+}  // namespace isph

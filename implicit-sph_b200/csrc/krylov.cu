@@ -1,0 +1,451 @@
+// Krylov solvers behind SolverLin_Belos::solveProblem (solver_lin_belos.h:130-222) with the parameter list of
+// setParameters (:224-264): right-preconditioned (flexible) GMRES(m) with DGKS orthogonalisation and PCG, the
+// PoissonProjection operator (solver_lin.h:130-140) for singular problems, null-vector handling of
+// solver_lin.cpp:59-77.  Belos itself is third-party code that is not vendored with the reference; its semantics are
+// restated in oracle/krylov_oracle.cpp (header there) and this file implements the same algorithm on the device:
+//   * every vector operation is a fused, grid-stride kernel with warp-shuffle reductions; per-block partial sums are
+//     combined in block order by the last block to finish (deterministic, no atomics on doubles);
+//   * all Krylov scalars (Hessenberg column, Givens rotations, DGKS decision, alpha/beta of CG) stay on the device;
+//     the Hessenberg least-squares update runs in a single warp; the host only reads the implicit residual, one
+//     iteration late, from pinned memory, so the GPU never waits for the host inside a restart cycle;
+//   * with several ranks the partial results are summed with one ncclAllReduce per reduction (halo.cu).
+// No tensor cores: nothing here is a dense contraction (largest dense object: the 51x50 Hessenberg).
+#include "isph_internal.h"
+
+namespace isph {
+
+static const int VB = 256;              // threads per block of the vector kernels
+static const double DEP_TOL = 0.70710678118654752440;   // DGKSOrthoManager dep_tol = 1/sqrt(2)
+
+// layout of the small device scalar block `hbuf`
+enum { S_H = 0, S_H2 = 64, S_G = 128, S_CS = 192, S_SN = 256, S_Y = 320, S_OLD = 384, S_NEW1 = 385, S_NEW2 = 386, S_PROJ = 387,
+       S_INV = 388, S_RES = 389, S_ALPHA = 390, S_BETA = 391, S_RZ = 392, S_PAP = 393, S_TMP = 394, S_HM = 448 /* H: 64 x 64 */, S_TOTAL = 448 + 64 * 64 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-reduce NACC per-thread accumulators, store the block's partials, and let the last block add the partials of
+// all blocks in block order into out[0..nacc)
+template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out) {
+  __shared__ double sm[NACC][VB / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
+  __syncthreads();
+  if (threadIdx.x < nacc) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < VB / 32; ++w) s += sm[threadIdx.x][w];
+    partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < nacc) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
+      out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// the pre-projection squared norm of pass 0 is stored right behind the nv coefficients (one allreduce covers both)
+__device__ __forceinline__ bool dgks_second(const double *S, int nv) { return S[S_NEW1] < DEP_TOL * S[S_H + nv]; }
+
+// out[0] = sum a_i b_i (b == nullptr: a_i a_i)
+__global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, int n, double *partials, unsigned *counter, double *out) {
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) acc[0] += a[i] * (b ? b[i] : a[i]);
+  reduce_finish<1>(acc, 1, partials, counter, out);
+}
+
+// pass 0: h[k] = V_k . w' (k < nv), old = w'.w'  with  w' = w - proj * nvec  (PoissonProjection tail applied on the fly)
+// pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w
+template <int NVT> __global__ void __launch_bounds__(VB)
+k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
+           double *S, int pass, double *partials, unsigned *counter) {
+  if (pass == 1 && !dgks_second(S, nv)) return;
+  const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
+  double acc[NVT];
+#pragma unroll
+  for (int k = 0; k < NVT; ++k) acc[k] = 0.0;
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+#pragma unroll
+    for (int k = 0; k < NVT - 1; ++k) if (k < nv) acc[k] += V[(size_t)k * ld + i] * wi;
+    acc[NVT - 1] += wi * wi;
+  }
+  // out layout: h[0..nv) then the squared norm
+  __shared__ double sm[NVT][VB / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NVT; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
+  __syncthreads();
+  if (threadIdx.x < NVT) { double s = 0.0; for (int q = 0; q < VB / 32; ++q) s += sm[threadIdx.x][q]; partials[(size_t)blockIdx.x * NVT + threadIdx.x] = s; }
+  __threadfence(); __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < NVT && (threadIdx.x < nv || threadIdx.x == NVT - 1)) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NVT + threadIdx.x];
+      if (threadIdx.x == NVT - 1) { if (pass == 0) S[S_H + nv] = s; }
+      else S[(pass == 0 ? S_H : S_H2) + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// w <- w' - sum_k h_k V_k ; new = ||w||^2
+__global__ void __launch_bounds__(VB)
+k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
+             double *S, int pass, double *partials, unsigned *counter) {
+  if (pass == 1 && !dgks_second(S, nv)) return;
+  __shared__ double sh[64];
+  if (threadIdx.x < nv) sh[threadIdx.x] = S[(pass == 0 ? S_H : S_H2) + threadIdx.x];
+  __syncthreads();
+  const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+#pragma unroll 8
+    for (int k = 0; k < nv; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
+    w[i] = wi; acc[0] += wi * wi;
+  }
+  reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2));
+}
+
+// Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp
+__global__ void k_givens(double *S, int j, int m, double *host_res, int slot) {
+  if (threadIdx.x != 0) return;
+  double *h = S + S_H, *g = S + S_G, *cs = S + S_CS, *sn = S + S_SN, *H = S + S_HM;
+  double newDot = S[S_NEW1];
+  if (dgks_second(S, j + 1)) { for (int k = 0; k <= j; ++k) h[k] += S[S_H2 + k]; newDot = S[S_NEW2]; }
+  const double hn = sqrt(newDot);
+  S[S_INV] = hn > 0.0 ? 1.0 / hn : 0.0;
+  h[j + 1] = hn;
+  for (int k = 0; k < j; ++k) {                       // previous rotations
+    const double a = h[k], b = h[k + 1];
+    h[k] = cs[k] * a + sn[k] * b; h[k + 1] = -sn[k] * a + cs[k] * b;
+  }
+  { const double a = h[j], b = h[j + 1], rr = hypot(a, b);
+    cs[j] = rr == 0.0 ? 1.0 : a / rr; sn[j] = rr == 0.0 ? 0.0 : b / rr; h[j] = rr; h[j + 1] = 0.0;
+    g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j]; }
+  for (int k = 0; k <= j; ++k) H[k * 64 + j] = h[k];
+  const double res = fabs(g[j + 1]);
+  S[S_RES] = res;
+  host_res[slot] = res;
+  __threadfence_system();
+}
+
+// y = H^-1 g for the first ncol columns
+__global__ void k_backsolve(double *S, int ncol) {
+  if (threadIdx.x != 0) return;
+  double *g = S + S_G, *y = S + S_Y, *H = S + S_HM;
+  for (int k = ncol - 1; k >= 0; --k) { double s = g[k]; for (int l = k + 1; l < ncol; ++l) s -= H[k * 64 + l] * y[l]; y[k] = s / H[k * 64 + k]; }
+}
+
+// x += sum_k y_k Z_k
+__global__ void __launch_bounds__(VB) k_update_x(double *x, const double *Z, int ld, int ncol, const double *S, int n) {
+  __shared__ double sy[64];
+  if (threadIdx.x < ncol) sy[threadIdx.x] = S[S_Y + threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    double xi = x[i];
+#pragma unroll 8
+    for (int k = 0; k < ncol; ++k) xi += sy[k] * Z[(size_t)k * ld + i];
+    x[i] = xi;
+  }
+}
+// t = sum_k y_k V_k
+__global__ void __launch_bounds__(VB) k_combine(double *t, const double *V, int ld, int ncol, const double *S, int n) {
+  __shared__ double sy[64];
+  if (threadIdx.x < ncol) sy[threadIdx.x] = S[S_Y + threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    double s = 0.0;
+    for (int k = 0; k < ncol; ++k) s += sy[k] * V[(size_t)k * ld + i];
+    t[i] = s;
+  }
+}
+
+// v <- w * S[S_INV] (in place) and, for Jacobi, z <- damping * invdiag * v in the same pass
+__global__ void __launch_bounds__(VB) k_normalize_prec(double *w, const double *S, const double *invdiag, double damping, double *z, int n) {
+  const double s = S[S_INV];
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const double v = w[i] * s; w[i] = v; if (z) z[i] = invdiag ? damping * invdiag[i] * v : v; }
+}
+// r = b - t (t may be null: r = b) ; out = ||r||^2
+__global__ void __launch_bounds__(VB) k_residual(const double *b, const double *t, double *r, int n, double *partials, unsigned *counter, double *out) {
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const double v = b[i] - (t ? t[i] : 0.0); r[i] = v; acc[0] += v * v; }
+  reduce_finish<1>(acc, 1, partials, counter, out);
+}
+// v0 = r / beta ; g = (beta, 0, ...)
+__global__ void __launch_bounds__(VB) k_start_cycle(const double *r, double *v0, double *S, double beta, int n) {
+  if (blockIdx.x == 0 && threadIdx.x < 64) S[S_G + threadIdx.x] = threadIdx.x == 0 ? beta : 0.0;
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) v0[i] = r[i] / beta;
+}
+// y <- y - (*coef) * nvec  (projection tail / x,b clean-up) ; sign -1 uses +coef
+__global__ void __launch_bounds__(VB) k_axpy_dev(double *y, const double *x, const double *coef, double sign, int n) {
+  const double a = sign * (*coef);
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) y[i] += a * x[i];
+}
+__global__ void __launch_bounds__(VB) k_fill(double *y, double v, int n) { for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) y[i] = v; }
+__global__ void __launch_bounds__(VB) k_mask_to_vec(const int *mask, double *nv, int n) { for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) nv[i] = mask ? (double)mask[i] : 1.0; }
+__global__ void __launch_bounds__(VB) k_scale_by(double *y, double s, int n) { for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) y[i] *= s; }
+__global__ void __launch_bounds__(VB) k_random(double *y, const int *tag, int n, int salt) {     // Epetra Random() stand-in: per-tag hash in (-1,1)
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    unsigned long long z = (unsigned long long)(tag ? tag[i] : i + 1) + 0x9E3779B97F4A7C15ULL * (unsigned long long)(salt + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z = z ^ (z >> 31);
+    y[i] = 2.0 * ((double)(z >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+  }
+}
+
+// ---- PCG kernels -------------------------------------------------------------------------------------------------
+// pAp = p.Ap ; alpha = rz / pAp   (alpha computed by whoever consumes it, so that an allreduce can sit in between)
+__global__ void __launch_bounds__(VB) k_cg_update(double *x, double *r, const double *p, const double *Ap, double *S, int n, double *partials, unsigned *counter) {
+  const double alpha = S[S_RZ] / S[S_PAP];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { x[i] += alpha * p[i]; const double ri = r[i] - alpha * Ap[i]; r[i] = ri; acc[0] += ri * ri; }
+  reduce_finish<1>(acc, 1, partials, counter, S + S_TMP);
+}
+__global__ void k_cg_publish(double *S, double *host_res, int slot) { if (threadIdx.x == 0) { const double res = sqrt(S[S_TMP]); S[S_RES] = res; host_res[slot] = res; __threadfence_system(); } }
+// z = damping * invdiag * r (Jacobi) fused with rz_new = r.z ; for other preconditioners z is given and only the dot is taken
+__global__ void __launch_bounds__(VB) k_cg_precdot(const double *r, double *z, const double *invdiag, double damping, int n, double *partials, unsigned *counter, double *out) {
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { double zi; if (invdiag) { zi = damping * invdiag[i] * r[i]; z[i] = zi; } else zi = z[i]; acc[0] += r[i] * zi; }
+  reduce_finish<1>(acc, 1, partials, counter, out);
+}
+// p = z + beta p with beta = rz_new / rz ; then rz <- rz_new (done by block 0 after everyone has read it: separate tiny kernel)
+__global__ void __launch_bounds__(VB) k_cg_direction(double *p, const double *z, const double *S, int n, int first) {
+  const double beta = first ? 0.0 : S[S_BETA] / S[S_RZ];
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+__global__ void k_cg_shift(double *S) { if (threadIdx.x == 0) S[S_RZ] = S[S_BETA]; }
+
+// ---------------------------------------------------------------------------------------------------------------
+static int vgrid(Ctx *c, int n) { (void)c; int g = ceil_div(n, VB); return g < 592 ? (g < 1 ? 1 : g) : 592; }   // 148 SMs x 4 CTAs
+
+void solver_prepare_vectors(Ctx *c) {
+  const int need = c->A.ncols > c->A.n ? c->A.ncols : c->A.n;
+  c->ld = (need + 31) / 32 * 32;
+}
+
+static void allreduce_if(Ctx *c, double *d, int count) { if (c->nranks > 1) halo_allreduce(c, d, count); }
+
+static void dot_dev(Ctx *c, const double *a, const double *b, int n, double *out) {
+  k_dot<<<vgrid(c, n), VB, 0, c->stream>>>(a, b, n, c->red.p, (unsigned *)c->flag.p + 8, out); ++c->launches;
+  allreduce_if(c, out, 1);
+}
+static double read_scalar(Ctx *c, const double *d) {
+  double v; CUDA_CHECK(cudaMemcpyAsync(c->h_scal.p, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  v = c->h_scal.p[0]; return v;
+}
+
+// operator apply: y = A x, or PoissonProjection::Apply  y = A x ; y -= (y.n) n  (solver_lin.h:130-140).
+// With `defer` the projection coefficient is left in S[S_PROJ] for the orthogonalisation kernels to apply on the fly.
+static void op_apply(Ctx *c, const double *x, double *y, bool defer) {
+  spmv(c, x, y, 1, c->ld, c->ld);
+  if (c->is_singular) {
+    double *S = c->hbuf.p;
+    dot_dev(c, y, c->nullvec.p, c->A.n, S + S_PROJ);
+    if (!defer) { k_axpy_dev<<<vgrid(c, c->A.n), VB, 0, c->stream>>>(y, c->nullvec.p, S + S_PROJ, -1.0, c->A.n); ++c->launches; }
+  }
+}
+
+static void apply_prec(Ctx *c, bool use_prec, const double *r, double *z) {
+  if (use_prec) precond_apply(c, r, z);
+  else CUDA_CHECK(cudaMemcpyAsync(z, r, sizeof(double) * c->A.n, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass) {
+  const int n = c->A.n, g = vgrid(c, n); double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 8;
+#define MD(T) k_multidot<T><<<g, VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt)
+  if (nv + 1 <= 4) MD(4); else if (nv + 1 <= 8) MD(8); else if (nv + 1 <= 16) MD(16); else if (nv + 1 <= 32) MD(32); else MD(52);
+#undef MD
+  ++c->launches;
+  if (c->nranks > 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
+}
+
+static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out, double *relres_out) {
+  const int n = c->A.n, ld = c->ld, m = c->sp.num_blocks; const bool flex = c->sp.flexible;
+  ISPH_REQUIRE(m >= 1 && m <= 51, "Num Blocks must be in 1..51");
+  double *S = c->hbuf.p, *V = c->V.p, *Z = c->Z.p, *r = c->wk.p; unsigned *cnt = (unsigned *)c->flag.p + 8;
+  const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
+  const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  std::vector<cudaEvent_t> ev(m);
+  for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  int iters = 0, restarts = 0; bool converged = false, first = true; double scale = 0.0, res = 0.0;
+  const int g = vgrid(c, n);
+  while (true) {
+    // r = b - Op x ; beta = ||r||
+    if (first && c->init_type == ISPH_INIT_ZERO) { k_residual<<<g, VB, 0, c->stream>>>(b, nullptr, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
+    else { op_apply(c, x, V + (size_t)ld, false); k_residual<<<g, VB, 0, c->stream>>>(b, V + (size_t)ld, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
+    allreduce_if(c, S + S_TMP, 1);
+    const double beta = sqrt(read_scalar(c, S + S_TMP));
+    if (first) { scale = beta; first = false; }
+    res = beta;
+    if (scale == 0.0 || res / scale <= c->sp.tol) { converged = true; break; }
+    k_start_cycle<<<g, VB, 0, c->stream>>>(r, V, S, beta, n); ++c->launches;
+    // z_0 = M^-1 v_0
+    apply_prec(c, use_prec, V, Z);
+    int ncol = 0; bool stop = false;
+    int j = 0;
+    for (; j < m; ++j) {
+      double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
+      op_apply(c, zj, vn, true);                                 // w = A z_j (projection coefficient deferred)
+      launch_multidot(c, V, j + 1, vn, 0);
+      k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_NEW1, 1);
+      launch_multidot(c, V, j + 1, vn, 1);
+      k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_NEW2, 1);
+      k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches;
+      CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
+      ++iters;
+      if (j + 1 < m) {                                           // prepare the next Arnoldi step before looking at the residual
+        double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
+        if (jacobi_fused) { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, c->invdiag.p, c->pp.damping, zn, n); ++c->launches; }
+        else { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, nullptr, 1.0, nullptr, n); ++c->launches; apply_prec(c, use_prec, vn, zn); }
+      }
+      // look at the residual of the PREVIOUS step (already finished on the device): no pipeline bubble
+      if (j >= 1) {
+        CUDA_CHECK(cudaEventSynchronize(ev[j - 1]));
+        res = c->h_scal.p[8 + iters - 1];
+        if (res / scale <= c->sp.tol) { converged = true; stop = true; ncol = j; --iters; break; }
+        if (iters - 1 >= c->sp.max_iters) { stop = true; ncol = j; --iters; break; }
+      }
+    }
+    if (!stop) {                                                  // last step of the cycle (or m == 1)
+      CUDA_CHECK(cudaEventSynchronize(ev[m - 1]));
+      res = c->h_scal.p[8 + iters]; ncol = m;
+      if (res / scale <= c->sp.tol) { converged = true; stop = true; }
+      else if (iters >= c->sp.max_iters) stop = true;
+    }
+    // x += Z y (flexible) or x += M^-1 (V y)
+    k_backsolve<<<1, 32, 0, c->stream>>>(S, ncol); ++c->launches;
+    if (flex) { k_update_x<<<g, VB, 0, c->stream>>>(x, Z, ld, ncol, S, n); ++c->launches; }
+    else { k_combine<<<g, VB, 0, c->stream>>>(r, V, ld, ncol, S, n); ++c->launches; apply_prec(c, use_prec, r, Z);
+           k_fill<<<1, 32, 0, c->stream>>>(S + S_TMP, 1.0, 1); ++c->launches;
+           k_axpy_dev<<<g, VB, 0, c->stream>>>(x, Z, S + S_TMP, 1.0, n); ++c->launches; }
+    if (stop) break;
+    if (restarts >= c->sp.max_restarts) break;
+    ++restarts;
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  *iters_out = iters; *relres_out = scale > 0.0 ? res / scale : 0.0;
+  return converged ? 1 : 0;
+}
+
+static int cg_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out, double *relres_out) {
+  const int n = c->A.n, ld = c->ld, g = vgrid(c, n);
+  double *S = c->hbuf.p, *r = c->wk.p, *z = c->V.p, *p = c->V.p + (size_t)ld, *Ap = c->V.p + (size_t)2 * ld; unsigned *cnt = (unsigned *)c->flag.p + 8;
+  const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  cudaEvent_t ev[2]; for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // R = b - A x ; Z = M^-1 R ; P = Z ; rz = R.Z
+  if (c->init_type == ISPH_INIT_ZERO) { k_residual<<<g, VB, 0, c->stream>>>(b, nullptr, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
+  else { op_apply(c, x, Ap, false); k_residual<<<g, VB, 0, c->stream>>>(b, Ap, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
+  allreduce_if(c, S + S_TMP, 1);
+  const double scale = sqrt(read_scalar(c, S + S_TMP)); double res = scale; int iters = 0; bool converged = false;
+  if (scale == 0.0 || res / scale <= c->sp.tol) converged = true;
+  else {
+    if (jacobi_fused) { k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, c->invdiag.p, c->pp.damping, n, c->red.p, cnt, S + S_RZ); ++c->launches; }
+    else { apply_prec(c, use_prec, r, z); k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, nullptr, 1.0, n, c->red.p, cnt, S + S_RZ); ++c->launches; }
+    allreduce_if(c, S + S_RZ, 1);
+    k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 1); ++c->launches;
+    while (true) {
+      ++iters;
+      op_apply(c, p, Ap, false);
+      dot_dev(c, p, Ap, n, S + S_PAP);
+      k_cg_update<<<g, VB, 0, c->stream>>>(x, r, p, Ap, S, n, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_TMP, 1);
+      k_cg_publish<<<1, 32, 0, c->stream>>>(S, c->h_scal.p + 8, iters); ++c->launches;
+      CUDA_CHECK(cudaEventRecord(ev[iters & 1], c->stream));
+      // next direction, enqueued before the residual of this step is inspected
+      if (jacobi_fused) { k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, c->invdiag.p, c->pp.damping, n, c->red.p, cnt, S + S_BETA); ++c->launches; }
+      else { apply_prec(c, use_prec, r, z); k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, nullptr, 1.0, n, c->red.p, cnt, S + S_BETA); ++c->launches; }
+      allreduce_if(c, S + S_BETA, 1);
+      k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 0); ++c->launches;
+      k_cg_shift<<<1, 32, 0, c->stream>>>(S); ++c->launches;
+      CUDA_CHECK(cudaEventSynchronize(ev[iters & 1]));
+      res = c->h_scal.p[8 + iters];
+      if (res / scale <= c->sp.tol) { converged = true; break; }
+      if (iters >= c->sp.max_iters) break;
+    }
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  *iters_out = iters; *relres_out = scale > 0.0 ? res / scale : 0.0;
+  return converged ? 1 : 0;
+}
+
+// SolverLin_Belos::solveProblem, solver_lin_belos.h:130-222
+void solver_solve(Ctx *c, bool use_prec, const char *label) {
+  Matrix &A = c->A; ISPH_REQUIRE(A.built, "solveProblem: no matrix (setMatrix)");
+  ISPH_REQUIRE(c->x_nvec >= 1 && c->b_nvec == c->x_nvec && c->xs.p && c->bs.p, "solveProblem: create the solution and load multivectors first");
+  const int n = A.n, ld = c->ld, m = c->sp.num_blocks, g = vgrid(c, n);
+  const bool is_cg = c->sp.solver_type == "Block CG";
+  ISPH_REQUIRE(is_cg || c->sp.solver_type == "Block GMRES", "Solver Type must be \"Block GMRES\" or \"Block CG\" (Recycling GMRES is not implemented)");
+  ISPH_REQUIRE(c->sp.block_size == 1, "Block Size must be 1");
+  std::string tname = std::string("solve") + (label ? label : "");
+  c->tic(tname.c_str());
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)592 * 64); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
+  c->h_scal.ensure(16 + c->sp.max_iters + m + 8);
+  c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
+  c->Z.ensure((size_t)(is_cg ? 1 : (c->sp.flexible ? m : 1)) * ld);
+  CUDA_CHECK(cudaMemsetAsync(c->flag.p + 8, 0, 4 * sizeof(int), c->stream));
+  // initial solution (setInitialSolution, solver_lin.cpp:141-147): applied here, on the device
+  const size_t xl = (size_t)ld * c->x_nvec;
+  if (c->init_type == ISPH_INIT_ZERO) CUDA_CHECK(cudaMemsetAsync(c->xs.p, 0, sizeof(double) * xl, c->stream));
+  else if (c->init_type == ISPH_INIT_VALUE) { k_fill<<<vgrid(c, (int)xl), VB, 0, c->stream>>>(c->xs.p, c->init_val, (int)xl); ++c->launches; }
+  else if (c->init_type == ISPH_INIT_RANDOM) { for (int q = 0; q < c->x_nvec; ++q) { k_random<<<g, VB, 0, c->stream>>>(c->xs.p + (size_t)q * ld, A.external ? nullptr : c->tag.p, n, 11 + q); ++c->launches; } }
+  else if (c->x_host) {     // caller's x is the initial guess (Helmholtz: x = v, pair_isph.cpp:932-941)
+    for (int q = 0; q < c->x_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * ld, c->x_host + (size_t)q * c->x_lda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (c->b_host && !c->b_owned) for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->bs.p + (size_t)q * ld, c->b_host + (size_t)q * c->b_lda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  double *S = c->hbuf.p;
+  if (c->is_singular) {     // createNullVector (solver_lin.cpp:59-77) ; b -= (b.n) n (solver_lin_belos.h:138-144)
+    c->nullvec.ensure(ld);
+    k_mask_to_vec<<<g, VB, 0, c->stream>>>(c->have_mask ? c->mask.p : nullptr, c->nullvec.p, n); ++c->launches;
+    dot_dev(c, c->nullvec.p, nullptr, n, S + S_TMP);
+    const double nrm = sqrt(read_scalar(c, S + S_TMP));
+    k_scale_by<<<g, VB, 0, c->stream>>>(c->nullvec.p, 1.0 / nrm, n); ++c->launches;
+    for (int q = 0; q < c->b_nvec; ++q) { dot_dev(c, c->bs.p + (size_t)q * ld, c->nullvec.p, n, S + S_TMP);
+      k_axpy_dev<<<g, VB, 0, c->stream>>>(c->bs.p + (size_t)q * ld, c->nullvec.p, S + S_TMP, -1.0, n); ++c->launches; }
+  }
+  if (use_prec) precond_create(c);                               // prec->create(), solver_lin_belos.h:153
+  int iters_tot = 0, conv_all = 1; double relres = 0.0;
+  for (int q = 0; q < c->x_nvec; ++q) {                          // block size 1: right-hand sides are solved one after another
+    int it = 0; double rr = 0.0;
+    const int ok = is_cg ? cg_solve(c, use_prec, c->xs.p + (size_t)q * ld, c->bs.p + (size_t)q * ld, &it, &rr)
+                         : gmres_solve(c, use_prec, c->xs.p + (size_t)q * ld, c->bs.p + (size_t)q * ld, &it, &rr);
+    iters_tot += it; conv_all &= ok; relres = rr > relres ? rr : relres;
+  }
+  if (use_prec) precond_free(c);                                 // prec->free(), :186-191
+  if (!conv_all && c->rank == 0) {                               // :197-213 : not an error, report ||b - A x|| / ||b||
+    double rn = 0.0, bn = 0.0;
+    spmv(c, c->xs.p, c->wk.p, 1, ld, ld);
+    k_residual<<<g, VB, 0, c->stream>>>(c->bs.p, c->wk.p, c->wk.p, n, c->red.p, (unsigned *)c->flag.p + 8, S + S_TMP); ++c->launches;
+    allreduce_if(c, S + S_TMP, 1); rn = sqrt(read_scalar(c, S + S_TMP));
+    dot_dev(c, c->bs.p, nullptr, n, S + S_TMP); bn = sqrt(read_scalar(c, S + S_TMP));
+    fprintf(stderr, ">> isph_b200::Status - Failed to converge! %s  ||r|| / ||b|| = %6.4e\n", label ? label : " ", bn > 0 ? rn / bn : rn);
+  }
+  if (c->is_singular) {                                          // x -= (x.n) n, :215-219
+    for (int q = 0; q < c->x_nvec; ++q) { dot_dev(c, c->xs.p + (size_t)q * ld, c->nullvec.p, n, S + S_TMP);
+      k_axpy_dev<<<g, VB, 0, c->stream>>>(c->xs.p + (size_t)q * ld, c->nullvec.p, S + S_TMP, -1.0, n); ++c->launches; }
+  }
+  if (c->x_host) for (int q = 0; q < c->x_nvec; ++q)             // x is a View of caller memory (solver_lin.cpp:52-58)
+    CUDA_CHECK(cudaMemcpyAsync(c->x_host + (size_t)q * c->x_lda, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  c->toc(tname.c_str());
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->last_iters = iters_tot; c->last_converged = conv_all; c->last_relres = relres;
+  c->init_type = -1;
+}
+
+}  // namespace isph

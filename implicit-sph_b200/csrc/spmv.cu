@@ -1,0 +1,61 @@
+// SpMV on the SELL-32 layout: y = A x (Epetra_CrsMatrix::Multiply/Apply as called by Belos and by
+// functor_incomp_navier_stokes_helmholtz.h:90; solver_lin.h:133).
+//
+// One thread per row, one warp per slice: the warp's loads of `col` (128 B) and `val` (256 B) for entry k of its 32
+// rows are single fully-used cache lines, streamed with evict-first hints so that they do not displace x from L2/L1;
+// x is gathered through the read-only path.  Because rows follow the particle order, the k-th neighbours of 32
+// consecutive rows are (nearly) consecutive columns, so the gather touches 2-3 lines per warp instead of 32 —
+// this is what keeps the kernel HBM-bound rather than L1-wavefront-bound ("SpMV").
+// Algorithmic traffic: 12 B per stored entry + 8 B x + 8 B y (+ slice metadata) per row.
+#include "isph_internal.h"
+
+namespace isph {
+
+template <int NV> __global__ void __launch_bounds__(256)
+k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col,
+            const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
+  if (s >= nslices) return;
+  const long long base = slice_off[s] + (row & 31);
+  const int slen = slice_len[s];
+  const int *cp = col + base; const double *vp = val + base;
+  double acc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+  int k = 0;
+  for (; k + 4 <= slen; k += 4) {
+    const int c0 = __ldcs(cp + 32 * (k + 0)), c1 = __ldcs(cp + 32 * (k + 1)), c2 = __ldcs(cp + 32 * (k + 2)), c3 = __ldcs(cp + 32 * (k + 3));
+    const double v0 = __ldcs(vp + 32 * (k + 0)), v1 = __ldcs(vp + 32 * (k + 1)), v2 = __ldcs(vp + 32 * (k + 2)), v3 = __ldcs(vp + 32 * (k + 3));
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const double *xq = x + (size_t)q * ldx;
+      acc[q] += v0 * __ldg(xq + c0); acc[q] += v1 * __ldg(xq + c1); acc[q] += v2 * __ldg(xq + c2); acc[q] += v3 * __ldg(xq + c3);
+    }
+  }
+  for (; k < slen; ++k) {
+    const int c0 = __ldcs(cp + 32 * k); const double v0 = __ldcs(vp + 32 * k);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) acc[q] += v0 * __ldg(x + (size_t)q * ldx + c0);
+  }
+  if (row < n) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) y[(size_t)q * ldy + row] = acc[q];
+  }
+}
+
+void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy) {
+  Matrix &A = c->A; ISPH_REQUIRE(A.built, "spmv: no matrix");
+  if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);     // import of off-rank x entries (Epetra_Import)
+  const int grid = ceil_div((long long)A.nslices * 32, 256);
+  int done = 0;
+  while (done < nvec) {
+    const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
+    const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy;
+    if (nv == 3) k_spmv_sell<3><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
+    else if (nv == 2) k_spmv_sell<2><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
+    else k_spmv_sell<1><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
+    ++c->launches; done += nv;
+  }
+}
+
+}  // namespace isph

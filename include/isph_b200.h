@@ -1,0 +1,153 @@
+/* isph_b200.h — C ABI of the B200-native linear-solve hot path of implicit-sph.
+ *
+ * Drop-in boundary: everything the reference does between "LAMMPS hands over atoms + full
+ * neighbor list" and "x holds the Krylov solution" — graph build, operator assembly, preconditioner, Krylov —
+ * runs on one B200 per process behind these entry points.  Plain pointers and sizes only; all pointers are HOST
+ * pointers unless a function says otherwise; nothing passed in is retained after the call returns except where
+ * stated ("borrowed", mirroring Teuchos::rcp(p,false) in the reference).  Every function returns
+ * ISPH_SUCCESS (0, = LAMMPS_SUCCESS, macrodef.h:23) or ISPH_FAILURE (-1, = LAMMPS_FAILURE, macrodef.h:20);
+ * isph_last_error() gives the message.  Non-convergence of a solve is NOT an error (solver_lin_belos.h:194-213).
+ *
+ * Each group cites the reference interface it replaces (paths relative to IMPLICIT-SPH/).
+ * The header-only C++ adapter include/solver_lin_b200.h re-creates the SolverLin / PrecondWrapper method names
+ * on top of this ABI; INTEGRATION.md shows the binding a reference maintainer would add.
+ */
+#ifndef ISPH_B200_H
+#define ISPH_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISPH_SUCCESS 0
+#define ISPH_FAILURE (-1)
+
+typedef struct isph_ctx isph_ctx;
+
+/* ParticleKind bit masks, pair_isph.h:113-123 */
+enum { ISPH_KIND_FLUID = 99, ISPH_KIND_SOLID = 12, ISPH_KIND_BOUNDARY = 16, ISPH_KIND_BUFFER_DIRICHLET = 32,
+       ISPH_KIND_BUFFER_NEUMANN = 64, ISPH_KIND_ALL = 127 };
+/* SingularPoisson, pair_isph.h:133-137 */
+enum { ISPH_NOT_SINGULAR = 0, ISPH_NULLSPACE = 1, ISPH_PINZERO = 2, ISPH_DOUBLEDIAG = 3 };
+/* kernel functions, pair_isph_corrected.cpp:1295-1302 */
+enum { ISPH_KERNEL_WENDLAND = 0, ISPH_KERNEL_CUBIC = 1, ISPH_KERNEL_QUINTIC = 2 };
+/* SolverLin::SolutionInitType, solver_lin.h:25 */
+enum { ISPH_INIT_RANDOM = 0, ISPH_INIT_ZERO = 1, ISPH_INIT_VALUE = 2 };
+/* per-particle fields, row-major [nlocal+nghost][ncomp]  (atom_vec_isph.h:56-89 / pair_isph.h work arrays) */
+enum { ISPH_F_VFRAC = 0,   /* 1 */ ISPH_F_GC = 1,       /* 9: dim x dim column-major (VIEW2, macrodef.h:61) in the first dim*dim */
+       ISPH_F_LC = 2,      /* 6: packed symmetric, first dim(dim+1)/2 */
+       ISPH_F_NORMAL = 3,  /* 3 */ ISPH_F_PND = 4,      /* 1 */
+       ISPH_F_DENSITY = 5, ISPH_F_VISCOSITY = 6, ISPH_F_PRESSURE = 7,
+       ISPH_F_VELOCITY = 8,/* 3 */ ISPH_F_VSTAR = 9,    /* 3 */ ISPH_F_FORCE = 10, /* 3 */
+       ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_COUNT = 13 };
+
+/* ---- context ------------------------------------------------------------------------------------------------
+ * replaces: SolverLin(MPI_Comm&) solver_lin.h:28, PrecondWrapper(MPI_Comm) precond.h:26 (one communicator per
+ * process; here one NCCL communicator per GPU).  nccl_unique_id: 128 bytes obtained from isph_nccl_unique_id() on
+ * rank 0 and broadcast by the host program (MPI in LAMMPS, torch.distributed in bench.py); NULL when nranks == 1. */
+int isph_ctx_create(isph_ctx **ctx, int device, int nranks, int rank, const void *nccl_unique_id);
+int isph_ctx_destroy(isph_ctx *ctx);
+int isph_nccl_unique_id(void *id128);
+const char *isph_last_error(const isph_ctx *ctx);
+int isph_set_stream(isph_ctx *ctx, void *cuda_stream);   /* run on the caller's CUDA stream (borrowed) */
+int isph_synchronize(isph_ctx *ctx);
+const char *isph_version(void);
+
+/* ---- pair / atom / neighbor data ------------------------------------------------------------------------------
+ * replaces: PairISPH_Corrected::coeff pair_isph_corrected.cpp:1273-1347 (kernel, cutsq, h tables, MorrisSafeCoeff)
+ *           and the FunctorOuter<PairIsph> constructor capture functor.h:64-91 (atom->{x,type,tag,vfrac}, list->...) */
+int isph_pair_coeff(isph_ctx *ctx, int dim, int ntypes, const int *kind_of_type /*[ntypes+1]*/, double h, double h_min,
+                    double cut_over_h, int kernel, double morris_safe);
+int isph_atoms_set(isph_ctx *ctx, int nlocal, int nghost, const double *x /*[nall][3]*/, const int *type, const int *tag);
+/* LAMMPS NeighList layout: numneigh[i], firstneigh[i] indexed by atom i = ilist[ii]; entries are masked with NEIGHMASK */
+int isph_neighbors_set(isph_ctx *ctx, int inum, const int *ilist, const int *numneigh, int *const *firstneigh);
+/* packed layout: row ii owns neigh[noff[ii] .. noff[ii+1]) */
+int isph_neighbors_set_packed(isph_ctx *ctx, int inum, const int *ilist, const long long *noff, const int *neigh);
+int isph_field_set(isph_ctx *ctx, int field, const double *data);
+int isph_field_get(isph_ctx *ctx, int field, double *data);
+/* owner -> ghost copy of a field: comm->forward_comm_pair(this), pair_isph.cpp:1924-2074 */
+int isph_forward_comm(isph_ctx *ctx, int field);
+
+/* ---- pre-computation (PairISPH_Corrected::computePre, pair_isph_corrected.cpp:302-313) ------------------------ */
+int isph_compute_volumes(isph_ctx *ctx);               /* functor_volume.h:42-81 */
+int isph_compute_gradient_correction(isph_ctx *ctx);   /* functor_gradient_correction.h:24-71 */
+int isph_compute_laplacian_correction(isph_ctx *ctx);  /* functor_laplacian_correction.h:25-153 */
+int isph_compute_normals(isph_ctx *ctx);               /* functor_normal.h:56-125, pair_isph_corrected.cpp:404-427 */
+
+/* ---- graph + matrix (the Epetra_CrsGraph / Epetra_CrsMatrix method set the functors call) -------
+ * isph_graph_build = nodal map (pair_isph.cpp:1258-1259) + FunctorOuterGraph (functor_graph.h:38-99)
+ *                    + new Epetra_CrsMatrix(Copy, graph) + zero diagonal vectors (pair_isph.cpp:1266-1270) */
+int isph_graph_build(isph_ctx *ctx);
+long long isph_graph_nnz(isph_ctx *ctx);                /* after duplicate merging (Epetra FillComplete) */
+int isph_graph_max_row(isph_ctx *ctx);                  /* Epetra_CrsGraph::MaxNumIndices */
+/* canonical form: rows in nodal-map order, columns = ascending global tag, duplicates merged */
+int isph_graph_get(isph_ctx *ctx, int *rowptr /*[nlocal+1]*/, int *col_tags /*[nnz]*/);
+int isph_matrix_get(isph_ctx *ctx, double *val /*[nnz], aligned with isph_graph_get*/);
+/* matrix supplied by the caller (second API client, USER-REAXC-T/fix_qeq_reax.cpp:509-694): local column ids */
+int isph_matrix_set_csr(isph_ctx *ctx, int n, const int *rowptr, const int *col, const double *val);
+int isph_matrix_put_scalar(isph_ctx *ctx, double a);                       /* PutScalar */
+int isph_matrix_scale(isph_ctx *ctx, double a);                            /* Scale */
+int isph_matrix_left_scale(isph_ctx *ctx, const double *s /*[nlocal]*/);   /* LeftScale */
+int isph_matrix_extract_diagonal(isph_ctx *ctx, double *d /*[nlocal]*/);   /* ExtractDiagonalCopy */
+int isph_matrix_replace_diagonal(isph_ctx *ctx, const double *d);          /* ReplaceDiagonalValues */
+int isph_matrix_multiply(isph_ctx *ctx, const double *x, double *y, int lda, int nvec);   /* Multiply(false, X, Y) */
+int isph_matrix_invalidate(isph_ctx *ctx);                                 /* A.is_filled = 0, pair_isph.cpp:982,1026 */
+/* Corrected::FunctorOuterLaplacianMatrix<Pair,Anti>[_MorrisHolmes], functor_laplacian_matrix.h:56-328, including the
+ * PutScalar(0.0) that precedes it at every call site.  material_field < 0: material == 1. */
+int isph_assemble_laplacian(isph_ctx *ctx, double alpha, int material_field, int anti, int morris_holmes,
+                            int filter_i, int filter_j);
+/* FunctorOuterGradientDotOperatorMatrix, functor_gradient_dot_operator_matrix.h:36-79 (SumInto) */
+int isph_assemble_gradient_dot(isph_ctx *ctx, double alpha, int vector_field, int filter_i, int filter_j);
+
+/* ---- system functors ----------------------------------------------------------------------------------------
+ * They fill A and the solver's load vector b on the device (b = li_solver->getLoadMultiVector()->Values()). */
+/* FunctorOuterIncompNavierStokesPoisson, functor_incomp_navier_stokes_poisson.h:47-181 (via computePoisson) */
+int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int morris_holmes);
+/* FunctorOuterIncompNavierStokesHelmholtz, functor_incomp_navier_stokes_helmholtz.h:48-159; b must hold v^n */
+int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int morris_holmes, int incremental_pressure,
+                      const double *g /*[3]*/);
+/* FunctorOuterPoissonBoltzmannJacobian, functor_poisson_boltzmann_jacobian.h:35-107 */
+int isph_pb_jacobian(isph_ctx *ctx, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+int isph_diagonals_get(isph_ctx *ctx, double *diagonal, double *scaled_laplace_diagonal);   /* A.diagonal, A.scaled_laplace_diagonal */
+
+/* ---- SolverLin / SolverLin_Belos mirror (solver_lin.h:23-98, solver_lin.cpp, solver_lin_belos.h:130-264) --------- */
+int isph_solver_create_solution_multivector(isph_ctx *ctx, double *x /*borrowed; NULL: owned*/, int lda, int nvec);
+int isph_solver_create_load_multivector(isph_ctx *ctx, double *b /*borrowed; NULL: owned, device-resident*/, int lda, int nvec);
+int isph_solver_load_set(isph_ctx *ctx, const double *b, int lda);        /* write getLoadMultiVector()->Values() */
+int isph_solver_load_get(isph_ctx *ctx, double *b, int lda);
+int isph_solver_solution_get(isph_ctx *ctx, double *x, int lda);
+int isph_solver_set_null_vector_mask(isph_ctx *ctx, const int *mask /*[nlocal] or NULL = all ones*/);
+int isph_solver_set_matrix_is_singular(isph_ctx *ctx, int is_singular);
+int isph_solver_set_initial_solution(isph_ctx *ctx, int init_type, double val);
+/* Belos parameter names are kept: "Solver Type" ("Block GMRES"|"Block CG"), "Flexible Gmres", "Num Blocks",
+ * "Maximum Iterations", "Maximum Restarts", "Convergence Tolerance", "Orthogonalization" ("DGKS") */
+int isph_solver_set_param_int(isph_ctx *ctx, const char *name, int v);
+int isph_solver_set_param_double(isph_ctx *ctx, const char *name, double v);
+int isph_solver_set_param_str(isph_ctx *ctx, const char *name, const char *v);
+int isph_solver_set_default_params(isph_ctx *ctx);                        /* setParameters(NULL), solver_lin_belos.h:224-264 */
+/* PrecondWrapper_Ifpack parameter names are kept (precond_ifpack.h:28-48): "Precond Type" ("point relaxation" |
+ * "Chebyshev" | "ILU" | "none"), "Overlap Level" (0), "fact: level-of-fill" (0), "relaxation: type" ("Jacobi"),
+ * "relaxation: sweeps", "relaxation: damping factor", "chebyshev: degree", "chebyshev: ratio eigenvalue",
+ * "chebyshev: max eigenvalue", "chebyshev: eigenvalue max iterations".  "b200: ilu blocks" = {bx,by,bz} split of the
+ * local rows into Ifpack-rank-equivalent bricks is set with isph_precond_set_blocks(). */
+int isph_precond_set_param_int(isph_ctx *ctx, const char *name, int v);
+int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v);
+int isph_precond_set_param_str(isph_ctx *ctx, const char *name, const char *v);
+int isph_precond_set_blocks(isph_ctx *ctx, const int *block_of_row /*[nlocal] or NULL = one block*/);
+int isph_precond_create(isph_ctx *ctx);     /* PrecondWrapper::create(), precond_ifpack.h:50-75 */
+int isph_precond_free(isph_ctx *ctx);       /* PrecondWrapper::free() */
+int isph_precond_apply(isph_ctx *ctx, const double *r, double *z);        /* ApplyInverse, host vectors (tests) */
+/* SolverLin_Belos::solveProblem(prec, name): use_prec != 0 creates and frees the preconditioner around the solve */
+int isph_solver_solve(isph_ctx *ctx, int use_prec, const char *label);
+int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged, double *lambda_max);
+
+/* ---- timers (the reference's Teuchos::Time scopes, utils.cpp:16-43): "computePoisson", "solvePoisson", ... ----- */
+double isph_timer_ms(isph_ctx *ctx, const char *name);    /* accumulated device time (CUDA events) */
+int isph_timer_reset(isph_ctx *ctx);
+long long isph_kernel_launches(isph_ctx *ctx);            /* number of kernels this context has launched */
+/* last SpMV-only micro benchmark: runs `reps` SpMVs on the current matrix, returns average ms (device events) */
+int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,65 @@
+"""Drives one problem through the CPU oracle or through the CUDA C-ABI with the same call sequence."""
+import importlib
+
+import numpy as np
+
+import oracle as O
+
+isph = importlib.import_module("implicit-sph_b200")
+
+
+def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
+    cs = P["case"]
+    o = O.Oracle(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"], kind=kind)
+    o.set_field(O.F_DENSITY, F["density"]); o.set_field(O.F_VISCOSITY, F["viscosity"]); o.set_field(O.F_PRESSURE, F["pressure"])
+    o.set_field(O.F_VSTAR, F["velocity"]); o.set_field(O.F_VELOCITY, F["velocity"]); o.set_field(O.F_FORCE, F["force"])
+    o.set_field(O.F_EPS, F["eps"]); o.set_field(O.F_PSI, F["psi"])
+    o.compute_pre(normals=cs["has_solid"])
+    out = dict(vfrac=o.get_field(O.F_VFRAC), gc=o.get_field(O.F_GC), lc=o.get_field(O.F_LC))
+    if cs["has_solid"]:
+        out["normal"] = o.get_field(O.F_NORMAL); out["pnd"] = o.get_field(O.F_PND)
+    out["rowptr"], out["col"] = o.graph()
+    nl, dim = P["nlocal"], P["dim"]
+    out["b_poisson"] = o.ns_poisson(cs["dt"], anti=anti, singular=singular, morris_holmes=mh); out["A_poisson"] = o.matrix()
+    out["diag_poisson"], out["sld_poisson"] = o.diagonals(); o.invalidate_matrix()
+    b0 = np.asfortranarray(F["velocity"][:nl, :dim])
+    out["b_helmholtz"] = o.ns_helmholtz(cs["dt"], cs["theta"], b0, anti=anti, morris_holmes=mh); out["A_helmholtz"] = o.matrix(); o.invalidate_matrix()
+    o.pb_jacobian(morris_holmes=mh); out["A_pb"] = o.matrix()
+    o.set_field(O.F_PSI, np.cos(P["xw"][:, 0])); o.pb_jacobian(morris_holmes=mh); out["A_pb2"] = o.matrix()
+    x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = o.spmv(x)
+    o.close()
+    return out
+
+
+def cuda_context(P, F, device=0):
+    cs = P["case"]
+    c = isph.Context(device)
+    c.set_particles(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"])
+    c.field_set(isph.F_DENSITY, F["density"]); c.field_set(isph.F_VISCOSITY, F["viscosity"]); c.field_set(isph.F_PRESSURE, F["pressure"])
+    c.field_set(isph.F_VSTAR, F["velocity"]); c.field_set(isph.F_VELOCITY, F["velocity"]); c.field_set(isph.F_FORCE, F["force"])
+    c.field_set(isph.F_EPS, F["eps"]); c.field_set(isph.F_PSI, F["psi"])
+    return c
+
+
+def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
+    cs = P["case"]
+    c = cuda_context(P, F, device)
+    c.compute_pre(normals=cs["has_solid"])
+    out = dict(vfrac=c.field_get(isph.F_VFRAC), gc=c.field_get(isph.F_GC), lc=c.field_get(isph.F_LC))
+    if cs["has_solid"]:
+        out["normal"] = c.field_get(isph.F_NORMAL); out["pnd"] = c.field_get(isph.F_PND)
+    c.graph_build()
+    out["rowptr"], out["col"] = c.graph_get()
+    nl, dim = P["nlocal"], P["dim"]
+    c.create_load(None, 1)
+    c.ns_poisson(cs["dt"], anti=anti, singular=singular, morris_holmes=mh)
+    out["b_poisson"] = c.load_get(1)[:, 0]; out["A_poisson"] = c.matrix_get(); out["diag_poisson"], out["sld_poisson"] = c.diagonals_get(); c.matrix_invalidate()
+    c.create_load(None, dim); c.load_set(np.asfortranarray(F["velocity"][:nl, :dim]))
+    c.ns_helmholtz(cs["dt"], cs["theta"], anti=anti, morris_holmes=mh)
+    out["b_helmholtz"] = c.load_get(dim); out["A_helmholtz"] = c.matrix_get(); c.matrix_invalidate()
+    c.pb_jacobian(morris_holmes=mh); out["A_pb"] = c.matrix_get()
+    c.field_set(isph.F_PSI, np.cos(P["xw"][:, 0])); c.pb_jacobian(morris_holmes=mh); out["A_pb2"] = c.matrix_get()
+    x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = c.matrix_multiply(x)
+    out["launches"] = c.launches
+    c.close()
+    return out
