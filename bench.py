@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — implicit-sph linear-solve hot path on B200 (see DESIGN.md "Measurement").
+
+One *step* = what `PairISPH::compute` does per time step for the pressure Poisson problem (pair_isph.cpp:1241-1380,
+:988-1026): pre-computation (volumes / gradient & Laplacian corrections), nodal map + graph, operator assembly + RHS
+(computePoisson), flexible GMRES(50) + preconditioner solve (solvePoisson) — everything rebuilt from scratch, as the
+reference does.  Metric: rows assembled-and-solved per second (whole job), with `ms_per_step` = the absolute Poisson
+step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM bandwidth inside the solve.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|c4j] [--n LATTICE]
+
+N=1 workload (default) = BASELINE.json configs[1]: 3-D pressure Poisson, 100^3 = 1M-particle periodic lattice, Wendland,
+GMRES + Jacobi.  `--impl reference` times the CPU path (oracle port, OpenMP over all host cores) on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dim, lattice edge, jitter, rs2, precond, solver, description
+    "c2": dict(dim=3, n=100, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES",
+               desc="BASELINE configs[1]: 3-D pressure Poisson, 1M-particle periodic cubic lattice, Wendland h=1.5dx cut=2h, NullSpace, flexible GMRES(50)+Jacobi"),
+    "c1": dict(dim=2, n=128, jitter=0.0, rs2=9, prec="ILU", solver="Block GMRES", origin=0.5,
+               desc="BASELINE configs[0]: 2-D TGV 128x128 pressure Poisson, flexible GMRES(50)+ILU(0)"),
+    "c2j": dict(dim=3, n=100, jitter=0.05, rs2=12, prec="point relaxation", solver="Block GMRES",
+                desc="configs[1] particle count with positions jittered by 0.05 dx (no pair on the cutoff)"),
+}
+
+
+def make_problem(w, n, lat, lo=None, nloc=None, nglobal=None):
+    dim = w["dim"]; ng = nglobal if nglobal is not None else (n,) * dim
+    dx = 2.0 * np.pi / ng[0]
+    P = lat.make_brick(dim, ng, dx, lo=lo, nloc=nloc, rs2=w["rs2"], jitter=w["jitter"], origin=w.get("origin", 0.0))
+    xw = P["xw"]
+    v = lat.tgv_velocity(xw)
+    # v* of a real step is not the analytic vortex: add a broadband (per-particle, tag-hashed => identical on every rank
+    # that holds a copy) perturbation so that the RHS -div(v*) excites the whole spectrum.  On the unperturbed periodic
+    # lattice the operator is translation invariant and the smooth vortex is (nearly) an eigenvector: GMRES would stop
+    # after 2-3 iterations and the benchmark would not exercise the Krylov loop at all.
+    for k in range(dim):
+        v[:, k] += 0.05 * (2.0 * lat._hash01(P["gidx"] + 1, 100 + k) - 1.0)
+    F = dict(vstar=v, density=np.ones(len(xw)))
+    dt = (0.05 * dx / 0.1) if dim == 2 else (0.1 * 1.5 * dx / 0.1)                    # taylor-green-vortex-{2d,3d}.lmp dt
+    return P, F, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False); self.p = None; self.gpu = gpu
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            t = [s.strip() for s in line.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_step(O, P, F, dt, w, threads):
+    """One step of the CPU path (oracle port): pre-computation, graph, assembly, Krylov solve."""
+    t0 = time.perf_counter()
+    o = O.Oracle(P, kind="port")
+    o.set_field(O.F_VSTAR, F["vstar"]); o.set_field(O.F_DENSITY, F["density"])
+    o.compute_pre()
+    rp, col = o.graph()
+    b = o.ns_poisson(dt)
+    A = o.matrix()
+    t1 = time.perf_counter()
+    nl = P["nlocal"]
+    colL = O.tags_to_local(col, P["tag"][:nl])
+    prec = {"point relaxation": O.PREC_JACOBI, "ILU": O.PREC_ILU0, "Chebyshev": O.PREC_CHEBYSHEV}[w["prec"]]
+    x, info = O.krylov_solve(rp, colL, A, b, params=O.krylov_params(precond=prec, row_gid=P["tag"][:nl]), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
+    t2 = time.perf_counter()
+    o.close()
+    return dict(assemble_s=t1 - t0, solve_s=t2 - t1, iters=info["iters"], converged=info["converged"], nnz=len(col))
+
+
+def run_reference(args, w, lat):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build(("port",))
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    n = args.cpu_n or (48 if w["dim"] == 3 else w["n"])
+    P, F, dt = make_problem(w, n, lat)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_step(O, P, F, dt, w, threads)
+    ts, last = [], None
+    for _ in range(args.steps):
+        t = time.perf_counter(); last = cpu_step(O, P, F, dt, w, threads); ts.append(time.perf_counter() - t)
+    sec = float(np.mean(ts)); val = P["nlocal"] / sec / 1e6
+    sample = f"{w['dim']}-D {n}^{w['dim']} = {P['nlocal']} rows of the same lattice/physics (full workload: {w['n']}^{w['dim']}), {last['iters']} GMRES its, all of graph+assembly+solve per step"
+    line = dict(metric="sph_poisson_step_throughput", value=val, unit="Mrow/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=args.workload, description=w["desc"], rows=P["nlocal"], nnz=last["nnz"], iters=last["iters"]),
+                cpu_baseline=dict(value=val, unit="Mrow/s", cores=threads, kind="port", sample=sample,
+                                  note="CPU restatement of the reference path (oracle port: reference functor algorithms + Belos/Ifpack semantics), OpenMP over rows; Trilinos/LAMMPS are not installable here"),
+                e2e=dict(value=val, unit="Mrow/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                assemble_ms=last["assemble_s"] * 1e3, solve_ms=last["solve_s"] * 1e3)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"]); ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="lattice edge override (per GPU)"); ap.add_argument("--cpu-n", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.n:
+        w["n"] = args.n
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, w, lat)
+        return
+
+    import torch
+    import torch.distributed as dist
+    isph = importlib.import_module("implicit-sph_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("gloo", init_method="env://")          # plumbing only: unique-id broadcast, barrier, max-over-ranks
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (isph.C.c_ubyte * 128)(); assert isph.lib().isph_nccl_unique_id(buf) == 0, "NCCL unique id"
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        dist.broadcast(idt, 0); nccl_id = bytes(idt.tolist())
+
+    # ---- this rank's brick of the periodic lattice (weak scaling: w['n']^dim rows per GPU)
+    dim = w["dim"]; grid = lat.brick_grid(world, dim); nglobal = tuple(w["n"] * g for g in grid)
+    lo, nloc = lat.brick_of_rank(rank, grid, nglobal)
+    P, F, dt = make_problem(w, w["n"], lat, lo=lo, nloc=nloc, nglobal=nglobal)
+    nl, nall = P["nlocal"], P["nlocal"] + P["nghost"]
+
+    # host inputs in pinned memory (what LAMMPS would hand over each step)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory(); return t, t.numpy()
+    keep = []
+    hx = pin(P["x"]); htype = pin(P["type"]); htag = pin(P["tag"]); hneigh = pin(P["neigh"]); hnoff = pin(P["noff"]); hil = pin(P["ilist"])
+    hv = pin(F["vstar"]); hrho = pin(F["density"]); hsol = pin(np.zeros(nl))
+    keep += [hx, htype, htag, hneigh, hnoff, hil, hv, hrho, hsol]
+
+    c = isph.Context(local_rank, world, rank, nccl_id)
+    stream = torch.cuda.Stream(); c.set_stream(stream.cuda_stream)
+    c.pair_coeff(dim, (0, isph.KIND_FLUID), 1.5 * P["dx"])
+    c.solver_param("Solver Type", w["solver"]); c.precond_param("Precond Type", w["prec"]); c.precond_param("Overlap Level", 0); c.precond_param("fact: level-of-fill", 0)
+
+    def upload():
+        c.atoms_set(nl, P["nghost"], hx[1], htype[1], htag[1])
+        c.neighbors_set_packed(hil[1], hnoff[1], hneigh[1])
+        c.field_set(isph.F_VSTAR, hv[1]); c.field_set(isph.F_DENSITY, hrho[1])
+    h2d_bytes = hx[1].nbytes + htype[1].nbytes + htag[1].nbytes + hneigh[1].nbytes + hnoff[1].nbytes + hil[1].nbytes + hv[1].nbytes + hrho[1].nbytes
+    d2h_bytes = hsol[1].nbytes
+
+    def device_step():
+        """inputs resident in HBM; everything else rebuilt (end-of-step delete, pair_isph.cpp:1351-1372)"""
+        c.graph_invalidate()
+        c.compute_pre()
+        c.graph_build()
+        c.create_solution(hsol[1], 1); c.create_load(None, 1)
+        c.ns_poisson(dt)
+        c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO)
+        st = c.solve(True, "Poisson")
+        c.matrix_invalidate()
+        return st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    upload()
+    st = None
+    for _ in range(max(args.warmup, 3)):
+        st = device_step()
+    # ---- timed region 1: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    c.timer_reset(); c.profile_spmv(True); c.profile_spmv_get()
+    launches0 = c.launches
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            st = device_step()
+        e1.record(stream)
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    spmv_ms, spmv_cnt = c.profile_spmv_get(); c.profile_spmv(False)
+    launches = (c.launches - launches0) // args.steps
+    timers = {k: c.timer_ms(k) / args.steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "computePoisson", "precondCreate", "solvePoisson")}
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            upload(); st = device_step()
+        e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    wall_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_e2e = max(ms_e2e, wall_e2e)          # host-side packing/validation inside the ABI calls is part of the end-to-end cost
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e = t.tolist()
+    nnz = c.nnz
+    if world > 1:
+        t = torch.tensor([float(nnz), float(nl)], dtype=torch.float64); dist.all_reduce(t); nnz_g, rows_g = t.tolist()
+    else:
+        nnz_g, rows_g = float(nnz), float(nl)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        spmv_bytes = 12.0 * nnz + 20.0 * nl                      # 12 B per nonzero + 20 B per row, this rank's launch
+        avg = spmv_ms / max(spmv_cnt, 1)
+        ach = spmv_bytes / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+        line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=args.workload, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
+                                iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"],
+                                l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),
+                    e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                    gpu_launches=int(launches), clocks=clocks,
+                    roofline=dict(bound="hbm", kernel="k_spmv_sell<1>", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                                  launches_timed=int(spmv_cnt), avg_launch_ms=avg, algorithmic_bytes_per_launch=spmv_bytes,
+                                  share_of_step=spmv_ms / args.steps / ms_dev),
+                    breakdown_ms=timers, ms_per_iter=timers["solvePoisson"] / max(st["iters"], 1))
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as O
+            O.build(("port",))
+            ncpu = args.cpu_n or (48 if dim == 3 else w["n"])
+            Pc, Fc, dtc = make_problem(w, ncpu, lat)
+            cpu_step(O, Pc, Fc, dtc, w, os.cpu_count())           # warm
+            t = time.perf_counter(); r = cpu_step(O, Pc, Fc, dtc, w, os.cpu_count()); sec = time.perf_counter() - t
+            line["cpu_baseline"] = dict(value=Pc["nlocal"] / sec / 1e6, unit="Mrow/s", cores=os.cpu_count(), kind="port",
+                                        sample=f"{dim}-D {ncpu}^{dim} = {Pc['nlocal']} rows of the same lattice/physics, {r['iters']} GMRES its, one full step (graph+assembly+solve), {sec:.1f} s")
+        print(json.dumps(line))
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -188,6 +188,15 @@ class Context:
     def matrix_invalidate(self):
         self.call("isph_matrix_invalidate")
 
+    def graph_invalidate(self):
+        self.call("isph_graph_invalidate")
+
+    def profile_spmv(self, enable=True):
+        self.call("isph_profile_spmv", int(enable))
+
+    def profile_spmv_get(self):
+        ms = C.c_double(); n = C.c_longlong(); self.call("isph_profile_spmv_get", C.byref(ms), C.byref(n)); return ms.value, n.value
+
     # ---- SolverLin mirror
     def create_solution(self, x=None, nvec=1):
         """x: Fortran-ordered (nlocal, nvec) float64 array that receives the solution (a View, like the reference), or None."""

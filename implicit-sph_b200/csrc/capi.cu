@@ -85,7 +85,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   if (!ctx) return ISPH_FAILURE; Ctx *c = reinterpret_cast<Ctx *>(ctx);
   cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
   if (c->prec_ready) { try { precond_free(c); } catch (...) {} }
-  halo_destroy(c);
+  halo_destroy(c); ilu_destroy(c);
   c->d_tab.release(); c->x.release(); c->type.release(); c->tag.release(); c->kind.release(); c->col_of_atom.release(); c->tag2own.release();
   for (auto &f : c->field) f.release();
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
@@ -93,6 +93,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   c->xs.release(); c->bs.release(); c->nullvec.release(); c->mask.release(); c->V.release(); c->Z.release(); c->wk.release(); c->red.release(); c->hbuf.release(); c->flag.release(); c->h_scal.release();
   c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+  for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c; return ISPH_SUCCESS;
 }
@@ -242,6 +243,7 @@ int isph_matrix_multiply(isph_ctx *ctx, const double *x, double *y, int lda, int
   CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
 }
 int isph_matrix_invalidate(isph_ctx *ctx) { API_BEGIN(ctx) c->A.is_filled = 0; API_END }
+int isph_graph_invalidate(isph_ctx *ctx) { API_BEGIN(ctx) c->A.built = false; c->A.is_filled = 0; API_END }
 int isph_assemble_laplacian(isph_ctx *ctx, double alpha, int mf, int anti, int mh, int f0, int f1) {
   API_BEGIN(ctx) ISPH_REQUIRE(mf < ISPH_F_COUNT, "bad material field"); assemble_laplacian(c, alpha, mf < 0 ? nullptr : c->field[mf].p, anti != 0, mh != 0, f0, f1); API_END
 }
@@ -361,6 +363,16 @@ double isph_timer_ms(isph_ctx *ctx, const char *name) { if (!ctx || !name) retur
 int isph_timer_reset(isph_ctx *ctx) { API_BEGIN(ctx) for (auto &kv : c->timers) { timer_flush(kv.second); kv.second.ms = 0.0; } API_END }
 long long isph_kernel_launches(isph_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->launches : -1; }
 
+int isph_profile_spmv(isph_ctx *ctx, int enable) { API_BEGIN(ctx) c->prof_spmv = enable != 0; API_END }
+int isph_profile_spmv_get(isph_ctx *ctx, double *total_ms, long long *launches) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (size_t q = 0; q + 1 < c->prof_used; q += 2) { float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, c->prof_ev[q], c->prof_ev[q + 1])); c->prof_ms += ms; ++c->prof_cnt; }
+  c->prof_used = 0;
+  if (total_ms) *total_ms = c->prof_ms; if (launches) *launches = c->prof_cnt;
+  c->prof_ms = 0.0; c->prof_cnt = 0;
+  API_END
+}
 int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->A.built && reps > 0 && avg_ms, "no matrix"); const int ld = c->ld; c->V.ensure((size_t)2 * ld);
   CUDA_CHECK(cudaMemsetAsync(c->V.p, 0, sizeof(double) * 2 * ld, c->stream));

@@ -1,8 +1,186 @@
-// ILU(0) block-Jacobi preconditioner (Ifpack_ILU level-of-fill 0, overlap 0) — see DESIGN.md.  Placeholder until the
-// level-scheduled factorisation lands; fails loudly instead of falling back to anything else.
+// Block-Jacobi ILU(0): Ifpack::Create("ILU", A, overlap 0) with "fact: level-of-fill" 0 (precond_ifpack.h:50-75 is the
+// call site; Ifpack_ILU itself is third-party and restated in oracle/krylov_oracle.cpp).
+//   * block = the set of rows one Ifpack/MPI rank would own ("block_of_row", default: all local rows); columns outside
+//     the row's block are dropped (Ifpack_LocalFilter), so blocks are independent;
+//   * factors in Ifpack's form: L unit-lower (l_ij = a_ij / d_j), D stored inverted, U unit-upper scaled by 1/d_i;
+//     row-wise IKJ elimination in ascending column order, multiplier taken before the 1/d_j scaling (Ifpack_ILU::Compute);
+//   * apply = L solve, D^-1 scale, U solve (Ifpack_ILU::ApplyInverse).
+// GPU execution is level-scheduled: row i of the factorisation / forward solve can run once every row j < i of its L
+// pattern is done; rows are bucketed by dependency level and one persistent cooperative kernel walks the levels with a
+// grid-wide barrier in between (one warp per row, lanes over the row's entries).  The critical path is the number of
+// levels (12 n_block - 11 for an open 3-D lattice block in lexicographic order, = the number of rows for a block that
+// is periodic in itself), so this kernel is latency-bound by design — DESIGN.md reports level counts.
 #include "isph_internal.h"
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include <algorithm>
+
+namespace cg = cooperative_groups;
+
 namespace isph {
-void ilu_create(Ctx *) { ISPH_REQUIRE(false, "Precond Type ILU: not built yet in this revision"); }
-void ilu_free(Ctx *) {}
-void ilu_apply(Ctx *, const double *, double *) { ISPH_REQUIRE(false, "Precond Type ILU: not built yet in this revision"); }
+
+struct IluData {
+  int n = 0; long long nnz = 0; int nlev_l = 0, nlev_u = 0, maxw_l = 0, maxw_u = 0;
+  DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt; DevBuf<double> fv, dinv, y; DevBuf<char> tmp;
+  int grid_f = 1, grid_s = 1;
+};
+
+// ---- block-restricted row-major copy of A --------------------------------------------------------------------------
+__global__ void k_ilu_count(const long long *slice_off, const int *row_len, const int *col, const int *blk, int n, int *cnt) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
+  const long long base = slice_off[row >> 5] + (row & 31); const int rlen = row_len[row]; const int mb = blk ? blk[row] : 0;
+  int c = 0, prev = -1;
+  for (int k = 0; k < rlen; ++k) { const int cc = col[base + 32ll * k]; if (cc < n && cc != prev && (!blk || blk[cc] == mb)) ++c; prev = cc; }
+  cnt[row] = c;
+}
+__global__ void k_ilu_fill(const long long *slice_off, const int *row_len, const int *col, const double *val, const int *blk, int n,
+                           const int *rp, int *ci, double *fv, int *dpos) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
+  const long long base = slice_off[row >> 5] + (row & 31); const int rlen = row_len[row]; const int mb = blk ? blk[row] : 0;
+  int o = rp[row], prev = -1, dp = -1;
+  for (int k = 0; k < rlen; ++k) {
+    const int cc = col[base + 32ll * k];
+    if (cc < n && cc != prev && (!blk || blk[cc] == mb)) { ci[o] = cc; fv[o] = val[base + 32ll * k]; if (cc == row) dp = o; ++o; }
+    prev = cc;
+  }
+  dpos[row] = dp;
+}
+
+// ---- numeric factorisation, one warp per row, levels separated by grid barriers ------------------------------------
+__device__ __forceinline__ int find_col(const int *ci, int lo, int hi, int key) {   // position of key in ci[lo,hi) or -1
+  while (lo < hi) { const int mid = (lo + hi) >> 1; const int v = ci[mid]; if (v < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__global__ void __launch_bounds__(256) k_ilu_factor(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
+                                                    const int *order, const int *lptr, int nlev) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int l = 0; l < nlev; ++l) {
+    for (int idx = lptr[l] + gw; idx < lptr[l + 1]; idx += nw) {
+      const int i = order[idx], b = rp[i], e = rp[i + 1], dp = dpos[i];
+      for (int q = b; q < dp; ++q) {                       // strictly-lower entries, ascending column
+        const int j = ci[q];
+        const double multiplier = fv[q];
+        __syncwarp();
+        if (lane == 0) fv[q] = multiplier * __ldcg(dinv + j);
+        const int ub = dpos[j] + 1, ue = rp[j + 1];
+        for (int u = ub + lane; u < ue; u += 32) {
+          const int k = ci[u]; const int pos = find_col(ci, q + 1, e, k);
+          if (pos < e && ci[pos] == k) fv[pos] -= multiplier * __ldcg(fv + u);      // row j was finished in an earlier level (other SM): read through L2
+        }
+        __syncwarp();
+      }
+      const double d = 1.0 / fv[dp];
+      __syncwarp();
+      if (lane == 0) dinv[i] = d;
+      for (int u = dp + 1 + lane; u < e; u += 32) fv[u] *= d;
+    }
+    __threadfence();
+    grid.sync();
+  }
+}
+
+// ---- apply: L solve (forward levels), D^-1, U solve (backward levels) ----------------------------------------------
+__global__ void __launch_bounds__(256) k_ilu_solve(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
+                                                   const int *order_l, const int *lptr_l, int nlev_l, const int *order_u, const int *lptr_u, int nlev_u,
+                                                   const double *r, double *y, double *z) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int l = 0; l < nlev_l; ++l) {
+    for (int idx = lptr_l[l] + gw; idx < lptr_l[l + 1]; idx += nw) {
+      const int i = order_l[idx], b = rp[i], dp = dpos[i];
+      double s = 0.0;
+      for (int q = b + lane; q < dp; q += 32) s += fv[q] * __ldcg(y + ci[q]);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) y[i] = r[i] - s;
+    }
+    __threadfence();
+    grid.sync();
+  }
+  for (int l = 0; l < nlev_u; ++l) {
+    for (int idx = lptr_u[l] + gw; idx < lptr_u[l + 1]; idx += nw) {
+      const int i = order_u[idx], e = rp[i + 1], dp = dpos[i];
+      double s = 0.0;
+      for (int q = dp + 1 + lane; q < e; q += 32) s += fv[q] * __ldcg(z + ci[q]);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) z[i] = y[i] * dinv[i] - s;
+    }
+    __threadfence();
+    grid.sync();
+  }
+}
+
+static void level_sets(int n, const std::vector<int> &rp, const std::vector<int> &ci, const std::vector<int> &dpos, bool lower,
+                       std::vector<int> &order, std::vector<int> &lptr, int &maxw) {
+  std::vector<int> lev(n, 0); int nlev = 0;
+  if (lower) { for (int i = 0; i < n; ++i) { int m = -1; for (int q = rp[i]; q < dpos[i]; ++q) m = std::max(m, lev[ci[q]]); lev[i] = m + 1; nlev = std::max(nlev, lev[i] + 1); } }
+  else { for (int i = n - 1; i >= 0; --i) { int m = -1; for (int q = dpos[i] + 1; q < rp[i + 1]; ++q) m = std::max(m, lev[ci[q]]); lev[i] = m + 1; nlev = std::max(nlev, lev[i] + 1); } }
+  lptr.assign(nlev + 1, 0);
+  for (int i = 0; i < n; ++i) ++lptr[lev[i] + 1];
+  maxw = 0; for (int l = 0; l < nlev; ++l) { maxw = std::max(maxw, lptr[l + 1]); lptr[l + 1] += lptr[l]; }
+  order.resize(n); std::vector<int> pos(lptr.begin(), lptr.end() - 1);
+  for (int i = 0; i < n; ++i) order[pos[lev[i]]++] = i;
+}
+
+static int coop_grid(Ctx *c, const void *fn, int max_width) {
+  int per_sm = 0, sms = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const int cap = std::max(1, per_sm * sms), want = std::max(1, (max_width + 7) / 8);     // 8 warps (rows) per block
+  return std::min(cap, want);
+}
+
+void ilu_create(Ctx *c) {
+  Matrix &A = c->A; const int n = A.n;
+  matrix_merge_duplicates(c);
+  if (!c->ilu) c->ilu = new IluData();
+  IluData &I = *c->ilu; I.n = n;
+  const int *blk = c->have_blocks ? c->block_of_row.p : nullptr;
+  I.cnt.ensure(n + 1); I.rp.ensure(n + 1); I.dpos.ensure(n); I.dinv.ensure(n); I.y.ensure(c->ld);
+  k_ilu_count<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, blk, n, I.cnt.p); ++c->launches;
+  CUDA_CHECK(cudaMemsetAsync(I.cnt.p + n, 0, sizeof(int), c->stream));
+  size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, I.cnt.p, I.rp.p, n + 1, c->stream);
+  I.tmp.ensure(tb);
+  cub::DeviceScan::ExclusiveSum(I.tmp.p, tb, I.cnt.p, I.rp.p, n + 1, c->stream); ++c->launches;
+  std::vector<int> rp(n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  I.nnz = rp[n]; I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
+  k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
+  // dependency levels (host pass over the pattern; the pattern of a step is shared by every solve of that step)
+  std::vector<int> ci(I.nnz), dpos(n);
+  CUDA_CHECK(cudaMemcpyAsync(ci.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(dpos.data(), I.dpos.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) ISPH_REQUIRE(dpos[i] >= 0, "ILU: a row has no diagonal entry");
+  std::vector<int> ol, pl, ou, pu;
+  level_sets(n, rp, ci, dpos, true, ol, pl, I.maxw_l); level_sets(n, rp, ci, dpos, false, ou, pu, I.maxw_u);
+  I.nlev_l = (int)pl.size() - 1; I.nlev_u = (int)pu.size() - 1;
+  I.order_l.ensure(n); I.order_u.ensure(n); I.lptr_l.ensure(pl.size()); I.lptr_u.ensure(pu.size());
+  CUDA_CHECK(cudaMemcpyAsync(I.order_l.p, ol.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(I.order_u.p, ou.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(I.lptr_l.p, pl.data(), sizeof(int) * pl.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(I.lptr_u.p, pu.data(), sizeof(int) * pu.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  I.grid_f = coop_grid(c, (const void *)k_ilu_factor, I.maxw_l);
+  I.grid_s = coop_grid(c, (const void *)k_ilu_solve, std::max(I.maxw_l, I.maxw_u));
+  const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p, *lp = I.lptr_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nlev = I.nlev_l;
+  void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ord, &lp, &nlev};
+  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_factor, dim3(I.grid_f), dim3(256), args, 0, c->stream)); ++c->launches;
+}
+
+void ilu_free(Ctx *c) { (void)c; /* buffers are grow-only and reused by the next create() (rebuilt every solve, solver_lin_belos.h:153,190) */ }
+
+void ilu_apply(Ctx *c, const double *r, double *z) {
+  IluData &I = *c->ilu;
+  const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ol = I.order_l.p, *pl = I.lptr_l.p, *ou = I.order_u.p, *pu = I.lptr_u.p;
+  const double *fv = I.fv.p, *dinv = I.dinv.p; double *y = I.y.p; int nl = I.nlev_l, nu = I.nlev_u;
+  void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ol, &pl, &nl, &ou, &pu, &nu, &r, &y, &z};
+  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve, dim3(I.grid_s), dim3(256), args, 0, c->stream)); ++c->launches;
+}
+
+void ilu_destroy(Ctx *c) {
+  if (!c->ilu) return; IluData &I = *c->ilu;
+  I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
+  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); delete c->ilu; c->ilu = nullptr;
+}
+
 }  // namespace isph

@@ -112,6 +112,7 @@ struct Ctx {
   unsigned char nccl_id[128]; bool have_nccl_id = false;
   // timers
   std::map<std::string, Timer> timers;
+  bool prof_spmv = false; std::vector<cudaEvent_t> prof_ev; size_t prof_used = 0; double prof_ms = 0.0; long long prof_cnt = 0;
 
   void tic(const char *name);
   void toc(const char *name);
@@ -147,6 +148,7 @@ void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy);  
 void precond_create(Ctx *c);                                 // precond.cu
 void precond_free(Ctx *c);
 void precond_apply(Ctx *c, const double *d_r, double *d_z);  // z = M^-1 r
+void ilu_destroy(Ctx *c);                                    // ilu.cu
 
 void solver_prepare_vectors(Ctx *c);                         // krylov.cu
 void solver_solve(Ctx *c, bool use_prec, const char *label);

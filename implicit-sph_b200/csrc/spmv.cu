@@ -47,6 +47,11 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy) {
   Matrix &A = c->A; ISPH_REQUIRE(A.built, "spmv: no matrix");
   if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);     // import of off-rank x entries (Epetra_Import)
   const int grid = ceil_div((long long)A.nslices * 32, 256);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->prof_spmv) {      // per-launch device timing on the launching stream (bench.py roofline)
+    if (c->prof_used + 2 > c->prof_ev.size()) { c->prof_ev.resize(c->prof_ev.size() + 512, nullptr); for (size_t q = c->prof_used; q < c->prof_ev.size(); ++q) if (!c->prof_ev[q]) CUDA_CHECK(cudaEventCreate(&c->prof_ev[q])); }
+    e0 = c->prof_ev[c->prof_used++]; e1 = c->prof_ev[c->prof_used++]; CUDA_CHECK(cudaEventRecord(e0, c->stream));
+  }
   int done = 0;
   while (done < nvec) {
     const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
@@ -56,6 +61,7 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy) {
     else k_spmv_sell<1><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
     ++c->launches; done += nv;
   }
+  if (e1) CUDA_CHECK(cudaEventRecord(e1, c->stream));
 }
 
 }  // namespace isph

