@@ -27,8 +27,8 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// block-reduce NACC per-thread accumulators, store the block's partials, and let the last block add the partials of
-// all blocks in block order into out[0..nacc)
+// block-reduce NACC per-thread accumulators, store the block's partials, and let the last block to finish add the
+// partials of all blocks (fixed assignment of blocks to lanes + fixed shuffle tree => deterministic) into out[0..nacc)
 template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out) {
   __shared__ double sm[NACC][VB / 32];
   __shared__ bool last;
@@ -48,10 +48,11 @@ template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc,
   __syncthreads();
   if (last) {
     __threadfence();
-    if (threadIdx.x < nacc) {
+    for (int k = warp; k < nacc; k += VB / 32) {
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
-      out[threadIdx.x] = s;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * NACC + k);
+      s = warp_sum(s);
+      if (lane == 0) out[k] = s;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
@@ -67,46 +68,69 @@ __global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, in
   reduce_finish<1>(acc, 1, partials, counter, out);
 }
 
-// pass 0: h[k] = V_k . w' (k < nv), old = w'.w'  with  w' = w - proj * nvec  (PoissonProjection tail applied on the fly)
-// pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w
-template <int NVT> __global__ void __launch_bounds__(VB)
+// Classical Gram-Schmidt coefficients.  grid = (row chunks, vector groups): block (bx, g) owns a CONTIGUOUS chunk of
+// rows and the G basis vectors [gG, gG+G): every thread streams one w value pair and G basis value pairs per step
+// (128-bit loads), keeps G+1 accumulators in registers, and a block touches only G+1 pages — the first version, where
+// every thread walked all <= 51 vectors, ran at ~1.4 TB/s (profiles/r01_launches_c2_first.txt).
+//   pass 0: h[k] = V_k . w' (k < nv), h[nv] = w'.w'  with  w' = w - proj * nvec  (PoissonProjection tail on the fly)
+//   pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w
+template <int G> __global__ void __launch_bounds__(VB)
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
-           double *S, int pass, double *partials, unsigned *counter) {
+           double *S, int pass, double *partials, unsigned *counters) {
   if (pass == 1 && !dgks_second(S, nv)) return;
+  const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
   const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
-  double acc[NVT];
+  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
+  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+  const double *Vg = V + (size_t)k0 * ld;
+  double acc[G + 1];
 #pragma unroll
-  for (int k = 0; k < NVT; ++k) acc[k] = 0.0;
-  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
-    double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+  for (int k = 0; k <= G; ++k) acc[k] = 0.0;
+  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+    double2 wi;
+    if (i + 1 < r1) { wi = *reinterpret_cast<const double2 *>(w + i); if (pass == 0 && nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; } }
+    else { wi.x = w[i]; if (pass == 0 && nvec) wi.x -= proj * nvec[i]; wi.y = 0.0; }
+    // all G loads are issued unconditionally and up front (vectors past the group's end alias its last one: L1 hits,
+    // results discarded) so that 16 independent 128-bit loads are in flight per thread; a predicated load/use chain
+    // here made the kernel latency-bound (~3 TB/s)
+    double2 v[G];
+    if (i + 1 < r1) {
 #pragma unroll
-    for (int k = 0; k < NVT - 1; ++k) if (k < nv) acc[k] += V[(size_t)k * ld + i] * wi;
-    acc[NVT - 1] += wi * wi;
+      for (int k = 0; k < G; ++k) v[k] = *reinterpret_cast<const double2 *>(Vg + (size_t)min(k, cnt - 1) * ld + i);
+    } else {
+#pragma unroll
+      for (int k = 0; k < G; ++k) { v[k].x = Vg[(size_t)min(k, cnt - 1) * ld + i]; v[k].y = 0.0; }
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) { acc[k] += v[k].x * wi.x; acc[k] += v[k].y * wi.y; }
+    if (g == 0) { acc[G] += wi.x * wi.x; acc[G] += wi.y * wi.y; }
   }
-  // out layout: h[0..nv) then the squared norm
-  __shared__ double sm[NVT][VB / 32];
+  __shared__ double sm[G + 1][VB / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NVT; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
+  for (int k = 0; k <= G; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
   __syncthreads();
-  if (threadIdx.x < NVT) { double s = 0.0; for (int q = 0; q < VB / 32; ++q) s += sm[threadIdx.x][q]; partials[(size_t)blockIdx.x * NVT + threadIdx.x] = s; }
+  double *mine = partials + ((size_t)g * gridDim.x + blockIdx.x) * (G + 1);
+  if (threadIdx.x <= G) { double s = 0.0; for (int q = 0; q < VB / 32; ++q) s += sm[threadIdx.x][q]; mine[threadIdx.x] = s; }
   __threadfence(); __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(counters + g, 1u) == gridDim.x - 1);
   __syncthreads();
   if (last) {
     __threadfence();
-    if (threadIdx.x < NVT && (threadIdx.x < nv || threadIdx.x == NVT - 1)) {
+    const double *grp = partials + (size_t)g * gridDim.x * (G + 1);
+    for (int k = warp; k <= G; k += VB / 32) {
+      if (!(k < cnt || (k == G && g == 0 && pass == 0))) continue;
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NVT + threadIdx.x];
-      if (threadIdx.x == NVT - 1) { if (pass == 0) S[S_H + nv] = s; }
-      else S[(pass == 0 ? S_H : S_H2) + threadIdx.x] = s;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(grp + (size_t)b * (G + 1) + k);
+      s = warp_sum(s);
+      if (lane == 0) { if (k == G) S[S_H + nv] = s; else S[(pass == 0 ? S_H : S_H2) + k0 + k] = s; }
     }
-    if (threadIdx.x == 0) *counter = 0u;
+    if (threadIdx.x == 0) counters[g] = 0u;
   }
 }
 
-// w <- w' - sum_k h_k V_k ; new = ||w||^2
+// w <- w' - sum_k h_k V_k ; new = ||w||^2.  One contiguous row chunk per block, 128-bit accesses.
 __global__ void __launch_bounds__(VB)
 k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
              double *S, int pass, double *partials, unsigned *counter) {
@@ -115,37 +139,54 @@ k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   if (threadIdx.x < nv) sh[threadIdx.x] = S[(pass == 0 ? S_H : S_H2) + threadIdx.x];
   __syncthreads();
   const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
+  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
+  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
   double acc[1] = {0.0};
-  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
-    double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+    if (i + 1 < r1) {
+      double2 wi = *reinterpret_cast<const double2 *>(w + i);
+      if (pass == 0 && nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; }
 #pragma unroll 8
-    for (int k = 0; k < nv; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
-    w[i] = wi; acc[0] += wi * wi;
+      for (int k = 0; k < nv; ++k) { const double2 v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + i); wi.x -= sh[k] * v.x; wi.y -= sh[k] * v.y; }
+      *reinterpret_cast<double2 *>(w + i) = wi; acc[0] += wi.x * wi.x; acc[0] += wi.y * wi.y;
+    } else {
+      double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+      for (int k = 0; k < nv; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
+      w[i] = wi; acc[0] += wi * wi;
+    }
   }
   reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2));
 }
 
-// Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp
+// Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp:
+// lanes stage the column and the rotations in shared memory, lane 0 runs the (inherently sequential) recurrence there
 __global__ void k_givens(double *S, int j, int m, double *host_res, int slot) {
-  if (threadIdx.x != 0) return;
-  double *h = S + S_H, *g = S + S_G, *cs = S + S_CS, *sn = S + S_SN, *H = S + S_HM;
-  double newDot = S[S_NEW1];
-  if (dgks_second(S, j + 1)) { for (int k = 0; k <= j; ++k) h[k] += S[S_H2 + k]; newDot = S[S_NEW2]; }
-  const double hn = sqrt(newDot);
-  S[S_INV] = hn > 0.0 ? 1.0 / hn : 0.0;
-  h[j + 1] = hn;
-  for (int k = 0; k < j; ++k) {                       // previous rotations
-    const double a = h[k], b = h[k + 1];
-    h[k] = cs[k] * a + sn[k] * b; h[k + 1] = -sn[k] * a + cs[k] * b;
+  __shared__ double h[64], cs[64], sn[64];
+  const int lane = threadIdx.x;
+  const bool second = dgks_second(S, j + 1);
+  for (int k = lane; k <= j; k += 32) { h[k] = S[S_H + k] + (second ? S[S_H2 + k] : 0.0); cs[k] = S[S_CS + k]; sn[k] = S[S_SN + k]; }
+  __syncwarp();
+  if (lane == 0) {
+    const double newDot = second ? S[S_NEW2] : S[S_NEW1];
+    const double hn = sqrt(newDot);
+    S[S_INV] = hn > 0.0 ? 1.0 / hn : 0.0;
+    h[j + 1] = hn;
+    for (int k = 0; k < j; ++k) {                       // previous rotations
+      const double a = h[k], b = h[k + 1];
+      h[k] = cs[k] * a + sn[k] * b; h[k + 1] = -sn[k] * a + cs[k] * b;
+    }
+    const double a = h[j], b = h[j + 1], rr = hypot(a, b);
+    const double c_ = rr == 0.0 ? 1.0 : a / rr, s_ = rr == 0.0 ? 0.0 : b / rr;
+    h[j] = rr; h[j + 1] = 0.0;
+    const double gj = S[S_G + j];
+    S[S_CS + j] = c_; S[S_SN + j] = s_; S[S_G + j + 1] = -s_ * gj; S[S_G + j] = c_ * gj;
+    const double res = fabs(s_ * gj);
+    S[S_RES] = res;
+    host_res[slot] = res;
+    __threadfence_system();
   }
-  { const double a = h[j], b = h[j + 1], rr = hypot(a, b);
-    cs[j] = rr == 0.0 ? 1.0 : a / rr; sn[j] = rr == 0.0 ? 0.0 : b / rr; h[j] = rr; h[j + 1] = 0.0;
-    g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j]; }
-  for (int k = 0; k <= j; ++k) H[k * 64 + j] = h[k];
-  const double res = fabs(g[j + 1]);
-  S[S_RES] = res;
-  host_res[slot] = res;
-  __threadfence_system();
+  __syncwarp();
+  for (int k = lane; k <= j; k += 32) S[S_HM + k * 64 + j] = h[k];
 }
 
 // y = H^-1 g for the first ncol columns
@@ -269,10 +310,11 @@ static void apply_prec(Ctx *c, bool use_prec, const double *r, double *z) {
 }
 
 static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass) {
-  const int n = c->A.n, g = vgrid(c, n); double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 8;
-#define MD(T) k_multidot<T><<<g, VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt)
-  if (nv + 1 <= 4) MD(4); else if (nv + 1 <= 8) MD(8); else if (nv + 1 <= 16) MD(16); else if (nv + 1 <= 32) MD(32); else MD(52);
-#undef MD
+  const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
+  constexpr int G = 16;
+  const int groups = (nv + G - 1) / G;
+  int gx = 592 / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
+  k_multidot<G><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
   ++c->launches;
   if (c->nranks > 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
 }
@@ -395,11 +437,11 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   ISPH_REQUIRE(c->sp.block_size == 1, "Block Size must be 1");
   std::string tname = std::string("solve") + (label ? label : "");
   c->tic(tname.c_str());
-  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)592 * 64); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
   c->h_scal.ensure(16 + c->sp.max_iters + m + 8);
   c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
   c->Z.ensure((size_t)(is_cg ? 1 : (c->sp.flexible ? m : 1)) * ld);
-  CUDA_CHECK(cudaMemsetAsync(c->flag.p + 8, 0, 4 * sizeof(int), c->stream));
+  CUDA_CHECK(cudaMemsetAsync(c->flag.p + 8, 0, 8 * sizeof(int), c->stream));
   // initial solution (setInitialSolution, solver_lin.cpp:141-147): applied here, on the device
   const size_t xl = (size_t)ld * c->x_nvec;
   if (c->init_type == ISPH_INIT_ZERO) CUDA_CHECK(cudaMemsetAsync(c->xs.p, 0, sizeof(double) * xl, c->stream));

@@ -47,6 +47,13 @@ enum { ISPH_F_VFRAC = 0,   /* 1 */ ISPH_F_GC = 1,       /* 9: dim x dim column-m
 int isph_ctx_create(isph_ctx **ctx, int device, int nranks, int rank, const void *nccl_unique_id);
 int isph_ctx_destroy(isph_ctx *ctx);
 int isph_nccl_unique_id(void *id128);
+/* Host-only (no CUDA, no context) halo planner used by the NCCL path: the role of Epetra's column map / Epetra_Import
+ * (SURVEY.md §2.2).  For every ghost atom: its tag, the rank that owns the tag and the owner-local index.  Out: the
+ * column id of every ghost (owner-local index for ghosts owned here, nlocal + halo slot otherwise; slots number the
+ * distinct remote tags in (owner, tag) order), how many values come from each peer, and the owner-local indices to
+ * request, in slot order. */
+int isph_halo_plan_host(int nranks, int rank, int nlocal, int nghost, const int *ghost_tag, const int *ghost_owner,
+                        const int *ghost_owner_idx, int *ghost_col, int *recv_count, int *request_idx, int *nhalo_out);
 const char *isph_last_error(const isph_ctx *ctx);
 int isph_set_stream(isph_ctx *ctx, void *cuda_stream);   /* run on the caller's CUDA stream (borrowed) */
 int isph_synchronize(isph_ctx *ctx);
