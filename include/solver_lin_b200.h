@@ -1,0 +1,98 @@
+// solver_lin_b200.h — header-only C++ adapter: the reference's SolverLin / PrecondWrapper method names on top of the
+// C ABI (isph_b200.h), so that the call sites in pair_isph.cpp (computeIncompressibleNavierStokes :910-1034,
+// computeAppliedElectricField :635-657, computeSoluteTransport :811-835) and USER-REAXC-T/fix_qeq_reax.cpp:671-693
+// read the same after the switch.  Same names, argument meaning, ownership (everything borrowed) and error behaviour
+// (int LAMMPS_SUCCESS / LAMMPS_FAILURE returns; non-convergence is reported, not an error) as
+//   IMPLICIT-SPH/solver_lin.h:23-98, solver_lin.cpp:30-160, solver_lin_belos.h:35-49,130-264,
+//   IMPLICIT-SPH/precond.h:17-46, precond_ifpack.h:14-85.
+// Differences that the type system forces (no Trilinos types cross the boundary):
+//   * Epetra_Map* / Epetra_CrsMatrix* arguments become the isph_ctx handle that owns the device-resident map+matrix
+//     (built by isph_graph_build / the assembly entry points, or uploaded with isph_matrix_set_csr);
+//   * Teuchos::ParameterList* becomes set(name, value) calls with the same Belos / Ifpack key names;
+//   * getLoadMultiVector()->Values() becomes loadSet()/loadGet() because b lives in HBM.
+#pragma once
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include "isph_b200.h"
+
+namespace isph_b200 {
+
+#ifndef LAMMPS_SUCCESS
+#define LAMMPS_SUCCESS 0
+#endif
+#ifndef LAMMPS_FAILURE
+#define LAMMPS_FAILURE (-1)
+#endif
+
+// PrecondWrapper / PrecondWrapper_Ifpack (precond.h:17-46, precond_ifpack.h:14-85)
+class PrecondWrapper_B200 {
+ public:
+  explicit PrecondWrapper_B200(isph_ctx *ctx) : _ctx(ctx) {}
+  virtual ~PrecondWrapper_B200() {}
+  // setMatrix(Epetra_CrsMatrix*) : the matrix is the context's device matrix; kept for call-site compatibility
+  virtual void setMatrix(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
+  // setParameters(NULL) loads the wrapper defaults of precond_ifpack.h:30-44 restricted to what BASELINE names (fill 0, overlap 0)
+  virtual void setParameters() { set("Precond Type", "ILU"); set("Overlap Level", 0); set("fact: level-of-fill", 0); }
+  int set(const char *name, int v) { return isph_precond_set_param_int(_ctx, name, v); }
+  int set(const char *name, double v) { return isph_precond_set_param_double(_ctx, name, v); }
+  int set(const char *name, const char *v) { return isph_precond_set_param_str(_ctx, name, v); }
+  virtual void setNullVector(double *) {}                       // ML only in the reference (precond_ml.h); no-op like the base class
+  virtual void create() { check(isph_precond_create(_ctx), "PrecondWrapper::create"); }
+  virtual void free() { isph_precond_free(_ctx); }
+  isph_ctx *getPrecondOperator() { return _ctx; }
+  // Ifpack factors one block per MPI rank; name the rank-equivalent brick of every local row to reproduce a CPU run
+  int setBlocks(const int *block_of_row) { return isph_precond_set_blocks(_ctx, block_of_row); }
+ protected:
+  void check(int rc, const char *what) { if (rc != ISPH_SUCCESS) throw std::runtime_error(std::string(what) + ": " + isph_last_error(_ctx)); }
+  isph_ctx *_ctx;
+};
+
+// SolverLin / SolverLin_Belos (solver_lin.h:23-98, solver_lin_belos.h:35-49)
+class SolverLin_B200 {
+ public:
+  enum SolutionInitType { Random = ISPH_INIT_RANDOM, Zero = ISPH_INIT_ZERO, Value = ISPH_INIT_VALUE };   // solver_lin.h:25
+
+  explicit SolverLin_B200(isph_ctx *ctx) : _ctx(ctx), _is_singular(false) {}
+  virtual ~SolverLin_B200() {}
+
+  // solver_lin.h:31-39
+  int createLoadMultiVector(double *b, int lda, int num_vectors) { return rc(isph_solver_create_load_multivector(_ctx, b, lda, num_vectors)); }
+  int createSolutionMultiVector(double *x, int lda, int num_vectors) { return rc(isph_solver_create_solution_multivector(_ctx, x, lda, num_vectors)); }
+  // solver_lin.h:46-52
+  void setNullVectorMask(const int *mask) { isph_solver_set_null_vector_mask(_ctx, mask); }
+  void setMatrixIsSingular(const bool is_singular) { _is_singular = is_singular; isph_solver_set_matrix_is_singular(_ctx, is_singular ? 1 : 0); }
+  void setNodalMap(isph_ctx *ctx) { if (ctx) _ctx = ctx; }        // the nodal map is part of the context (isph_atoms_set)
+  void setMatrix(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
+  // solver_lin.h:58
+  void setInitialSolution(SolutionInitType init, double val = 0.0) { isph_solver_set_initial_solution(_ctx, (int)init, val); }
+  // getLoadMultiVector()->Values() replacement (b is device resident)
+  int loadSet(const double *b, int lda) { return rc(isph_solver_load_set(_ctx, b, lda)); }
+  int loadGet(double *b, int lda) { return rc(isph_solver_load_get(_ctx, b, lda)); }
+
+  // setParameters(NULL): the hard-coded Belos list of solver_lin_belos.h:224-264
+  virtual void setParameters() { isph_solver_set_default_params(_ctx); }
+  int set(const char *name, int v) { return isph_solver_set_param_int(_ctx, name, v); }
+  int set(const char *name, double v) { return isph_solver_set_param_double(_ctx, name, v); }
+  int set(const char *name, const char *v) { return isph_solver_set_param_str(_ctx, name, v); }
+
+  // SolverLin_Belos::solveProblem(prec, name), solver_lin_belos.h:130-222 — always returns LAMMPS_SUCCESS unless the
+  // device path itself failed; prints the Belos-style status lines on rank 0 (the ABI prints the residual on failure)
+  virtual int solveProblem(PrecondWrapper_B200 *prec = NULL, const char *name = NULL) {
+    if (name != NULL) std::printf(">> isph_b200::Label - %s\n", name);
+    const int r = isph_solver_solve(_ctx, prec != NULL ? 1 : 0, name);
+    if (r != ISPH_SUCCESS) { std::fprintf(stderr, ">> isph_b200 error: %s\n", isph_last_error(_ctx)); return LAMMPS_FAILURE; }
+    int iters = 0, conv = 0; double relres = 0.0;
+    isph_solver_stats(_ctx, &iters, &relres, &conv, NULL);
+    if (conv) std::printf(">> isph_b200::Status - Passed! %s (%d iterations, %.3e)\n", name ? name : " ", iters, relres);
+    return LAMMPS_SUCCESS;
+  }
+  int iterations() const { int it = 0; isph_solver_stats(_ctx, &it, NULL, NULL, NULL); return it; }
+
+ protected:
+  static int rc(int r) { return r == ISPH_SUCCESS ? LAMMPS_SUCCESS : LAMMPS_FAILURE; }
+  isph_ctx *_ctx;
+  bool _is_singular;
+};
+
+}  // namespace isph_b200
