@@ -113,12 +113,25 @@ struct Ctx {
   // timers
   std::map<std::string, Timer> timers;
   bool prof_spmv = false; std::vector<cudaEvent_t> prof_ev; size_t prof_used = 0; double prof_ms = 0.0; long long prof_cnt = 0;
+  // optional per-phase device timing of the Krylov loop (ISPH_PROFILE=1): name -> event pairs
+  bool prof_phases = false; std::map<std::string, std::vector<cudaEvent_t>> phase_ev; std::map<std::string, size_t> phase_used;
 
   void tic(const char *name);
   void toc(const char *name);
 };
 
 inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+struct ProfScope {          // CUDA-event bracket around a phase of the solver when ISPH_PROFILE is set (off: zero cost)
+  Ctx *c; cudaEvent_t e1 = nullptr;
+  ProfScope(Ctx *c_, const char *name) : c(c_) {
+    if (!c->prof_phases) return;
+    auto &v = c->phase_ev[name]; size_t &u = c->phase_used[name];
+    if (u + 2 > v.size()) { size_t o = v.size(); v.resize(o + 256, nullptr); for (size_t q = o; q < v.size(); ++q) cudaEventCreate(&v[q]); }
+    cudaEventRecord(v[u], c->stream); e1 = v[u + 1]; u += 2;
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
+};
 
 // ---- kernels / drivers implemented across the .cu files ---------------------------------------------------------
 void build_column_map(Ctx *c);                               // graph.cu
@@ -143,7 +156,7 @@ void ns_poisson(Ctx *c, double dt, bool anti, int singular, bool mh);
 void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp, const double *g);
 void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma);
 
-void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy);   // spmv.cu (does the halo exchange when nranks > 1)
+void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, const double *dot_vec = nullptr, double *dot_out = nullptr);   // spmv.cu (does the halo exchange when nranks > 1)
 
 void precond_create(Ctx *c);                                 // precond.cu
 void precond_free(Ctx *c);

@@ -133,13 +133,15 @@ k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restric
 // w <- w' - sum_k h_k V_k ; new = ||w||^2.  One contiguous row chunk per block, 128-bit accesses.
 __global__ void __launch_bounds__(VB)
 k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
-             double *S, int pass, double *partials, unsigned *counter) {
+             double *S, int pass, double *partials, unsigned *counter, int rev) {
   if (pass == 1 && !dgks_second(S, nv)) return;
   __shared__ double sh[64];
   if (threadIdx.x < nv) sh[threadIdx.x] = S[(pass == 0 ? S_H : S_H2) + threadIdx.x];
   __syncthreads();
   const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
+  (void)rev;   // reversed sweeps (to catch the tail of the previous sweep in L2) were measured: no gain on B200, and the
+               // indexed loop they need costs ~40 % on this kernel
   const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
   double acc[1] = {0.0};
   for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
@@ -296,10 +298,10 @@ static double read_scalar(Ctx *c, const double *d) {
 // operator apply: y = A x, or PoissonProjection::Apply  y = A x ; y -= (y.n) n  (solver_lin.h:130-140).
 // With `defer` the projection coefficient is left in S[S_PROJ] for the orthogonalisation kernels to apply on the fly.
 static void op_apply(Ctx *c, const double *x, double *y, bool defer) {
-  spmv(c, x, y, 1, c->ld, c->ld);
+  double *S = c->hbuf.p;
+  spmv(c, x, y, 1, c->ld, c->ld, c->is_singular ? c->nullvec.p : nullptr, S + S_PROJ);     // (y.n) reduced in the SpMV epilogue
   if (c->is_singular) {
-    double *S = c->hbuf.p;
-    dot_dev(c, y, c->nullvec.p, c->A.n, S + S_PROJ);
+    allreduce_if(c, S + S_PROJ, 1);
     if (!defer) { k_axpy_dev<<<vgrid(c, c->A.n), VB, 0, c->stream>>>(y, c->nullvec.p, S + S_PROJ, -1.0, c->A.n); ++c->launches; }
   }
 }
@@ -325,6 +327,7 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   double *S = c->hbuf.p, *V = c->V.p, *Z = c->Z.p, *r = c->wk.p; unsigned *cnt = (unsigned *)c->flag.p + 8;
   const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
   const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  const int opt_rev = 0;   // reversed sweeps were measured: no L2 reuse gain on B200 (both dies stream concurrently), kept off
   std::vector<cudaEvent_t> ev(m);
   for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   int iters = 0, restarts = 0; bool converged = false, first = true; double scale = 0.0, res = 0.0;
@@ -345,15 +348,16 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
     int j = 0;
     for (; j < m; ++j) {
       double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
-      op_apply(c, zj, vn, true);                                 // w = A z_j (projection coefficient deferred)
-      launch_multidot(c, V, j + 1, vn, 0);
-      k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_NEW1, 1);
-      launch_multidot(c, V, j + 1, vn, 1);
-      k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_NEW2, 1);
-      k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches;
+      { ProfScope ps(c, "op_apply"); op_apply(c, zj, vn, true); }         // w = A z_j (projection coefficient deferred)
+      { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); }
+      { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW1, 1); }
+      { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
+      { ProfScope ps(c, "update1"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW2, 1); }
+      { ProfScope ps(c, "givens"); k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches; }
       CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
       ++iters;
       if (j + 1 < m) {                                           // prepare the next Arnoldi step before looking at the residual
+        ProfScope ps(c, "normalize_prec");
         double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
         if (jacobi_fused) { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, c->invdiag.p, c->pp.damping, zn, n); ++c->launches; }
         else { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, nullptr, 1.0, nullptr, n); ++c->launches; apply_prec(c, use_prec, vn, zn); }
@@ -435,9 +439,10 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   const bool is_cg = c->sp.solver_type == "Block CG";
   ISPH_REQUIRE(is_cg || c->sp.solver_type == "Block GMRES", "Solver Type must be \"Block GMRES\" or \"Block CG\" (Recycling GMRES is not implemented)");
   ISPH_REQUIRE(c->sp.block_size == 1, "Block Size must be 1");
+  c->prof_phases = getenv("ISPH_PROFILE") != nullptr;
   std::string tname = std::string("solve") + (label ? label : "");
   c->tic(tname.c_str());
-  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024 + (size_t)A.nslices / 8 + 64); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
   c->h_scal.ensure(16 + c->sp.max_iters + m + 8);
   c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
   c->Z.ensure((size_t)(is_cg ? 1 : (c->sp.flexible ? m : 1)) * ld);
@@ -486,6 +491,11 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
     CUDA_CHECK(cudaMemcpyAsync(c->x_host + (size_t)q * c->x_lda, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   c->toc(tname.c_str());
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->prof_phases && c->rank == 0) {
+    fprintf(stderr, "[isph profile] %s: %d iterations\n", tname.c_str(), iters_tot);
+    for (auto &kv : c->phase_ev) { size_t u = c->phase_used[kv.first]; double tot = 0.0; for (size_t q = 0; q + 1 < u; q += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, kv.second[q], kv.second[q + 1]); tot += ms; }
+      fprintf(stderr, "[isph profile]   %-16s %6zu x  avg %8.2f us  total %8.3f ms\n", kv.first.c_str(), u / 2, u ? 1e3 * tot / (u / 2) : 0.0, tot); c->phase_used[kv.first] = 0; }
+  }
   c->last_iters = iters_tot; c->last_converged = conv_all; c->last_relres = relres;
   c->init_type = -1;
 }

@@ -11,11 +11,37 @@
 
 namespace isph {
 
-template <int NV> __global__ void __launch_bounds__(256)
+__device__ __forceinline__ void spmv_dot_finish(double v, double *partials, unsigned *counter, double *out) {
+  __shared__ double sm[8]; __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += sm[w]; partials[blockIdx.x] = t; __threadfence(); last = (atomicAdd(counter, 1u) == gridDim.x - 1); }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) t += __ldcg(partials + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if (lane == 0) sm[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) { double r = 0.0; for (int w = 0; w < 8; ++w) r += sm[w]; *out = r; *counter = 0u; }
+  }
+}
+
+// DOT: additionally out[0] = sum_i y_i d_i (the (y.n) of PoissonProjection::Apply, solver_lin.h:133-137) reduced in the
+// epilogue: block partials in block order, combined by the last block to finish — saves a pass over y per iteration.
+template <int NV, bool DOT> __global__ void __launch_bounds__(256, 8)     // 32 registers: 8 CTAs = 2048 threads per SM
 k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col,
-            const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy) {
+            const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy,
+            const double *__restrict__ dvec, double *partials, unsigned *counter, double *out) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
-  if (s >= nslices) return;
+  if (!DOT && s >= nslices) return;
+  if (DOT && s >= nslices) { spmv_dot_finish(0.0, partials, counter, out); return; }
   const long long base = slice_off[s] + (row & 31);
   const int slen = slice_len[s];
   const int *cp = col + base; const double *vp = val + base;
@@ -41,9 +67,10 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
 #pragma unroll
     for (int q = 0; q < NV; ++q) y[(size_t)q * ldy + row] = acc[q];
   }
+  if (DOT) spmv_dot_finish(row < n ? acc[0] * dvec[row] : 0.0, partials, counter, out);
 }
 
-void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy) {
+void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const double *dot_vec, double *dot_out) {
   Matrix &A = c->A; ISPH_REQUIRE(A.built, "spmv: no matrix");
   if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);     // import of off-rank x entries (Epetra_Import)
   const int grid = ceil_div((long long)A.nslices * 32, 256);
@@ -56,9 +83,11 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy) {
   while (done < nvec) {
     const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
     const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy;
-    if (nv == 3) k_spmv_sell<3><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
-    else if (nv == 2) k_spmv_sell<2><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
-    else k_spmv_sell<1><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy);
+    if (nv == 3) k_spmv_sell<3, false><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, nullptr, nullptr, nullptr, nullptr);
+    else if (nv == 2) k_spmv_sell<2, false><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, nullptr, nullptr, nullptr, nullptr);
+    else if (dot_vec && nvec == 1) { ISPH_REQUIRE(c->red.cap >= (size_t)grid, "spmv: reduction workspace too small");
+      k_spmv_sell<1, true><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dot_vec, c->red.p, (unsigned *)c->flag.p + 13, dot_out); }
+    else k_spmv_sell<1, false><<<grid, 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, nullptr, nullptr, nullptr, nullptr);
     ++c->launches; done += nv;
   }
   if (e1) CUDA_CHECK(cudaEventRecord(e1, c->stream));

@@ -1,0 +1,80 @@
+"""BASELINE-size checks through size-independent properties (the CPU oracle does not finish these sizes in seconds):
+C2 = 3-D 100^3 = 1M-particle lattice pressure Poisson (GMRES + Jacobi); a 64^3 corrected-operator case for C4's
+operator family; Helmholtz 3-RHS for C3's."""
+import importlib
+
+import numpy as np
+import pytest
+
+isph = importlib.import_module("implicit-sph_b200")
+lat = importlib.import_module("implicit-sph_b200.lattice")
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n, jitter, rs2, dim=3):
+    dx = 2 * np.pi / n
+    P = lat.make_brick(dim, (n,) * dim, dx, rs2=rs2, jitter=jitter)
+    v = lat.tgv_velocity(P["xw"])
+    for k in range(dim):
+        v[:, k] += 0.05 * (2.0 * lat._hash01(P["gidx"] + 1, 100 + k) - 1.0)
+    c = isph.Context(); c.set_particles(P); c.field_set(isph.F_VSTAR, v); c.field_set(isph.F_VELOCITY, v)
+    c.field_set(isph.F_VISCOSITY, np.full(len(v), 0.1))
+    return P, v, c, dx
+
+
+def test_c2_one_million_rows_poisson_gmres_jacobi():
+    n = 100
+    P, v, c, dx = _setup(n, 0.0, 9)
+    nl = P["nlocal"]
+    c.compute_pre(); c.graph_build()
+    nnz1 = c.nnz
+    assert 93 * nl <= nnz1 <= 123 * nl                      # 92 interior neighbours + self, up to 30 borderline-shell entries
+    c.graph_invalidate(); c.graph_build(); assert c.nnz == nnz1                           # rebuild is idempotent
+    vf = c.field_get(isph.F_VFRAC)[:nl]
+    assert abs(vf.sum() - (2 * np.pi) ** 3) / (2 * np.pi) ** 3 < 2e-2 and np.ptp(vf) < 1e-12 * vf.mean()    # lattice: uniform quadrature weights
+    c.create_load(None, 1); c.ns_poisson(0.1 * 1.5 * dx / 0.1)
+    b = c.load_get(1)[:, 0]
+    ones = np.ones(nl)
+    y = c.matrix_multiply(ones)[:, 0]
+    d, _ = c.diagonals_get()
+    assert np.abs(y).max() <= 1e-11 * np.abs(d).max()       # pure-Neumann Laplacian: A 1 = 0 (zero row sums)
+    x = np.zeros(nl); c.create_solution(x, 1)
+    c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO); c.precond_param("Precond Type", "point relaxation")
+    st = c.solve(True, "Poisson")
+    assert st["converged"] and st["relres"] <= 1e-8 and 20 < st["iters"] <= 500
+    bp = c.load_get(1)[:, 0]                                # b after the in-place projection (solver_lin_belos.h:141-143)
+    assert abs(bp.sum()) <= 1e-9 * np.abs(bp).sum() and abs(x.sum()) <= 1e-9 * np.abs(x).sum()
+    r = bp - c.matrix_multiply(x)[:, 0]; r -= r.mean()      # residual of the projected operator
+    assert np.linalg.norm(r) / np.linalg.norm(bp) <= 5e-8   # explicit residual agrees with the implicit one GMRES stopped on
+    # linearity of the operator application at full size
+    z = np.random.default_rng(0).standard_normal((nl, 2))
+    yz = c.matrix_multiply(z); y3 = c.matrix_multiply(2.0 * z[:, 0] - 3.0 * z[:, 1])[:, 0]
+    assert np.abs(y3 - (2.0 * yz[:, 0] - 3.0 * yz[:, 1])).max() <= 1e-12 * np.abs(yz).max()
+    c.close()
+
+
+def test_corrected_operator_and_helmholtz_properties_64cubed():
+    n = 64
+    P, v, c, dx = _setup(n, 0.04, 12)
+    nl, dim = P["nlocal"], 3
+    c.compute_pre(); c.graph_build()
+    gc = c.field_get(isph.F_GC)[:nl]; lc = c.field_get(isph.F_LC)[:nl]
+    assert np.abs(gc[:, [0, 4, 8]] - 1.0).max() < 0.2 and np.abs(lc[:, [0, 2, 5]] - 1.0).max() < 0.5     # corrections are near-identity on a mildly jittered lattice
+    dt = 0.1 * 1.5 * dx / 0.1
+    # corrected (symmetric-form) Poisson operator: first-order consistency => A applied to a constant is zero
+    c.create_load(None, 1); c.ns_poisson(dt, anti=False)
+    y = c.matrix_multiply(np.ones(nl))[:, 0]; d, _ = c.diagonals_get()
+    assert np.abs(y).max() <= 1e-10 * np.abs(d).max()
+    c.matrix_invalidate()
+    # Helmholtz: I - theta dt nu Lap  => unit row sums; CG + Chebyshev solves all three right-hand sides
+    x = np.asfortranarray(v[:nl, :dim].copy()); c.create_solution(x, dim); c.create_load(None, dim); c.load_set(np.asfortranarray(v[:nl, :dim]))
+    c.ns_helmholtz(dt, 0.5)
+    y = c.matrix_multiply(np.ones(nl))[:, 0]
+    assert np.abs(y - 1.0).max() <= 1e-11
+    b = c.load_get(dim)
+    c.solver_param("Solver Type", "Block CG"); c.precond_param("Precond Type", "Chebyshev"); c.precond_param("chebyshev: degree", 3)
+    st = c.solve(True, "Helmholtz")
+    assert st["converged"]
+    r = b - c.matrix_multiply(x)
+    assert np.linalg.norm(r, axis=0).max() / np.linalg.norm(b, axis=0).min() <= 1e-7
+    c.close()
