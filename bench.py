@@ -35,6 +35,9 @@ WORKLOADS = {
                desc="BASELINE configs[0]: 2-D TGV 128x128 pressure Poisson, flexible GMRES(50)+ILU(0)"),
     "c2j": dict(dim=3, n=100, jitter=0.05, rs2=12, prec="point relaxation", solver="Block GMRES",
                 desc="configs[1] particle count with positions jittered by 0.05 dx (no pair on the cutoff)"),
+    # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
+    "p8m": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True,
+                desc="north_star target: 3-D 8M-particle (200^3) pressure Poisson, flexible GMRES(50)+Jacobi, fixed global size (strong scaling)"),
 }
 
 
@@ -186,7 +189,8 @@ def main():
         dist.broadcast(idt, 0); nccl_id = bytes(idt.tolist())
 
     # ---- this rank's brick of the periodic lattice (weak scaling: w['n']^dim rows per GPU)
-    dim = w["dim"]; grid = lat.brick_grid(world, dim); nglobal = tuple(w["n"] * g for g in grid)
+    dim = w["dim"]; grid = lat.brick_grid(world, dim)
+    nglobal = (w["n"],) * dim if w.get("strong") else tuple(w["n"] * g for g in grid)
     lo, nloc = lat.brick_of_rank(rank, grid, nglobal)
     P, F, dt = make_problem(w, w["n"], lat, lo=lo, nloc=nloc, nglobal=nglobal)
     nl, nall = P["nlocal"], P["nlocal"] + P["nghost"]
@@ -277,7 +281,7 @@ def main():
         avg = spmv_ms / max(spmv_cnt, 1)
         ach = spmv_bytes / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
         line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                     config=dict(workload=args.workload, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
                                 iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"],
                                 l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),

@@ -160,6 +160,74 @@ k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2));
 }
 
+// Fused first Gram-Schmidt update + second-pass coefficients: ONE sweep over the basis instead of two.
+//   w1 = w' - sum_k h_k V_k   (pass-0 update, ||w1||^2 -> S_NEW1)   and   h2[k] = V_k . w1   (pass-1 dots, speculative:
+//   whether the DGKS test uses them is decided afterwards by k_cgs_update(pass 1) / k_givens from S_NEW1).
+// Each block owns a contiguous row chunk and walks it in tiles of UT rows: the tile of all nv basis vectors is staged in
+// shared memory (<= 52 x 64 x 8 B = 26 KB), w1 of the tile is formed from it, and the same staged values feed the dots.
+static const int UT = 64;
+__global__ void __launch_bounds__(VB)
+k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
+             double *S, double *partials, unsigned *counter) {
+  extern __shared__ __align__(16) double smem[];
+  double *tile = smem;                     // [nv][UT]
+  double *w1 = smem + (size_t)nv * UT;     // [UT]
+  double *psum = w1 + UT;                  // [VB/UT][UT]
+  __shared__ double sh[64], red[VB / 32];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < nv) sh[tid] = S[S_H + tid];
+  const double proj = nvec ? S[S_PROJ] : 0.0;
+  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + UT - 1) / UT * UT;
+  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0}, nd = 0.0;
+  __syncthreads();
+  for (int t0 = r0; t0 < r1; t0 += UT) {
+    const int tl = min(UT, r1 - t0);
+    for (int e = tid; e < nv * (UT / 2); e += VB) {            // stage the tile, 128-bit loads (t0 and ld are even)
+      const int k = e / (UT / 2), r = 2 * (e % (UT / 2));
+      double2 v = make_double2(0.0, 0.0);
+      if (r + 1 < tl) v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + t0 + r); else if (r < tl) v.x = V[(size_t)k * ld + t0 + r];
+      *reinterpret_cast<double2 *>(tile + (size_t)k * UT + r) = v;
+    }
+    __syncthreads();
+    { const int r = tid & (UT - 1), gq = tid / UT;               // 4 thread groups share the k loop of one row
+      double s = 0.0;
+      for (int k = gq; k < nv; k += VB / UT) s += sh[k] * tile[(size_t)k * UT + r];
+      psum[gq * UT + r] = s; }
+    __syncthreads();
+    if (tid < UT) {
+      double wi = 0.0;
+      if (tid < tl) { wi = w[t0 + tid]; if (nvec) wi -= proj * nvec[t0 + tid]; double ps = 0.0; for (int q = 0; q < VB / UT; ++q) ps += psum[q * UT + tid]; wi -= ps; w[t0 + tid] = wi; nd += wi * wi; }
+      w1[tid] = wi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 7; ++q) { const int k = warp + 8 * q; if (k < nv) { for (int r = lane; r < UT; r += 32) acc[q] += tile[(size_t)k * UT + r] * w1[r]; } }
+    __syncthreads();
+  }
+  double *mine = partials + (size_t)blockIdx.x * 64;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) { const int k = warp + 8 * q; const double v = warp_sum(acc[q]); if (lane == 0 && k < nv) mine[k] = v; }
+  nd = warp_sum(nd); if (lane == 0) red[warp] = nd;
+  __syncthreads();
+  if (tid == 0) { double t = 0.0; for (int q = 0; q < (UT + 31) / 32; ++q) t += red[q]; mine[63] = t; }
+  __threadfence(); __syncthreads();
+  if (tid == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int k = warp; k < 64; k += VB / 32) {
+      if (!(k < nv || k == 63)) continue;
+      double s = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
+      s = warp_sum(s);
+      if (lane == 0) { if (k == 63) { S[S_NEW1] = s; S[S_H2 + nv] = s; } else S[S_H2 + k] = s; }
+    }
+    if (tid == 0) *counter = 0u;
+  }
+}
+
 // Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp:
 // lanes stage the column and the rotations in shared memory, lane 0 runs the (inherently sequential) recurrence there
 __global__ void k_givens(double *S, int j, int m, double *host_res, int slot) {
@@ -321,12 +389,21 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   if (c->nranks > 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
 }
 
+static void dbg(Ctx *c, const char *what) {      // ISPH_DEBUG_SYNC=1: synchronise after every phase and name the one that faulted
+  static const bool on = getenv("ISPH_DEBUG_SYNC") != nullptr; if (!on) return;
+  cudaError_t e = cudaStreamSynchronize(c->stream); if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("device fault after ") + what + ": " + cudaGetErrorString(e));
+}
+
 static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out, double *relres_out) {
   const int n = c->A.n, ld = c->ld, m = c->sp.num_blocks; const bool flex = c->sp.flexible;
   ISPH_REQUIRE(m >= 1 && m <= 51, "Num Blocks must be in 1..51");
   double *S = c->hbuf.p, *V = c->V.p, *Z = c->Z.p, *r = c->wk.p; unsigned *cnt = (unsigned *)c->flag.p + 8;
   const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
   const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  // fused update+second-pass dots (k_update_dot): measured 109-141 us vs 48+45 us for the two streaming kernels on B200
+  // (the staged tile is not pipelined), so it stays opt-in until it carries a cp.async double buffer
+  static const int opt_fuse = getenv("ISPH_FUSE") ? 1 : 0;
   const int opt_rev = 0;   // reversed sweeps were measured: no L2 reuse gain on B200 (both dies stream concurrently), kept off
   std::vector<cudaEvent_t> ev(m);
   for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -348,12 +425,23 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
     int j = 0;
     for (; j < m; ++j) {
       double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
-      { ProfScope ps(c, "op_apply"); op_apply(c, zj, vn, true); }         // w = A z_j (projection coefficient deferred)
-      { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); }
-      { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW1, 1); }
-      { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
+      dbg(c, "prologue");
+      { ProfScope ps(c, "op_apply"); op_apply(c, zj, vn, true); } dbg(c, "op_apply");         // w = A z_j (projection coefficient deferred)
+      { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); } dbg(c, "multidot0");
+      if (opt_fuse) {
+        ProfScope ps(c, "update0+dot1");
+        const int nvj = j + 1; const size_t sm = ((size_t)nvj * UT + (1 + VB / UT) * UT) * sizeof(double);
+        k_update_dot<<<g, VB, sm, c->stream>>>(V, ld, nvj, vn, nvp, n, S, c->red.p, cnt); ++c->launches;
+        if (c->nranks > 1) { halo_allreduce(c, S + S_H2, nvj + 1); CUDA_CHECK(cudaMemcpyAsync(S + S_NEW1, S + S_H2 + nvj, sizeof(double), cudaMemcpyDeviceToDevice, c->stream)); }
+      } else {
+        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW1, 1); }
+        { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
+      }
+      dbg(c, "update0/dot1");
       { ProfScope ps(c, "update1"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW2, 1); }
+      dbg(c, "update1");
       { ProfScope ps(c, "givens"); k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches; }
+      dbg(c, "givens");
       CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
       ++iters;
       if (j + 1 < m) {                                           // prepare the next Arnoldi step before looking at the residual
@@ -442,7 +530,8 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   c->prof_phases = getenv("ISPH_PROFILE") != nullptr;
   std::string tname = std::string("solve") + (label ? label : "");
   c->tic(tname.c_str());
-  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024 + (size_t)A.nslices / 8 + 64); c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024 + (size_t)A.nslices / 8 + 64);
+  c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
   c->h_scal.ensure(16 + c->sp.max_iters + m + 8);
   c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
   c->Z.ensure((size_t)(is_cg ? 1 : (c->sp.flexible ? m : 1)) * ld);
