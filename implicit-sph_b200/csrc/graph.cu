@@ -52,7 +52,9 @@ template <int CAP> __global__ void __launch_bounds__(128) k_graph_slice(GraphArg
   __shared__ int s_len[32], s_selfcol[32], s_dup[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slice = blockIdx.x;
   const unsigned long long INVALID = ~0ull;
+  constexpr int E = CAP / 32;
   for (int rr = 0; rr < 8; ++rr) {
+    unsigned long long keys[E];
     const int r = warp * 8 + rr, row = slice * 32 + r;
     unsigned long long *kb = skey + (size_t)r * (CAP + 1);
     int selfcol = row < a.n ? row : 0;
@@ -61,7 +63,9 @@ template <int CAP> __global__ void __launch_bounds__(128) k_graph_slice(GraphArg
       const double xi0 = a.x[3 * (size_t)i], xi1 = a.x[3 * (size_t)i + 1], xi2 = a.x[3 * (size_t)i + 2];
       const long long beg = a.noff[row]; const int cnt = (int)(a.noff[row + 1] - beg);
       selfcol = a.col_of_atom[i];
-      for (int t = lane; t < CAP; t += 32) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int t = e * 32 + lane;
         unsigned long long key = INVALID;
         if (t < cnt) {
           const int j = a.neigh[beg + t] & ISPH_NEIGHMASK, jtype = a.type[j];
@@ -73,24 +77,43 @@ template <int CAP> __global__ void __launch_bounds__(128) k_graph_slice(GraphArg
         } else if (t == cnt) {
           key = ((unsigned long long)(unsigned)selfcol << 32) | (unsigned)i;      // self connectivity, functor_graph.h:87
         }
-        kb[t] = key;
+        keys[e] = key;
       }
     } else {
-      for (int t = lane; t < CAP; t += 32) kb[t] = INVALID;
+#pragma unroll
+      for (int e = 0; e < E; ++e) keys[e] = INVALID;
     }
-    __syncwarp();
-    // bitonic sort, ascending
+    // bitonic sort over the index space idx = e*32 + lane, entirely in registers: partners at distance < 32 are reached
+    // with shuffles, larger distances are register-to-register in the same lane (the shared-memory version of this
+    // network kept the L1/shared pipe at 92 %: profiles/r01_asm_ncu_full.txt)
+#pragma unroll
     for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = lane; t < CAP / 2; t += 32) {
-          const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
-          const bool asc = ((lo & k) == 0);
-          const unsigned long long u = kb[lo], v = kb[hi];
-          if ((u > v) == asc) { kb[lo] = v; kb[hi] = u; }
+        if (j >= 32) {
+          const int je = j >> 5;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            if ((e & je) == 0) {
+              const int idx = e * 32 + lane; const bool asc = ((idx & k) == 0);
+              const unsigned long long u = keys[e], v = keys[e | je];
+              if ((u > v) == asc) { keys[e] = v; keys[e | je] = u; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int idx = e * 32 + lane; const bool asc = ((idx & k) == 0), lower = ((lane & j) == 0);
+            const unsigned long long u = keys[e], v = __shfl_xor_sync(0xffffffffu, u, j);
+            const bool take_min = (lower == asc);
+            keys[e] = take_min ? (u < v ? u : v) : (u > v ? u : v);
+          }
         }
-        __syncwarp();
       }
     }
+#pragma unroll
+    for (int e = 0; e < E; ++e) kb[e * 32 + lane] = keys[e];
+    __syncwarp();
     int valid = 0, dup = 0;
     for (int t = lane; t < CAP; t += 32) {
       const unsigned long long u = kb[t];

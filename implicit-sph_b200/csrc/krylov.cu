@@ -381,10 +381,12 @@ static void apply_prec(Ctx *c, bool use_prec, const double *r, double *z) {
 
 static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass) {
   const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
-  constexpr int G = 16;
+  const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
   const int groups = (nv + G - 1) / G;
   int gx = 592 / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
-  k_multidot<G><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
+  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
+  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
+  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
   ++c->launches;
   if (c->nranks > 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
 }
