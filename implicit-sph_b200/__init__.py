@@ -20,8 +20,8 @@ KIND_FLUID, KIND_SOLID, KIND_BOUNDARY, KIND_BUFFER_DIRICHLET, KIND_BUFFER_NEUMAN
 NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
 WENDLAND, CUBIC, QUINTIC = 0, 1, 2
 INIT_RANDOM, INIT_ZERO, INIT_VALUE = 0, 1, 2
-F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI = range(13)
-FIELD_NCOMP = (1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1)
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP = range(14)
+FIELD_NCOMP = (1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -184,6 +184,11 @@ class Context:
 
     def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
         self.call("isph_pb_jacobian", int(morris_holmes), int(linearized), C.c_double(ezcb), C.c_double(psiref), C.c_double(gamma))
+
+    def ns_correct(self, dt, anti=True, incremental_pressure=True, dp=None):
+        if dp is not None:
+            dp = np.ascontiguousarray(dp, dtype=np.float64); assert dp.size == self.nlocal
+        self.call("isph_ns_correct", C.c_double(dt), int(anti), int(incremental_pressure), _d(dp))
 
     def matrix_invalidate(self):
         self.call("isph_matrix_invalidate")

@@ -13,6 +13,7 @@
 // the reference at 1e-12 and near-cutoff entries cancel catastrophically in 1-s/2).  Sums over a row run in column
 // order instead of neighbor-list order; that is the only reassociation.
 #include "isph_internal.h"
+#include <algorithm>
 
 namespace isph {
 
@@ -158,7 +159,7 @@ template <int N> __device__ void gesv_small(double *A, double *b) {
   for (int k = N - 1; k >= 0; --k) { b[k] /= A[k + k * N]; for (int r = 0; r < k; ++r) b[r] -= A[r + k * N] * b[k]; }
 }
 
-template <int DIM> __global__ void __launch_bounds__(128) k_laplacian_correction(Dev d, double *Lc_out) {  // functor_laplacian_correction.h:25-153
+template <int DIM> __global__ void __launch_bounds__(128, 4) k_laplacian_correction(Dev d, double *Lc_out) {  // functor_laplacian_correction.h:25-153
   constexpr int DIMSQ = DIM * DIM, DIML = DIM * (DIM + 1) / 2;
   LIST_SETUP(d)
   double A[DIM * DIMSQ], L[DIML * DIML];
@@ -260,7 +261,7 @@ __global__ void k_forward(const int *col_of_atom, int nlocal, int nall, int nc, 
 // ---- operator rows -------------------------------------------------------------------------------------------
 // Corrected::FunctorOuterLaplacianMatrix<Pair,ANTI>[_MorrisHolmes]::operator(), functor_laplacian_matrix.h:72-316
 // (iblock < 0, normal == NULL), fused with the PutScalar(0) that precedes it at every call site.
-template <int DIM, bool ANTI> __global__ void __launch_bounds__(128)
+template <int DIM, bool ANTI> __global__ void __launch_bounds__(128, 8)
 k_laplacian_rows(Dev d, double alpha, const double *material, bool mh, int f0, int f1) {
   ROW_SETUP(d)
   if (!fyes1(f0, ikind)) {                                                        // :88-96 (row left at zero)
@@ -480,6 +481,42 @@ __global__ void k_pb_rows(Dev d, bool linearized, double kappasq, double gamma, 
   const int kd = d.diag_k[row]; if (kd >= 0) d.val[base + 32ll * kd] = diag;
 }
 
+// ---- the step right after the Poisson solve (pair_isph.cpp:1017-1031) -------------------------------------------
+// computeZeroMeanPressure, pair_isph.cpp:422-464: solid rows are cleaned to 0, the mean over the other owned rows is removed
+__global__ void __launch_bounds__(256) k_dp_sum(const int *kind, int nlocal, double *dp, double *partials) {
+  double s = 0.0, cnt = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nlocal; i += gridDim.x * 256) { if (kind[i] == ISPH_KIND_SOLID) dp[i] = 0.0; else { s += dp[i]; cnt += 1.0; } }
+  __shared__ double sm[2][8];
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = s; sm[1][threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 2) { double t = 0.0; for (int w = 0; w < 8; ++w) t += sm[threadIdx.x][w]; partials[2 * blockIdx.x + threadIdx.x] = t; }
+}
+__global__ void k_dp_sum_final(const double *partials, int nblocks, double *out) {     // fixed order: deterministic
+  if (threadIdx.x < 2) { double t = 0.0; for (int b = 0; b < nblocks; ++b) t += partials[2 * b + threadIdx.x]; out[threadIdx.x] = t; }
+}
+__global__ void k_dp_sub_mean(const int *kind, int nall, double *dp, const double *sum_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nall) return;
+  const double mean_val = sum_cnt[0] / sum_cnt[1];
+  dp[i] -= mean_val * (kind[i] != ISPH_KIND_SOLID ? 1.0 : 0.0);
+}
+// FunctorOuterCorrectVelocity::operator(), functor_correct_velocity.h:52-69
+template <int DIM, bool ANTI> __global__ void __launch_bounds__(128)
+k_correct_velocity(Dev d, double dt, const double *rho, const double *dp, double *vstar) {
+  ROW_SETUP(d)
+  if (!fyes1(ISPH_KIND_FLUID, ikind)) return;
+  double g[3] = {0, 0, 0};
+  grad_like_loop<DIM, ANTI>(d, i, itype, ikind, xi0, xi1, xi2, base, rlen, false, ISPH_KIND_FLUID, ISPH_KIND_FLUID,
+    [&](int j, int k2, double gitmp, double vjtmp) { const double ijtmp = gitmp * vjtmp; g[k2] += ijtmp * (sph_op(ANTI, dp[i], dp[j])); });
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) { g[q] *= 1.0; vstar[3 * (size_t)i + q] -= dt / rho[i] * g[q]; }
+}
+// FunctorOuterCorrectPressure::operator(), functor_correct_pressure.h:29-43 (owned and ghost particles)
+__global__ void k_correct_pressure(double *p, const double *dp, int nall, int incp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nall) return;
+  if (incp) p[i] += dp[i]; else p[i] = dp[i];
+}
+
 __global__ void k_recip(const double *a, double *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = 1.0 / a[i]; }
 __global__ void k_mul(const double *a, const double *b, double *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = a[i] * b[i]; }
 __global__ void k_scale_vec(double *a, double s, int n, int ld, int nvec) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) for (int q = 0; q < nvec; ++q) a[(size_t)q * ld + i] *= s; }
@@ -499,7 +536,7 @@ static Dev make_dev(Ctx *c, bool need_graph = true) {
 #define LGRID(c) ceil_div((c)->inum, 128), 128, 0, (c)->stream
 
 void forward_comm(Ctx *c, int field) {
-  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1};
+  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
   if (c->nghost == 0) return;
   if (c->nranks > 1) halo_forward_field(c, field, nc[field]);      // ghosts owned by other ranks
   k_forward<<<ceil_div(c->nghost, 256), 256, 0, c->stream>>>(c->col_of_atom.p, c->nlocal, c->nall, nc[field], c->field[field].p); ++c->launches;
@@ -588,6 +625,31 @@ void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp
 #undef HR
   ++c->launches;
   c->toc("computeHelmholtz");
+}
+
+void ns_correct(Ctx *c, double dt, bool anti, bool incp, const double *dp_host) {
+  Dev d = make_dev(c);
+  double *dp = c->field[ISPH_F_DP].p;
+  c->tic("correctVelocityPressure");
+  if (dp_host) CUDA_CHECK(cudaMemcpyAsync(dp, dp_host, sizeof(double) * c->nlocal, cudaMemcpyHostToDevice, c->stream));
+  else { ISPH_REQUIRE(c->x_nvec >= 1 && c->xs.p, "isph_ns_correct: no solution vector"); CUDA_CHECK(cudaMemcpyAsync(dp, c->xs.p, sizeof(double) * c->nlocal, cudaMemcpyDeviceToDevice, c->stream)); }
+  forward_comm(c, ISPH_F_DP);                                                                     // pair_isph.cpp:1017-1019
+  if (incp) {                                                                                     // :1022-1023
+    c->red.ensure(4096); c->hbuf.ensure(8192);
+    const int nb = std::min(592, ceil_div(c->nlocal, 256)); double *sc = c->hbuf.p + 4100;
+    k_dp_sum<<<nb, 256, 0, c->stream>>>(c->kind.p, c->nlocal, dp, c->red.p);
+    k_dp_sum_final<<<1, 32, 0, c->stream>>>(c->red.p, nb, sc); c->launches += 2;
+    if (c->nranks > 1) halo_allreduce(c, sc, 2);
+    k_dp_sub_mean<<<ceil_div(c->nall, 256), 256, 0, c->stream>>>(c->kind.p, c->nall, dp, sc); ++c->launches;
+  }
+  const double *rho = c->field[ISPH_F_DENSITY].p; double *vstar = c->field[ISPH_F_VSTAR].p;
+#define CV(D, AN) k_correct_velocity<D, AN><<<GRID(c)>>>(d, dt, rho, dp, vstar)
+  if (d.dim == 2) { if (anti) CV(2, true); else CV(2, false); } else { if (anti) CV(3, true); else CV(3, false); }
+#undef CV
+  ++c->launches;
+  forward_comm(c, ISPH_F_VSTAR);                                                                  // functor_correct_velocity.h:71-78
+  k_correct_pressure<<<ceil_div(c->nall, 256), 256, 0, c->stream>>>(c->field[ISPH_F_PRESSURE].p, dp, c->nall, incp ? 1 : 0); ++c->launches;
+  c->toc("correctVelocityPressure");
 }
 
 void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma) {

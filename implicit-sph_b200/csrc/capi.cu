@@ -19,7 +19,7 @@ void Ctx::toc(const char *name) {      // no host synchronisation here: the elap
   cudaEventRecord(t.b, stream); t.open = false; t.pending = true;
 }
 
-static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1};
+static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
 
 static void ensure_fields(Ctx *c) {
   for (int f = 0; f < ISPH_F_COUNT; ++f) {
@@ -254,6 +254,7 @@ int isph_assemble_gradient_dot(isph_ctx *ctx, double alpha, int vf, int f0, int 
 int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int mh) { API_BEGIN(ctx) ns_poisson(c, dt, anti != 0, singular, mh != 0); API_END }
 int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int mh, int incp, const double *g) { API_BEGIN(ctx) ns_helmholtz(c, dt, theta, anti != 0, mh != 0, incp != 0, g); API_END }
 int isph_pb_jacobian(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma) { API_BEGIN(ctx) pb_jacobian(c, mh != 0, lin != 0, ezcb, psiref, gamma); API_END }
+int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incp, const double *dp) { API_BEGIN(ctx) ns_correct(c, dt, anti != 0, incp != 0, dp); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END }
 int isph_diagonals_get(isph_ctx *ctx, double *d, double *s) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->A.built, "no matrix");
   if (d) CUDA_CHECK(cudaMemcpyAsync(d, c->A.diagonal.p, sizeof(double) * c->A.n, cudaMemcpyDeviceToHost, c->stream));

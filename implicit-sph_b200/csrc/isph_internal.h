@@ -155,6 +155,7 @@ void assemble_gradient_dot(Ctx *c, double alpha, const double *d_vec, int f0, in
 void ns_poisson(Ctx *c, double dt, bool anti, int singular, bool mh);
 void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp, const double *g);
 void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma);
+void ns_correct(Ctx *c, double dt, bool anti, bool incp, const double *dp_owned_host);
 
 void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, const double *dot_vec = nullptr, double *dot_out = nullptr);   // spmv.cu (does the halo exchange when nranks > 1)
 

@@ -38,7 +38,7 @@ enum { ISPH_F_VFRAC = 0,   /* 1 */ ISPH_F_GC = 1,       /* 9: dim x dim column-m
        ISPH_F_NORMAL = 3,  /* 3 */ ISPH_F_PND = 4,      /* 1 */
        ISPH_F_DENSITY = 5, ISPH_F_VISCOSITY = 6, ISPH_F_PRESSURE = 7,
        ISPH_F_VELOCITY = 8,/* 3 */ ISPH_F_VSTAR = 9,    /* 3 */ ISPH_F_FORCE = 10, /* 3 */
-       ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_COUNT = 13 };
+       ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_DP = 13 /* 1: pressure increment dp, owned + ghost */, ISPH_F_COUNT = 14 };
 
 /* ---- context ------------------------------------------------------------------------------------------------
  * replaces: SolverLin(MPI_Comm&) solver_lin.h:28, PrecondWrapper(MPI_Comm) precond.h:26 (one communicator per
@@ -116,6 +116,11 @@ int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int morr
                       const double *g /*[3]*/);
 /* FunctorOuterPoissonBoltzmannJacobian, functor_poisson_boltzmann_jacobian.h:35-107 */
 int isph_pb_jacobian(isph_ctx *ctx, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+/* the block right after the Poisson solve, pair_isph.cpp:1017-1031: forward_comm(DeltaP),
+ * computeZeroMeanPressure(dp) (:422-464, only with incremental pressure), correctVelocity (functor_correct_velocity.h:52-78:
+ * vstar -= dt/rho grad(dp), then forward_comm(Vstar)), correctPressure (functor_correct_pressure.h:29-43).  dp = the device
+ * solution of the last solve, or dp_owned[nlocal] when given.  Results: fields ISPH_F_DP, ISPH_F_VSTAR, ISPH_F_PRESSURE. */
+int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incremental_pressure, const double *dp_owned);
 int isph_diagonals_get(isph_ctx *ctx, double *diagonal, double *scaled_laplace_diagonal);   /* A.diagonal, A.scaled_laplace_diagonal */
 
 /* ---- SolverLin / SolverLin_Belos mirror (solver_lin.h:23-98, solver_lin.cpp, solver_lin_belos.h:130-264) --------- */

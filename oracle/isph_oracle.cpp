@@ -112,7 +112,7 @@ extern "C" {
 const char *orc_name(void) { return "C++ restatement (oracle port)"; }
 
 int orc_field_ncomp(int fl) {
-  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1};
+  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
   return (fl >= 0 && fl < ORC_F_COUNT) ? nc[fl] : -1;
 }
 
@@ -600,6 +600,33 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
   return 0;
 }
 
+// pair_isph.cpp:1017-1031: forward_comm(DeltaP) ; computeZeroMeanPressure :422-464 ; correctVelocity
+// (functor_correct_velocity.h:52-78: vstar_i -= dt/rho_i grad(dp)_i, gradient filter (Fluid,Fluid), then forward_comm(Vstar)) ;
+// correctPressure (functor_correct_pressure.h:29-43: p += dp or p = dp for owned AND ghost particles)
+int orc_ns_correct(orc_problem *q, double dt, int anti, int incp, const double *dp_owned) {
+  const int dim = q->dim; double *dp = q->f[ORC_F_DP].data(), *vstar = q->f[ORC_F_VSTAR].data(), *pr = q->f[ORC_F_PRESSURE].data();
+  const double *rho = q->f[ORC_F_DENSITY].data();
+  memcpy(dp, dp_owned, sizeof(double) * q->nlocal);
+  q->forward(ORC_F_DP);
+  if (incp) {
+    int nloc = 0; double mysum = 0.0;
+    for (int ii = 0; ii < q->inum; ++ii) { const int i = q->ilist[ii], ikind = q->kind(q->type[i]); if (ikind == ORC_SOLID) dp[i] = 0.0; else { mysum += dp[i]; ++nloc; } }
+    const double mean_val = mysum / nloc;
+    for (int i = 0; i < q->nall; ++i) dp[i] -= mean_val * (q->kind(q->type[i]) != ORC_SOLID);
+  }
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii], ikind = q->kind(q->type[i]);
+    if (!fyes1(ORC_FLUID, ikind)) continue;
+    double g[3] = {};
+    grad_like_loop(q, ii, anti != 0, false, ORC_FLUID, ORC_FLUID, [&](int j, int k2, double gitmp, double vjtmp) { const double ijtmp = gitmp * vjtmp; g[k2] += ijtmp * (sph_op(anti != 0, dp[i], dp[j])); });
+    for (int k = 0; k < dim; ++k) g[k] *= 1.0;
+    for (int k = 0; k < dim; ++k) vstar[3 * (size_t)i + k] -= dt / rho[i] * g[k];
+  }
+  q->forward(ORC_F_VSTAR);
+  for (int i = 0; i < q->nall; ++i) { if (incp) pr[i] += dp[i]; else pr[i] = dp[i]; }
+  return 0;
+}
 int orc_invalidate_matrix(orc_problem *q) { q->is_filled = 0; return 0; }
 int orc_matrix_get(orc_problem *q, double *val) { if (!q->have_graph) return -1; memcpy(val, q->val.data(), sizeof(double) * q->val.size()); return 0; }
 int orc_diag_get(orc_problem *q, double *d, double *s) {

@@ -19,7 +19,7 @@ REF_SO = os.path.join(HERE, "_ref", "libisph_ref.so")
 FLUID, SOLID, BOUNDARY, BUFFER_DIRICHLET, BUFFER_NEUMANN, ALL = 99, 12, 16, 32, 64, 127
 NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
 WENDLAND, CUBIC, QUINTIC = 0, 1, 2
-F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI = range(13)
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP = range(14)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -69,6 +69,7 @@ def _load(kind):
     L.orc_ns_poisson.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, _dp]
     L.orc_ns_helmholtz.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]
     L.orc_pb_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.orc_ns_correct.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp]
     L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
     L.orc_diag_get.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_spmv.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
@@ -150,6 +151,10 @@ class Oracle:
 
     def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
         self._ck(self.L.orc_pb_jacobian(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma), "pb_jacobian")
+
+    def ns_correct(self, dt, dp, anti=True, incremental_pressure=True):
+        dp = np.ascontiguousarray(dp, dtype=np.float64); assert dp.size == self.nlocal
+        self._ck(self.L.orc_ns_correct(self.p, dt, int(anti), int(incremental_pressure), _d(dp)), "ns_correct")
 
     def invalidate_matrix(self):
         self.L.orc_invalidate_matrix(self.p)

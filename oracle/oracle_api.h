@@ -25,7 +25,7 @@ enum { ORC_F_VFRAC = 0,   /* 1  */  ORC_F_GC = 1,       /* 9: dim x dim column-m
        ORC_F_NORMAL = 3,  /* 3  */  ORC_F_PND = 4,      /* 1 */
        ORC_F_DENSITY = 5, ORC_F_VISCOSITY = 6, ORC_F_PRESSURE = 7,
        ORC_F_VELOCITY = 8,/* 3  */  ORC_F_VSTAR = 9,    /* 3 */  ORC_F_FORCE = 10, /* 3 */
-       ORC_F_EPS = 11,    ORC_F_PSI = 12, ORC_F_COUNT = 13 };
+       ORC_F_EPS = 11,    ORC_F_PSI = 12, ORC_F_DP = 13 /* 1: pressure increment, owned + ghost */, ORC_F_COUNT = 14 };
 
 typedef struct orc_problem orc_problem;
 
@@ -56,6 +56,10 @@ int orc_ns_helmholtz(orc_problem *p, double dt, double theta, int anti, int morr
                      int incremental_pressure, const double *g, double *b);
 /* functor_poisson_boltzmann_jacobian.h:35-107 (A.is_filled kept between calls) */
 int orc_pb_jacobian(orc_problem *p, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+/* the block right after the Poisson solve, pair_isph.cpp:1017-1031: forward_comm(DeltaP), computeZeroMeanPressure(dp)
+ * (:422-464, when incremental pressure is used), correctVelocity (functor_correct_velocity.h:52-78, pair_isph_corrected.cpp
+ * :1019-1034) incl. forward_comm(Vstar), correctPressure (functor_correct_pressure.h:29-43).  dp_owned[nlocal] = the solution. */
+int orc_ns_correct(orc_problem *p, double dt, int anti, int incremental_pressure, const double *dp_owned);
 int orc_invalidate_matrix(orc_problem *p);              /* A.is_filled = 0, pair_isph.cpp:982,1026 */
 
 int orc_matrix_get(orc_problem *p, double *val);        /* aligned with orc_graph_get order */

@@ -43,6 +43,8 @@ namespace LAMMPS_NS { Utils util; }
 #include "functor_incomp_navier_stokes_helmholtz.h"
 #include "functor_incomp_navier_stokes_poisson.h"
 #include "functor_poisson_boltzmann_jacobian.h"
+#include "functor_correct_velocity.h"
+#include "functor_correct_pressure.h"
 
 #include "oracle_api.h"
 
@@ -68,7 +70,7 @@ struct MockPair {
   MockAtom *atom; MockList *list; MockDomain *domain; MockError *error; MockComm *comm;
   double **cutsq, **h; KernelFunction *kernel;
   double **Gc, **Lc, Gi[9], Li[6];
-  double **normal, *pnd, **vstar, morris_safe_coeff;
+  double **normal, *pnd, **vstar, *dp, morris_safe_coeff;
   struct { Epetra_CrsMatrix *crs; Epetra_Vector *diagonal, *scaled_laplace_diagonal; int is_filled; } A;
   MockBlk A_blk;
   Epetra_CrsGraph *tags_in_cut; Epetra_Map *nodalmap;
@@ -101,6 +103,8 @@ void MockComm::forward_comm_pair(MockPair *p) {
     switch (p->comm_variable) {
     case MockPair::Vfrac: p->atom->vfrac[a] = p->atom->vfrac[o]; break;
     case MockPair::NormalVector: for (int k = 0; k < 3; ++k) p->normal[a][k] = p->normal[o][k]; p->pnd[a] = p->pnd[o]; break;
+    case MockPair::Vstar: for (int k = 0; k < 3; ++k) p->vstar[a][k] = p->vstar[o][k]; break;
+    case MockPair::DeltaP: p->dp[a] = p->dp[o]; break;
     default: break;
     }
   }
@@ -118,7 +122,7 @@ typedef MockPair P;
 struct orc_problem {
   int dim, nlocal, nghost, nall, ntypes;
   Arr2<double> x, v, f, vstar, normal, Gc, Lc, cutsq, h;
-  std::vector<double> vfrac, density, viscosity, pressure, eps, psi, pnd, work, work3;
+  std::vector<double> vfrac, density, viscosity, pressure, eps, psi, pnd, work, work3, dpv;
   std::vector<int> type, tag, ilist, numneigh, neigh; std::vector<int *> firstneigh;
   MockAtom atom; MockList list; MockDomain domain; MockError error; MockComm comm; MockPair pair;
   KernelFunction *kernel;
@@ -134,7 +138,7 @@ extern "C" {
 const char *orc_name(void) { return "reference functors (IMPLICIT-SPH/functor_*.h) + stand-in Epetra"; }
 
 int orc_field_ncomp(int f) {
-  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1};
+  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
   return (f >= 0 && f < ORC_F_COUNT) ? nc[f] : -1;
 }
 
@@ -149,7 +153,7 @@ orc_problem *orc_create(int dim, int nlocal, int nghost, const double *x, const 
   q->Gc.init(nall, 9); q->Lc.init(nall, 6);
   memcpy(q->x.d.data(), x, sizeof(double) * 3 * nall);
   q->vfrac.assign(nall, 0.0); q->density.assign(nall, 1.0); q->viscosity.assign(nall, 0.0); q->pressure.assign(nall, 0.0);
-  q->eps.assign(nall, 1.0); q->psi.assign(nall, 0.0); q->pnd.assign(nall, 0.0); q->work.assign(nall, 0.0); q->work3.assign((size_t)nall * 3, 0.0);
+  q->eps.assign(nall, 1.0); q->psi.assign(nall, 0.0); q->dpv.assign(nall, 0.0); q->pnd.assign(nall, 0.0); q->work.assign(nall, 0.0); q->work3.assign((size_t)nall * 3, 0.0);
   q->type.assign(type, type + nall); q->tag.assign(tag, tag + nall);
   q->ilist.assign(ilist, ilist + inum);
   q->neigh.assign(neigh, neigh + noff[inum]);
@@ -179,7 +183,7 @@ orc_problem *orc_create(int dim, int nlocal, int nghost, const double *x, const 
     q->h.ptr()[i][j] = (p.getParticleKind(i) == p.getParticleKind(j)) ? h_one : h_min;
   }
   p.cutsq = q->cutsq.ptr(); p.h = q->h.ptr(); p.morris_safe_coeff = morris_safe;
-  p.Gc = q->Gc.ptr(); p.Lc = q->Lc.ptr(); p.normal = q->normal.ptr(); p.pnd = q->pnd.data(); p.vstar = q->vstar.ptr();
+  p.Gc = q->Gc.ptr(); p.Lc = q->Lc.ptr(); p.normal = q->normal.ptr(); p.pnd = q->pnd.data(); p.vstar = q->vstar.ptr(); p.dp = q->dpv.data();
   // identity correction operators, restated from pair_isph_corrected.cpp:342-346,363-366
   memset(p.Gi, 0, sizeof(p.Gi)); memset(p.Li, 0, sizeof(p.Li));
   for (int k2 = 0; k2 < dim; ++k2) for (int k1 = 0; k1 < dim; ++k1) VIEW2(p.Gi, dim, k1, k2) = (k1 == k2);
@@ -202,7 +206,7 @@ static double *field_ptr(orc_problem *q, int f) {
   case ORC_F_VFRAC: return q->vfrac.data(); case ORC_F_GC: return q->Gc.d.data(); case ORC_F_LC: return q->Lc.d.data();
   case ORC_F_NORMAL: return q->normal.d.data(); case ORC_F_PND: return q->pnd.data(); case ORC_F_DENSITY: return q->density.data();
   case ORC_F_VISCOSITY: return q->viscosity.data(); case ORC_F_PRESSURE: return q->pressure.data(); case ORC_F_VELOCITY: return q->v.d.data();
-  case ORC_F_VSTAR: return q->vstar.d.data(); case ORC_F_FORCE: return q->f.d.data(); case ORC_F_EPS: return q->eps.data(); case ORC_F_PSI: return q->psi.data();
+  case ORC_F_VSTAR: return q->vstar.d.data(); case ORC_F_FORCE: return q->f.d.data(); case ORC_F_EPS: return q->eps.data(); case ORC_F_PSI: return q->psi.data(); case ORC_F_DP: return q->dpv.data();
   }
   return nullptr;
 }
@@ -293,6 +297,24 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
   })
 }
 
+int orc_ns_correct(orc_problem *q, double dt, int anti, int incp, const double *dp_owned) {
+  ORC_TRY({
+    MockPair &p = q->pair; p.ns.is_incremental_pressure_used = incp != 0;
+    memcpy(p.dp, dp_owned, sizeof(double) * q->nlocal);
+    p.comm_variable = P::DeltaP; p.comm_forward = 1; p.comm->forward_comm_pair(&p);                  // pair_isph.cpp:1017-1019
+    if (incp) {                                                                                       // restated from pair_isph.cpp:422-464 (computeZeroMeanPressure)
+      int nloc = 0; double mysum = 0.0;
+      for (int ii = 0; ii < q->list.inum; ++ii) { const int i = q->list.ilist[ii]; const int ikind = p.getParticleKind(q->type[i]);
+        if (ikind == P::Solid) p.dp[i] = 0.0; else { mysum += p.dp[i]; ++nloc; } }
+      const double mean_val = mysum / nloc;
+      for (int i = 0; i < q->nall; ++i) p.dp[i] -= mean_val * (p.getParticleKind(q->type[i]) != P::Solid);
+    }
+    using namespace Corrected;                                                                        // bindings: pair_isph_corrected.cpp:180-182,221-223
+    if (anti) { FunctorOuterCorrectVelocity<P, FunctorOuterGradientAntiSymmetric> f(&p, dt, p.atom->density, p.dp, p.vstar); PairFor(f, f.getNumberOfWork()); }
+    else { FunctorOuterCorrectVelocity<P, FunctorOuterGradientSymmetric> f(&p, dt, p.atom->density, p.dp, p.vstar); PairFor(f, f.getNumberOfWork()); }
+    { FunctorOuterCorrectPressure<P> f(&p, p.atom->pressure, p.dp, p.atom->nghost); PairFor(f, f.getNumberOfWork()); }   // pair_isph_corrected.cpp:1039-1052
+  })
+}
 int orc_invalidate_matrix(orc_problem *q) { q->pair.A.is_filled = 0; return 0; }
 int orc_matrix_get(orc_problem *q, double *val) { if (!q->pair.A.crs) return -1; memcpy(val, q->pair.A.crs->val.data(), sizeof(double) * q->pair.A.crs->val.size()); return 0; }
 int orc_diag_get(orc_problem *q, double *d, double *s) {

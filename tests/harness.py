@@ -27,6 +27,8 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     o.pb_jacobian(morris_holmes=mh); out["A_pb"] = o.matrix()
     o.set_field(O.F_PSI, np.cos(P["xw"][:, 0])); o.pb_jacobian(morris_holmes=mh); out["A_pb2"] = o.matrix()
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = o.spmv(x)
+    dp = np.sin(2 * P["xw"][:nl, 0]) * np.cos(P["xw"][:nl, 1]) + 0.3          # stand-in Poisson solution for the post-solve block
+    o.ns_correct(cs["dt"], dp, anti=anti); out["corr_vstar"] = o.get_field(O.F_VSTAR); out["corr_p"] = o.get_field(O.F_PRESSURE); out["corr_dp"] = o.get_field(O.F_DP)
     o.close()
     return out
 
@@ -60,6 +62,8 @@ def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
     c.pb_jacobian(morris_holmes=mh); out["A_pb"] = c.matrix_get()
     c.field_set(isph.F_PSI, np.cos(P["xw"][:, 0])); c.pb_jacobian(morris_holmes=mh); out["A_pb2"] = c.matrix_get()
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = c.matrix_multiply(x)
+    dp = np.sin(2 * P["xw"][:nl, 0]) * np.cos(P["xw"][:nl, 1]) + 0.3
+    c.ns_correct(cs["dt"], anti=anti, dp=dp); out["corr_vstar"] = c.field_get(isph.F_VSTAR); out["corr_p"] = c.field_get(isph.F_PRESSURE); out["corr_dp"] = c.field_get(isph.F_DP)
     out["launches"] = c.launches
     c.close()
     return out
