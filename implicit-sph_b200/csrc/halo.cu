@@ -2,13 +2,19 @@
 // pair_isph.cpp:1258-1259).  Replaces what Epetra does through MPI underneath the reference's calls:
 //   * column map / importer  -> halo plan: every ghost atom whose tag is owned by another rank gets a halo column
 //     (distinct remote tags, grouped by owner so that each peer's data lands contiguously behind the owned rows);
-//   * Epetra_Import in CrsMatrix::Multiply -> pack kernel + grouped ncclSend/ncclRecv straight into the halo part of x;
-//   * Epetra_MpiComm::SumAll -> ncclAllReduce(double, sum) on the device scalars of the Krylov kernels;
-//   * comm->forward_comm_pair (owner -> ghost field copy) -> the same plan with ncomp doubles per particle.
-// NCCL is loaded with dlopen so that the library also loads on hosts without it (single-GPU use, CPU-side ABI tests).
+//   * Epetra_Import in CrsMatrix::Multiply -> ONE kernel that gathers the requested x entries and stores them straight
+//     into the peers' halo staging buffers over NVLink (peer memory mapped with cudaIpc), raises sequence flags and
+//     waits for the peers' flags; the SpMV then reads halo columns from the local staging buffer.  Fallback (no peer
+//     access): pack kernel + grouped ncclSend/ncclRecv into the halo tail of x;
+//   * Epetra_MpiComm::SumAll -> the last block of every reduction kernel exchanges its partial sums through peer
+//     mailboxes (p2p_device.cuh); fallback ncclAllReduce;
+//   * comm->forward_comm_pair (owner -> ghost field copy) -> the same plan with ncomp doubles per particle (NCCL).
+// NCCL is loaded with dlopen so that the library also loads on hosts without it (single-GPU use, CPU-side ABI tests);
+// it remains the bootstrap (unique id from the host program, all-gathers of plan data and of the IPC handles).
 // The plan itself (isph_halo_plan_host) is pure host code without any CUDA call: tests/test_multirank_cpu.py drives it
 // with a gloo transport at world_size 2.
 #include "isph_internal.h"
+#include "p2p_device.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
 #include <algorithm>
@@ -41,8 +47,62 @@ struct NcclApi {
 static NcclApi g_nccl;
 #define NCCL_CHECK(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) throw std::runtime_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); } while (0)
 
+// stand-alone small all-reduce (reductions whose kernel does not carry the exchange in its epilogue)
+__global__ void k_allreduce_p2p(P2PRed r, double *buf, int count) { p2p_allreduce_block(r, buf, count); }
+
+// halo staging buffer of a rank (IPC-shared): [MB_SLOTS][ISPH_MAX_RANKS] flag words, then [MB_SLOTS][3][cap] doubles
+#define HB_FLAGS (MB_SLOTS * ISPH_MAX_RANKS)
+struct HaloPush {
+  double *peer[ISPH_MAX_RANKS]; double *mine;
+  int send_off[ISPH_MAX_RANKS + 1], dst_off[ISPH_MAX_RANKS], recv_cnt[ISPH_MAX_RANKS];
+  int nranks, rank; unsigned long long seq; long long cap; int *fault;
+};
+// gather the x entries the peers asked for and store them into THEIR staging buffers over NVLink; the last block to
+// finish raises the flags and waits until every peer's data for this sequence number has landed here
+__global__ void __launch_bounds__(256) k_halo_push(HaloPush hp, const double *x, int ldx, int nvec, const int *send_idx, int nsend, unsigned *counter) {
+  const int slot = (int)(hp.seq % MB_SLOTS);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nsend) {
+    int p = 0; while (k >= hp.send_off[p + 1]) ++p;
+    const int s = send_idx[k]; const long long pos = hp.dst_off[p] + (k - hp.send_off[p]);
+    double *dst = hp.peer[p] + HB_FLAGS + (size_t)slot * 3 * hp.cap + pos;
+    for (int q = 0; q < nvec; ++q) dst[(size_t)q * hp.cap] = x[(size_t)q * ldx + s];
+  }
+  __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  const int t = threadIdx.x;
+  if (t < hp.nranks && t != hp.rank) {
+    if (hp.send_off[t + 1] > hp.send_off[t]) {
+      volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(hp.peer[t]) + slot * ISPH_MAX_RANKS + hp.rank;
+      *f = hp.seq + 1;
+    }
+    if (hp.recv_cnt[t] > 0) {
+      volatile unsigned long long *w = reinterpret_cast<volatile unsigned long long *>(hp.mine) + slot * ISPH_MAX_RANKS + t;
+      long long spins = 0;
+      while (*w < hp.seq + 1) { if (++spins > (1ll << 31)) { *hp.fault = 1; break; } }
+    }
+    __threadfence_system();
+  }
+  if (t == 0) *counter = 0u;
+}
+
+__global__ void k_halo_unstage(const double *stage, long long cap, double *x, int ldx, int nlocal, int nhalo, int nvec) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= nhalo) return;
+  for (int q = 0; q < nvec; ++q) x[(size_t)q * ldx + nlocal + k] = __ldcg(stage + (size_t)q * cap + k);
+}
+
 struct Halo {
   ncclComm_t comm = nullptr; bool inited = false;
+  // peer-memory exchange
+  bool p2p = false; double *mbox = nullptr; double *mpeer[ISPH_MAX_RANKS] = {}; void *mopened[ISPH_MAX_RANKS] = {};
+  double *hbox = nullptr; double *hpeer[ISPH_MAX_RANKS] = {}; void *hopened[ISPH_MAX_RANKS] = {}; long long hcap = 0;
+  unsigned long long seq = 0, hseq = 0; int *fault = nullptr; int dst_off[ISPH_MAX_RANKS] = {}; P2PTab *d_tab = nullptr;
+  // plan
   int nhalo = 0, nsend = 0;
   std::vector<int> recv_count, recv_off, send_count, send_off;
   DevBuf<int> send_idx, itmp, itmp2; DevBuf<long long> owner_tab; DevBuf<double> sendbuf, fieldbuf;
@@ -71,6 +131,31 @@ __global__ void k_ghost_from_halo(const int *col_of_atom, int nlocal, int nall, 
   for (int q = 0; q < nc; ++q) f[(size_t)a * nc + q] = halobuf[(size_t)(c - nlocal) * nc + q];
 }
 
+// map `mine` (a cudaMalloc'ed buffer of this rank) into every peer: all-gather of the IPC handles over NCCL.
+// Collective; returns false (on every rank alike) when any rank could not open a peer mapping.
+static bool ipc_share(Ctx *c, Halo *h, double *mine, double **peer, void **opened) {
+  const int R = c->nranks;
+  cudaIpcMemHandle_t mh; bool ok = cudaIpcGetMemHandle(&mh, mine) == cudaSuccess; if (!ok) { cudaGetLastError(); memset(&mh, 0, sizeof(mh)); }
+  char *dsend = nullptr, *dall = nullptr; const size_t hs = sizeof(mh);
+  CUDA_CHECK(cudaMalloc(&dsend, hs)); CUDA_CHECK(cudaMalloc(&dall, hs * R));
+  CUDA_CHECK(cudaMemcpy(dsend, &mh, hs, cudaMemcpyHostToDevice));
+  NCCL_CHECK(g_nccl.AllGather(dsend, dall, hs, ncclChar, h->comm, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  std::vector<cudaIpcMemHandle_t> all(R); CUDA_CHECK(cudaMemcpy(all.data(), dall, hs * R, cudaMemcpyDeviceToHost));
+  cudaFree(dsend); cudaFree(dall);
+  for (int p = 0; p < R && ok; ++p) {
+    if (p == c->rank) { peer[p] = mine; continue; }
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    opened[p] = ptr; peer[p] = (double *)ptr;
+  }
+  double *flag = nullptr; CUDA_CHECK(cudaMalloc(&flag, sizeof(double))); const double bad = ok ? 0.0 : 1.0;   // every rank must take the same path
+  CUDA_CHECK(cudaMemcpy(flag, &bad, sizeof(double), cudaMemcpyHostToDevice));
+  NCCL_CHECK(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclSum, h->comm, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  double tot = 1.0; CUDA_CHECK(cudaMemcpy(&tot, flag, sizeof(double), cudaMemcpyDeviceToHost)); cudaFree(flag);
+  return tot == 0.0;
+}
+static void ipc_close(void **opened) { for (int p = 0; p < ISPH_MAX_RANKS; ++p) if (opened[p]) { cudaIpcCloseMemHandle(opened[p]); opened[p] = nullptr; } }
+
 static Halo *get(Ctx *c) {
   if (!c->halo) c->halo = new Halo();
   Halo *h = c->halo;
@@ -80,8 +165,24 @@ static Halo *get(Ctx *c) {
     ncclUniqueId id; memcpy(&id, c->nccl_id, sizeof(id) < 128 ? sizeof(id) : 128);
     NCCL_CHECK(g_nccl.CommInitRank(&h->comm, c->nranks, id, c->rank));
     h->inited = true;
+    if (!getenv("ISPH_NO_P2P") && c->nranks <= ISPH_MAX_RANKS) {   // peer mailboxes for the small all-reduces
+      const size_t bytes = sizeof(double) * MB_SLOTS * c->nranks * MB_STRIDE;
+      CUDA_CHECK(cudaMalloc(&h->mbox, bytes)); CUDA_CHECK(cudaMemset(h->mbox, 0, bytes));
+      CUDA_CHECK(cudaMalloc(&h->fault, sizeof(int))); CUDA_CHECK(cudaMemset(h->fault, 0, sizeof(int)));
+      h->p2p = ipc_share(c, h, h->mbox, h->mpeer, h->mopened);
+      if (h->p2p) { P2PTab t; memset(&t, 0, sizeof(t)); for (int p = 0; p < c->nranks; ++p) t.box[p] = h->mpeer[p]; t.mine = h->mbox; t.nranks = c->nranks; t.rank = c->rank; t.fault = h->fault;
+        CUDA_CHECK(cudaMalloc(&h->d_tab, sizeof(t))); CUDA_CHECK(cudaMemcpy(h->d_tab, &t, sizeof(t), cudaMemcpyHostToDevice)); }
+    }
   }
   return h;
+}
+
+P2PRed halo_p2p_ticket(Ctx *c) {
+  P2PRed r; r.tab = nullptr; r.seq = 0; r.nranks = 1;
+  if (c->nranks <= 1) return r;
+  Halo *h = get(c); if (!h->p2p) return r;
+  r.tab = h->d_tab; r.seq = h->seq++; r.nranks = c->nranks;
+  return r;
 }
 
 static void exchange(Ctx *c, Halo *h, const double *sendbuf, double *recv_base, int nc) {
@@ -123,10 +224,16 @@ void halo_setup(Ctx *c) {
   // who needs what from me: allgather the request-count matrix, then swap the index lists
   CUDA_CHECK(cudaMemcpyAsync(h->itmp.p, h->recv_count.data(), sizeof(int) * R, cudaMemcpyHostToDevice, c->stream));
   NCCL_CHECK(g_nccl.AllGather(h->itmp.p, h->itmp2.p, R, ncclInt, h->comm, c->stream));
-  std::vector<int> M((size_t)R * R);
+  std::vector<int> M((size_t)R * R);                       // M[r][p] = how many values rank r receives from rank p
   CUDA_CHECK(cudaMemcpyAsync(M.data(), h->itmp2.p, sizeof(int) * R * R, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
   h->send_count.assign(R, 0); h->send_off.assign(R + 1, 0); h->recv_off.assign(R + 1, 0);
-  for (int p = 0; p < R; ++p) { h->send_count[p] = M[(size_t)p * R + c->rank]; h->send_off[p + 1] = h->send_off[p] + h->send_count[p]; h->recv_off[p + 1] = h->recv_off[p] + h->recv_count[p]; }
+  long long max_halo = 0;
+  for (int p = 0; p < R; ++p) {
+    h->send_count[p] = M[(size_t)p * R + c->rank]; h->send_off[p + 1] = h->send_off[p] + h->send_count[p]; h->recv_off[p + 1] = h->recv_off[p] + h->recv_count[p];
+    long long tot = 0; int before_me = 0;                  // where my block starts in rank p's staging buffer
+    for (int q = 0; q < R; ++q) { if (q < c->rank) before_me += M[(size_t)p * R + q]; tot += M[(size_t)p * R + q]; }
+    h->dst_off[p] = before_me; max_halo = std::max(max_halo, tot);
+  }
   h->nsend = h->send_off[R];
   DevBuf<int> req; req.ensure(h->nhalo + 1); h->send_idx.ensure(h->nsend + 1);
   CUDA_CHECK(cudaMemcpyAsync(req.p, request.data(), sizeof(int) * h->nhalo, cudaMemcpyHostToDevice, c->stream));
@@ -139,19 +246,47 @@ void halo_setup(Ctx *c) {
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   req.release();
   h->sendbuf.ensure((size_t)h->nsend * 9 + 8); h->fieldbuf.ensure((size_t)h->nhalo * 9 + 8);
+  // halo staging buffers in peer-addressable memory; every rank sees the same max_halo, so growth is collective
+  if (h->p2p && max_halo > h->hcap) {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    ipc_close(h->hopened); if (h->hbox) cudaFree(h->hbox);
+    h->hcap = max_halo + max_halo / 4 + 1024;
+    const size_t bytes = sizeof(double) * (HB_FLAGS + (size_t)MB_SLOTS * 3 * h->hcap);
+    CUDA_CHECK(cudaMalloc(&h->hbox, bytes)); CUDA_CHECK(cudaMemset(h->hbox, 0, bytes));
+    h->hseq = 0;
+    if (!ipc_share(c, h, h->hbox, h->hpeer, h->hopened)) { cudaFree(h->hbox); h->hbox = nullptr; h->hcap = 0; }
+  }
   c->toc("haloSetup");
 }
 
 int halo_ncols(Ctx *c) { return c->nlocal + (c->halo ? c->halo->nhalo : 0); }
 
-// x[nlocal .. nlocal+nhalo) <- owners' values (per vector)
-void halo_exchange(Ctx *c, double *x, int nvec, int ldx) {
-  Halo *h = get(c); if (h->nhalo == 0 && h->nsend == 0) return;
+// Halo import for an SpMV.  Returns the device address the halo columns of vector 0 can be read from (vector q at
+// + q * (*stride)); nullptr means "they were written behind the owned rows of x" (NCCL path).
+const double *halo_exchange(Ctx *c, double *x, int nvec, int ldx, long long *stride) {
+  Halo *h = get(c); *stride = 0;
+  if (h->nhalo == 0 && h->nsend == 0) return nullptr;
+  if (h->p2p && h->hbox && nvec <= 3) {
+    HaloPush hp; memset(&hp, 0, sizeof(hp));
+    for (int p = 0; p < c->nranks; ++p) { hp.peer[p] = h->hpeer[p]; hp.send_off[p] = h->send_off[p]; hp.dst_off[p] = h->dst_off[p]; hp.recv_cnt[p] = h->recv_count[p]; }
+    hp.send_off[c->nranks] = h->send_off[c->nranks]; for (int p = c->nranks + 1; p <= ISPH_MAX_RANKS; ++p) hp.send_off[p] = hp.send_off[c->nranks];
+    hp.mine = h->hbox; hp.nranks = c->nranks; hp.rank = c->rank; hp.seq = h->hseq++; hp.cap = h->hcap; hp.fault = h->fault;
+    const int slot = (int)(hp.seq % MB_SLOTS);
+    k_halo_push<<<std::max(1, ceil_div(h->nsend, 256)), 256, 0, c->stream>>>(hp, x, ldx, nvec, h->send_idx.p, h->nsend, (unsigned *)c->flag.p + 14); ++c->launches;
+    const double *stage = h->hbox + HB_FLAGS + (size_t)slot * 3 * h->hcap;
+    if (!getenv("ISPH_HALO_INKERNEL")) {   // default: land the halo behind the owned rows of x (a 1.5 MB copy) so that the SpMV keeps its
+      if (h->nhalo) { k_halo_unstage<<<ceil_div(h->nhalo, 256), 256, 0, c->stream>>>(stage, h->hcap, x, ldx, c->nlocal, h->nhalo, nvec); ++c->launches; }   // branch-free gather
+      return nullptr;                      // (reading the staging buffer from inside the SpMV costs 12 % of its bandwidth: measured)
+    }
+    *stride = h->hcap;
+    return stage;
+  }
   for (int q = 0; q < nvec; ++q) {
     double *xq = x + (size_t)q * ldx;
     if (h->nsend) { k_pack<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(xq, h->send_idx.p, h->nsend, 1, h->sendbuf.p + (size_t)q * h->nsend); ++c->launches; }
     exchange(c, h, h->sendbuf.p + (size_t)q * h->nsend, xq + c->nlocal, 1);
   }
+  return nullptr;
 }
 
 void halo_forward_field(Ctx *c, int field, int nc) {
@@ -164,11 +299,23 @@ void halo_forward_field(Ctx *c, int field, int nc) {
 
 void halo_allreduce(Ctx *c, double *buf, int count) {
   Halo *h = get(c);
+  if (h->p2p && count <= 64) {
+    P2PRed r = halo_p2p_ticket(c);
+    k_allreduce_p2p<<<1, 64, 0, c->stream>>>(r, buf, count); ++c->launches;
+    return;
+  }
   NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, c->stream));
+}
+
+bool halo_fault(Ctx *c) {
+  if (!c->halo || !c->halo->fault) return false;
+  int f = 0; cudaMemcpy(&f, c->halo->fault, sizeof(int), cudaMemcpyDeviceToHost); return f != 0;
 }
 
 void halo_destroy(Ctx *c) {
   if (!c->halo) return; Halo *h = c->halo;
+  ipc_close(h->mopened); ipc_close(h->hopened);
+  if (h->mbox) cudaFree(h->mbox); if (h->hbox) cudaFree(h->hbox); if (h->fault) cudaFree(h->fault); if (h->d_tab) cudaFree(h->d_tab);
   if (h->inited && h->comm) g_nccl.CommDestroy(h->comm);
   h->send_idx.release(); h->itmp.release(); h->itmp2.release(); h->owner_tab.release(); h->sendbuf.release(); h->fieldbuf.release();
   delete h; c->halo = nullptr;

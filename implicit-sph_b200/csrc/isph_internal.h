@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../include/isph_b200.h"
+#include "p2p_device.cuh"
 
 #define ISPH_NEIGHMASK 0x3FFFFFFF        /* LAMMPS NEIGHMASK, functor_graph.h:72 */
 #define ISPH_EPS_R 1.0e-24               /* ISPH_EPSILON, macrodef.h:6 */
@@ -168,7 +169,9 @@ void solver_prepare_vectors(Ctx *c);                         // krylov.cu
 void solver_solve(Ctx *c, bool use_prec, const char *label);
 
 void halo_setup(Ctx *c);                                     // halo.cu
-void halo_exchange(Ctx *c, double *d_x, int nvec, int ldx);
+const double *halo_exchange(Ctx *c, double *d_x, int nvec, int ldx, long long *stride);   // nullptr: halo written behind x's owned rows
+P2PRed halo_p2p_ticket(Ctx *c);          // sequence ticket for an in-kernel peer all-reduce (nranks <= 1 in it: not available)
+bool halo_fault(Ctx *c);
 void halo_allreduce(Ctx *c, double *d_buf, int count);
 void halo_forward_field(Ctx *c, int field, int ncomp);
 void halo_destroy(Ctx *c);

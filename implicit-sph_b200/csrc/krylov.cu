@@ -29,7 +29,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // block-reduce NACC per-thread accumulators, store the block's partials, and let the last block to finish add the
 // partials of all blocks (fixed assignment of blocks to lanes + fixed shuffle tree => deterministic) into out[0..nacc)
-template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out) {
+template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out, const P2PRed &pr) {
   __shared__ double sm[NACC][VB / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,6 +55,7 @@ template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc,
       if (lane == 0) out[k] = s;
     }
     if (threadIdx.x == 0) *counter = 0u;
+    if (pr.nranks > 1) p2p_allreduce_block(pr, out, nacc);      // sum over ranks through the NVLink mailboxes
   }
 }
 
@@ -62,10 +63,10 @@ template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc,
 __device__ __forceinline__ bool dgks_second(const double *S, int nv) { return S[S_NEW1] < DEP_TOL * S[S_H + nv]; }
 
 // out[0] = sum a_i b_i (b == nullptr: a_i a_i)
-__global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, int n, double *partials, unsigned *counter, double *out) {
+__global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
   double acc[1] = {0.0};
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) acc[0] += a[i] * (b ? b[i] : a[i]);
-  reduce_finish<1>(acc, 1, partials, counter, out);
+  reduce_finish<1>(acc, 1, partials, counter, out, pr);
 }
 
 // Classical Gram-Schmidt coefficients.  grid = (row chunks, vector groups): block (bx, g) owns a CONTIGUOUS chunk of
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, in
 //   pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w
 template <int G> __global__ void __launch_bounds__(VB)
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
-           double *S, int pass, double *partials, unsigned *counters) {
+           double *S, int pass, double *partials, unsigned *counters, P2PRed pr) {
   if (pass == 1 && !dgks_second(S, nv)) return;
   const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
   const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
@@ -127,13 +128,20 @@ k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restric
       if (lane == 0) { if (k == G) S[S_H + nv] = s; else S[(pass == 0 ? S_H : S_H2) + k0 + k] = s; }
     }
     if (threadIdx.x == 0) counters[g] = 0u;
+    if (pr.nranks > 1) {                                   // the last group to finish exchanges h[0..nv) (+ the norm) with the peers
+      __shared__ bool all_done;
+      __threadfence(); __syncthreads();
+      if (threadIdx.x == 0) { all_done = (atomicAdd(counters + 6, 1u) == gridDim.y - 1); if (all_done) counters[6] = 0u; }   // flag word 15
+      __syncthreads();
+      if (all_done) { __threadfence(); p2p_allreduce_block(pr, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv); }
+    }
   }
 }
 
 // w <- w' - sum_k h_k V_k ; new = ||w||^2.  One contiguous row chunk per block, 128-bit accesses.
 __global__ void __launch_bounds__(VB)
 k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
-             double *S, int pass, double *partials, unsigned *counter, int rev) {
+             double *S, int pass, double *partials, unsigned *counter, int rev, P2PRed pr) {
   if (pass == 1 && !dgks_second(S, nv)) return;
   __shared__ double sh[64];
   if (threadIdx.x < nv) sh[threadIdx.x] = S[(pass == 0 ? S_H : S_H2) + threadIdx.x];
@@ -157,7 +165,7 @@ k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
       w[i] = wi; acc[0] += wi * wi;
     }
   }
-  reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2));
+  reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2), pr);
 }
 
 // Fused first Gram-Schmidt update + second-pass coefficients: ONE sweep over the basis instead of two.
@@ -296,10 +304,10 @@ __global__ void __launch_bounds__(VB) k_normalize_prec(double *w, const double *
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const double v = w[i] * s; w[i] = v; if (z) z[i] = invdiag ? damping * invdiag[i] * v : v; }
 }
 // r = b - t (t may be null: r = b) ; out = ||r||^2
-__global__ void __launch_bounds__(VB) k_residual(const double *b, const double *t, double *r, int n, double *partials, unsigned *counter, double *out) {
+__global__ void __launch_bounds__(VB) k_residual(const double *b, const double *t, double *r, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
   double acc[1] = {0.0};
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const double v = b[i] - (t ? t[i] : 0.0); r[i] = v; acc[0] += v * v; }
-  reduce_finish<1>(acc, 1, partials, counter, out);
+  reduce_finish<1>(acc, 1, partials, counter, out, pr);
 }
 // v0 = r / beta ; g = (beta, 0, ...)
 __global__ void __launch_bounds__(VB) k_start_cycle(const double *r, double *v0, double *S, double beta, int n) {
@@ -324,18 +332,18 @@ __global__ void __launch_bounds__(VB) k_random(double *y, const int *tag, int n,
 
 // ---- PCG kernels -------------------------------------------------------------------------------------------------
 // pAp = p.Ap ; alpha = rz / pAp   (alpha computed by whoever consumes it, so that an allreduce can sit in between)
-__global__ void __launch_bounds__(VB) k_cg_update(double *x, double *r, const double *p, const double *Ap, double *S, int n, double *partials, unsigned *counter) {
+__global__ void __launch_bounds__(VB) k_cg_update(double *x, double *r, const double *p, const double *Ap, double *S, int n, double *partials, unsigned *counter, P2PRed pr) {
   const double alpha = S[S_RZ] / S[S_PAP];
   double acc[1] = {0.0};
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { x[i] += alpha * p[i]; const double ri = r[i] - alpha * Ap[i]; r[i] = ri; acc[0] += ri * ri; }
-  reduce_finish<1>(acc, 1, partials, counter, S + S_TMP);
+  reduce_finish<1>(acc, 1, partials, counter, S + S_TMP, pr);
 }
 __global__ void k_cg_publish(double *S, double *host_res, int slot) { if (threadIdx.x == 0) { const double res = sqrt(S[S_TMP]); S[S_RES] = res; host_res[slot] = res; __threadfence_system(); } }
 // z = damping * invdiag * r (Jacobi) fused with rz_new = r.z ; for other preconditioners z is given and only the dot is taken
-__global__ void __launch_bounds__(VB) k_cg_precdot(const double *r, double *z, const double *invdiag, double damping, int n, double *partials, unsigned *counter, double *out) {
+__global__ void __launch_bounds__(VB) k_cg_precdot(const double *r, double *z, const double *invdiag, double damping, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
   double acc[1] = {0.0};
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { double zi; if (invdiag) { zi = damping * invdiag[i] * r[i]; z[i] = zi; } else zi = z[i]; acc[0] += r[i] * zi; }
-  reduce_finish<1>(acc, 1, partials, counter, out);
+  reduce_finish<1>(acc, 1, partials, counter, out, pr);
 }
 // p = z + beta p with beta = rz_new / rz ; then rz <- rz_new (done by block 0 after everyone has read it: separate tiny kernel)
 __global__ void __launch_bounds__(VB) k_cg_direction(double *p, const double *z, const double *S, int n, int first) {
@@ -352,11 +360,11 @@ void solver_prepare_vectors(Ctx *c) {
   c->ld = (need + 31) / 32 * 32;
 }
 
-static void allreduce_if(Ctx *c, double *d, int count) { if (c->nranks > 1) halo_allreduce(c, d, count); }
 
 static void dot_dev(Ctx *c, const double *a, const double *b, int n, double *out) {
-  k_dot<<<vgrid(c, n), VB, 0, c->stream>>>(a, b, n, c->red.p, (unsigned *)c->flag.p + 8, out); ++c->launches;
-  allreduce_if(c, out, 1);
+  P2PRed pr = halo_p2p_ticket(c);
+  k_dot<<<vgrid(c, n), VB, 0, c->stream>>>(a, b, n, c->red.p, (unsigned *)c->flag.p + 8, out, pr); ++c->launches;
+  if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, out, 1);
 }
 static double read_scalar(Ctx *c, const double *d) {
   double v; CUDA_CHECK(cudaMemcpyAsync(c->h_scal.p, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -369,7 +377,6 @@ static void op_apply(Ctx *c, const double *x, double *y, bool defer) {
   double *S = c->hbuf.p;
   spmv(c, x, y, 1, c->ld, c->ld, c->is_singular ? c->nullvec.p : nullptr, S + S_PROJ);     // (y.n) reduced in the SpMV epilogue
   if (c->is_singular) {
-    allreduce_if(c, S + S_PROJ, 1);
     if (!defer) { k_axpy_dev<<<vgrid(c, c->A.n), VB, 0, c->stream>>>(y, c->nullvec.p, S + S_PROJ, -1.0, c->A.n); ++c->launches; }
   }
 }
@@ -384,11 +391,12 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
   const int groups = (nv + G - 1) / G;
   int gx = 592 / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
-  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
-  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
-  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt);
+  P2PRed pr = halo_p2p_ticket(c);
+  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
+  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
+  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
   ++c->launches;
-  if (c->nranks > 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
+  if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
 }
 
 static void dbg(Ctx *c, const char *what) {      // ISPH_DEBUG_SYNC=1: synchronise after every phase and name the one that faulted
@@ -413,9 +421,10 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   const int g = vgrid(c, n);
   while (true) {
     // r = b - Op x ; beta = ||r||
-    if (first && c->init_type == ISPH_INIT_ZERO) { k_residual<<<g, VB, 0, c->stream>>>(b, nullptr, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
-    else { op_apply(c, x, V + (size_t)ld, false); k_residual<<<g, VB, 0, c->stream>>>(b, V + (size_t)ld, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
-    allreduce_if(c, S + S_TMP, 1);
+    if (!(first && c->init_type == ISPH_INIT_ZERO)) op_apply(c, x, V + (size_t)ld, false);
+    { P2PRed pr = halo_p2p_ticket(c);
+      k_residual<<<g, VB, 0, c->stream>>>(b, (first && c->init_type == ISPH_INIT_ZERO) ? nullptr : V + (size_t)ld, r, n, c->red.p, cnt, S + S_TMP, pr); ++c->launches;
+      if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_TMP, 1); }
     const double beta = sqrt(read_scalar(c, S + S_TMP));
     if (first) { scale = beta; first = false; }
     res = beta;
@@ -436,11 +445,11 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
         k_update_dot<<<g, VB, sm, c->stream>>>(V, ld, nvj, vn, nvp, n, S, c->red.p, cnt); ++c->launches;
         if (c->nranks > 1) { halo_allreduce(c, S + S_H2, nvj + 1); CUDA_CHECK(cudaMemcpyAsync(S + S_NEW1, S + S_H2 + nvj, sizeof(double), cudaMemcpyDeviceToDevice, c->stream)); }
       } else {
-        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW1, 1); }
+        { ProfScope ps(c, "update0"); P2PRed pr = halo_p2p_ticket(c); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_NEW1, 1); }
         { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
       }
       dbg(c, "update0/dot1");
-      { ProfScope ps(c, "update1"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt, opt_rev); ++c->launches; allreduce_if(c, S + S_NEW2, 1); }
+      { ProfScope ps(c, "update1"); P2PRed pr = halo_p2p_ticket(c); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt, opt_rev, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_NEW2, 1); }
       dbg(c, "update1");
       { ProfScope ps(c, "givens"); k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches; }
       dbg(c, "givens");
@@ -487,27 +496,30 @@ static int cg_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out,
   const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
   cudaEvent_t ev[2]; for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // R = b - A x ; Z = M^-1 R ; P = Z ; rz = R.Z
-  if (c->init_type == ISPH_INIT_ZERO) { k_residual<<<g, VB, 0, c->stream>>>(b, nullptr, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
-  else { op_apply(c, x, Ap, false); k_residual<<<g, VB, 0, c->stream>>>(b, Ap, r, n, c->red.p, cnt, S + S_TMP); ++c->launches; }
-  allreduce_if(c, S + S_TMP, 1);
+  if (c->init_type != ISPH_INIT_ZERO) op_apply(c, x, Ap, false);
+  { P2PRed pr = halo_p2p_ticket(c);
+    k_residual<<<g, VB, 0, c->stream>>>(b, c->init_type == ISPH_INIT_ZERO ? nullptr : Ap, r, n, c->red.p, cnt, S + S_TMP, pr); ++c->launches;
+    if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_TMP, 1); }
   const double scale = sqrt(read_scalar(c, S + S_TMP)); double res = scale; int iters = 0; bool converged = false;
   if (scale == 0.0 || res / scale <= c->sp.tol) converged = true;
   else {
-    if (jacobi_fused) { k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, c->invdiag.p, c->pp.damping, n, c->red.p, cnt, S + S_RZ); ++c->launches; }
-    else { apply_prec(c, use_prec, r, z); k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, nullptr, 1.0, n, c->red.p, cnt, S + S_RZ); ++c->launches; }
-    allreduce_if(c, S + S_RZ, 1);
+    if (!jacobi_fused) apply_prec(c, use_prec, r, z);
+    { P2PRed pr = halo_p2p_ticket(c);
+      k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, jacobi_fused ? c->invdiag.p : nullptr, jacobi_fused ? c->pp.damping : 1.0, n, c->red.p, cnt, S + S_RZ, pr); ++c->launches;
+      if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_RZ, 1); }
     k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 1); ++c->launches;
     while (true) {
       ++iters;
       op_apply(c, p, Ap, false);
       dot_dev(c, p, Ap, n, S + S_PAP);
-      k_cg_update<<<g, VB, 0, c->stream>>>(x, r, p, Ap, S, n, c->red.p, cnt); ++c->launches; allreduce_if(c, S + S_TMP, 1);
+      { P2PRed pr = halo_p2p_ticket(c); k_cg_update<<<g, VB, 0, c->stream>>>(x, r, p, Ap, S, n, c->red.p, cnt, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_TMP, 1); }
       k_cg_publish<<<1, 32, 0, c->stream>>>(S, c->h_scal.p + 8, iters); ++c->launches;
       CUDA_CHECK(cudaEventRecord(ev[iters & 1], c->stream));
       // next direction, enqueued before the residual of this step is inspected
-      if (jacobi_fused) { k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, c->invdiag.p, c->pp.damping, n, c->red.p, cnt, S + S_BETA); ++c->launches; }
-      else { apply_prec(c, use_prec, r, z); k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, nullptr, 1.0, n, c->red.p, cnt, S + S_BETA); ++c->launches; }
-      allreduce_if(c, S + S_BETA, 1);
+      if (!jacobi_fused) apply_prec(c, use_prec, r, z);
+      { P2PRed pr = halo_p2p_ticket(c);
+        k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, jacobi_fused ? c->invdiag.p : nullptr, jacobi_fused ? c->pp.damping : 1.0, n, c->red.p, cnt, S + S_BETA, pr); ++c->launches;
+        if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_BETA, 1); }
       k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 0); ++c->launches;
       k_cg_shift<<<1, 32, 0, c->stream>>>(S); ++c->launches;
       CUDA_CHECK(cudaEventSynchronize(ev[iters & 1]));
@@ -566,13 +578,14 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
     iters_tot += it; conv_all &= ok; relres = rr > relres ? rr : relres;
   }
   if (use_prec) precond_free(c);                                 // prec->free(), :186-191
-  if (!conv_all && c->rank == 0) {                               // :197-213 : not an error, report ||b - A x|| / ||b||
+  if (!conv_all) {                                               // :197-213 : not an error, report ||b - A x|| / ||b|| (collective: every rank takes part)
     double rn = 0.0, bn = 0.0;
     spmv(c, c->xs.p, c->wk.p, 1, ld, ld);
-    k_residual<<<g, VB, 0, c->stream>>>(c->bs.p, c->wk.p, c->wk.p, n, c->red.p, (unsigned *)c->flag.p + 8, S + S_TMP); ++c->launches;
-    allreduce_if(c, S + S_TMP, 1); rn = sqrt(read_scalar(c, S + S_TMP));
+    { P2PRed pr = halo_p2p_ticket(c); k_residual<<<g, VB, 0, c->stream>>>(c->bs.p, c->wk.p, c->wk.p, n, c->red.p, (unsigned *)c->flag.p + 8, S + S_TMP, pr); ++c->launches;
+      if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_TMP, 1); }
+    rn = sqrt(read_scalar(c, S + S_TMP));
     dot_dev(c, c->bs.p, nullptr, n, S + S_TMP); bn = sqrt(read_scalar(c, S + S_TMP));
-    fprintf(stderr, ">> isph_b200::Status - Failed to converge! %s  ||r|| / ||b|| = %6.4e\n", label ? label : " ", bn > 0 ? rn / bn : rn);
+    if (c->rank == 0) fprintf(stderr, ">> isph_b200::Status - Failed to converge! %s  ||r|| / ||b|| = %6.4e\n", label ? label : " ", bn > 0 ? rn / bn : rn);
   }
   if (c->is_singular) {                                          // x -= (x.n) n, :215-219
     for (int q = 0; q < c->x_nvec; ++q) { dot_dev(c, c->xs.p + (size_t)q * ld, c->nullvec.p, n, S + S_TMP);
@@ -587,6 +600,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
     for (auto &kv : c->phase_ev) { size_t u = c->phase_used[kv.first]; double tot = 0.0; for (size_t q = 0; q + 1 < u; q += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, kv.second[q], kv.second[q + 1]); tot += ms; }
       fprintf(stderr, "[isph profile]   %-16s %6zu x  avg %8.2f us  total %8.3f ms\n", kv.first.c_str(), u / 2, u ? 1e3 * tot / (u / 2) : 0.0, tot); c->phase_used[kv.first] = 0; }
   }
+  if (c->nranks > 1) ISPH_REQUIRE(!halo_fault(c), "peer exchange timed out: a rank stopped responding");
   c->last_iters = iters_tot; c->last_converged = conv_all; c->last_relres = relres;
   c->init_type = -1;
 }
