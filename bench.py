@@ -35,6 +35,10 @@ WORKLOADS = {
                desc="BASELINE configs[0]: 2-D TGV 128x128 pressure Poisson, flexible GMRES(50)+ILU(0)"),
     "c2j": dict(dim=3, n=100, jitter=0.05, rs2=12, prec="point relaxation", solver="Block GMRES",
                 desc="configs[1] particle count with positions jittered by 0.05 dx (no pair on the cutoff)"),
+    # BASELINE configs[3] operator family per GPU: corrected (Gc/Lc) operators, jittered particles, block-Jacobi ILU(0) with
+    # 2x2x2 Ifpack-rank-equivalent bricks per GPU (= 4x4x4 bricks of 50^3 at 8 GPUs)
+    "c4": dict(dim=3, n=100, jitter=0.04, rs2=12, prec="ILU", solver="Block GMRES", anti=False, blocks=2,
+               desc="BASELINE configs[3] per GPU: corrected-operator (Gc/Lc) pressure Poisson, 1M particles per GPU, GMRES(50) + block-Jacobi ILU(0), 8 bricks of 50^3 per GPU"),
     # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
     "p8m": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True,
                 desc="north_star target: 3-D 8M-particle (200^3) pressure Poisson, flexible GMRES(50)+Jacobi, fixed global size (strong scaling)"),
@@ -207,6 +211,12 @@ def main():
     stream = torch.cuda.Stream(); c.set_stream(stream.cuda_stream)
     c.pair_coeff(dim, (0, isph.KIND_FLUID), 1.5 * P["dx"])
     c.solver_param("Solver Type", w["solver"]); c.precond_param("Precond Type", w["prec"]); c.precond_param("Overlap Level", 0); c.precond_param("fact: level-of-fill", 0)
+    anti = w.get("anti", True)
+    blk = None
+    if w.get("blocks"):          # Ifpack-rank-equivalent bricks inside this GPU's brick
+        nb = w["blocks"]; li = P["gidx"][:nl]; ng = nglobal
+        gx = li % ng[0] - lo[0]; gy = (li // ng[0]) % ng[1] - lo[1]; gz = (li // (ng[0] * ng[1])) - (lo[2] if dim == 3 else 0)
+        blk = ((gx * nb) // nloc[0] + nb * ((gy * nb) // nloc[1]) + (nb * nb * ((gz * nb) // nloc[2]) if dim == 3 else 0)).astype(np.int32)
 
     def upload():
         c.atoms_set(nl, P["nghost"], hx[1], htype[1], htag[1])
@@ -221,7 +231,9 @@ def main():
         c.compute_pre()
         c.graph_build()
         c.create_solution(hsol[1], 1); c.create_load(None, 1)
-        c.ns_poisson(dt)
+        c.ns_poisson(dt, anti=anti)
+        if blk is not None:
+            c.precond_set_blocks(blk)
         c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO)
         st = c.solve(True, "Poisson")
         c.matrix_invalidate()

@@ -16,12 +16,13 @@
 #include <algorithm>
 
 namespace cg = cooperative_groups;
+#define ILU_TB 1024
 
 namespace isph {
 
 struct IluData {
   int n = 0; long long nnz = 0; int nlev_l = 0, nlev_u = 0, maxw_l = 0, maxw_u = 0;
-  DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt; DevBuf<double> fv, dinv, y; DevBuf<char> tmp;
+  DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt, lev, hist; DevBuf<double> fv, dinv, y; DevBuf<char> tmp;
   int grid_f = 1, grid_s = 1;
 };
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ int find_col(const int *ci, int lo, int hi, int key) 
   while (lo < hi) { const int mid = (lo + hi) >> 1; const int v = ci[mid]; if (v < key) lo = mid + 1; else hi = mid; }
   return lo;
 }
-__global__ void __launch_bounds__(256) k_ilu_factor(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
+__global__ void __launch_bounds__(ILU_TB) k_ilu_factor(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
                                                     const int *order, const int *lptr, int nlev) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) k_ilu_factor(const int *rp, const int *ci
 }
 
 // ---- apply: L solve (forward levels), D^-1, U solve (backward levels) ----------------------------------------------
-__global__ void __launch_bounds__(256) k_ilu_solve(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
+__global__ void __launch_bounds__(ILU_TB) k_ilu_solve(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
                                                    const int *order_l, const int *lptr_l, int nlev_l, const int *order_u, const int *lptr_u, int nlev_u,
                                                    const double *r, double *y, double *z) {
   cg::grid_group grid = cg::this_grid();
@@ -110,6 +111,29 @@ __global__ void __launch_bounds__(256) k_ilu_solve(const int *rp, const int *ci,
   }
 }
 
+// ---- dependency levels on the device -----------------------------------------------------------------------------
+// level[i] = 1 + max(level[j] : j in L(i)) (0 without dependencies).  One warp per row in dependency order (ascending
+// rows for L, descending for U): lanes read the levels of the row's dependencies and spin until they are published.
+// CTAs are dispatched in index order, so a waiting warp only ever waits for rows of CTAs that were dispatched before its
+// own (resident or finished) — the scheme of the "synchronisation-free" triangular solvers.  The spin is bounded; on a
+// timeout the host-side pass below is used instead.
+__global__ void __launch_bounds__(256) k_ilu_levels(const int *rp, const int *ci, const int *dpos, int n, int lower, int *level, int *maxlev, int *fault) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31; if (w >= n) return;
+  const int i = lower ? w : n - 1 - w;
+  if (dpos[i] < 0) { if (lane == 0) { *fault = 2; level[i] = 0; } return; }          // a row without a diagonal entry
+  const int b = lower ? rp[i] : dpos[i] + 1, e = lower ? dpos[i] : rp[i + 1];
+  int m = -1;
+  for (int q = b + lane; q < e; q += 32) {
+    const volatile int *p = level + ci[q]; int l; long long spins = 0;
+    while ((l = *p) < 0) { if (++spins > (1ll << 26)) { *fault = 1; l = 0; break; } }
+    m = max(m, l);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) { level[i] = m + 1; __threadfence(); atomicMax(maxlev, m + 1); }
+}
+__global__ void k_ilu_hist(const int *level, int n, int *hist) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) atomicAdd(hist + level[i] + 1, 1); }
+__global__ void k_ilu_scatter(const int *level, int n, int *cursor, int *order) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) order[atomicAdd(cursor + level[i], 1)] = i; }
+
 static void level_sets(int n, const std::vector<int> &rp, const std::vector<int> &ci, const std::vector<int> &dpos, bool lower,
                        std::vector<int> &order, std::vector<int> &lptr, int &maxw) {
   std::vector<int> lev(n, 0); int nlev = 0;
@@ -124,9 +148,11 @@ static void level_sets(int n, const std::vector<int> &rp, const std::vector<int>
 
 static int coop_grid(Ctx *c, const void *fn, int max_width) {
   int per_sm = 0, sms = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ILU_TB, 0));
   CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-  const int cap = std::max(1, per_sm * sms), want = std::max(1, (max_width + 7) / 8);     // 8 warps (rows) per block
+  // at most ONE fat CTA per SM: the cost of a grid-wide barrier grows with the number of CTAs (850 CTAs: ~10 us per
+  // level, measured), and a level of an 8-brick 1M-row problem holds only ~1700 rows anyway
+  const int cap = std::max(1, std::min(per_sm, 1) * sms), want = std::max(1, (max_width + ILU_TB / 32 - 1) / (ILU_TB / 32));
   return std::min(cap, want);
 }
 
@@ -146,25 +172,49 @@ void ilu_create(Ctx *c) {
   CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
   I.nnz = rp[n]; I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
   k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
-  // dependency levels (host pass over the pattern; the pattern of a step is shared by every solve of that step)
-  std::vector<int> ci(I.nnz), dpos(n);
-  CUDA_CHECK(cudaMemcpyAsync(ci.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(dpos.data(), I.dpos.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < n; ++i) ISPH_REQUIRE(dpos[i] >= 0, "ILU: a row has no diagonal entry");
-  std::vector<int> ol, pl, ou, pu;
-  level_sets(n, rp, ci, dpos, true, ol, pl, I.maxw_l); level_sets(n, rp, ci, dpos, false, ou, pu, I.maxw_u);
-  I.nlev_l = (int)pl.size() - 1; I.nlev_u = (int)pu.size() - 1;
-  I.order_l.ensure(n); I.order_u.ensure(n); I.lptr_l.ensure(pl.size()); I.lptr_u.ensure(pu.size());
-  CUDA_CHECK(cudaMemcpyAsync(I.order_l.p, ol.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(I.order_u.p, ou.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(I.lptr_l.p, pl.data(), sizeof(int) * pl.size(), cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(I.lptr_u.p, pu.data(), sizeof(int) * pu.size(), cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  // dependency levels + level sets, on the device (no download of the pattern)
+  I.order_l.ensure(n); I.order_u.ensure(n); I.lev.ensure(n); I.hist.ensure(n + 2); I.lptr_l.ensure(n + 2); I.lptr_u.ensure(n + 2);
+  bool device_ok = !getenv("ISPH_ILU_HOST_LEVELS");
+  for (int pass = 0; pass < 2 && device_ok; ++pass) {
+    const int lower = pass == 0; int *order = lower ? I.order_l.p : I.order_u.p, *lptr = lower ? I.lptr_l.p : I.lptr_u.p;
+    CUDA_CHECK(cudaMemsetAsync(I.lev.p, 0xff, sizeof(int) * n, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->flag.p, 0, 4 * sizeof(int), c->stream));                 // [0] max level, [1] fault
+    k_ilu_levels<<<ceil_div((long long)n * 32, 256), 256, 0, c->stream>>>(I.rp.p, I.ci.p, I.dpos.p, n, lower, I.lev.p, c->flag.p, c->flag.p + 1); ++c->launches;
+    int h[2]; CUDA_CHECK(cudaMemcpyAsync(h, c->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    ISPH_REQUIRE(h[1] != 2, "ILU: a row has no diagonal entry");
+    if (h[1]) { device_ok = false; break; }
+    const int nlev = h[0] + 1;
+    CUDA_CHECK(cudaMemsetAsync(I.hist.p, 0, sizeof(int) * (nlev + 1), c->stream));
+    k_ilu_hist<<<ceil_div(n, 256), 256, 0, c->stream>>>(I.lev.p, n, I.hist.p); ++c->launches;
+    size_t tb2 = 0; cub::DeviceScan::InclusiveSum(nullptr, tb2, I.hist.p, lptr, nlev + 1, c->stream); I.tmp.ensure(tb2);
+    cub::DeviceScan::InclusiveSum(I.tmp.p, tb2, I.hist.p, lptr, nlev + 1, c->stream); ++c->launches;     // lptr[l] = first position of level l
+    std::vector<int> hh(nlev + 1);
+    CUDA_CHECK(cudaMemcpyAsync(hh.data(), I.hist.p, sizeof(int) * (nlev + 1), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.hist.p, lptr, sizeof(int) * (nlev + 1), cudaMemcpyDeviceToDevice, c->stream));   // cursors
+    k_ilu_scatter<<<ceil_div(n, 256), 256, 0, c->stream>>>(I.lev.p, n, I.hist.p, order); ++c->launches;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int mw = 0; for (int l = 1; l <= nlev; ++l) mw = std::max(mw, hh[l]);
+    if (lower) { I.nlev_l = nlev; I.maxw_l = mw; } else { I.nlev_u = nlev; I.maxw_u = mw; }
+  }
+  if (!device_ok) {   // host pass over the pattern (fallback)
+    std::vector<int> ci(I.nnz), dpos(n);
+    CUDA_CHECK(cudaMemcpyAsync(ci.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dpos.data(), I.dpos.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) ISPH_REQUIRE(dpos[i] >= 0, "ILU: a row has no diagonal entry");
+    std::vector<int> ol, pl, ou, pu;
+    level_sets(n, rp, ci, dpos, true, ol, pl, I.maxw_l); level_sets(n, rp, ci, dpos, false, ou, pu, I.maxw_u);
+    I.nlev_l = (int)pl.size() - 1; I.nlev_u = (int)pu.size() - 1;
+    CUDA_CHECK(cudaMemcpyAsync(I.order_l.p, ol.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.order_u.p, ou.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.lptr_l.p, pl.data(), sizeof(int) * pl.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.lptr_u.p, pu.data(), sizeof(int) * pu.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
   I.grid_f = coop_grid(c, (const void *)k_ilu_factor, I.maxw_l);
   I.grid_s = coop_grid(c, (const void *)k_ilu_solve, std::max(I.maxw_l, I.maxw_u));
   const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p, *lp = I.lptr_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nlev = I.nlev_l;
   void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ord, &lp, &nlev};
-  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_factor, dim3(I.grid_f), dim3(256), args, 0, c->stream)); ++c->launches;
+  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_factor, dim3(I.grid_f), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
 }
 
 void ilu_free(Ctx *c) { (void)c; /* buffers are grow-only and reused by the next create() (rebuilt every solve, solver_lin_belos.h:153,190) */ }
@@ -174,13 +224,13 @@ void ilu_apply(Ctx *c, const double *r, double *z) {
   const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ol = I.order_l.p, *pl = I.lptr_l.p, *ou = I.order_u.p, *pu = I.lptr_u.p;
   const double *fv = I.fv.p, *dinv = I.dinv.p; double *y = I.y.p; int nl = I.nlev_l, nu = I.nlev_u;
   void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ol, &pl, &nl, &ou, &pu, &nu, &r, &y, &z};
-  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve, dim3(I.grid_s), dim3(256), args, 0, c->stream)); ++c->launches;
+  CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve, dim3(I.grid_s), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
 }
 
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
-  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); delete c->ilu; c->ilu = nullptr;
+  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.lev.release(); I.hist.release(); delete c->ilu; c->ilu = nullptr;
 }
 
 }  // namespace isph

@@ -117,6 +117,17 @@ def test_sph_pressure_poisson_nullspace(name, prec, degree):
     assert abs(x.sum()) <= 1e-9 * np.abs(x).sum()
 
 
+def test_block_jacobi_ilu0_follows_the_rank_partition():
+    """Ifpack factors one open block per MPI rank (overlap 0 drops off-rank columns): with block_of_row = the brick a CPU
+    run would give each rank (here 2 x 2 bricks of the 2-D box), preconditioner and iteration count match the oracle."""
+    import harness
+    P, F = make_case("jitter2d")
+    N = P["nglobal"][0]; g = P["gidx"][:P["nlocal"]]
+    blocks = ((g % N) >= N // 2).astype(np.int32) + 2 * ((g // N) >= N // 2).astype(np.int32)
+    st, info, x, xo = _sph_poisson("jitter2d", O.PREC_ILU0, blocks=blocks)
+    check(st, info, x, xo, sol_tol=1e-6)
+
+
 def test_c1_tgv128_gmres_ilu0():
     """BASELINE config 1: 2-D TGV 128x128 pressure Poisson, flexible GMRES(50) + ILU(0) (fill 0, overlap 0), one rank."""
     st, info, x, xo = _sph_poisson("tgv128", O.PREC_ILU0)
