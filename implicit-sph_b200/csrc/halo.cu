@@ -2,10 +2,12 @@
 // pair_isph.cpp:1258-1259).  Replaces what Epetra does through MPI underneath the reference's calls:
 //   * column map / importer  -> halo plan: every ghost atom whose tag is owned by another rank gets a halo column
 //     (distinct remote tags, grouped by owner so that each peer's data lands contiguously behind the owned rows);
-//   * Epetra_Import in CrsMatrix::Multiply -> ONE kernel that gathers the requested x entries and stores them straight
-//     into the peers' halo staging buffers over NVLink (peer memory mapped with cudaIpc), raises sequence flags and
-//     waits for the peers' flags; the SpMV then reads halo columns from the local staging buffer.  Fallback (no peer
-//     access): pack kernel + grouped ncclSend/ncclRecv into the halo tail of x;
+//   * Epetra_Import in CrsMatrix::Multiply -> the requested x entries are stored straight into the peers' halo staging
+//     buffers over NVLink (peer memory mapped with cudaIpc; protocol in p2p_device.cuh: the data is its own flag), either
+//     by the kernel that PRODUCES x (k_finish in krylov.cu pushes z_{j+1} while it writes it, so the import overlaps the
+//     end of the Arnoldi step) or by a small gather kernel; a second small kernel takes the arrived values behind the
+//     owned rows of x and re-arms the slot; the SpMV itself stays branch-free.  Fallback (no peer access): pack kernel
+//     + grouped ncclSend/ncclRecv into the halo tail of x;
 //   * Epetra_MpiComm::SumAll -> the last block of every reduction kernel exchanges its partial sums through peer
 //     mailboxes (p2p_device.cuh); fallback ncclAllReduce;
 //   * comm->forward_comm_pair (owner -> ghost field copy) -> the same plan with ncomp doubles per particle (NCCL).
@@ -19,6 +21,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <tuple>
+#include <cub/cub.cuh>
 
 namespace isph {
 
@@ -50,50 +53,22 @@ static NcclApi g_nccl;
 // stand-alone small all-reduce (reductions whose kernel does not carry the exchange in its epilogue)
 __global__ void k_allreduce_p2p(P2PRed r, double *buf, int count) { p2p_allreduce_block(r, buf, count); }
 
-// halo staging buffer of a rank (IPC-shared): [MB_SLOTS][ISPH_MAX_RANKS] flag words, then [MB_SLOTS][3][cap] doubles
-#define HB_FLAGS (MB_SLOTS * ISPH_MAX_RANKS)
-struct HaloPush {
-  double *peer[ISPH_MAX_RANKS]; double *mine;
-  int send_off[ISPH_MAX_RANKS + 1], dst_off[ISPH_MAX_RANKS], recv_cnt[ISPH_MAX_RANKS];
-  int nranks, rank; unsigned long long seq; long long cap; int *fault;
-};
-// gather the x entries the peers asked for and store them into THEIR staging buffers over NVLink; the last block to
-// finish raises the flags and waits until every peer's data for this sequence number has landed here
-__global__ void __launch_bounds__(256) k_halo_push(HaloPush hp, const double *x, int ldx, int nvec, const int *send_idx, int nsend, unsigned *counter) {
-  const int slot = (int)(hp.seq % MB_SLOTS);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nsend) {
-    int p = 0; while (k >= hp.send_off[p + 1]) ++p;
-    const int s = send_idx[k]; const long long pos = hp.dst_off[p] + (k - hp.send_off[p]);
-    double *dst = hp.peer[p] + HB_FLAGS + (size_t)slot * 3 * hp.cap + pos;
-    for (int q = 0; q < nvec; ++q) dst[(size_t)q * hp.cap] = x[(size_t)q * ldx + s];
-  }
-  __threadfence_system();
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence_system();
-  const int t = threadIdx.x;
-  if (t < hp.nranks && t != hp.rank) {
-    if (hp.send_off[t + 1] > hp.send_off[t]) {
-      volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(hp.peer[t]) + slot * ISPH_MAX_RANKS + hp.rank;
-      *f = hp.seq + 1;
-    }
-    if (hp.recv_cnt[t] > 0) {
-      volatile unsigned long long *w = reinterpret_cast<volatile unsigned long long *>(hp.mine) + slot * ISPH_MAX_RANKS + t;
-      long long spins = 0;
-      while (*w < hp.seq + 1) { if (++spins > (1ll << 31)) { *hp.fault = 1; break; } }
-    }
-    __threadfence_system();
-  }
-  if (t == 0) *counter = 0u;
+// gather the x entries the peers asked for and store them into THEIR staging buffers over NVLink (fire and forget)
+__global__ void __launch_bounds__(256) k_halo_push(const HaloDev *hp, unsigned long long seq, const double *x, int ldx, int nvec, const int *send_idx, int nsend) {
+  const int slot = (int)(seq % MB_SLOTS);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= nsend) return;
+  int p = 0; while (k >= hp->send_off[p + 1]) ++p;
+  const int s = send_idx[k];
+  double *dst = hp->peer[p] + (size_t)slot * 3 * hp->cap + hp->dst_off[p] + (k - hp->send_off[p]);
+  for (int q = 0; q < nvec; ++q) *reinterpret_cast<volatile double *>(dst + (size_t)q * hp->cap) = p2p_payload(x[(size_t)q * ldx + s]);
 }
-
-__global__ void k_halo_unstage(const double *stage, long long cap, double *x, int ldx, int nlocal, int nhalo, int nvec) {
+// take the arrived halo values out of this rank's staging slot (poll until each has landed, re-arm the cell) and put them
+// behind the owned rows of x
+__global__ void __launch_bounds__(256) k_halo_unstage(const HaloDev *hp, unsigned long long seq, double *x, int ldx, int nlocal, int nhalo, int nvec) {
+  const int slot = (int)(seq % MB_SLOTS);
   const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= nhalo) return;
-  for (int q = 0; q < nvec; ++q) x[(size_t)q * ldx + nlocal + k] = __ldcg(stage + (size_t)q * cap + k);
+  double *cell = hp->mine + (size_t)slot * 3 * hp->cap + k;
+  for (int q = 0; q < nvec; ++q) x[(size_t)q * ldx + nlocal + k] = p2p_take(cell + (size_t)q * hp->cap, hp->fault);
 }
 
 struct Halo {
@@ -106,8 +81,18 @@ struct Halo {
   int nhalo = 0, nsend = 0;
   std::vector<int> recv_count, recv_off, send_count, send_off;
   DevBuf<int> send_idx, itmp, itmp2; DevBuf<long long> owner_tab; DevBuf<double> sendbuf, fieldbuf;
+  // fused halo + SpMV
+  DevBuf<HaloDev> d_plan; bool plan_ok = false;
+  DevBuf<int> row_sp, row_sd, row_cur; DevBuf<char> cubtmp; bool rows_ok = false;      // per-row send list (push from the producer)
 };
 
+// per-row send list: count, scan, fill (order within a row is irrelevant)
+__global__ void k_rowsend_count(const int *send_idx, int nsend, int *cnt) { const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < nsend) atomicAdd(cnt + send_idx[k], 1); }
+__global__ void k_rowsend_fill(const HaloDev *hp, const int *send_idx, int nsend, int *cursor, int *sd) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= nsend) return;
+  int p = 0; while (k >= hp->send_off[p + 1]) ++p;
+  sd[atomicAdd(cursor + send_idx[k], 1)] = (p << 28) | (hp->dst_off[p] + (k - hp->send_off[p]));
+}
 __global__ void k_owner_tab(const int *all_tags, const int *nloc_all, int maxn, int nranks, int max_tag, long long *tab) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (t >= (long long)nranks * maxn) return;
   const int r = (int)(t / maxn), i = (int)(t % maxn); if (i >= nloc_all[r]) return;
@@ -167,7 +152,7 @@ static Halo *get(Ctx *c) {
     h->inited = true;
     if (!getenv("ISPH_NO_P2P") && c->nranks <= ISPH_MAX_RANKS) {   // peer mailboxes for the small all-reduces
       const size_t bytes = sizeof(double) * MB_SLOTS * c->nranks * MB_STRIDE;
-      CUDA_CHECK(cudaMalloc(&h->mbox, bytes)); CUDA_CHECK(cudaMemset(h->mbox, 0, bytes));
+      CUDA_CHECK(cudaMalloc(&h->mbox, bytes)); CUDA_CHECK(cudaMemset(h->mbox, 0xff, bytes));     // every cell armed (sentinel)
       CUDA_CHECK(cudaMalloc(&h->fault, sizeof(int))); CUDA_CHECK(cudaMemset(h->fault, 0, sizeof(int)));
       h->p2p = ipc_share(c, h, h->mbox, h->mpeer, h->mopened);
       if (h->p2p) { P2PTab t; memset(&t, 0, sizeof(t)); for (int p = 0; p < c->nranks; ++p) t.box[p] = h->mpeer[p]; t.mine = h->mbox; t.nranks = c->nranks; t.rank = c->rank; t.fault = h->fault;
@@ -251,42 +236,66 @@ void halo_setup(Ctx *c) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     ipc_close(h->hopened); if (h->hbox) cudaFree(h->hbox);
     h->hcap = max_halo + max_halo / 4 + 1024;
-    const size_t bytes = sizeof(double) * (HB_FLAGS + (size_t)MB_SLOTS * 3 * h->hcap);
-    CUDA_CHECK(cudaMalloc(&h->hbox, bytes)); CUDA_CHECK(cudaMemset(h->hbox, 0, bytes));
+    const size_t bytes = sizeof(double) * ((size_t)MB_SLOTS * 3 * h->hcap);
+    CUDA_CHECK(cudaMalloc(&h->hbox, bytes)); CUDA_CHECK(cudaMemset(h->hbox, 0xff, bytes));     // every cell armed (sentinel)
     h->hseq = 0;
     if (!ipc_share(c, h, h->hbox, h->hpeer, h->hopened)) { cudaFree(h->hbox); h->hbox = nullptr; h->hcap = 0; }
+  }
+  h->plan_ok = false;
+  if (h->p2p && h->hbox) {                                       // device copy of the plan for the fused halo + SpMV kernel
+    HaloDev hd; memset(&hd, 0, sizeof(hd));
+    for (int p = 0; p < R; ++p) { hd.peer[p] = h->hpeer[p]; hd.send_off[p] = h->send_off[p]; hd.dst_off[p] = h->dst_off[p]; hd.recv_cnt[p] = h->recv_count[p]; }
+    for (int p = R; p <= ISPH_MAX_RANKS; ++p) hd.send_off[p] = h->send_off[R];
+    hd.mine = h->hbox; hd.nranks = R; hd.rank = c->rank; hd.cap = h->hcap; hd.fault = h->fault;
+    h->d_plan.ensure(1);
+    CUDA_CHECK(cudaMemcpyAsync(h->d_plan.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    h->plan_ok = true;
+    h->rows_ok = false;
+    if (!getenv("ISPH_NO_PREPUSH") && h->nsend > 0 && h->hcap < (1ll << 28)) {
+      h->row_sp.ensure(nl + 2); h->row_cur.ensure(nl + 2); h->row_sd.ensure(h->nsend + 1);
+      CUDA_CHECK(cudaMemsetAsync(h->row_cur.p, 0, sizeof(int) * (nl + 1), c->stream));
+      k_rowsend_count<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(h->send_idx.p, h->nsend, h->row_cur.p); ++c->launches;
+      size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, h->row_cur.p, h->row_sp.p, nl + 1, c->stream); h->cubtmp.ensure(tb);
+      cub::DeviceScan::ExclusiveSum(h->cubtmp.p, tb, h->row_cur.p, h->row_sp.p, nl + 1, c->stream); ++c->launches;
+      CUDA_CHECK(cudaMemcpyAsync(h->row_cur.p, h->row_sp.p, sizeof(int) * (nl + 1), cudaMemcpyDeviceToDevice, c->stream));
+      k_rowsend_fill<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(h->d_plan.p, h->send_idx.p, h->nsend, h->row_cur.p, h->row_sd.p); ++c->launches;
+      h->rows_ok = true;
+    }
   }
   c->toc("haloSetup");
 }
 
+bool halo_prepush_begin(Ctx *c, const double *x_next, PrePush *pp) {
+  pp->plan = nullptr; pp->sp = pp->sd = nullptr; pp->seq = 0;
+  if (c->nranks <= 1) return false;
+  Halo *h = get(c);
+  if (!h->plan_ok || !h->rows_ok) return false;
+  pp->plan = h->d_plan.p; pp->sp = h->row_sp.p; pp->sd = h->row_sd.p; pp->seq = h->hseq++;
+  c->prepush_x = x_next; c->prepush_seq = pp->seq;
+  return true;
+}
+void halo_wait_unstage(Ctx *c, double *x, unsigned long long seq) {
+  Halo *h = get(c);
+  if (h->nhalo) { k_halo_unstage<<<ceil_div(h->nhalo, 256), 256, 0, c->stream>>>(h->d_plan.p, seq, x, 0, c->nlocal, h->nhalo, 1); ++c->launches; }
+}
+
 int halo_ncols(Ctx *c) { return c->nlocal + (c->halo ? c->halo->nhalo : 0); }
 
-// Halo import for an SpMV.  Returns the device address the halo columns of vector 0 can be read from (vector q at
-// + q * (*stride)); nullptr means "they were written behind the owned rows of x" (NCCL path).
-const double *halo_exchange(Ctx *c, double *x, int nvec, int ldx, long long *stride) {
-  Halo *h = get(c); *stride = 0;
-  if (h->nhalo == 0 && h->nsend == 0) return nullptr;
-  if (h->p2p && h->hbox && nvec <= 3) {
-    HaloPush hp; memset(&hp, 0, sizeof(hp));
-    for (int p = 0; p < c->nranks; ++p) { hp.peer[p] = h->hpeer[p]; hp.send_off[p] = h->send_off[p]; hp.dst_off[p] = h->dst_off[p]; hp.recv_cnt[p] = h->recv_count[p]; }
-    hp.send_off[c->nranks] = h->send_off[c->nranks]; for (int p = c->nranks + 1; p <= ISPH_MAX_RANKS; ++p) hp.send_off[p] = hp.send_off[c->nranks];
-    hp.mine = h->hbox; hp.nranks = c->nranks; hp.rank = c->rank; hp.seq = h->hseq++; hp.cap = h->hcap; hp.fault = h->fault;
-    const int slot = (int)(hp.seq % MB_SLOTS);
-    k_halo_push<<<std::max(1, ceil_div(h->nsend, 256)), 256, 0, c->stream>>>(hp, x, ldx, nvec, h->send_idx.p, h->nsend, (unsigned *)c->flag.p + 14); ++c->launches;
-    const double *stage = h->hbox + HB_FLAGS + (size_t)slot * 3 * h->hcap;
-    if (!getenv("ISPH_HALO_INKERNEL")) {   // default: land the halo behind the owned rows of x (a 1.5 MB copy) so that the SpMV keeps its
-      if (h->nhalo) { k_halo_unstage<<<ceil_div(h->nhalo, 256), 256, 0, c->stream>>>(stage, h->hcap, x, ldx, c->nlocal, h->nhalo, nvec); ++c->launches; }   // branch-free gather
-      return nullptr;                      // (reading the staging buffer from inside the SpMV costs 12 % of its bandwidth: measured)
-    }
-    *stride = h->hcap;
-    return stage;
+// Halo import for an SpMV (Epetra_Import): the off-rank entries of x land behind its owned rows.
+void halo_exchange(Ctx *c, double *x, int nvec, int ldx) {
+  Halo *h = get(c);
+  if (h->nhalo == 0 && h->nsend == 0) return;
+  if (h->plan_ok && nvec <= 3) {
+    const unsigned long long seq = h->hseq++;
+    if (h->nsend) { k_halo_push<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(h->d_plan.p, seq, x, ldx, nvec, h->send_idx.p, h->nsend); ++c->launches; }
+    if (h->nhalo) { k_halo_unstage<<<ceil_div(h->nhalo, 256), 256, 0, c->stream>>>(h->d_plan.p, seq, x, ldx, c->nlocal, h->nhalo, nvec); ++c->launches; }
+    return;
   }
   for (int q = 0; q < nvec; ++q) {
     double *xq = x + (size_t)q * ldx;
     if (h->nsend) { k_pack<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(xq, h->send_idx.p, h->nsend, 1, h->sendbuf.p + (size_t)q * h->nsend); ++c->launches; }
     exchange(c, h, h->sendbuf.p + (size_t)q * h->nsend, xq + c->nlocal, 1);
   }
-  return nullptr;
 }
 
 void halo_forward_field(Ctx *c, int field, int nc) {
@@ -317,6 +326,7 @@ void halo_destroy(Ctx *c) {
   ipc_close(h->mopened); ipc_close(h->hopened);
   if (h->mbox) cudaFree(h->mbox); if (h->hbox) cudaFree(h->hbox); if (h->fault) cudaFree(h->fault); if (h->d_tab) cudaFree(h->d_tab);
   if (h->inited && h->comm) g_nccl.CommDestroy(h->comm);
+  h->d_plan.release(); h->row_sp.release(); h->row_sd.release(); h->row_cur.release(); h->cubtmp.release();
   h->send_idx.release(); h->itmp.release(); h->itmp2.release(); h->owner_tab.release(); h->sendbuf.release(); h->fieldbuf.release();
   delete h; c->halo = nullptr;
 }

@@ -23,7 +23,7 @@ namespace isph {
 struct IluData {
   int n = 0; long long nnz = 0; int nlev_l = 0, nlev_u = 0, maxw_l = 0, maxw_u = 0;
   DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt, lev, hist; DevBuf<double> fv, dinv, y; DevBuf<char> tmp;
-  int grid_f = 1, grid_s = 1;
+  int grid_f = 1, grid_s = 1, maxlen = 0, tb_f = ILU_TB; bool sync_free = true; size_t smem_f = 0; DevBuf<int> fault;
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
@@ -111,6 +111,82 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve(const int *rp, const int *
   }
 }
 
+// ---- synchronisation-free variants (default) -----------------------------------------------------------------------
+// No grid barriers: the data is its own "ready" flag.  dinv / y / z are preset to NaN (memset 0xff); a consumer polls the
+// value it depends on until it is a number.  Persistent, co-resident warps (cooperative launch) take rows in level order,
+// so the lowest unfinished row never waits on an unfinished one: no deadlock.  The critical path becomes
+// (#levels x one L2 round trip) instead of (#levels x one grid barrier).  Waits are bounded; a timeout or a computed NaN
+// is published as 0 with the fault word raised, so that nobody downstream spins on it.
+__device__ __forceinline__ double wait_value(const double *p, int *fault) {
+  const volatile double *vp = p; double v = *vp; int spins = 0;
+  while (v != v) {
+    if ((++spins & 1023) == 0) {                               // once a fault is raised anywhere, every wait drains immediately
+      if (*reinterpret_cast<volatile int *>(fault)) return 0.0;
+      if (spins > (1 << 22)) { *fault = 1; return 0.0; }
+    }
+    v = *vp;
+  }
+  return v;
+}
+__device__ __forceinline__ double publishable(double v, int *fault) { if (v != v) { *fault = 2; return 0.0; } return v; }
+
+// shared memory per warp: the row's columns and values (maxlen each); row j's U part is read through L2
+__global__ void __launch_bounds__(ILU_TB) k_ilu_factor_sf(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
+                                                          const int *order, int n, int maxlen, int *fault) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  double *s_val = reinterpret_cast<double *>(smem_raw) + (size_t)wib * maxlen;
+  int *s_col = reinterpret_cast<int *>(smem_raw + (size_t)(blockDim.x >> 5) * maxlen * sizeof(double)) + (size_t)wib * maxlen;
+  for (int idx = gw; idx < n; idx += nw) {
+    const int i = order[idx], b = rp[i], len = rp[i + 1] - b, dp = dpos[i] - b;
+    for (int t = lane; t < len; t += 32) { s_col[t] = ci[b + t]; s_val[t] = fv[b + t]; }
+    __syncwarp();
+    for (int q = 0; q < dp; ++q) {                          // strictly-lower entries, ascending column
+      const int j = s_col[q];
+      double dj = 0.0;
+      if (lane == 0) dj = wait_value(dinv + j, fault);      // row j finished (its U part was fenced before dinv[j] was published)
+      dj = __shfl_sync(0xffffffffu, dj, 0);
+      __threadfence();
+      const double multiplier = s_val[q];
+      const int ub = dpos[j] + 1, ue = rp[j + 1];
+      for (int u = ub + lane; u < ue; u += 32) {
+        const int k = __ldcg(ci + u);
+        int lo = q + 1, hi = len;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < k) lo = mid + 1; else hi = mid; }
+        if (lo < len && s_col[lo] == k) s_val[lo] -= multiplier * __ldcg(fv + u);
+      }
+      __syncwarp();
+      if (lane == 0) s_val[q] = multiplier * dj;
+      __syncwarp();
+    }
+    const double d = 1.0 / s_val[dp];
+    __syncwarp();
+    for (int t = lane; t < len; t += 32) fv[b + t] = t > dp ? s_val[t] * d : s_val[t];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile double *>(dinv + i) = publishable(d, fault);
+  }
+}
+
+__global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sf(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
+                                                         const int *order_l, const int *order_u, int n, const double *r, double *y, double *z, int *fault) {
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int idx = gw; idx < n; idx += nw) {                   // L solve
+    const int i = order_l[idx], b = rp[i], dp = dpos[i];
+    double s = 0.0;
+    for (int q = b + lane; q < dp; q += 32) s += fv[q] * wait_value(y + ci[q], fault);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) *reinterpret_cast<volatile double *>(y + i) = publishable(r[i] - s, fault);
+  }
+  for (int idx = gw; idx < n; idx += nw) {                   // D^-1 and U solve
+    const int i = order_u[idx], e = rp[i + 1], dp = dpos[i];
+    double s = 0.0;
+    for (int q = dp + 1 + lane; q < e; q += 32) s += fv[q] * wait_value(z + ci[q], fault);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { const double yi = wait_value(y + i, fault); *reinterpret_cast<volatile double *>(z + i) = publishable(yi * dinv[i] - s, fault); }
+  }
+}
+
 // ---- dependency levels on the device -----------------------------------------------------------------------------
 // level[i] = 1 + max(level[j] : j in L(i)) (0 without dependencies).  One warp per row in dependency order (ascending
 // rows for L, descending for U): lanes read the levels of the row's dependencies and spin until they are published.
@@ -171,6 +247,8 @@ void ilu_create(Ctx *c) {
   std::vector<int> rp(n + 1);
   CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
   I.nnz = rp[n]; I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
+  I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
+  I.sync_free = !getenv("ISPH_ILU_BARRIER"); I.fault.ensure(4); CUDA_CHECK(cudaMemsetAsync(I.fault.p, 0, 4 * sizeof(int), c->stream));
   k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
   // dependency levels + level sets, on the device (no download of the pattern)
   I.order_l.ensure(n); I.order_u.ensure(n); I.lev.ensure(n); I.hist.ensure(n + 2); I.lptr_l.ensure(n + 2); I.lptr_u.ensure(n + 2);
@@ -210,6 +288,22 @@ void ilu_create(Ctx *c) {
     CUDA_CHECK(cudaMemcpyAsync(I.lptr_u.p, pu.data(), sizeof(int) * pu.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
+  if (I.sync_free) {
+    int sms = 0, per_sm = 0; CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    // factorisation: per-warp staging of the row in shared memory (12 B per entry); shrink the CTA until it fits
+    I.tb_f = ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * 12 > 200 * 1024) I.tb_f >>= 1;
+    I.smem_f = (size_t)(I.tb_f / 32) * I.maxlen * 12; ISPH_REQUIRE(I.smem_f <= 200 * 1024, "ILU: a row is too long for the factorisation kernel");
+    CUDA_CHECK(cudaFuncSetAttribute(k_ilu_factor_sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_f));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_factor_sf, I.tb_f, I.smem_f)); ISPH_REQUIRE(per_sm >= 1, "ILU: factorisation kernel does not fit an SM");
+    I.grid_f = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, I.tb_f)));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_solve_sf, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: solve kernel does not fit an SM");
+    I.grid_s = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, ILU_TB)));
+    CUDA_CHECK(cudaMemsetAsync(I.dinv.p, 0xff, sizeof(double) * n, c->stream));           // NaN = "row not factored yet"
+    const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nn = n, ml = I.maxlen; int *flt = I.fault.p;
+    void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ord, &nn, &ml, &flt};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_factor_sf, dim3(I.grid_f), dim3(I.tb_f), args, I.smem_f, c->stream)); ++c->launches;
+    return;
+  }
   I.grid_f = coop_grid(c, (const void *)k_ilu_factor, I.maxw_l);
   I.grid_s = coop_grid(c, (const void *)k_ilu_solve, std::max(I.maxw_l, I.maxw_u));
   const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p, *lp = I.lptr_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nlev = I.nlev_l;
@@ -219,8 +313,20 @@ void ilu_create(Ctx *c) {
 
 void ilu_free(Ctx *c) { (void)c; /* buffers are grow-only and reused by the next create() (rebuilt every solve, solver_lin_belos.h:153,190) */ }
 
+bool ilu_fault(Ctx *c) {
+  if (!c->ilu || !c->ilu->fault.p) return false;
+  int f = 0; cudaMemcpy(&f, c->ilu->fault.p, sizeof(int), cudaMemcpyDeviceToHost); return f != 0;
+}
+
 void ilu_apply(Ctx *c, const double *r, double *z) {
   IluData &I = *c->ilu;
+  if (I.sync_free) {
+    CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"
+    const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ol = I.order_l.p, *ou = I.order_u.p; const double *fv = I.fv.p, *dinv = I.dinv.p; double *y = I.y.p; int nn = I.n; int *flt = I.fault.p;
+    void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ol, &ou, &nn, &r, &y, &z, &flt};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve_sf, dim3(I.grid_s), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
+    return;
+  }
   const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ol = I.order_l.p, *pl = I.lptr_l.p, *ou = I.order_u.p, *pu = I.lptr_u.p;
   const double *fv = I.fv.p, *dinv = I.dinv.p; double *y = I.y.p; int nl = I.nlev_l, nu = I.nlev_u;
   void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ol, &pl, &nl, &ou, &pu, &nu, &r, &y, &z};
@@ -230,7 +336,7 @@ void ilu_apply(Ctx *c, const double *r, double *z) {
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
-  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.lev.release(); I.hist.release(); delete c->ilu; c->ilu = nullptr;
+  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
 }
 
 }  // namespace isph

@@ -110,6 +110,7 @@ struct Ctx {
   IluData *ilu = nullptr;
   // multi-GPU
   Halo *halo = nullptr;
+  const double *prepush_x = nullptr; unsigned long long prepush_seq = 0;   // SpMV input whose halo was pushed by its producer kernel
   unsigned char nccl_id[128]; bool have_nccl_id = false;
   // timers
   std::map<std::string, Timer> timers;
@@ -164,12 +165,27 @@ void precond_create(Ctx *c);                                 // precond.cu
 void precond_free(Ctx *c);
 void precond_apply(Ctx *c, const double *d_r, double *d_z);  // z = M^-1 r
 void ilu_destroy(Ctx *c);                                    // ilu.cu
+bool ilu_fault(Ctx *c);
 
 void solver_prepare_vectors(Ctx *c);                         // krylov.cu
 void solver_solve(Ctx *c, bool use_prec, const char *label);
 
+// device-resident exchange plan of the halo kernels (written once per halo_setup; indexed dynamically on the device,
+// which is why it is not a by-value kernel parameter).  Staging buffer of a rank: [MB_SLOTS][3 vectors][cap] doubles.
+struct HaloDev {
+  double *peer[ISPH_MAX_RANKS]; double *mine;                 // halo staging buffers (peer-mapped) and this rank's own
+  int send_off[ISPH_MAX_RANKS + 1], dst_off[ISPH_MAX_RANKS], recv_cnt[ISPH_MAX_RANKS];
+  int nranks, rank; long long cap; int *fault;
+};
+// "push from the producer": the kernel that WRITES the next SpMV input (k_finish: z_{j+1} = D^-1 v_{j+1}) also stores the
+// rows on the send list straight into the peers' staging buffers, so the import of that SpMV is already under way (usually
+// complete) when the SpMV is launched.  sp/sd = per-row send list (CSR over owned rows; entry = peer << 28 | offset).
+struct PrePush { const HaloDev *plan; const int *sp, *sd; unsigned long long seq; };
+
 void halo_setup(Ctx *c);                                     // halo.cu
-const double *halo_exchange(Ctx *c, double *d_x, int nvec, int ldx, long long *stride);   // nullptr: halo written behind x's owned rows
+bool halo_prepush_begin(Ctx *c, const double *x_next, PrePush *pp);   // reserves the exchange of the SpMV that will read x_next
+void halo_wait_unstage(Ctx *c, double *d_x, unsigned long long seq);  // completes a pre-pushed exchange: halo lands behind x's owned rows
+void halo_exchange(Ctx *c, double *d_x, int nvec, int ldx);   // import: off-rank entries of x land behind its owned rows
 P2PRed halo_p2p_ticket(Ctx *c);          // sequence ticket for an in-kernel peer all-reduce (nranks <= 1 in it: not available)
 bool halo_fault(Ctx *c);
 void halo_allreduce(Ctx *c, double *d_buf, int count);

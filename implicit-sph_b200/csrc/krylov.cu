@@ -59,8 +59,34 @@ template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc,
   }
 }
 
-// the pre-projection squared norm of pass 0 is stored right behind the nv coefficients (one allreduce covers both)
-__device__ __forceinline__ bool dgks_second(const double *S, int nv) { return S[S_NEW1] < DEP_TOL * S[S_H + nv]; }
+// ---- DGKS bookkeeping without extra reductions ----------------------------------------------------------------------
+// Belos' DGKS manager takes four to five global reductions per Arnoldi step (oldDot, Q^T w, newDot, [second pass], norm).
+// Here an Arnoldi step takes TWO: the pass-0 message carries h = V^T y together with y.y and (singular problems) n.y, the
+// pass-1 message carries h2 = V^T w1 together with w1.w1.  Everything else follows from Pythagoras, which is exact up to
+// rounding because the basis is orthonormal:
+//   PoissonProjection tail (solver_lin.h:135-137): w' = y - (n.y) n is never formed on its own; n is treated as one more
+//     (unit, orthogonal to V up to rounding) direction of the same classical Gram-Schmidt sweep;
+//   oldDot = ||w'||^2 = y.y - (n.y)^2 ;  newDot = ||w1||^2 ~ oldDot - sum h_k^2  — used ONLY for the DGKS decision
+//     newDot < dep_tol * oldDot (a threshold test; when cancellation is severe the estimate is tiny or negative and the
+//     second pass is taken, as it should be);
+//   the norm that enters the Hessenberg matrix: second pass taken -> ||w2||^2 = w1.w1 - sum h2_k^2 (h2 is O(eps) relative
+//     to w1: no cancellation); not taken -> oldDot - sum h_k^2 with newDot >= 0.707 oldDot (relative error <= 2 eps).
+// Message layout: S_H[0..nv) = h, S_H[nv] = y.y, S_H[nv+1] = n.y ; S_H2[0..nv) = h2, S_H2[nv] = w1.w1.
+struct DgksNorm { bool second; double hn2; };
+__device__ __forceinline__ DgksNorm dgks_norm(const double *S, int nv, bool singular) {      // serial, fixed order: identical wherever it is evaluated
+  double old = S[S_H + nv]; if (singular) { const double p = S[S_H + nv + 1]; old -= p * p; }
+  double s = 0.0; for (int k = 0; k < nv; ++k) { const double h = S[S_H + k]; s += h * h; }
+  const double new1 = old - s;
+  DgksNorm d; d.second = new1 < DEP_TOL * old; d.hn2 = new1;
+  if (d.second) { double s2 = 0.0; for (int k = 0; k < nv; ++k) { const double h = S[S_H2 + k]; s2 += h * h; } d.hn2 = S[S_H2 + nv] - s2; }
+  if (!(d.hn2 > 0.0)) d.hn2 = 0.0;
+  return d;
+}
+__device__ __forceinline__ bool dgks_second(const double *S, int nv, bool singular) {
+  double old = S[S_H + nv]; if (singular) { const double p = S[S_H + nv + 1]; old -= p * p; }
+  double s = 0.0; for (int k = 0; k < nv; ++k) { const double h = S[S_H + k]; s += h * h; }
+  return old - s < DEP_TOL * old;
+}
 
 // out[0] = sum a_i b_i (b == nullptr: a_i a_i)
 __global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
@@ -71,26 +97,27 @@ __global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, in
 
 // Classical Gram-Schmidt coefficients.  grid = (row chunks, vector groups): block (bx, g) owns a CONTIGUOUS chunk of
 // rows and the G basis vectors [gG, gG+G): every thread streams one w value pair and G basis value pairs per step
-// (128-bit loads), keeps G+1 accumulators in registers, and a block touches only G+1 pages — the first version, where
+// (128-bit loads), keeps G+2 accumulators in registers, and a block touches only G+2 pages — the first version, where
 // every thread walked all <= 51 vectors, ran at ~1.4 TB/s (profiles/r01_launches_c2_first.txt).
-//   pass 0: h[k] = V_k . w' (k < nv), h[nv] = w'.w'  with  w' = w - proj * nvec  (PoissonProjection tail on the fly)
-//   pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w
-template <int G> __global__ void __launch_bounds__(VB)
+//   pass 0: h[k] = V_k . y (k < nv), h[nv] = y.y, h[nv+1] = n.y (group 0; n = null vector of a singular problem)
+//   pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w1, h2[nv] = w1.w1
+template <int G> __global__ void __launch_bounds__(VB, G == 16 ? 2 : (G == 8 ? 3 : 5))
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
            double *S, int pass, double *partials, unsigned *counters, P2PRed pr) {
-  if (pass == 1 && !dgks_second(S, nv)) return;
+  __shared__ bool go;
+  if (pass == 1) { if (threadIdx.x == 0) go = dgks_second(S, nv, nvec != nullptr); __syncthreads(); if (!go) return; }
   const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
-  const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
+  const bool with_n = (pass == 0 && nvec != nullptr && g == 0);
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
   const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
   const double *Vg = V + (size_t)k0 * ld;
-  double acc[G + 1];
+  double acc[G + 2];
 #pragma unroll
-  for (int k = 0; k <= G; ++k) acc[k] = 0.0;
+  for (int k = 0; k < G + 2; ++k) acc[k] = 0.0;
   for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
-    double2 wi;
-    if (i + 1 < r1) { wi = *reinterpret_cast<const double2 *>(w + i); if (pass == 0 && nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; } }
-    else { wi.x = w[i]; if (pass == 0 && nvec) wi.x -= proj * nvec[i]; wi.y = 0.0; }
+    double2 wi, nn = make_double2(0.0, 0.0);
+    if (i + 1 < r1) { wi = *reinterpret_cast<const double2 *>(w + i); if (with_n) nn = *reinterpret_cast<const double2 *>(nvec + i); }
+    else { wi.x = w[i]; wi.y = 0.0; if (with_n) nn.x = nvec[i]; }
     // all G loads are issued unconditionally and up front (vectors past the group's end alias its last one: L1 hits,
     // results discarded) so that 16 independent 128-bit loads are in flight per thread; a predicated load/use chain
     // here made the kernel latency-bound (~3 TB/s)
@@ -104,150 +131,75 @@ k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restric
     }
 #pragma unroll
     for (int k = 0; k < G; ++k) { acc[k] += v[k].x * wi.x; acc[k] += v[k].y * wi.y; }
-    if (g == 0) { acc[G] += wi.x * wi.x; acc[G] += wi.y * wi.y; }
+    if (g == 0) { acc[G] += wi.x * wi.x; acc[G] += wi.y * wi.y; acc[G + 1] += nn.x * wi.x; acc[G + 1] += nn.y * wi.y; }
   }
-  __shared__ double sm[G + 1][VB / 32];
+  __shared__ double sm[G + 2][VB / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k <= G; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
+  for (int k = 0; k < G + 2; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) sm[k][warp] = v; }
   __syncthreads();
-  double *mine = partials + ((size_t)g * gridDim.x + blockIdx.x) * (G + 1);
-  if (threadIdx.x <= G) { double s = 0.0; for (int q = 0; q < VB / 32; ++q) s += sm[threadIdx.x][q]; mine[threadIdx.x] = s; }
+  double *mine = partials + ((size_t)g * gridDim.x + blockIdx.x) * (G + 2);
+  if (threadIdx.x < G + 2) { double s = 0.0; for (int q = 0; q < VB / 32; ++q) s += sm[threadIdx.x][q]; mine[threadIdx.x] = s; }
   __threadfence(); __syncthreads();
   if (threadIdx.x == 0) last = (atomicAdd(counters + g, 1u) == gridDim.x - 1);
   __syncthreads();
   if (last) {
     __threadfence();
-    const double *grp = partials + (size_t)g * gridDim.x * (G + 1);
-    for (int k = warp; k <= G; k += VB / 32) {
-      if (!(k < cnt || (k == G && g == 0 && pass == 0))) continue;
+    const double *grp = partials + (size_t)g * gridDim.x * (G + 2);
+    for (int k = warp; k < G + 2; k += VB / 32) {
+      if (!(k < cnt || (k == G && g == 0) || (k == G + 1 && with_n))) continue;
       double s = 0.0;
-      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(grp + (size_t)b * (G + 1) + k);
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(grp + (size_t)b * (G + 2) + k);
       s = warp_sum(s);
-      if (lane == 0) { if (k == G) S[S_H + nv] = s; else S[(pass == 0 ? S_H : S_H2) + k0 + k] = s; }
+      if (lane == 0) S[(pass == 0 ? S_H : S_H2) + (k < G ? k0 + k : nv + (k - G))] = s;
     }
     if (threadIdx.x == 0) counters[g] = 0u;
-    if (pr.nranks > 1) {                                   // the last group to finish exchanges h[0..nv) (+ the norm) with the peers
+    if (pr.nranks > 1) {                                   // the last group to finish exchanges the whole message with the peers
       __shared__ bool all_done;
       __threadfence(); __syncthreads();
       if (threadIdx.x == 0) { all_done = (atomicAdd(counters + 6, 1u) == gridDim.y - 1); if (all_done) counters[6] = 0u; }   // flag word 15
       __syncthreads();
-      if (all_done) { __threadfence(); p2p_allreduce_block(pr, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv); }
+      if (all_done) { __threadfence(); p2p_allreduce_block(pr, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + (nvec ? 2 : 1) : nv + 1); }
     }
   }
 }
 
-// w <- w' - sum_k h_k V_k ; new = ||w||^2.  One contiguous row chunk per block, 128-bit accesses.
+// first Gram-Schmidt update: w1 = y - (n.y) n - sum_k h_k V_k.  One contiguous row chunk per block, 128-bit accesses; no
+// reduction (||w1||^2 travels with the pass-1 message, see above).
 __global__ void __launch_bounds__(VB)
-k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
-             double *S, int pass, double *partials, unsigned *counter, int rev, P2PRed pr) {
-  if (pass == 1 && !dgks_second(S, nv)) return;
+k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, const double *S) {
   __shared__ double sh[64];
-  if (threadIdx.x < nv) sh[threadIdx.x] = S[(pass == 0 ? S_H : S_H2) + threadIdx.x];
+  if (threadIdx.x < nv) sh[threadIdx.x] = S[S_H + threadIdx.x];
   __syncthreads();
-  const double proj = (pass == 0 && nvec) ? S[S_PROJ] : 0.0;
+  const double proj = nvec ? S[S_H + nv + 1] : 0.0;
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
-  (void)rev;   // reversed sweeps (to catch the tail of the previous sweep in L2) were measured: no gain on B200, and the
-               // indexed loop they need costs ~40 % on this kernel
   const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
-  double acc[1] = {0.0};
   for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
     if (i + 1 < r1) {
       double2 wi = *reinterpret_cast<const double2 *>(w + i);
-      if (pass == 0 && nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; }
+      if (nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; }
 #pragma unroll 8
       for (int k = 0; k < nv; ++k) { const double2 v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + i); wi.x -= sh[k] * v.x; wi.y -= sh[k] * v.y; }
-      *reinterpret_cast<double2 *>(w + i) = wi; acc[0] += wi.x * wi.x; acc[0] += wi.y * wi.y;
+      *reinterpret_cast<double2 *>(w + i) = wi;
     } else {
-      double wi = w[i]; if (pass == 0 && nvec) wi -= proj * nvec[i];
+      double wi = w[i]; if (nvec) wi -= proj * nvec[i];
       for (int k = 0; k < nv; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
-      w[i] = wi; acc[0] += wi * wi;
+      w[i] = wi;
     }
-  }
-  reduce_finish<1>(acc, 1, partials, counter, S + (pass == 0 ? S_NEW1 : S_NEW2), pr);
-}
-
-// Fused first Gram-Schmidt update + second-pass coefficients: ONE sweep over the basis instead of two.
-//   w1 = w' - sum_k h_k V_k   (pass-0 update, ||w1||^2 -> S_NEW1)   and   h2[k] = V_k . w1   (pass-1 dots, speculative:
-//   whether the DGKS test uses them is decided afterwards by k_cgs_update(pass 1) / k_givens from S_NEW1).
-// Each block owns a contiguous row chunk and walks it in tiles of UT rows: the tile of all nv basis vectors is staged in
-// shared memory (<= 52 x 64 x 8 B = 26 KB), w1 of the tile is formed from it, and the same staged values feed the dots.
-static const int UT = 64;
-__global__ void __launch_bounds__(VB)
-k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
-             double *S, double *partials, unsigned *counter) {
-  extern __shared__ __align__(16) double smem[];
-  double *tile = smem;                     // [nv][UT]
-  double *w1 = smem + (size_t)nv * UT;     // [UT]
-  double *psum = w1 + UT;                  // [VB/UT][UT]
-  __shared__ double sh[64], red[VB / 32];
-  __shared__ bool last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < nv) sh[tid] = S[S_H + tid];
-  const double proj = nvec ? S[S_PROJ] : 0.0;
-  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + UT - 1) / UT * UT;
-  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
-  double acc[7] = {0, 0, 0, 0, 0, 0, 0}, nd = 0.0;
-  __syncthreads();
-  for (int t0 = r0; t0 < r1; t0 += UT) {
-    const int tl = min(UT, r1 - t0);
-    for (int e = tid; e < nv * (UT / 2); e += VB) {            // stage the tile, 128-bit loads (t0 and ld are even)
-      const int k = e / (UT / 2), r = 2 * (e % (UT / 2));
-      double2 v = make_double2(0.0, 0.0);
-      if (r + 1 < tl) v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + t0 + r); else if (r < tl) v.x = V[(size_t)k * ld + t0 + r];
-      *reinterpret_cast<double2 *>(tile + (size_t)k * UT + r) = v;
-    }
-    __syncthreads();
-    { const int r = tid & (UT - 1), gq = tid / UT;               // 4 thread groups share the k loop of one row
-      double s = 0.0;
-      for (int k = gq; k < nv; k += VB / UT) s += sh[k] * tile[(size_t)k * UT + r];
-      psum[gq * UT + r] = s; }
-    __syncthreads();
-    if (tid < UT) {
-      double wi = 0.0;
-      if (tid < tl) { wi = w[t0 + tid]; if (nvec) wi -= proj * nvec[t0 + tid]; double ps = 0.0; for (int q = 0; q < VB / UT; ++q) ps += psum[q * UT + tid]; wi -= ps; w[t0 + tid] = wi; nd += wi * wi; }
-      w1[tid] = wi;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 7; ++q) { const int k = warp + 8 * q; if (k < nv) { for (int r = lane; r < UT; r += 32) acc[q] += tile[(size_t)k * UT + r] * w1[r]; } }
-    __syncthreads();
-  }
-  double *mine = partials + (size_t)blockIdx.x * 64;
-#pragma unroll
-  for (int q = 0; q < 7; ++q) { const int k = warp + 8 * q; const double v = warp_sum(acc[q]); if (lane == 0 && k < nv) mine[k] = v; }
-  nd = warp_sum(nd); if (lane == 0) red[warp] = nd;
-  __syncthreads();
-  if (tid == 0) { double t = 0.0; for (int q = 0; q < (UT + 31) / 32; ++q) t += red[q]; mine[63] = t; }
-  __threadfence(); __syncthreads();
-  if (tid == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    for (int k = warp; k < 64; k += VB / 32) {
-      if (!(k < nv || k == 63)) continue;
-      double s = 0.0;
-      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
-      s = warp_sum(s);
-      if (lane == 0) { if (k == 63) { S[S_NEW1] = s; S[S_H2 + nv] = s; } else S[S_H2 + k] = s; }
-    }
-    if (tid == 0) *counter = 0u;
   }
 }
 
 // Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp:
 // lanes stage the column and the rotations in shared memory, lane 0 runs the (inherently sequential) recurrence there
-__global__ void k_givens(double *S, int j, int m, double *host_res, int slot) {
+__device__ void givens_step(double *S, int j, bool singular, double *host_res, int slot) {
   __shared__ double h[64], cs[64], sn[64];
-  const int lane = threadIdx.x;
-  const bool second = dgks_second(S, j + 1);
-  for (int k = lane; k <= j; k += 32) { h[k] = S[S_H + k] + (second ? S[S_H2 + k] : 0.0); cs[k] = S[S_CS + k]; sn[k] = S[S_SN + k]; }
+  const int lane = threadIdx.x & 31;
+  const DgksNorm d = dgks_norm(S, j + 1, singular);
+  for (int k = lane; k <= j; k += 32) { h[k] = S[S_H + k] + (d.second ? S[S_H2 + k] : 0.0); cs[k] = S[S_CS + k]; sn[k] = S[S_SN + k]; }
   __syncwarp();
   if (lane == 0) {
-    const double newDot = second ? S[S_NEW2] : S[S_NEW1];
-    const double hn = sqrt(newDot);
-    S[S_INV] = hn > 0.0 ? 1.0 / hn : 0.0;
+    const double hn = sqrt(d.hn2);
     h[j + 1] = hn;
     for (int k = 0; k < j; ++k) {                       // previous rotations
       const double a = h[k], b = h[k + 1];
@@ -265,6 +217,48 @@ __global__ void k_givens(double *S, int j, int m, double *host_res, int slot) {
   }
   __syncwarp();
   for (int k = lane; k <= j; k += 32) S[S_HM + k * 64 + j] = h[k];
+}
+__global__ void k_givens(double *S, int j, int singular, double *host_res, int slot) { givens_step(S, j, singular != 0, host_res, slot); }
+
+// End of an Arnoldi step in ONE sweep: second Gram-Schmidt update (when the DGKS test asked for it), normalisation
+// v_{j+1} = w2 / ||w2|| (norm from dgks_norm, no reduction) and — Jacobi — the next preconditioned vector
+// z_{j+1} = damping * D^-1 v_{j+1}.  Warp 0 of block 0 also does the Hessenberg/Givens step of this column.
+// store z_i into the staging buffers of the peers that have row i on their halo list
+__device__ __forceinline__ void prepush_row(const PrePush &pp, int hslot, int b, int e, double v) {
+  v = p2p_payload(v);
+  for (; b < e; ++b) { const int code = __ldg(pp.sd + b); *reinterpret_cast<volatile double *>(pp.plan->peer[code >> 28] + (size_t)hslot * 3 * pp.plan->cap + (code & 0x0fffffff)) = v; }
+}
+__global__ void __launch_bounds__(VB)
+k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, int n, double *S, int singular,
+         const double *__restrict__ invdiag, double damping, double *__restrict__ z, double *host_res, int slot, PrePush pp) {
+  if (blockIdx.x == 0) {      // block 0 is dedicated to the (sequential, ~10 us) Hessenberg/Givens step: hidden behind the sweep
+    if (threadIdx.x < 32) givens_step(S, nv - 1, singular != 0, host_res, slot);
+    return;
+  }
+  __shared__ double sh[64]; __shared__ double s_inv; __shared__ int s_second;
+  if (threadIdx.x == 0) { const DgksNorm d = dgks_norm(S, nv, singular != 0); const double hn = sqrt(d.hn2); s_inv = hn > 0.0 ? 1.0 / hn : 0.0; s_second = d.second ? 1 : 0; }
+  if (threadIdx.x < nv) sh[threadIdx.x] = S[S_H2 + threadIdx.x];
+  __syncthreads();
+  const double inv = s_inv; const int nk = s_second ? nv : 0;
+  const int nb = gridDim.x - 1, bx = blockIdx.x - 1, hslot = (int)(pp.seq % MB_SLOTS);
+  int chunk = (n + nb - 1) / nb; chunk = (chunk + 1) & ~1;
+  const int r0 = bx * chunk, r1 = min(n, r0 + chunk);
+  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+    if (i + 1 < r1) {
+      double2 wi = *reinterpret_cast<const double2 *>(w + i);
+#pragma unroll 8
+      for (int k = 0; k < nk; ++k) { const double2 v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + i); wi.x -= sh[k] * v.x; wi.y -= sh[k] * v.y; }
+      wi.x *= inv; wi.y *= inv;
+      *reinterpret_cast<double2 *>(w + i) = wi;
+      if (z) { double2 zi = wi; if (invdiag) { const double2 dd = *reinterpret_cast<const double2 *>(invdiag + i); zi.x = damping * dd.x * wi.x; zi.y = damping * dd.y * wi.y; } *reinterpret_cast<double2 *>(z + i) = zi;
+        if (pp.plan) { const int s0 = __ldg(pp.sp + i), s1 = __ldg(pp.sp + i + 1), s2 = __ldg(pp.sp + i + 2); if (s2 > s0) { prepush_row(pp, hslot, s0, s1, zi.x); prepush_row(pp, hslot, s1, s2, zi.y); } } }
+    } else {
+      double wi = w[i];
+      for (int k = 0; k < nk; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
+      wi *= inv; w[i] = wi;
+      if (z) { const double zi = invdiag ? damping * invdiag[i] * wi : wi; z[i] = zi; if (pp.plan) prepush_row(pp, hslot, __ldg(pp.sp + i), __ldg(pp.sp + i + 1), zi); }
+    }
+  }
 }
 
 // y = H^-1 g for the first ncol columns
@@ -298,11 +292,6 @@ __global__ void __launch_bounds__(VB) k_combine(double *t, const double *V, int 
   }
 }
 
-// v <- w * S[S_INV] (in place) and, for Jacobi, z <- damping * invdiag * v in the same pass
-__global__ void __launch_bounds__(VB) k_normalize_prec(double *w, const double *S, const double *invdiag, double damping, double *z, int n) {
-  const double s = S[S_INV];
-  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const double v = w[i] * s; w[i] = v; if (z) z[i] = invdiag ? damping * invdiag[i] * v : v; }
-}
 // r = b - t (t may be null: r = b) ; out = ||r||^2
 __global__ void __launch_bounds__(VB) k_residual(const double *b, const double *t, double *r, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
   double acc[1] = {0.0};
@@ -353,7 +342,10 @@ __global__ void __launch_bounds__(VB) k_cg_direction(double *p, const double *z,
 __global__ void k_cg_shift(double *S) { if (threadIdx.x == 0) S[S_RZ] = S[S_BETA]; }
 
 // ---------------------------------------------------------------------------------------------------------------
-static int vgrid(Ctx *c, int n) { (void)c; int g = ceil_div(n, VB); return g < 592 ? (g < 1 ? 1 : g) : 592; }   // 148 SMs x 4 CTAs
+static int vgrid(Ctx *c, int n) {      // default 148 SMs x 16 chunks (measured best for the streaming updates on 1M rows: 6.2 TB/s vs 4.9 at 592); ISPH_VGRID overrides
+  (void)c; static const int cap = getenv("ISPH_VGRID") ? atoi(getenv("ISPH_VGRID")) : 2368;
+  int g = ceil_div(n, 2 * VB); return g < cap ? (g < 1 ? 1 : g) : cap;
+}
 
 void solver_prepare_vectors(Ctx *c) {
   const int need = c->A.ncols > c->A.n ? c->A.ncols : c->A.n;
@@ -390,13 +382,16 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
   const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
   const int groups = (nv + G - 1) / G;
-  int gx = 592 / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
+  static const int mdcap = getenv("ISPH_MDGRID") ? atoi(getenv("ISPH_MDGRID")) : 296;   // one wave of the 128-register G = 16 variant (2 CTAs per SM)
+  int gx = mdcap / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
   P2PRed pr = halo_p2p_ticket(c);
   if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
   else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
   else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
   ++c->launches;
-  if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + 1 : nv);
+  // NCCL fallback (no peer access).  Pass 1 is conditional on the device: a rank-independent decision (it is taken from the
+  // already reduced pass-0 message), so every rank either contributes fresh sums or the same stale, unused ones.
+  if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + (nv_ ? 2 : 1) : nv + 1);
 }
 
 static void dbg(Ctx *c, const char *what) {      // ISPH_DEBUG_SYNC=1: synchronise after every phase and name the one that faulted
@@ -411,10 +406,7 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   double *S = c->hbuf.p, *V = c->V.p, *Z = c->Z.p, *r = c->wk.p; unsigned *cnt = (unsigned *)c->flag.p + 8;
   const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
   const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
-  // fused update+second-pass dots (k_update_dot): measured 109-141 us vs 48+45 us for the two streaming kernels on B200
-  // (the staged tile is not pipelined), so it stays opt-in until it carries a cp.async double buffer
-  static const int opt_fuse = getenv("ISPH_FUSE") ? 1 : 0;
-  const int opt_rev = 0;   // reversed sweeps were measured: no L2 reuse gain on B200 (both dies stream concurrently), kept off
+  const int sing = c->is_singular ? 1 : 0;
   std::vector<cudaEvent_t> ev(m);
   for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   int iters = 0, restarts = 0; bool converged = false, first = true; double scale = 0.0, res = 0.0;
@@ -437,30 +429,22 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
     for (; j < m; ++j) {
       double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
       dbg(c, "prologue");
-      { ProfScope ps(c, "op_apply"); op_apply(c, zj, vn, true); } dbg(c, "op_apply");         // w = A z_j (projection coefficient deferred)
+      { ProfScope ps(c, "op_apply"); spmv(c, zj, vn, 1, ld, ld); } dbg(c, "op_apply");          // y = A z_j ; the PoissonProjection tail rides on the Gram-Schmidt sweep
       { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); } dbg(c, "multidot0");
-      if (opt_fuse) {
-        ProfScope ps(c, "update0+dot1");
-        const int nvj = j + 1; const size_t sm = ((size_t)nvj * UT + (1 + VB / UT) * UT) * sizeof(double);
-        k_update_dot<<<g, VB, sm, c->stream>>>(V, ld, nvj, vn, nvp, n, S, c->red.p, cnt); ++c->launches;
-        if (c->nranks > 1) { halo_allreduce(c, S + S_H2, nvj + 1); CUDA_CHECK(cudaMemcpyAsync(S + S_NEW1, S + S_H2 + nvj, sizeof(double), cudaMemcpyDeviceToDevice, c->stream)); }
-      } else {
-        { ProfScope ps(c, "update0"); P2PRed pr = halo_p2p_ticket(c); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, 0, c->red.p, cnt, opt_rev, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_NEW1, 1); }
-        { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
-      }
-      dbg(c, "update0/dot1");
-      { ProfScope ps(c, "update1"); P2PRed pr = halo_p2p_ticket(c); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nullptr, n, S, 1, c->red.p, cnt, opt_rev, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_NEW2, 1); }
-      dbg(c, "update1");
-      { ProfScope ps(c, "givens"); k_givens<<<1, 32, 0, c->stream>>>(S, j, m, c->h_scal.p + 8, iters + 1); ++c->launches; }
-      dbg(c, "givens");
-      CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
+      { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S); ++c->launches; } dbg(c, "update0");
+      { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); } dbg(c, "multidot1");
       ++iters;
-      if (j + 1 < m) {                                           // prepare the next Arnoldi step before looking at the residual
-        ProfScope ps(c, "normalize_prec");
+      if (j + 1 < m) {                                           // second update + normalisation + next preconditioned vector + Givens, one sweep
+        ProfScope ps(c, "finish");
         double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
-        if (jacobi_fused) { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, c->invdiag.p, c->pp.damping, zn, n); ++c->launches; }
-        else { k_normalize_prec<<<g, VB, 0, c->stream>>>(vn, S, nullptr, 1.0, nullptr, n); ++c->launches; apply_prec(c, use_prec, vn, zn); }
-      }
+        PrePush pp; pp.plan = nullptr; pp.sp = pp.sd = nullptr; pp.seq = 0;
+        if (jacobi_fused) { halo_prepush_begin(c, zn, &pp);       // z_{j+1} is the next SpMV input: its halo rows leave from this kernel
+          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, c->invdiag.p, c->pp.damping, zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
+        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
+      } else { k_givens<<<1, 32, 0, c->stream>>>(S, j, sing, c->h_scal.p + 8, iters); ++c->launches; }   // last column of the cycle: v_{m} is never used
+      dbg(c, "finish");
+      CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
+      if (j + 1 < m && !jacobi_fused && use_prec) { ProfScope ps(c, "precond"); apply_prec(c, true, vn, flex ? Z + (size_t)(j + 1) * ld : Z); }
       // look at the residual of the PREVIOUS step (already finished on the device): no pipeline bubble
       if (j >= 1) {
         CUDA_CHECK(cudaEventSynchronize(ev[j - 1]));
@@ -486,6 +470,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
     ++restarts;
   }
   for (auto &e : ev) cudaEventDestroy(e);
+  // a push whose SpMV was never issued (converged one step late): take it anyway so that the staging cells are re-armed
+  if (c->prepush_x) { halo_wait_unstage(c, const_cast<double *>(c->prepush_x), c->prepush_seq); c->prepush_x = nullptr; }
   *iters_out = iters; *relres_out = scale > 0.0 ? res / scale : 0.0;
   return converged ? 1 : 0;
 }
@@ -544,7 +530,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   c->prof_phases = getenv("ISPH_PROFILE") != nullptr;
   std::string tname = std::string("solve") + (label ? label : "");
   c->tic(tname.c_str());
-  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)4 * 592 * 17 + 1024 + (size_t)A.nslices / 8 + 64);
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)8 * 592 * 18 + 1024 + (size_t)A.nslices / 8 + 64);
   c->wk.ensure((size_t)ld + c->nall + 3 * (size_t)ld);
   c->h_scal.ensure(16 + c->sp.max_iters + m + 8);
   c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
@@ -601,6 +587,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
       fprintf(stderr, "[isph profile]   %-16s %6zu x  avg %8.2f us  total %8.3f ms\n", kv.first.c_str(), u / 2, u ? 1e3 * tot / (u / 2) : 0.0, tot); c->phase_used[kv.first] = 0; }
   }
   if (c->nranks > 1) ISPH_REQUIRE(!halo_fault(c), "peer exchange timed out: a rank stopped responding");
+  if (use_prec && c->prec_kind == 3) ISPH_REQUIRE(!ilu_fault(c), "ILU(0): a dependency wait timed out or a factor entry is not a number (zero pivot?)");
   c->last_iters = iters_tot; c->last_converged = conv_all; c->last_relres = relres;
   c->init_type = -1;
 }

@@ -1,16 +1,22 @@
-// Device-side pieces of the NVLink peer-memory exchange (see halo.cu for the set-up and the protocol).
+// Device-side pieces of the NVLink peer-memory exchange (see halo.cu for the set-up).
 //
-// Every rank owns a mailbox in its own HBM that all peers can address through cudaIpc mappings.  A reduction / halo
-// "call" carries a sequence number that is identical on all ranks (every rank executes the same sequence of calls on
-// its stream); a slot ring of MB_SLOTS entries is indexed by seq % MB_SLOTS.  Producer: NVLink stores of the payload into
-// every peer's slot, __threadfence_system(), then a monotonic flag (= seq + 1).  Consumer: polls the flags in its OWN
-// mailbox (local memory, written by the peers), then reads the payloads in rank order, so every rank forms the
-// bit-identical sum.  A rank can never overwrite a slot a peer still reads: to get MB_SLOTS calls ahead it would need
-// the peer's contributions to the calls in between, which the peer only issues after it has consumed the older call.
+// Every rank owns a mailbox (small all-reduces) and a halo staging buffer in its own HBM that all peers can address
+// through cudaIpc mappings.  A reduction / halo "call" carries a sequence number that is identical on all ranks (every
+// rank executes the same sequence of calls on its stream); a ring of MB_SLOTS slots is indexed by seq % MB_SLOTS.
+//
+// Protocol: THE DATA IS ITS OWN FLAG.  Every 8-byte cell of a slot rests at a sentinel bit pattern (all ones: a NaN that
+// arithmetic never produces; a payload that happens to carry it is canonicalised first).  Producer: one plain NVLink
+// store per value — no fence, no flag, no counter.  Consumer: polls the cells in its OWN buffer (local memory) until they
+// differ from the sentinel, uses them, and writes the sentinel back for the slot's next use.  One one-way NVLink store
+// latency per exchange instead of store -> system fence -> flag -> poll.  All-reduce payloads are summed in rank order,
+// so every rank forms the bit-identical sum.  A rank can never overwrite a cell a peer has not consumed yet: to get
+// MB_SLOTS calls ahead it would need the peer's contributions to the calls in between, which the peer only issues after
+// it has consumed (and re-armed) the older call.  Waits are bounded: a dead peer raises the fault word, after which every
+// wait on this GPU drains immediately.
 #pragma once
 #include <cuda_runtime.h>
 
-#define MB_STRIDE 72          /* 64 payload doubles + 1 flag word (+ padding), in doubles */
+#define MB_STRIDE 64          /* payload doubles per (slot, rank) cell block */
 #define MB_SLOTS 4
 #define ISPH_MAX_RANKS 8
 
@@ -28,6 +34,22 @@ struct P2PRed {               // passed by value to kernels; tab == nullptr mean
   int nranks;                 // copy of tab->nranks (1 when disabled) for cheap host/device tests
 };
 
+#define ISPH_SENTINEL 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ double p2p_payload(double v) {      // a value that may be stored into a peer cell
+  return (unsigned long long)__double_as_longlong(v) == ISPH_SENTINEL ? __longlong_as_double(0x7FF8000000000000ll) : v;
+}
+// poll a cell of this rank's own buffer until a peer's value has landed, then re-arm it
+__device__ __forceinline__ double p2p_take(double *cell, int *fault) {
+  volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(cell);
+  unsigned long long bits = *q; int spins = 0;
+  while (bits == ISPH_SENTINEL) {
+    if ((++spins & 1023) == 0) { if (*reinterpret_cast<volatile int *>(fault)) return 0.0; if (spins > (1 << 23)) { *fault = 1; return 0.0; } }
+    bits = *q;
+  }
+  *q = ISPH_SENTINEL;
+  return __longlong_as_double((long long)bits);
+}
+
 // All threads of ONE block (>= 64 threads) call this; vals[0..count) (global memory, count <= 64) is replaced by the
 // sum over ranks.  Used in the "last block" epilogue of the reduction kernels, so no other block of the grid is waiting.
 static __device__ __noinline__ void p2p_allreduce_block(const P2PRed &r, double *vals, int count) {
@@ -35,26 +57,14 @@ static __device__ __noinline__ void p2p_allreduce_block(const P2PRed &r, double 
   const int slot = (int)(r.seq % MB_SLOTS), t = threadIdx.x;
   __syncthreads();
   if (t < count) {
-    const double v = __ldcg(vals + t);
-    for (int p = 0; p < nr; ++p) T->box[p][(size_t)(slot * nr + me) * MB_STRIDE + t] = v;
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (t < nr) {
-    volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(T->box[t] + (size_t)(slot * nr + me) * MB_STRIDE + 64);
-    *f = r.seq + 1;                                              // my contribution to rank t is complete
-    volatile unsigned long long *w = reinterpret_cast<volatile unsigned long long *>(T->mine + (size_t)(slot * nr + t) * MB_STRIDE + 64);
-    long long spins = 0;
-    while (*w < r.seq + 1) { if (++spins > (1ll << 31)) { *T->fault = 1; break; } }   // bounded: a dead peer must not hang the GPU
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (t < count) {
+    const double v = p2p_payload(__ldcg(vals + t));
+    for (int p = 0; p < nr; ++p) *reinterpret_cast<volatile double *>(T->box[p] + (size_t)(slot * nr + me) * MB_STRIDE + t) = v;
     double s = 0.0;
-    for (int p = 0; p < nr; ++p) s += __ldcv(T->mine + (size_t)(slot * nr + p) * MB_STRIDE + t);
+    for (int p = 0; p < nr; ++p) s += p2p_take(T->mine + (size_t)(slot * nr + p) * MB_STRIDE + t, T->fault);
     vals[t] = s;
   }
   __syncthreads();
 }
 
 }  // namespace isph
+

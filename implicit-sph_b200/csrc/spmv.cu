@@ -36,11 +36,10 @@ __device__ __forceinline__ void spmv_dot_finish(double v, double *partials, unsi
 
 // DOT: additionally out[0] = sum_i y_i d_i (the (y.n) of PoissonProjection::Apply, solver_lin.h:133-137) reduced in the
 // epilogue: block partials in block order, combined by the last block to finish — saves a pass over y per iteration.
-template <int NV, bool DOT, bool HALO> __global__ void __launch_bounds__(256, 8)     // 32 registers: 8 CTAs = 2048 threads per SM
+template <int NV, bool DOT> __global__ void __launch_bounds__(256, 8)     // 32 registers: 8 CTAs = 2048 threads per SM
 k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col,
             const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy,
-            const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr,
-            const double *__restrict__ hx, long long hstride) {
+            const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
   if (!DOT && s >= nslices) return;
   if (DOT && s >= nslices) { spmv_dot_finish(0.0, partials, counter, out, pr); return; }
@@ -57,16 +56,13 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
       const double *xq = x + (size_t)q * ldx;
-      if (HALO) { const double *hq = hx + (size_t)q * hstride - n;      // columns >= n live in the peer-filled staging buffer
-        acc[q] += v0 * (c0 < n ? __ldg(xq + c0) : __ldcg(hq + c0)); acc[q] += v1 * (c1 < n ? __ldg(xq + c1) : __ldcg(hq + c1));
-        acc[q] += v2 * (c2 < n ? __ldg(xq + c2) : __ldcg(hq + c2)); acc[q] += v3 * (c3 < n ? __ldg(xq + c3) : __ldcg(hq + c3)); }
-      else { acc[q] += v0 * __ldg(xq + c0); acc[q] += v1 * __ldg(xq + c1); acc[q] += v2 * __ldg(xq + c2); acc[q] += v3 * __ldg(xq + c3); }
+      acc[q] += v0 * __ldg(xq + c0); acc[q] += v1 * __ldg(xq + c1); acc[q] += v2 * __ldg(xq + c2); acc[q] += v3 * __ldg(xq + c3);
     }
   }
   for (; k < slen; ++k) {
     const int c0 = __ldcs(cp + 32 * k); const double v0 = __ldcs(vp + 32 * k);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) acc[q] += v0 * ((!HALO || c0 < n) ? __ldg(x + (size_t)q * ldx + c0) : __ldcg(hx + (size_t)q * hstride - n + c0));
+    for (int q = 0; q < NV; ++q) acc[q] += v0 * __ldg(x + (size_t)q * ldx + c0);
   }
   if (row < n) {
 #pragma unroll
@@ -75,31 +71,35 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
   if (DOT) spmv_dot_finish(row < n ? acc[0] * dvec[row] : 0.0, partials, counter, out, pr);
 }
 
+// With several ranks the off-rank x entries (Epetra_Import) land behind the owned rows of x before the multiply starts —
+// pushed by the kernel that produced x (krylov.cu: k_finish) or by halo_exchange — so the multiply itself is the same
+// branch-free kernel on one GPU and on eight (reading the staging buffer from inside the SpMV cost 12 % of its bandwidth,
+// and splitting it into a halo-free and a halo phase inside one kernel was slower still: profiles/r01_halo_variants.md).
 void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const double *dot_vec, double *dot_out) {
   Matrix &A = c->A; ISPH_REQUIRE(A.built, "spmv: no matrix");
-  const double *hx = nullptr; long long hs = 0;
-  if (c->nranks > 1) hx = halo_exchange(c, const_cast<double *>(x), nvec, ldx, &hs);     // import of off-rank x entries (Epetra_Import)
   const int grid = ceil_div((long long)A.nslices * 32, 256);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->prof_spmv) {      // per-launch device timing on the launching stream (bench.py roofline)
+  if (c->prof_spmv) {      // per-launch device timing on the launching stream (bench.py roofline); with several ranks it includes the import
     if (c->prof_used + 2 > c->prof_ev.size()) { c->prof_ev.resize(c->prof_ev.size() + 512, nullptr); for (size_t q = c->prof_used; q < c->prof_ev.size(); ++q) if (!c->prof_ev[q]) CUDA_CHECK(cudaEventCreate(&c->prof_ev[q])); }
     e0 = c->prof_ev[c->prof_used++]; e1 = c->prof_ev[c->prof_used++]; CUDA_CHECK(cudaEventRecord(e0, c->stream));
   }
+  if (c->nranks > 1 && nvec == 1 && c->prepush_x == x) { halo_wait_unstage(c, const_cast<double *>(x), c->prepush_seq); c->prepush_x = nullptr; }   // pushed by the producer of x
+  else if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);
   P2PRed none; none.tab = nullptr; none.seq = 0; none.nranks = 1;
-#define SPMV_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr, hxx, hs
+#define SPMV_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr
   int done = 0;
   while (done < nvec) {
     const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
-    const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy; const double *hxx = hx ? hx + (size_t)done * hs : nullptr;
-    if (nv == 3) { if (hx) k_spmv_sell<3, false, true><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); else k_spmv_sell<3, false, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); }
-    else if (nv == 2) { if (hx) k_spmv_sell<2, false, true><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); else k_spmv_sell<2, false, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); }
+    const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy;
+    if (nv == 3) k_spmv_sell<3, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
+    else if (nv == 2) k_spmv_sell<2, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     else if (dot_vec && nvec == 1) {
       ISPH_REQUIRE(c->red.cap >= (size_t)grid, "spmv: reduction workspace too small");
       P2PRed pr = halo_p2p_ticket(c);
-      if (hx) k_spmv_sell<1, true, true><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, dot_vec, pr)); else k_spmv_sell<1, true, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, dot_vec, pr));
+      k_spmv_sell<1, true><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, dot_vec, pr));
       if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, dot_out, 1);
     }
-    else { if (hx) k_spmv_sell<1, false, true><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); else k_spmv_sell<1, false, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none)); }
+    else k_spmv_sell<1, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     ++c->launches; done += nv;
   }
 #undef SPMV_ARGS
