@@ -7,10 +7,12 @@ One *step* = what `PairISPH::compute` does per time step for the pressure Poisso
 reference does.  Metric: rows assembled-and-solved per second (whole job), with `ms_per_step` = the absolute Poisson
 step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM bandwidth inside the solve.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|c4j] [--n LATTICE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|c2|c1|c4|c2j] [--n LATTICE]
 
-N=1 workload (default) = BASELINE.json configs[1]: 3-D pressure Poisson, 100^3 = 1M-particle periodic lattice, Wendland,
-GMRES + Jacobi.  `--impl reference` times the CPU path (oracle port, OpenMP over all host cores) on a bounded sample.
+Default workload = the configuration BASELINE.json's metric and target are quoted on: the 3-D 8M-particle (200^3) pressure
+Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  At N=1
+the line also carries BASELINE configs[1] (1M particles, `configs1_c2`) measured in the same run.  `--impl reference` times
+the CPU path (oracle port, OpenMP over all host cores) on a bounded sample.
 """
 import argparse
 import importlib
@@ -139,7 +141,7 @@ def run_reference(args, w, lat):
     O.build(("port",))
     threads = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    n = args.cpu_n or (48 if w["dim"] == 3 else w["n"])
+    n = args.cpu_n or (min(96, w["n"]) if w["dim"] == 3 else w["n"])     # ~10-30 s of CPU work per step on the bench box
     P, F, dt = make_problem(w, n, lat)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_step(O, P, F, dt, w, threads)
@@ -149,63 +151,59 @@ def run_reference(args, w, lat):
     sec = float(np.mean(ts)); val = P["nlocal"] / sec / 1e6
     sample = f"{w['dim']}-D {n}^{w['dim']} = {P['nlocal']} rows of the same lattice/physics (full workload: {w['n']}^{w['dim']}), {last['iters']} GMRES its, all of graph+assembly+solve per step"
     line = dict(metric="sph_poisson_step_throughput", value=val, unit="Mrow/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
                 config=dict(workload=args.workload, description=w["desc"], rows=P["nlocal"], nnz=last["nnz"], iters=last["iters"]),
                 cpu_baseline=dict(value=val, unit="Mrow/s", cores=threads, kind="port", sample=sample,
                                   note="CPU restatement of the reference path (oracle port: reference functor algorithms + Belos/Ifpack semantics), OpenMP over rows; Trilinos/LAMMPS are not installable here"),
                 e2e=dict(value=val, unit="Mrow/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 assemble_ms=last["assemble_s"] * 1e3, solve_ms=last["solve_s"] * 1e3)
+    # the sample converges in fewer GMRES iterations than the full lattice (Jacobi is not mesh independent), so its Mrow/s
+    # flatters the CPU; the per-row, per-iteration costs measured on the sample give the full-workload estimate
+    full_iters = FULL_ITERS.get(args.workload)
+    if full_iters and n != w["n"]:
+        rows_full = float(w["n"]) ** w["dim"]
+        t_asm = last["assemble_s"] / P["nlocal"]; t_it = last["solve_s"] / (max(last["iters"], 1) * P["nlocal"])
+        sec_full = rows_full * (t_asm + full_iters * t_it)
+        line["full_workload_estimate"] = dict(value=rows_full / sec_full / 1e6, unit="Mrow/s", ms_per_step=sec_full * 1e3, iters=full_iters,
+                                              how="rows_full x (assembly s/row + iters_full x solve s/(row x iteration)), both measured on the sample; iters_full = the "
+                                                  "iteration count of the full workload (B200 run; the oracle matches it within +-2 on the parity cases)")
     print(json.dumps(line))
 
 
+FULL_ITERS = {"p8m": 452, "c2": 188, "c4": 81}          # GMRES iterations of the full-size workloads (gpurun_out/*.json, profiles/)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"]); ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="lattice edge override (per GPU)"); ap.add_argument("--cpu-n", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload])
+def krylov_bytes_per_solve(n, nnz, iters, second, m=50):
+    """Algorithmic HBM bytes of one flexible GMRES(m)+Jacobi solve on one GPU: per Arnoldi step with basis
+    size nv: SpMV 12 nnz + 20 n; pass-0 coefficients 8 n (nv+2); first update 8 n (nv+3); and, when the DGKS test asks for
+    it (`second` of the `iters` steps), pass-1 coefficients 8 n (nv+1) and the second update inside the closing sweep
+    8 n nv; closing sweep (normalise + Jacobi) 8 n 4.  The x update at the end of a cycle: 8 n (ncol + 2)."""
+    tot = 0.0; frac2 = second / max(iters, 1)
+    for it in range(iters):
+        nv = it % m + 1
+        tot += 12.0 * nnz + 20.0 * n + 8.0 * n * ((nv + 2) + (nv + 3) + 4) + frac2 * 8.0 * n * ((nv + 1) + nv)
+    cycles = (iters + m - 1) // m
+    tot += cycles * 8.0 * n * (min(iters, m) + 2)
+    return tot
+
+
+def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu):
+    w = dict(WORKLOADS[wname])
     if args.n:
         w["n"] = args.n
-    lat = importlib.import_module("implicit-sph_b200.lattice")
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        if rank == 0:
-            run_reference(args, w, lat)
-        return
-
-    import torch
-    import torch.distributed as dist
-    isph = importlib.import_module("implicit-sph_b200")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("gloo", init_method="env://")          # plumbing only: unique-id broadcast, barrier, max-over-ranks
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (isph.C.c_ubyte * 128)(); assert isph.lib().isph_nccl_unique_id(buf) == 0, "NCCL unique id"
-            idt = torch.tensor(list(buf), dtype=torch.uint8)
-        dist.broadcast(idt, 0); nccl_id = bytes(idt.tolist())
-
-    # ---- this rank's brick of the periodic lattice (weak scaling: w['n']^dim rows per GPU)
+    # ---- this rank's brick of the periodic lattice (weak: w['n']^dim rows per GPU; strong: the global lattice is split)
     dim = w["dim"]; grid = lat.brick_grid(world, dim)
     nglobal = (w["n"],) * dim if w.get("strong") else tuple(w["n"] * g for g in grid)
     lo, nloc = lat.brick_of_rank(rank, grid, nglobal)
     P, F, dt = make_problem(w, w["n"], lat, lo=lo, nloc=nloc, nglobal=nglobal)
-    nl, nall = P["nlocal"], P["nlocal"] + P["nghost"]
+    nl = P["nlocal"]
 
     # host inputs in pinned memory (what LAMMPS would hand over each step)
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory(); return t, t.numpy()
-    keep = []
     hx = pin(P["x"]); htype = pin(P["type"]); htag = pin(P["tag"]); hneigh = pin(P["neigh"]); hnoff = pin(P["noff"]); hil = pin(P["ilist"])
     hv = pin(F["vstar"]); hrho = pin(F["density"]); hsol = pin(np.zeros(nl))
-    keep += [hx, htype, htag, hneigh, hnoff, hil, hv, hrho, hsol]
 
     c = isph.Context(local_rank, world, rank, nccl_id)
     stream = torch.cuda.Stream(); c.set_stream(stream.cuda_stream)
@@ -258,63 +256,124 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             st = device_step()
         e1.record(stream)
     barrier()
-    ms_dev = e0.elapsed_time(e1) / args.steps
+    ms_dev = e0.elapsed_time(e1) / steps
     spmv_ms, spmv_cnt = c.profile_spmv_get(); c.profile_spmv(False)
-    launches = (c.launches - launches0) // args.steps
-    timers = {k: c.timer_ms(k) / args.steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "computePoisson", "precondCreate", "solvePoisson")}
+    launches = (c.launches - launches0) // steps
+    timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "computePoisson", "precondCreate", "solvePoisson")}
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
     barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             upload(); st = device_step()
         e1.record(stream)
     barrier()
-    ms_e2e = e0.elapsed_time(e1) / args.steps
-    wall_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_e2e = e0.elapsed_time(e1) / steps
+    wall_e2e = (time.perf_counter() - t0) * 1e3 / steps
     ms_e2e = max(ms_e2e, wall_e2e)          # host-side packing/validation inside the ABI calls is part of the end-to-end cost
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e = t.tolist()
+        t = torch.tensor([ms_dev, ms_e2e, timers["solvePoisson"]], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms = t.tolist()
+    else:
+        solve_ms = timers["solvePoisson"]
     nnz = c.nnz
     if world > 1:
         t = torch.tensor([float(nnz), float(nl)], dtype=torch.float64); dist.all_reduce(t); nnz_g, rows_g = t.tolist()
     else:
         nnz_g, rows_g = float(nnz), float(nl)
-
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        spmv_bytes = 12.0 * nnz + 20.0 * nl                      # 12 B per nonzero + 20 B per row, this rank's launch
-        avg = spmv_ms / max(spmv_cnt, 1)
-        ach = spmv_bytes / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
-        line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload=args.workload, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
-                                iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"],
-                                l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),
-                    e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
-                    gpu_launches=int(launches), clocks=clocks,
-                    roofline=dict(bound="hbm", kernel="k_spmv_sell<1>", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
-                                  launches_timed=int(spmv_cnt), avg_launch_ms=avg, algorithmic_bytes_per_launch=spmv_bytes,
-                                  share_of_step=spmv_ms / args.steps / ms_dev),
-                    breakdown_ms=timers, ms_per_iter=timers["solvePoisson"] / max(st["iters"], 1))
-        if not args.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import oracle as O
-            O.build(("port",))
-            ncpu = args.cpu_n or (48 if dim == 3 else w["n"])
-            Pc, Fc, dtc = make_problem(w, ncpu, lat)
-            cpu_step(O, Pc, Fc, dtc, w, os.cpu_count())           # warm
-            t = time.perf_counter(); r = cpu_step(O, Pc, Fc, dtc, w, os.cpu_count()); sec = time.perf_counter() - t
-            line["cpu_baseline"] = dict(value=Pc["nlocal"] / sec / 1e6, unit="Mrow/s", cores=os.cpu_count(), kind="port",
-                                        sample=f"{dim}-D {ncpu}^{dim} = {Pc['nlocal']} rows of the same lattice/physics, {r['iters']} GMRES its, one full step (graph+assembly+solve), {sec:.1f} s")
-        print(json.dumps(line))
     c.close()
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peak()
+    spmv_bytes = 12.0 * nnz + 20.0 * nl                      # 12 B per nonzero + 20 B per row, this rank's launch
+    avg = spmv_ms / max(spmv_cnt, 1)
+    ach = spmv_bytes / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+    traffic = None
+    try:                                                     # dram bytes per SpMV launch from the committed ncu --set full capture of this workload (1 GPU)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))
+        if world == 1 and not args.n and wname in tj:
+            traffic = float(tj[wname]["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=wname, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
+                            iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"],
+                            l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),
+                e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                gpu_launches=int(launches), clocks=clocks,
+                roofline=dict(bound="hbm", kernel="k_spmv_sell<1>", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
+                              launches_timed=int(spmv_cnt), avg_launch_ms=avg, algorithmic_bytes_per_launch=spmv_bytes,
+                              share_of_step=spmv_ms / steps / ms_dev,
+                              note="per-launch time from CUDA events on the launching stream; at n_gpus > 1 it includes the NVLink import of the halo"),
+                breakdown_ms=timers, ms_per_iter=solve_ms / max(st["iters"], 1))
+    if w["prec"] == "point relaxation" and w["solver"] == "Block GMRES":
+        kb = krylov_bytes_per_solve(nl, nnz, st["iters"], st.get("second_passes", st["iters"]))
+        sg = kb / (solve_ms * 1e-3) / 1e9
+        line["solve_roofline"] = dict(bound="hbm", what="whole GMRES(50)+Jacobi solve on one GPU of the job: SpMV + Gram-Schmidt sweeps + solution update (DESIGN.md §3), rank 0's rows",
+                                      achieved=sg, peak=peak, unit="GB/s", frac=sg / peak, algorithmic_bytes_per_solve=kb, solve_ms=solve_ms,
+                                      iters=st["iters"], second_pass_steps=st.get("second_passes"))
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        O.build(("port",))
+        ncpu = args.cpu_n or (min(96, w["n"]) if dim == 3 else w["n"])     # ~10-30 s of CPU work on the bench box
+        Pc, Fc, dtc = make_problem(w, ncpu, lat)
+        cpu_step(O, Pc, Fc, dtc, w, os.cpu_count())           # warm
+        t = time.perf_counter(); r = cpu_step(O, Pc, Fc, dtc, w, os.cpu_count()); sec = time.perf_counter() - t
+        line["cpu_baseline"] = dict(value=Pc["nlocal"] / sec / 1e6, unit="Mrow/s", cores=os.cpu_count(), kind="port",
+                                    sample=f"{dim}-D {ncpu}^{dim} = {Pc['nlocal']} rows of the same lattice/physics, {r['iters']} GMRES its, one full step (graph+assembly+solve), {sec:.1f} s")
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"]); ap.add_argument("--workload", default="p8m", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="lattice edge override (per GPU)"); ap.add_argument("--cpu-n", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            w = dict(WORKLOADS[args.workload])
+            if args.n:
+                w["n"] = args.n
+            run_reference(args, w, lat)
+        return
+
+    import torch
+    import torch.distributed as dist
+    isph = importlib.import_module("implicit-sph_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("gloo", init_method="env://")          # plumbing only: unique-id broadcast, barrier, max-over-ranks
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (isph.C.c_ubyte * 128)(); assert isph.lib().isph_nccl_unique_id(buf) == 0, "NCCL unique id"
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        dist.broadcast(idt, 0); nccl_id = bytes(idt.tolist())
+
+    line = measure(args, args.workload, args.steps, isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu=(not args.no_cpu_baseline and world == 1))
+    # BASELINE configs[1] (1M particles on 1 B200) beside the headline 8M-particle line: same code path, measured in the same run
+    if world == 1 and args.workload == "p8m" and not args.n and not args.no_secondary:
+        sec = measure(args, "c2", min(args.steps, 5), isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu=False)
+        line["configs1_c2"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "breakdown_ms", "ms_per_iter") if k in sec}
+        line["configs1_c2"].update(workload=sec["config"]["description"], iters=sec["config"]["iters"], spmv_roofline_frac=sec["roofline"]["frac"],
+                                   spmv_gbs=sec["roofline"]["achieved"], solve_roofline_frac=sec.get("solve_roofline", {}).get("frac"))
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -50,6 +50,7 @@ def lib():
         L.isph_version.restype = C.c_char_p
         L.isph_graph_nnz.restype = C.c_longlong
         L.isph_kernel_launches.restype = C.c_longlong
+        L.isph_solver_second_passes.restype = C.c_longlong
         L.isph_timer_ms.restype = C.c_double
         L.isph_timer_ms.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
@@ -276,7 +277,8 @@ class Context:
         self.call("isph_solver_solve", int(use_prec), label.encode())
         it = C.c_int(); rr = C.c_double(); cv = C.c_int(); lm = C.c_double()
         self.call("isph_solver_stats", C.byref(it), C.byref(rr), C.byref(cv), C.byref(lm))
-        return dict(iters=it.value, relres=rr.value, converged=bool(cv.value), lambda_max=lm.value)
+        return dict(iters=it.value, relres=rr.value, converged=bool(cv.value), lambda_max=lm.value,
+                    second_passes=int(self.L.isph_solver_second_passes(self.h)))
 
     def timer_ms(self, name):
         return float(self.L.isph_timer_ms(self.h, name.encode()))

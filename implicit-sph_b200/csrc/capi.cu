@@ -360,6 +360,8 @@ int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged,
   API_BEGIN(ctx) if (iters) *iters = c->last_iters; if (relres) *relres = c->last_relres; if (converged) *converged = c->last_converged; if (lmax) *lmax = c->last_lmax; API_END
 }
 
+long long isph_solver_second_passes(isph_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->last_second_passes : -1; }
+
 double isph_timer_ms(isph_ctx *ctx, const char *name) { if (!ctx || !name) return -1.0; Ctx *c = reinterpret_cast<Ctx *>(ctx); auto it = c->timers.find(name); if (it == c->timers.end()) return 0.0; timer_flush(it->second); return it->second.ms; }
 int isph_timer_reset(isph_ctx *ctx) { API_BEGIN(ctx) for (auto &kv : c->timers) { timer_flush(kv.second); kv.second.ms = 0.0; } API_END }
 long long isph_kernel_launches(isph_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->launches : -1; }

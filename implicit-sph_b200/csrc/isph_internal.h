@@ -104,7 +104,7 @@ struct Ctx {
   int init_type = -1; double init_val = 0.0;
   DevBuf<double> V, Z, wk, red, hbuf; DevBuf<int> flag;      // Krylov workspace
   PinBuf<double> h_scal;
-  int last_iters = 0, last_converged = 0; double last_relres = 0.0, last_lmax = 0.0;
+  long long last_second_passes = 0; int last_iters = 0, last_converged = 0; double last_relres = 0.0, last_lmax = 0.0;
   // preconditioner
   bool prec_ready = false; int prec_kind = 0; DevBuf<double> invdiag, cw, cv; DevBuf<int> block_of_row; bool have_blocks = false;
   IluData *ilu = nullptr;

@@ -19,7 +19,7 @@ static const double DEP_TOL = 0.70710678118654752440;   // DGKSOrthoManager dep_
 
 // layout of the small device scalar block `hbuf`
 enum { S_H = 0, S_H2 = 64, S_G = 128, S_CS = 192, S_SN = 256, S_Y = 320, S_OLD = 384, S_NEW1 = 385, S_NEW2 = 386, S_PROJ = 387,
-       S_INV = 388, S_RES = 389, S_ALPHA = 390, S_BETA = 391, S_RZ = 392, S_PAP = 393, S_TMP = 394, S_HM = 448 /* H: 64 x 64 */, S_TOTAL = 448 + 64 * 64 };
+       S_INV = 388, S_RES = 389, S_ALPHA = 390, S_BETA = 391, S_RZ = 392, S_PAP = 393, S_TMP = 394, S_NSEC = 395, S_HM = 448 /* H: 64 x 64 */, S_TOTAL = 448 + 64 * 64 };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -201,6 +201,7 @@ __device__ void givens_step(double *S, int j, bool singular, double *host_res, i
   if (lane == 0) {
     const double hn = sqrt(d.hn2);
     h[j + 1] = hn;
+    if (d.second) S[S_NSEC] += 1.0;                     // statistics: Arnoldi steps that took the DGKS second pass
     for (int k = 0; k < j; ++k) {                       // previous rotations
       const double a = h[k], b = h[k + 1];
       h[k] = cs[k] * a + sn[k] * b; h[k + 1] = -sn[k] * a + cs[k] * b;
@@ -382,8 +383,10 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
   const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
   const int groups = (nv + G - 1) / G;
-  static const int mdcap = getenv("ISPH_MDGRID") ? atoi(getenv("ISPH_MDGRID")) : 296;   // one wave of the 128-register G = 16 variant (2 CTAs per SM)
-  int gx = mdcap / groups; if (gx < 148) gx = 148; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
+  // one wave of resident CTAs: 2 / 3 / 5 CTAs per SM for the 128 / 72 / 48-register variants (a second, partial wave cost 5-10 %)
+  static const int mdenv = getenv("ISPH_MDGRID") ? atoi(getenv("ISPH_MDGRID")) : 0;
+  const int mdcap = mdenv ? mdenv : (G == 16 ? 296 : (G == 8 ? 444 : 740));
+  int gx = mdcap / groups; if (gx < 74) gx = 74; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
   P2PRed pr = halo_p2p_ticket(c);
   if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
   else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
@@ -536,6 +539,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   c->V.ensure((size_t)(is_cg ? 3 : m + 1) * ld);
   c->Z.ensure((size_t)(is_cg ? 1 : (c->sp.flexible ? m : 1)) * ld);
   CUDA_CHECK(cudaMemsetAsync(c->flag.p + 8, 0, 8 * sizeof(int), c->stream));
+  CUDA_CHECK(cudaMemsetAsync(c->hbuf.p + S_NSEC, 0, sizeof(double), c->stream));
   // initial solution (setInitialSolution, solver_lin.cpp:141-147): applied here, on the device
   const size_t xl = (size_t)ld * c->x_nvec;
   if (c->init_type == ISPH_INIT_ZERO) CUDA_CHECK(cudaMemsetAsync(c->xs.p, 0, sizeof(double) * xl, c->stream));
@@ -579,8 +583,10 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   }
   if (c->x_host) for (int q = 0; q < c->x_nvec; ++q)             // x is a View of caller memory (solver_lin.cpp:52-58)
     CUDA_CHECK(cudaMemcpyAsync(c->x_host + (size_t)q * c->x_lda, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->h_scal.p + 1, c->hbuf.p + S_NSEC, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   c->toc(tname.c_str());
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->last_second_passes = (long long)c->h_scal.p[1];
   if (c->prof_phases && c->rank == 0) {
     fprintf(stderr, "[isph profile] %s: %d iterations\n", tname.c_str(), iters_tot);
     for (auto &kv : c->phase_ev) { size_t u = c->phase_used[kv.first]; double tot = 0.0; for (size_t q = 0; q + 1 < u; q += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, kv.second[q], kv.second[q + 1]); tot += ms; }

@@ -153,6 +153,8 @@ int isph_precond_apply(isph_ctx *ctx, const double *r, double *z);        /* App
 /* SolverLin_Belos::solveProblem(prec, name): use_prec != 0 creates and frees the preconditioner around the solve */
 int isph_solver_solve(isph_ctx *ctx, int use_prec, const char *label);
 int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged, double *lambda_max);
+/* Arnoldi steps of the last GMRES solve that took the second (DGKS) Gram-Schmidt pass — bookkeeping for the traffic model */
+long long isph_solver_second_passes(isph_ctx *ctx);
 
 /* ---- timers (the reference's Teuchos::Time scopes, utils.cpp:16-43): "computePoisson", "solvePoisson", ... ----- */
 double isph_timer_ms(isph_ctx *ctx, const char *name);    /* accumulated device time (CUDA events) */
