@@ -2,9 +2,12 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
-Every rank owns one brick of a periodic jittered lattice; graph + assembly + (NullSpace) GMRES/Jacobi run distributed
-(halo exchange with ncclSend/ncclRecv, reductions with ncclAllReduce) and are compared on rank 0 with the CPU oracle on
-the GLOBAL problem: graph bit-exact, values <= 1e-12, iteration count +-2, solution <= 1e-6 (kappa ~ 1e3).
+Every rank owns one brick of a periodic jittered lattice; graph + assembly + three solves run distributed (halo import and
+all-reduces over NVLink peer memory, or NCCL with ISPH_NO_P2P=1) and are compared on rank 0 with the CPU oracle on the
+GLOBAL problem: graph bit-exact, values <= 1e-12, iteration counts +-2, solutions <= 1e-6 (kappa ~ 1e3).
+  1. pressure Poisson, NullSpace, flexible GMRES(50) + Jacobi                       (BASELINE configs[1])
+  2. the same system with block-Jacobi ILU(0), one open block per rank (= Ifpack overlap 0 on an MPI run)   (configs[3])
+  3. velocity Helmholtz, 3 right-hand sides one after another, CG + Chebyshev(2)     (configs[2]; SpMM with a 3-vector import)
 tests/test_gpu_multi.py wraps this for pytest when >= 2 GPUs are visible.
 """
 import importlib
@@ -40,14 +43,26 @@ def main():
         v[:, k] += 0.05 * (2.0 * lat._hash01(P["gidx"] + 1, 100 + k) - 1.0)
     c = isph.Context(lr, world, rank, bytes(idt.tolist()))
     c.set_particles(P)
-    c.field_set(isph.F_VSTAR, v)
+    nu = 0.1 + 0.01 * np.cos(xw[:, 1]); pr = np.sin(xw[:, 0]) * np.cos(xw[:, 1])
+    c.field_set(isph.F_VSTAR, v); c.field_set(isph.F_VELOCITY, v); c.field_set(isph.F_VISCOSITY, nu); c.field_set(isph.F_PRESSURE, pr)
     c.compute_pre(); c.graph_build()
     c.create_load(None, 1); dt = 0.05; c.ns_poisson(dt)
     rp, col = c.graph_get(); A = c.matrix_get(); b = c.load_get(1)[:, 0]; vf = c.field_get(isph.F_VFRAC)[:nl]
     x = np.zeros(nl); c.create_solution(x, 1)
     c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO); c.precond_param("Precond Type", "point relaxation")
     st = c.solve(True, "Poisson")
-    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st)
+    # 2. block-Jacobi ILU(0): default block = this rank's rows (off-rank columns dropped)
+    x2 = np.zeros(nl); c.create_solution(x2, 1); c.set_initial_solution(isph.INIT_ZERO)
+    c.precond_param("Precond Type", "ILU"); c.precond_param("Overlap Level", 0); c.precond_param("fact: level-of-fill", 0)
+    st2 = c.solve(True, "PoissonILU")
+    # 3. Helmholtz, dim right-hand sides, CG + Chebyshev(2)
+    theta = 0.5
+    c.matrix_invalidate(); c.create_load(None, dim); c.load_set(np.asfortranarray(v[:nl, :dim])); c.ns_helmholtz(dt, theta)
+    Ah = c.matrix_get(); bh = c.load_get(dim)
+    x3 = np.asfortranarray(np.zeros((nl, dim))); c.create_solution(x3, dim); c.set_matrix_is_singular(False); c.set_initial_solution(isph.INIT_ZERO)
+    c.solver_param("Solver Type", "Block CG"); c.precond_param("Precond Type", "Chebyshev"); c.precond_param("chebyshev: degree", 2)
+    st3 = c.solve(True, "Helmholtz")
+    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, Ah=Ah, bh=bh, x3=x3, st3=st3)
     allr = [None] * world
     dist.gather_object(mine, allr if rank == 0 else None, 0)
     ok = True
@@ -58,7 +73,9 @@ def main():
         vg = lat.tgv_velocity(G["xw"])
         for k in range(dim):
             vg[:, k] += 0.05 * (2.0 * lat._hash01(G["gidx"] + 1, 100 + k) - 1.0)
-        o = O.Oracle(G, kind="port"); o.set_field(O.F_VSTAR, vg); o.compute_pre(); grp, gcol = o.graph(); gb = o.ns_poisson(dt); gA = o.matrix(); gvf = o.get_field(O.F_VFRAC)
+        xg = G["xw"]
+        o = O.Oracle(G, kind="port"); o.set_field(O.F_VSTAR, vg); o.set_field(O.F_VELOCITY, vg)
+        o.set_field(O.F_VISCOSITY, 0.1 + 0.01 * np.cos(xg[:, 1])); o.set_field(O.F_PRESSURE, np.sin(xg[:, 0]) * np.cos(xg[:, 1])); o.compute_pre(); grp, gcol = o.graph(); gb = o.ns_poisson(dt); gA = o.matrix(); gvf = o.get_field(O.F_VFRAC)
         n = G["nlocal"]
         xo, info = O.krylov_solve(grp, O.tags_to_local(gcol, G["tag"][:n]), gA, gb.copy(), params=O.krylov_params(precond=O.PREC_JACOBI), null_mask=np.ones(n, dtype=np.int32), use_null=True)
         row_of_tag = -np.ones(n + 2, dtype=np.int64); row_of_tag[G["tag"][:n]] = np.arange(n)
@@ -75,6 +92,29 @@ def main():
         xerr = np.linalg.norm(xd - xo) / np.linalg.norm(xo)
         print(f"multi_gpu_check world={world} rows={n}: values/b/vfrac max err {worst:.2e}; iters gpu {its} vs oracle {info['iters']}; x rel diff {xerr:.2e}; converged {allr[0]['st']['converged']}")
         ok = worst <= 1e-12 and abs(its - info["iters"]) <= 2 and xerr <= 1e-6 and allr[0]["st"]["converged"] and all(d["st"]["iters"] == its for d in allr)
+        # 2. ILU(0), one block per rank
+        colL = O.tags_to_local(gcol, G["tag"][:n]); blocks = np.zeros(n, dtype=np.int32); x2d = np.zeros(n)
+        for r_, d in enumerate(allr):
+            gi = row_of_tag[d["tag"]]; blocks[gi] = r_; x2d[gi] = d["x2"]
+        x2o, info2 = O.krylov_solve(grp, colL, gA, gb.copy(), params=O.krylov_params(precond=O.PREC_ILU0, row_gid=G["tag"][:n]), null_mask=np.ones(n, dtype=np.int32), use_null=True, blocks=blocks)
+        its2 = allr[0]["st2"]["iters"]; x2err = np.linalg.norm(x2d - x2o) / np.linalg.norm(x2o)
+        print(f"  block-Jacobi ILU(0): iters gpu {its2} vs oracle {info2['iters']}; x rel diff {x2err:.2e}; converged {allr[0]['st2']['converged']}")
+        ok = ok and abs(its2 - info2["iters"]) <= 2 and x2err <= 1e-6 and allr[0]["st2"]["converged"]
+        # 3. Helmholtz, CG + Chebyshev(2), dim right-hand sides
+        o.invalidate_matrix(); gbh = o.ns_helmholtz(dt, 0.5, np.asfortranarray(vg[:n, :dim])); gAh = o.matrix()
+        x3d = np.zeros((n, dim)); worst3 = 0.0
+        for d in allr:
+            gi = row_of_tag[d["tag"]]; x3d[gi] = d["x3"]
+            worst3 = max(worst3, float(np.abs(gbh[gi] - d["bh"]).max() / np.abs(gbh).max()))
+            for li, gr in enumerate(gi):
+                worst3 = max(worst3, relerr(gAh[grp[gr]:grp[gr + 1]], d["Ah"][d["rp"][li]:d["rp"][li + 1]]))
+        prm = O.krylov_params(solver=O.SOLVER_CG, precond=O.PREC_CHEBYSHEV, cheb_degree=2, row_gid=G["tag"][:n]); its3o = 0; x3err = 0.0
+        for k in range(dim):
+            xk, ik = O.krylov_solve(grp, colL, gAh, gbh[:, k], params=prm); its3o += ik["iters"]
+            x3err = max(x3err, np.linalg.norm(x3d[:, k] - xk) / np.linalg.norm(xk))
+        its3 = allr[0]["st3"]["iters"]
+        print(f"  Helmholtz CG+Chebyshev(2) x{dim}: values/b max err {worst3:.2e}; iters gpu {its3} vs oracle {its3o}; x rel diff {x3err:.2e}; converged {allr[0]['st3']['converged']}")
+        ok = ok and worst3 <= 1e-12 and abs(its3 - its3o) <= 2 * dim and x3err <= 1e-7 and allr[0]["st3"]["converged"]
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
     c.close()
     flag = torch.tensor([1 if ok else 0]); dist.broadcast(flag, 0)
