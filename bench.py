@@ -41,6 +41,9 @@ WORKLOADS = {
     # 2x2x2 Ifpack-rank-equivalent bricks per GPU (= 4x4x4 bricks of 50^3 at 8 GPUs)
     "c4": dict(dim=3, n=100, jitter=0.04, rs2=12, prec="ILU", solver="Block GMRES", anti=False, blocks=2,
                desc="BASELINE configs[3] per GPU: corrected-operator (Gc/Lc) pressure Poisson, 1M particles per GPU, GMRES(50) + block-Jacobi ILU(0), 8 bricks of 50^3 per GPU"),
+    # BASELINE configs[2]: velocity Helmholtz (I - theta dt nu lap) v* = rhs, dim right-hand sides one after another, CG + Chebyshev
+    "c3": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="Chebyshev", solver="Block CG", strong=True, system="helmholtz", theta=0.5,
+               desc="BASELINE configs[2]: 3-D velocity Helmholtz (functor_incomp_navier_stokes_helmholtz), 8M particles, 3 right-hand sides, CG + Chebyshev(1), x0 = v^n, fixed global size (strong scaling)"),
     # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
     "p8m": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True,
                 desc="north_star target: 3-D 8M-particle (200^3) pressure Poisson, flexible GMRES(50)+Jacobi, fixed global size (strong scaling)"),
@@ -59,7 +62,7 @@ def make_problem(w, n, lat, lo=None, nloc=None, nglobal=None):
     # after 2-3 iterations and the benchmark would not exercise the Krylov loop at all.
     for k in range(dim):
         v[:, k] += 0.05 * (2.0 * lat._hash01(P["gidx"] + 1, 100 + k) - 1.0)
-    F = dict(vstar=v, density=np.ones(len(xw)))
+    F = dict(vstar=v, density=np.ones(len(xw)), viscosity=np.full(len(xw), 0.1))      # rho = 1, nu = 0.1 (taylor-green-vortex-2d.lmp:138-140)
     dt = (0.05 * dx / 0.1) if dim == 2 else (0.1 * 1.5 * dx / 0.1)                    # taylor-green-vortex-{2d,3d}.lmp dt
     return P, F, dt
 
@@ -204,6 +207,9 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory(); return t, t.numpy()
     hx = pin(P["x"]); htype = pin(P["type"]); htag = pin(P["tag"]); hneigh = pin(P["neigh"]); hnoff = pin(P["noff"]); hil = pin(P["ilist"])
     hv = pin(F["vstar"]); hrho = pin(F["density"]); hsol = pin(np.zeros(nl))
+    helm = w.get("system") == "helmholtz"
+    if helm:
+        hnu = pin(F["viscosity"]); hvn = pin(np.asfortranarray(F["vstar"][:nl, :dim]).reshape(-1, order="F")); hsol = pin(np.zeros((nl, dim), order="F").reshape(-1, order="F"))
 
     c = isph.Context(local_rank, world, rank, nccl_id)
     stream = torch.cuda.Stream(); c.set_stream(stream.cuda_stream)
@@ -220,8 +226,27 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         c.atoms_set(nl, P["nghost"], hx[1], htype[1], htag[1])
         c.neighbors_set_packed(hil[1], hnoff[1], hneigh[1])
         c.field_set(isph.F_VSTAR, hv[1]); c.field_set(isph.F_DENSITY, hrho[1])
+        if helm:
+            c.field_set(isph.F_VELOCITY, hv[1]); c.field_set(isph.F_VISCOSITY, hnu[1])
     h2d_bytes = hx[1].nbytes + htype[1].nbytes + htag[1].nbytes + hneigh[1].nbytes + hnoff[1].nbytes + hil[1].nbytes + hv[1].nbytes + hrho[1].nbytes
+    if helm:
+        h2d_bytes += hv[1].nbytes + hnu[1].nbytes + 2 * hvn[1].nbytes      # + load and initial guess (both = v^n) written every step
     d2h_bytes = hsol[1].nbytes
+    solve_label = "Helmholtz" if helm else "Poisson"
+
+    def helmholtz_step():
+        """pair_isph.cpp:924-982: x = b = v^n (transposed view), computeHelmholtz, solveHelmholtz (dim right-hand sides)"""
+        c.graph_invalidate()
+        c.compute_pre()
+        c.graph_build()
+        c.create_solution(None, dim); c.create_load(None, dim)
+        c.call("isph_solver_load_set", isph._d(hvn[1]), nl); c.call("isph_solver_solution_set", isph._d(hvn[1]), nl)
+        c.ns_helmholtz(dt, w["theta"], anti=anti)
+        c.set_matrix_is_singular(False)
+        st = c.solve(True, "Helmholtz")
+        c.call("isph_solver_solution_get", isph._d(hsol[1]), nl)
+        c.matrix_invalidate()
+        return st
 
     def device_step():
         """inputs resident in HBM; everything else rebuilt (end-of-step delete, pair_isph.cpp:1351-1372)"""
@@ -236,6 +261,9 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         st = c.solve(True, "Poisson")
         c.matrix_invalidate()
         return st
+
+    if helm:
+        device_step = helmholtz_step
 
     def barrier():
         torch.cuda.synchronize()
@@ -263,7 +291,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     ms_dev = e0.elapsed_time(e1) / steps
     spmv_ms, spmv_cnt = c.profile_spmv_get(); c.profile_spmv(False)
     launches = (c.launches - launches0) // steps
-    timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "computePoisson", "precondCreate", "solvePoisson")}
+    timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "compute" + solve_label, "precondCreate", "solve" + solve_label)}
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
     barrier()
@@ -278,9 +306,9 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     wall_e2e = (time.perf_counter() - t0) * 1e3 / steps
     ms_e2e = max(ms_e2e, wall_e2e)          # host-side packing/validation inside the ABI calls is part of the end-to-end cost
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, timers["solvePoisson"]], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms = t.tolist()
+        t = torch.tensor([ms_dev, ms_e2e, timers["solve" + solve_label]], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms = t.tolist()
     else:
-        solve_ms = timers["solvePoisson"]
+        solve_ms = timers["solve" + solve_label]
     nnz = c.nnz
     if world > 1:
         t = torch.tensor([float(nnz), float(nl)], dtype=torch.float64); dist.all_reduce(t); nnz_g, rows_g = t.tolist()

@@ -225,6 +225,9 @@ class Context:
     def load_get(self, nvec=1):
         b = np.zeros((self.nlocal, nvec), order="F"); self.call("isph_solver_load_get", _d(b), self.nlocal); return b
 
+    def solution_set(self, x):
+        x = np.asfortranarray(np.asarray(x, dtype=np.float64).reshape(self.nlocal, -1, order="F")); self.call("isph_solver_solution_set", _d(x), self.nlocal)
+
     def solution_get(self, nvec=1):
         x = np.zeros((self.nlocal, nvec), order="F"); self.call("isph_solver_solution_get", _d(x), self.nlocal); return x
 

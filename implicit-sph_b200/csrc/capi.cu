@@ -286,6 +286,11 @@ int isph_solver_load_get(isph_ctx *ctx, double *b, int lda) {
   for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(b + (size_t)q * lda, c->bs.p + (size_t)q * c->ld, sizeof(double) * c->A.n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
 }
+int isph_solver_solution_set(isph_ctx *ctx, const double *x, int lda) {      // write getSolutionMultiVector()->Values(): the initial guess of an owned x
+  API_BEGIN(ctx) ISPH_REQUIRE(c->x_nvec >= 1 && x && lda >= c->A.n, "no solution multivector");
+  for (int q = 0; q < c->x_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * c->ld, x + (size_t)q * lda, sizeof(double) * c->A.n, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+}
 int isph_solver_solution_get(isph_ctx *ctx, double *x, int lda) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->x_nvec >= 1 && x && lda >= c->A.n, "no solution multivector");
   for (int q = 0; q < c->x_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(x + (size_t)q * lda, c->xs.p + (size_t)q * c->ld, sizeof(double) * c->A.n, cudaMemcpyDeviceToHost, c->stream));

@@ -29,7 +29,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // block-reduce NACC per-thread accumulators, store the block's partials, and let the last block to finish add the
 // partials of all blocks (fixed assignment of blocks to lanes + fixed shuffle tree => deterministic) into out[0..nacc)
-template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out, const P2PRed &pr) {
+template <int NACC> __device__ bool reduce_finish(double (&acc)[NACC], int nacc, double *partials, unsigned *counter, double *out, const P2PRed &pr) {
   __shared__ double sm[NACC][VB / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -57,7 +57,12 @@ template <int NACC> __device__ void reduce_finish(double (&acc)[NACC], int nacc,
     if (threadIdx.x == 0) *counter = 0u;
     if (pr.nranks > 1) p2p_allreduce_block(pr, out, nacc);      // sum over ranks through the NVLink mailboxes
   }
+  return last;                                                   // true in every thread of the one block that holds the final sums
 }
+
+// diagonal preconditioners: Ifpack_PointRelaxation (Jacobi) forms (damping * invdiag) * v, Ifpack_Chebyshev of degree 1 forms
+// (invdiag * v) / theta — the association is kept so that both stay bit-identical to the oracle
+__device__ __forceinline__ double diag_prec(double invd, double v, double s, int post) { return post ? invd * v * s : s * invd * v; }
 
 // ---- DGKS bookkeeping without extra reductions ----------------------------------------------------------------------
 // Belos' DGKS manager takes four to five global reductions per Arnoldi step (oldDot, Q^T w, newDot, [second pass], norm).
@@ -231,7 +236,7 @@ __device__ __forceinline__ void prepush_row(const PrePush &pp, int hslot, int b,
 }
 __global__ void __launch_bounds__(VB)
 k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, int n, double *S, int singular,
-         const double *__restrict__ invdiag, double damping, double *__restrict__ z, double *host_res, int slot, PrePush pp) {
+         const double *__restrict__ invdiag, double damping, int post, double *__restrict__ z, double *host_res, int slot, PrePush pp) {
   if (blockIdx.x == 0) {      // block 0 is dedicated to the (sequential, ~10 us) Hessenberg/Givens step: hidden behind the sweep
     if (threadIdx.x < 32) givens_step(S, nv - 1, singular != 0, host_res, slot);
     return;
@@ -251,13 +256,13 @@ k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, i
       for (int k = 0; k < nk; ++k) { const double2 v = *reinterpret_cast<const double2 *>(V + (size_t)k * ld + i); wi.x -= sh[k] * v.x; wi.y -= sh[k] * v.y; }
       wi.x *= inv; wi.y *= inv;
       *reinterpret_cast<double2 *>(w + i) = wi;
-      if (z) { double2 zi = wi; if (invdiag) { const double2 dd = *reinterpret_cast<const double2 *>(invdiag + i); zi.x = damping * dd.x * wi.x; zi.y = damping * dd.y * wi.y; } *reinterpret_cast<double2 *>(z + i) = zi;
+      if (z) { double2 zi = wi; if (invdiag) { const double2 dd = *reinterpret_cast<const double2 *>(invdiag + i); zi.x = diag_prec(dd.x, wi.x, damping, post); zi.y = diag_prec(dd.y, wi.y, damping, post); } *reinterpret_cast<double2 *>(z + i) = zi;
         if (pp.plan) { const int s0 = __ldg(pp.sp + i), s1 = __ldg(pp.sp + i + 1), s2 = __ldg(pp.sp + i + 2); if (s2 > s0) { prepush_row(pp, hslot, s0, s1, zi.x); prepush_row(pp, hslot, s1, s2, zi.y); } } }
     } else {
       double wi = w[i];
       for (int k = 0; k < nk; ++k) wi -= sh[k] * V[(size_t)k * ld + i];
       wi *= inv; w[i] = wi;
-      if (z) { const double zi = invdiag ? damping * invdiag[i] * wi : wi; z[i] = zi; if (pp.plan) prepush_row(pp, hslot, __ldg(pp.sp + i), __ldg(pp.sp + i + 1), zi); }
+      if (z) { const double zi = invdiag ? diag_prec(invdiag[i], wi, damping, post) : wi; z[i] = zi; if (pp.plan) prepush_row(pp, hslot, __ldg(pp.sp + i), __ldg(pp.sp + i + 1), zi); }
     }
   }
 }
@@ -321,26 +326,33 @@ __global__ void __launch_bounds__(VB) k_random(double *y, const int *tag, int n,
 }
 
 // ---- PCG kernels -------------------------------------------------------------------------------------------------
-// pAp = p.Ap ; alpha = rz / pAp   (alpha computed by whoever consumes it, so that an allreduce can sit in between)
-__global__ void __launch_bounds__(VB) k_cg_update(double *x, double *r, const double *p, const double *Ap, double *S, int n, double *partials, unsigned *counter, P2PRed pr) {
-  const double alpha = S[S_RZ] / S[S_PAP];
+// One PCG iteration = 4 launches, 3 reductions: [SpMV with p.Ap in its epilogue] -> k_cg_update (x, r, ||r||^2, publishes the
+// residual) -> k_cg_precdot (diagonal preconditioner fused, r.z) -> k_cg_direction (p = z + beta p; pushes the halo rows of p).
+// r.z lives in two slots used alternately (rz_cur / rz_new), so no kernel has to shift it.
+__global__ void __launch_bounds__(VB) k_cg_update(double *x, double *r, const double *p, const double *Ap, double *S, int rz_cur, int n, double *partials, unsigned *counter, P2PRed pr,
+                                                  double *host_res, int slot) {
+  const double alpha = S[rz_cur] / S[S_PAP];
   double acc[1] = {0.0};
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { x[i] += alpha * p[i]; const double ri = r[i] - alpha * Ap[i]; r[i] = ri; acc[0] += ri * ri; }
-  reduce_finish<1>(acc, 1, partials, counter, S + S_TMP, pr);
+  const bool last = reduce_finish<1>(acc, 1, partials, counter, S + S_TMP, pr);
+  if (last && host_res && threadIdx.x == 0) { const double res = sqrt(S[S_TMP]); S[S_RES] = res; host_res[slot] = res; __threadfence_system(); }
 }
 __global__ void k_cg_publish(double *S, double *host_res, int slot) { if (threadIdx.x == 0) { const double res = sqrt(S[S_TMP]); S[S_RES] = res; host_res[slot] = res; __threadfence_system(); } }
-// z = damping * invdiag * r (Jacobi) fused with rz_new = r.z ; for other preconditioners z is given and only the dot is taken
-__global__ void __launch_bounds__(VB) k_cg_precdot(const double *r, double *z, const double *invdiag, double damping, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
+// z = diagonal preconditioner applied to r, fused with out = r.z ; for other preconditioners z is given and only the dot is taken
+__global__ void __launch_bounds__(VB) k_cg_precdot(const double *r, double *z, const double *invdiag, double damping, int post, int n, double *partials, unsigned *counter, double *out, P2PRed pr) {
   double acc[1] = {0.0};
-  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { double zi; if (invdiag) { zi = damping * invdiag[i] * r[i]; z[i] = zi; } else zi = z[i]; acc[0] += r[i] * zi; }
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { double zi; if (invdiag) { zi = diag_prec(invdiag[i], r[i], damping, post); z[i] = zi; } else zi = z[i]; acc[0] += r[i] * zi; }
   reduce_finish<1>(acc, 1, partials, counter, out, pr);
 }
-// p = z + beta p with beta = rz_new / rz ; then rz <- rz_new (done by block 0 after everyone has read it: separate tiny kernel)
-__global__ void __launch_bounds__(VB) k_cg_direction(double *p, const double *z, const double *S, int n, int first) {
-  const double beta = first ? 0.0 : S[S_BETA] / S[S_RZ];
-  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) p[i] = first ? z[i] : z[i] + beta * p[i];
+// p = z + beta p with beta = rz_new / rz_cur ; p is the next SpMV input: its halo rows leave from here
+__global__ void __launch_bounds__(VB) k_cg_direction(double *p, const double *z, const double *S, int rz_cur, int rz_new, int n, int first, PrePush pp) {
+  const double beta = first ? 0.0 : S[rz_new] / S[rz_cur];
+  const int hslot = (int)(pp.seq % MB_SLOTS);
+  for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+    const double pi = first ? z[i] : z[i] + beta * p[i]; p[i] = pi;
+    if (pp.plan) { const int s0 = __ldg(pp.sp + i), s1 = __ldg(pp.sp + i + 1); if (s1 > s0) prepush_row(pp, hslot, s0, s1, pi); }
+  }
 }
-__global__ void k_cg_shift(double *S) { if (threadIdx.x == 0) S[S_RZ] = S[S_BETA]; }
 
 // ---------------------------------------------------------------------------------------------------------------
 static int vgrid(Ctx *c, int n) {      // default 148 SMs x 16 chunks (measured best for the streaming updates on 1M rows: 6.2 TB/s vs 4.9 at 592); ISPH_VGRID overrides
@@ -379,6 +391,19 @@ static void apply_prec(Ctx *c, bool use_prec, const double *r, double *z) {
   else CUDA_CHECK(cudaMemcpyAsync(z, r, sizeof(double) * c->A.n, cudaMemcpyDeviceToDevice, c->stream));
 }
 
+// preconditioners that are one diagonal scaling and can ride on another sweep: Jacobi with one sweep, Chebyshev of degree 1
+struct DiagPrec { bool on; const double *invdiag; double scale; int post; };
+static DiagPrec diag_prec_of(Ctx *c, bool use_prec) {
+  DiagPrec d{false, nullptr, 1.0, 0};
+  if (!use_prec) return d;
+  if (c->prec_kind == 1 && c->pp.sweeps == 1) { d.on = true; d.invdiag = c->invdiag.p; d.scale = c->pp.damping; d.post = 0; }
+  else if (c->prec_kind == 2 && c->pp.cheb_degree == 1) {        // Ifpack_Chebyshev, degree 1, zero start: z = invDiag * r / theta
+    const double lmax = c->last_lmax, alpha = lmax / c->pp.cheb_ratio, beta = 1.1 * lmax, theta = 0.5 * (beta + alpha);
+    d.on = true; d.invdiag = c->invdiag.p; d.scale = 1.0 / theta; d.post = 1;
+  }
+  return d;
+}
+
 static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass) {
   const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
   const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
@@ -408,7 +433,7 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   ISPH_REQUIRE(m >= 1 && m <= 51, "Num Blocks must be in 1..51");
   double *S = c->hbuf.p, *V = c->V.p, *Z = c->Z.p, *r = c->wk.p; unsigned *cnt = (unsigned *)c->flag.p + 8;
   const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
-  const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  const DiagPrec dp = diag_prec_of(c, use_prec); const bool jacobi_fused = dp.on;
   const int sing = c->is_singular ? 1 : 0;
   std::vector<cudaEvent_t> ev(m);
   for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -442,8 +467,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
         double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
         PrePush pp; pp.plan = nullptr; pp.sp = pp.sd = nullptr; pp.seq = 0;
         if (jacobi_fused) { halo_prepush_begin(c, zn, &pp);       // z_{j+1} is the next SpMV input: its halo rows leave from this kernel
-          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, c->invdiag.p, c->pp.damping, zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
-        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
+          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, dp.invdiag, dp.scale, dp.post, zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
+        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, 0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
       } else { k_givens<<<1, 32, 0, c->stream>>>(S, j, sing, c->h_scal.p + 8, iters); ++c->launches; }   // last column of the cycle: v_{m} is never used
       dbg(c, "finish");
       CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
@@ -482,8 +507,19 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
 static int cg_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out, double *relres_out) {
   const int n = c->A.n, ld = c->ld, g = vgrid(c, n);
   double *S = c->hbuf.p, *r = c->wk.p, *z = c->V.p, *p = c->V.p + (size_t)ld, *Ap = c->V.p + (size_t)2 * ld; unsigned *cnt = (unsigned *)c->flag.p + 8;
-  const bool jacobi_fused = use_prec && c->prec_kind == 1 && c->pp.sweeps == 1;
+  const DiagPrec dp = diag_prec_of(c, use_prec);
+  const int RZ[2] = {S_RZ, S_BETA};                              // r.z of the current / next iteration, used alternately
   cudaEvent_t ev[2]; for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto precdot = [&](int slot) {
+    if (!dp.on) apply_prec(c, use_prec, r, z);
+    P2PRed pr = halo_p2p_ticket(c);
+    k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, dp.on ? dp.invdiag : nullptr, dp.scale, dp.post, n, c->red.p, cnt, S + slot, pr); ++c->launches;
+    if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + slot, 1);
+  };
+  auto direction = [&](int cur, int nxt, int first) {
+    PrePush pp; halo_prepush_begin(c, p, &pp);                   // p is the next SpMV input: its halo rows leave from this kernel
+    k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, cur, nxt, n, first, pp); ++c->launches;
+  };
   // R = b - A x ; Z = M^-1 R ; P = Z ; rz = R.Z
   if (c->init_type != ISPH_INIT_ZERO) op_apply(c, x, Ap, false);
   { P2PRed pr = halo_p2p_ticket(c);
@@ -492,25 +528,20 @@ static int cg_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out,
   const double scale = sqrt(read_scalar(c, S + S_TMP)); double res = scale; int iters = 0; bool converged = false;
   if (scale == 0.0 || res / scale <= c->sp.tol) converged = true;
   else {
-    if (!jacobi_fused) apply_prec(c, use_prec, r, z);
-    { P2PRed pr = halo_p2p_ticket(c);
-      k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, jacobi_fused ? c->invdiag.p : nullptr, jacobi_fused ? c->pp.damping : 1.0, n, c->red.p, cnt, S + S_RZ, pr); ++c->launches;
-      if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_RZ, 1); }
-    k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 1); ++c->launches;
+    precdot(RZ[0]);
+    direction(RZ[0], RZ[0], 1);
     while (true) {
       ++iters;
-      op_apply(c, p, Ap, false);
-      dot_dev(c, p, Ap, n, S + S_PAP);
-      { P2PRed pr = halo_p2p_ticket(c); k_cg_update<<<g, VB, 0, c->stream>>>(x, r, p, Ap, S, n, c->red.p, cnt, pr); ++c->launches; if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_TMP, 1); }
-      k_cg_publish<<<1, 32, 0, c->stream>>>(S, c->h_scal.p + 8, iters); ++c->launches;
+      const int cur = RZ[(iters - 1) & 1], nxt = RZ[iters & 1];
+      if (c->is_singular) { op_apply(c, p, Ap, false); dot_dev(c, p, Ap, n, S + S_PAP); }
+      else spmv(c, p, Ap, 1, ld, ld, p, S + S_PAP);               // Ap = A p with p.Ap reduced in the SpMV epilogue
+      { P2PRed pr = halo_p2p_ticket(c); const bool fold = c->nranks == 1 || pr.nranks > 1;       // residual published by the kernel that reduces it
+        k_cg_update<<<g, VB, 0, c->stream>>>(x, r, p, Ap, S, cur, n, c->red.p, cnt, pr, fold ? c->h_scal.p + 8 : nullptr, iters); ++c->launches;
+        if (!fold) { halo_allreduce(c, S + S_TMP, 1); k_cg_publish<<<1, 32, 0, c->stream>>>(S, c->h_scal.p + 8, iters); ++c->launches; } }
       CUDA_CHECK(cudaEventRecord(ev[iters & 1], c->stream));
       // next direction, enqueued before the residual of this step is inspected
-      if (!jacobi_fused) apply_prec(c, use_prec, r, z);
-      { P2PRed pr = halo_p2p_ticket(c);
-        k_cg_precdot<<<g, VB, 0, c->stream>>>(r, z, jacobi_fused ? c->invdiag.p : nullptr, jacobi_fused ? c->pp.damping : 1.0, n, c->red.p, cnt, S + S_BETA, pr); ++c->launches;
-        if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_BETA, 1); }
-      k_cg_direction<<<g, VB, 0, c->stream>>>(p, z, S, n, 0); ++c->launches;
-      k_cg_shift<<<1, 32, 0, c->stream>>>(S); ++c->launches;
+      precdot(nxt);
+      direction(cur, nxt, 0);
       CUDA_CHECK(cudaEventSynchronize(ev[iters & 1]));
       res = c->h_scal.p[8 + iters];
       if (res / scale <= c->sp.tol) { converged = true; break; }
@@ -518,6 +549,8 @@ static int cg_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_out,
     }
   }
   for (auto &e : ev) cudaEventDestroy(e);
+  // a push whose SpMV was never issued: take it anyway so that the staging cells are re-armed
+  if (c->prepush_x) { halo_wait_unstage(c, const_cast<double *>(c->prepush_x), c->prepush_seq); c->prepush_x = nullptr; }
   *iters_out = iters; *relres_out = scale > 0.0 ? res / scale : 0.0;
   return converged ? 1 : 0;
 }

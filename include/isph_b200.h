@@ -128,6 +128,7 @@ int isph_solver_create_solution_multivector(isph_ctx *ctx, double *x /*borrowed;
 int isph_solver_create_load_multivector(isph_ctx *ctx, double *b /*borrowed; NULL: owned, device-resident*/, int lda, int nvec);
 int isph_solver_load_set(isph_ctx *ctx, const double *b, int lda);        /* write getLoadMultiVector()->Values() */
 int isph_solver_load_get(isph_ctx *ctx, double *b, int lda);
+int isph_solver_solution_set(isph_ctx *ctx, const double *x, int lda);    /* write getSolutionMultiVector()->Values() (initial guess of an owned x) */
 int isph_solver_solution_get(isph_ctx *ctx, double *x, int lda);
 int isph_solver_set_null_vector_mask(isph_ctx *ctx, const int *mask /*[nlocal] or NULL = all ones*/);
 int isph_solver_set_matrix_is_singular(isph_ctx *ctx, int is_singular);
