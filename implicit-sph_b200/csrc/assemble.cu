@@ -481,6 +481,88 @@ __global__ void k_pb_rows(Dev d, bool linearized, double kappasq, double gamma, 
   const int kd = d.diag_k[row]; if (kd >= 0) d.val[base + 32ll * kd] = diag;
 }
 
+// FunctorOuterPoissonBoltzmannF::operator() (functor_poisson_boltzmann_f.h:58-88) on top of the matrix-free corrected
+// Laplacian Corrected::FunctorOuterLaplacianHelper::operator() (functor_laplacian.h:67-277; scalar field, alpha = -1,
+// material = eps, filter (Fluid, All)).  The reference's Jacobian is NOT the exact derivative of this residual next to
+// solids (the matrix functor weights the mirror coefficient and the material gradient differently), so the residual cannot
+// be taken from the assembled matrix: the three neighbor passes are done here, in list order and with the reference's
+// operation order (a_ij is recomputed in the third pass instead of being stored per neighbor).
+template <int DIM> __global__ void __launch_bounds__(128)
+k_pb_residual(Dev d, bool mh, bool linearized, double kappasq, double gamma, const double *psi, const double *psi0, const double *eps,
+              const double *extra, double *f) {
+  LIST_SETUP(d)
+  const int f0 = ISPH_KIND_FLUID, f1 = ISPH_KIND_ALL;
+  if (ikind == ISPH_KIND_SOLID || ikind == ISPH_KIND_BOUNDARY) f[i] = (-psi[i] + psi0[i]);
+  else if (ikind == ISPH_KIND_BUFFER_DIRICHLET || ikind == ISPH_KIND_BUFFER_NEUMANN || ikind == ISPH_KIND_FLUID) {
+    const double m_i = eps[i], psi_i = psi[i];
+    double gm[3] = {0.0, 0.0, 0.0}, gf[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    if (ikind & f0) {                                                                             // functor_laplacian.h:99-100
+      const double *G = d.Gc + 9 * (size_t)i, *L = d.Lc + 6 * (size_t)i;
+      LIST_FOR(d) {                                                                               // :111-158 corrected gradients of psi and eps
+        const int jk = d.kind[d.neigh[p] & ISPH_NEIGHMASK];
+        if (!((ikind & f0) && (jk & f1))) continue;
+        LIST_PAIR(d, DIM)
+        double coeff = 1.0;
+        if (jk & ISPH_KIND_SOLID) coeff = mirror_coeff(d, mh, i, j, itype, jtype);
+        const double r = sqrt(rsq) + ISPH_EPS_R, dwdr = kern_dval(d.T, itype, jtype, r);
+        const double vjtmp = dwdr / r * d.vfrac[j] * coeff;
+#pragma unroll
+        for (int k2 = 0; k2 < DIM; ++k2) {
+          double gitmp = 0.0;
+#pragma unroll
+          for (int k1 = 0; k1 < DIM; ++k1) gitmp += G[k2 * DIM + k1] * rij[k1];
+          const double ijtmp = gitmp * vjtmp;
+          if (jk & f0) gm[k2] += ijtmp * (eps[j] - m_i);
+          gf[k2] += ijtmp * (psi[j] - psi_i);
+        }
+      }
+      LIST_FOR(d) {                                                                               // :161-216 (no filter on this pass)
+        LIST_PAIR(d, DIM)
+        const double r = sqrt(rsq) + ISPH_EPS_R, dwdr = kern_dval(d.T, itype, jtype, r);
+        double eij[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) eij[k] = rij[k] / r;
+        double aij = 0.0;
+#pragma unroll
+        for (int k2 = 0, op = 0; k2 < DIM; ++k2)
+#pragma unroll
+          for (int k1 = 0; k1 < (k2 + 1); ++k1, ++op) aij += L[op] * eij[k1] * eij[k2] * (k1 == k2 ? 1.0 : 2.0);
+        aij *= 2.0 * dwdr * d.vfrac[j];
+        double dotv = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) dotv += eij[k] * gf[k];
+        lap += aij * (-1.0 * dotv);
+      }
+      LIST_FOR(d) {                                                                               // :219-263
+        const int jk = d.kind[d.neigh[p] & ISPH_NEIGHMASK];
+        if (!((ikind & f0) && (jk & f1))) continue;
+        LIST_PAIR(d, DIM)
+        double coeff = 1.0;
+        if (jk & ISPH_KIND_SOLID) coeff = mirror_coeff(d, mh, i, j, itype, jtype);
+        const double r = sqrt(rsq) + ISPH_EPS_R, dwdr = kern_dval(d.T, itype, jtype, r);
+        double eij[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) eij[k] = rij[k] / r;
+        double aij = 0.0;
+#pragma unroll
+        for (int k2 = 0, op = 0; k2 < DIM; ++k2)
+#pragma unroll
+          for (int k1 = 0; k1 < (k2 + 1); ++k1, ++op) aij += L[op] * eij[k1] * eij[k2] * (k1 == k2 ? 1.0 : 2.0);
+        aij *= 2.0 * dwdr * d.vfrac[j];
+        lap += aij * (coeff * (psi_i - psi[j]) / r);
+      }
+    }
+    double dotm = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) dotm += gm[k] * gf[k];
+    double out = -1.0 * (m_i * lap + dotm);                                                       // :266-268 with alpha = -1
+    if (linearized) out += kappasq * (psi_i / (1.0 + 2.0 * gamma * pow(psi_i / 2, 2.0)));
+    else out += kappasq * (sinh(psi_i) / (1.0 + 2.0 * gamma * pow(sinh(psi_i / 2.0), 2.0)));
+    f[i] = out;
+  }
+  if (extra && !(ikind & ISPH_KIND_SOLID)) f[i] += extra[i];                                      // functor_poisson_boltzmann_extra_f.h:76-90
+}
+
 // ---- the step right after the Poisson solve (pair_isph.cpp:1017-1031) -------------------------------------------
 // computeZeroMeanPressure, pair_isph.cpp:422-464: solid rows are cleaned to 0, the mean over the other owned rows is removed
 __global__ void __launch_bounds__(256) k_dp_sum(const int *kind, int nlocal, double *dp, double *partials) {
@@ -536,7 +618,7 @@ static Dev make_dev(Ctx *c, bool need_graph = true) {
 #define LGRID(c) ceil_div((c)->inum, 128), 128, 0, (c)->stream
 
 void forward_comm(Ctx *c, int field) {
-  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
+  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
   if (c->nghost == 0) return;
   if (c->nranks > 1) halo_forward_field(c, field, nc[field]);      // ghosts owned by other ranks
   k_forward<<<ceil_div(c->nghost, 256), 256, 0, c->stream>>>(c->col_of_atom.p, c->nlocal, c->nall, nc[field], c->field[field].p); ++c->launches;
@@ -663,6 +745,19 @@ void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, d
   }
   k_pb_rows<<<GRID(c)>>>(d, linearized, kappasq, gamma, c->field[ISPH_F_PSI].p, c->A.diagonal.p, c->A.sld.p); ++c->launches;
   c->toc("computeJacobianPoissonBoltzmann");
+}
+
+// PairISPH_Corrected::computeF, pair_isph_corrected.cpp:438-485: psi is communicated to the ghosts, then the functor runs
+void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f) {
+  Dev d = make_dev(c, false);
+  c->tic("computeFPoissonBoltzmann");
+  forward_comm(c, ISPH_F_PSI);
+  const double kappasq = 2.0 * ezcb / psiref;
+  const double *psi = c->field[ISPH_F_PSI].p, *psi0 = c->field[ISPH_F_PSI0].p, *eps = c->field[ISPH_F_EPS].p;
+  if (d.dim == 2) k_pb_residual<2><<<LGRID(c)>>>(d, mh, linearized, kappasq, gamma, psi, psi0, eps, d_extra, d_f);
+  else k_pb_residual<3><<<LGRID(c)>>>(d, mh, linearized, kappasq, gamma, psi, psi0, eps, d_extra, d_f);
+  ++c->launches;
+  c->toc("computeFPoissonBoltzmann");
 }
 
 }  // namespace isph

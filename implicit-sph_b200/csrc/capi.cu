@@ -19,7 +19,7 @@ void Ctx::toc(const char *name) {      // no host synchronisation here: the elap
   cudaEventRecord(t.b, stream); t.open = false; t.pending = true;
 }
 
-static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
+static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
 
 static void ensure_fields(Ctx *c) {
   for (int f = 0; f < ISPH_F_COUNT; ++f) {
@@ -91,7 +91,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
   Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
   c->xs.release(); c->bs.release(); c->nullvec.release(); c->mask.release(); c->V.release(); c->Z.release(); c->wk.release(); c->red.release(); c->hbuf.release(); c->flag.release(); c->h_scal.release();
-  c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release();
+  c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -254,6 +254,30 @@ int isph_assemble_gradient_dot(isph_ctx *ctx, double alpha, int vf, int f0, int 
 int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int mh) { API_BEGIN(ctx) ns_poisson(c, dt, anti != 0, singular, mh != 0); API_END }
 int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int mh, int incp, const double *g) { API_BEGIN(ctx) ns_helmholtz(c, dt, theta, anti != 0, mh != 0, incp != 0, g); API_END }
 int isph_pb_jacobian(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma) { API_BEGIN(ctx) pb_jacobian(c, mh != 0, lin != 0, ezcb, psiref, gamma); API_END }
+// extra source (functor_poisson_boltzmann_extra_f.h) staged on the device, indexed by owned atom
+static const double *stage_extra(Ctx *c, const double *extra_f) {
+  if (!extra_f) return nullptr;
+  c->cv.ensure(c->ld > c->nlocal ? c->ld : c->nlocal);
+  CUDA_CHECK(cudaMemcpyAsync(c->cv.p, extra_f, sizeof(double) * c->nlocal, cudaMemcpyHostToDevice, c->stream));
+  return c->cv.p;
+}
+int isph_pb_residual(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma, const double *extra_f, double *f_out) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->have_atoms && c->have_neigh, "atoms and neighbors must be set first");
+  double *df; if (c->b_nvec >= 1 && c->bs.p) df = c->bs.p; else { c->wk.ensure((size_t)c->nall + (size_t)c->nlocal); df = c->wk.p + c->nall; }
+  pb_residual(c, mh != 0, lin != 0, ezcb, psiref, gamma, stage_extra(c, extra_f), df);
+  if (f_out) CUDA_CHECK(cudaMemcpyAsync(f_out, df, sizeof(double) * c->nlocal, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+}
+int isph_pb_newton(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma, const double *extra_f, int max_newton, double tol_f, double tol_update,
+                   int use_prec, int *newton_iters, int *linear_iters, double *normf, int *converged) {
+  API_BEGIN(ctx) int a = 0, b = 0, cv = 0; double nf = 0.0;
+  // the extra source must not share a buffer with the preconditioner work vectors used inside the solves
+  const double *dex = nullptr;
+  if (extra_f) { c->pb_extra.ensure(c->nlocal); CUDA_CHECK(cudaMemcpyAsync(c->pb_extra.p, extra_f, sizeof(double) * c->nlocal, cudaMemcpyHostToDevice, c->stream)); dex = c->pb_extra.p; }
+  pb_newton(c, mh != 0, lin != 0, ezcb, psiref, gamma, dex, max_newton, tol_f, tol_update, use_prec != 0, &a, &b, &nf, &cv);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (newton_iters) *newton_iters = a; if (linear_iters) *linear_iters = b; if (normf) *normf = nf; if (converged) *converged = cv; API_END
+}
 int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incp, const double *dp) { API_BEGIN(ctx) ns_correct(c, dt, anti != 0, incp != 0, dp); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END }
 int isph_diagonals_get(isph_ctx *ctx, double *d, double *s) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->A.built, "no matrix");

@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve(const int *rp, const int *
 // so the lowest unfinished row never waits on an unfinished one: no deadlock.  The critical path becomes
 // (#levels x one L2 round trip) instead of (#levels x one grid barrier).  Waits are bounded; a timeout or a computed NaN
 // is published as 0 with the fault word raised, so that nobody downstream spins on it.
+__device__ int g_ilu_backoff = 0;      // ns to sleep after a failed poll (0: spin); rows far ahead of the wavefront then stop hammering L2
 __device__ __forceinline__ double wait_value(const double *p, int *fault) {
   const volatile double *vp = p; double v = *vp; int spins = 0;
   while (v != v) {
+    if (g_ilu_backoff) __nanosleep(g_ilu_backoff);
     if ((++spins & 1023) == 0) {                               // once a fault is raised anywhere, every wait drains immediately
       if (*reinterpret_cast<volatile int *>(fault)) return 0.0;
       if (spins > (1 << 22)) { *fault = 1; return 0.0; }
@@ -290,6 +292,7 @@ void ilu_create(Ctx *c) {
   }
   if (I.sync_free) {
     int sms = 0, per_sm = 0; CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    { const char *e = getenv("ISPH_ILU_BACKOFF"); const int bo = (e && *e) ? atoi(e) : 0; CUDA_CHECK(cudaMemcpyToSymbolAsync(g_ilu_backoff, &bo, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream)); }
     // factorisation: per-warp staging of the row in shared memory (12 B per entry); shrink the CTA until it fits
     I.tb_f = ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * 12 > 200 * 1024) I.tb_f >>= 1;
     I.smem_f = (size_t)(I.tb_f / 32) * I.maxlen * 12; ISPH_REQUIRE(I.smem_f <= 200 * 1024, "ILU: a row is too long for the factorisation kernel");

@@ -108,6 +108,7 @@ struct Ctx {
   // preconditioner
   bool prec_ready = false; int prec_kind = 0; DevBuf<double> invdiag, cw, cv; DevBuf<int> block_of_row; bool have_blocks = false;
   IluData *ilu = nullptr;
+  DevBuf<double> pb_extra;         // Poisson-Boltzmann extra source term staged for the Newton loop
   // multi-GPU
   Halo *halo = nullptr;
   const double *prepush_x = nullptr; unsigned long long prepush_seq = 0;   // SpMV input whose halo was pushed by its producer kernel
@@ -158,6 +159,8 @@ void ns_poisson(Ctx *c, double dt, bool anti, int singular, bool mh);
 void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp, const double *g);
 void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma);
 void ns_correct(Ctx *c, double dt, bool anti, bool incp, const double *dp_owned_host);
+void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f);
+void forward_comm(Ctx *c, int field);
 
 void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, const double *dot_vec = nullptr, double *dot_out = nullptr);   // spmv.cu (does the halo exchange when nranks > 1)
 
@@ -169,6 +172,8 @@ bool ilu_fault(Ctx *c);
 
 void solver_prepare_vectors(Ctx *c);                         // krylov.cu
 void solver_solve(Ctx *c, bool use_prec, const char *label);
+void pb_newton(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, int max_newton, double tol_f, double tol_update,
+               bool use_prec, int *newton_iters, int *linear_iters, double *normf, int *converged);
 
 // device-resident exchange plan of the halo kernels (written once per halo_setup; indexed dynamically on the device,
 // which is why it is not a by-value kernel parameter).  Staging buffer of a rank: [MB_SLOTS][3 vectors][cap] doubles.

@@ -631,4 +631,41 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   c->init_type = -1;
 }
 
+// ---- Newton's method for the Poisson-Boltzmann problem ------------------------------------------------------------------
+// What NOX does for PairISPH::computePoissonBoltzmann (pair_isph.cpp:572-600) with the reference's default lists
+// (solver_nox_impl.h:76-160): line search "Full Step", direction Newton, stop when NormF <= tol_f AND NormUpdate <= tol_update
+// (NOX::StatusTest::NormF / NormUpdate, 2-norms scaled by sqrt(N)), at most max_newton iterations.  NOX itself is third-party
+// and out of scope; what is on the path is what each iteration calls back into: computeF (pb_residual), computeJacobian
+// (pb_jacobian) and the Jacobian solve, which runs through solver_solve with the context's Krylov / preconditioner lists.
+// psi (field ISPH_F_PSI) is the initial guess and the result; F stays in the load vector.
+__global__ void __launch_bounds__(VB) k_add_rows(double *field, const double *dx, int n) { for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) field[i] += dx[i]; }
+
+void pb_newton(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, int max_newton, double tol_f, double tol_update,
+               bool use_prec, int *newton_iters, int *linear_iters, double *normf_out, int *converged_out) {
+  ISPH_REQUIRE(c->A.built && !c->A.external, "isph_pb_newton: build the graph first");
+  ISPH_REQUIRE(c->x_nvec == 1 && c->b_nvec == 1 && c->xs.p && c->bs.p, "isph_pb_newton: create one solution and one load vector first");
+  const int n = c->A.n, g = vgrid(c, n);
+  c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)8 * 592 * 18 + 1024 + (size_t)c->A.nslices / 8 + 64); c->h_scal.ensure(16 + c->sp.max_iters + c->sp.num_blocks + 8);
+  CUDA_CHECK(cudaMemsetAsync(c->flag.p + 8, 0, 8 * sizeof(int), c->stream));
+  double *S = c->hbuf.p;
+  double nglobal = (double)n;
+  if (c->nranks > 1) { CUDA_CHECK(cudaMemcpyAsync(S + S_TMP, &nglobal, sizeof(double), cudaMemcpyHostToDevice, c->stream)); halo_allreduce(c, S + S_TMP, 1); nglobal = read_scalar(c, S + S_TMP); }
+  int k = 0, lin_total = 0; bool converged = false; double nf = 0.0, nup = 0.0;
+  for (;; ++k) {
+    pb_residual(c, mh, linearized, ezcb, psiref, gamma, d_extra, c->bs.p);                       // F(psi_k)
+    dot_dev(c, c->bs.p, nullptr, n, S + S_TMP); nf = sqrt(read_scalar(c, S + S_TMP) / nglobal);
+    if (!(nf == nf)) break;                                                                       // NOX::StatusTest::FiniteValue
+    if (k > 0 && nf <= tol_f && nup <= tol_update) { converged = true; break; }
+    if (k >= max_newton) break;
+    pb_jacobian(c, mh, linearized, ezcb, psiref, gamma);                                          // J(psi_k): diagonal refreshed, Laplacian block kept
+    k_scale_by<<<g, VB, 0, c->stream>>>(c->bs.p, -1.0, n); ++c->launches;                         // J dpsi = -F
+    c->init_type = ISPH_INIT_ZERO;
+    solver_solve(c, use_prec, "PoissonBoltzmannJacobian"); lin_total += c->last_iters;
+    k_add_rows<<<g, VB, 0, c->stream>>>(c->field[ISPH_F_PSI].p, c->xs.p, n); ++c->launches;       // full step
+    dot_dev(c, c->xs.p, nullptr, n, S + S_TMP); nup = sqrt(read_scalar(c, S + S_TMP) / nglobal);
+  }
+  forward_comm(c, ISPH_F_PSI);                                                                    // pair_isph.cpp:595-598
+  *newton_iters = k; *linear_iters = lin_total; *normf_out = nf; *converged_out = converged ? 1 : 0;
+}
+
 }  // namespace isph

@@ -38,7 +38,8 @@ enum { ISPH_F_VFRAC = 0,   /* 1 */ ISPH_F_GC = 1,       /* 9: dim x dim column-m
        ISPH_F_NORMAL = 3,  /* 3 */ ISPH_F_PND = 4,      /* 1 */
        ISPH_F_DENSITY = 5, ISPH_F_VISCOSITY = 6, ISPH_F_PRESSURE = 7,
        ISPH_F_VELOCITY = 8,/* 3 */ ISPH_F_VSTAR = 9,    /* 3 */ ISPH_F_FORCE = 10, /* 3 */
-       ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_DP = 13 /* 1: pressure increment dp, owned + ghost */, ISPH_F_COUNT = 14 };
+       ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_DP = 13 /* 1: pressure increment dp, owned + ghost */,
+       ISPH_F_PSI0 = 14 /* 1: prescribed (normalised) potential of solid / boundary particles, atom->psi0 */, ISPH_F_COUNT = 15 };
 
 /* ---- context ------------------------------------------------------------------------------------------------
  * replaces: SolverLin(MPI_Comm&) solver_lin.h:28, PrecondWrapper(MPI_Comm) precond.h:26 (one communicator per
@@ -121,6 +122,21 @@ int isph_pb_jacobian(isph_ctx *ctx, int morris_holmes, int linearized, double ez
  * vstar -= dt/rho grad(dp), then forward_comm(Vstar)), correctPressure (functor_correct_pressure.h:29-43).  dp = the device
  * solution of the last solve, or dp_owned[nlocal] when given.  Results: fields ISPH_F_DP, ISPH_F_VSTAR, ISPH_F_PRESSURE. */
 int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incremental_pressure, const double *dp_owned);
+/* PairISPH_Corrected::computeF (pair_isph_corrected.cpp:438-485): forward_comm(psi), then FunctorOuterPoissonBoltzmannF
+ * (functor_poisson_boltzmann_f.h:58-88; fields ISPH_F_PSI, ISPH_F_PSI0, ISPH_F_EPS) on the matrix-free corrected Laplacian
+ * (functor_laplacian.h:67-277), plus the caller-evaluated source of FunctorOuterPoissonBoltzmannExtraF
+ * (functor_poisson_boltzmann_extra_f.h:76-90; extra_f[nlocal] or NULL).  F is left in the load vector when one exists and
+ * copied to f_out[nlocal] when given. */
+int isph_pb_residual(isph_ctx *ctx, int morris_holmes, int linearized, double ezcb, double psiref, double gamma,
+                     const double *extra_f, double *f_out);
+/* The Newton iteration NOX runs for PairISPH::computePoissonBoltzmann (pair_isph.cpp:572-600) with the reference's default
+ * lists (solver_nox_impl.h:76-160: full steps; converged when ||F||_2/sqrt(N) <= tol_f AND ||dpsi||_2/sqrt(N) <= tol_update;
+ * reference values 1e-8, 1e-5, 100 iterations): computeF, computeJacobian and the Jacobian solve of every iteration stay on
+ * the device; the solve uses this context's Krylov / preconditioner parameter lists.  ISPH_F_PSI holds the initial guess on
+ * entry and the solution (owned + ghost) on return.  One solution and one load vector must exist. */
+int isph_pb_newton(isph_ctx *ctx, int morris_holmes, int linearized, double ezcb, double psiref, double gamma, const double *extra_f,
+                   int max_newton, double tol_f, double tol_update, int use_prec,
+                   int *newton_iters, int *linear_iters, double *normf, int *converged);
 int isph_diagonals_get(isph_ctx *ctx, double *diagonal, double *scaled_laplace_diagonal);   /* A.diagonal, A.scaled_laplace_diagonal */
 
 /* ---- SolverLin / SolverLin_Belos mirror (solver_lin.h:23-98, solver_lin.cpp, solver_lin_belos.h:130-264) --------- */

@@ -112,7 +112,7 @@ extern "C" {
 const char *orc_name(void) { return "C++ restatement (oracle port)"; }
 
 int orc_field_ncomp(int fl) {
-  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
+  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
   return (fl >= 0 && fl < ORC_F_COUNT) ? nc[fl] : -1;
 }
 
@@ -597,6 +597,91 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
     }
   }
   replace_diag(q, q->diagonal);                                                                       // :105
+  return 0;
+}
+
+// Matrix-free corrected Laplacian of a scalar field, Corrected::FunctorOuterLaplacianHelper::operator() with scalar_diff
+// (functor_laplacian.h:67-277): corrected gradient of psi and of the material first, then sum a_ij (coeff (psi_i-psi_j)/r -
+// e_ij . grad psi), combined as alpha (m_i lap + grad m . grad psi).  Same operation order as the reference.
+static double scalar_laplacian(const Q *q, int ii, const double *fld, double alpha, const double *material, bool mh, int f0, int f1) {
+  const int dim = q->dim, i = q->ilist[ii], itype = q->type[i], ikind = q->kind(itype); const double *vfrac = q->f[ORC_F_VFRAC].data();
+  const double m_i = material ? material[i] : 1.0;
+  if (!fyes1(f0, ikind)) return 0.0;                                                                 // :99-100
+  const long long nb = q->noff[ii], ne = q->noff[ii + 1];
+  std::vector<double> aijs(ne - nb, 0.0);
+  double gm[3] = {}, gf[3] = {}, lap = 0.0;
+  const double *G = &q->f[ORC_F_GC][(size_t)9 * i], *L = &q->f[ORC_F_LC][(size_t)6 * i];
+  for (long long p = nb; p < ne; ++p) {                                                              // :111-158
+    const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j], jkind = q->kind(jtype);
+    const double m_j = material ? material[j] : 1.0;
+    if (!fyes2(f0, f1, ikind, jkind)) continue;
+    double rsq = 0.0, rij[3] = {};
+    for (int k = 0; k < dim; ++k) { rij[k] = q->X(i)[k] - q->X(j)[k]; rsq += (rij[k] * rij[k]); }
+    const double cutsq = q->cut2(itype, jtype);
+    if (rsq < cutsq) {
+      double coeff = 1.0;
+      if (jkind & ORC_SOLID) coeff = q->mirror(mh, i, j, sqrt(cutsq));
+      const double r = sqrt(rsq) + EPS_R, dwdr = q->kern.dval(r, q->hh(itype, jtype));
+      const double vjtmp = dwdr / r * vfrac[j] * coeff;
+      for (int k2 = 0; k2 < dim; ++k2) {
+        double gitmp = 0.0; for (int k1 = 0; k1 < dim; ++k1) gitmp += G[k2 * dim + k1] * rij[k1];
+        const double ijtmp = gitmp * vjtmp;
+        if (fyes1(f0, jkind)) gm[k2] += ijtmp * (m_j - m_i);
+        gf[k2] += ijtmp * (fld[j] - fld[i]);
+      }
+    }
+  }
+  for (long long p = nb; p < ne; ++p) {                                                              // :161-216 (no filter on this pass)
+    const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j];
+    double rsq = 0.0, rij[3] = {};
+    for (int k = 0; k < dim; ++k) { rij[k] = q->X(i)[k] - q->X(j)[k]; rsq += (rij[k] * rij[k]); }
+    const double cutsq = q->cut2(itype, jtype);
+    if (rsq < cutsq) {
+      const double r = sqrt(rsq) + EPS_R, dwdr = q->kern.dval(r, q->hh(itype, jtype));
+      double eij[3]; for (int k = 0; k < dim; ++k) eij[k] = rij[k] / r;
+      double aij = 0.0; const double scale_a[2] = {2.0, 1.0};
+      for (int k2 = 0, op = 0; k2 < dim; ++k2) for (int k1 = 0; k1 < (k2 + 1); ++k1, ++op) aij += L[op] * eij[k1] * eij[k2] * scale_a[k1 == k2];
+      aij *= 2.0 * dwdr * vfrac[j];
+      double dotv = 0.0; for (int k = 0; k < dim; ++k) dotv += eij[k] * gf[k];
+      const double bij = -1.0 * dotv;
+      lap += aij * bij;
+      aijs[p - nb] = aij;
+    }
+  }
+  for (long long p = nb; p < ne; ++p) {                                                              // :219-263
+    const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j], jkind = q->kind(jtype);
+    if (!fyes2(f0, f1, ikind, jkind)) continue;
+    double rsq = 0.0, rij[3] = {};
+    for (int k = 0; k < dim; ++k) { rij[k] = q->X(i)[k] - q->X(j)[k]; rsq += (rij[k] * rij[k]); }
+    const double cutsq = q->cut2(itype, jtype);
+    if (rsq < cutsq) {
+      double coeff = 1.0;
+      if (jkind & ORC_SOLID) coeff = q->mirror(mh, i, j, sqrt(cutsq));
+      const double r = sqrt(rsq) + EPS_R;
+      const double bij = coeff * (fld[i] - fld[j]) / r;
+      lap += aijs[p - nb] * bij;
+    }
+  }
+  double dotm = 0.0; for (int k = 0; k < dim; ++k) dotm += gm[k] * gf[k];
+  return alpha * (m_i * lap + dotm);                                                                 // :266-268
+}
+
+// FunctorOuterPoissonBoltzmannF, functor_poisson_boltzmann_f.h:58-88 (+ extra source, functor_poisson_boltzmann_extra_f.h:76-90)
+int orc_pb_residual(orc_problem *q, int mh, int linearized, double ezcb, double psiref, double gamma, const double *extra_f, double *fout) {
+  const double kappasq = 2.0 * ezcb / psiref;
+  q->forward(ORC_F_PSI);                                                                              // pair_isph_corrected.cpp:446-450
+  const double *psi = q->f[ORC_F_PSI].data(), *psi0 = q->f[ORC_F_PSI0].data(), *eps = q->f[ORC_F_EPS].data();
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii], ikind = q->kind(q->type[i]);
+    if (ikind == ORC_SOLID || ikind == ORC_BOUNDARY) fout[i] = (-psi[i] + psi0[i]);
+    else if (ikind == ORC_BUFFER_DIRICHLET || ikind == ORC_BUFFER_NEUMANN || ikind == ORC_FLUID) {
+      fout[i] = scalar_laplacian(q, ii, psi, -1.0, eps, mh != 0, ORC_FLUID, ORC_ALL);
+      if (linearized) fout[i] += kappasq * (psi[i] / (1.0 + 2.0 * gamma * pow(psi[i] / 2, 2)));
+      else fout[i] += kappasq * (sinh(psi[i]) / (1.0 + 2.0 * gamma * pow(sinh(psi[i] / 2.0), 2)));
+    }
+    if (extra_f && !(ikind & ORC_SOLID)) fout[i] += extra_f[i];
+  }
   return 0;
 }
 

@@ -19,7 +19,7 @@ REF_SO = os.path.join(HERE, "_ref", "libisph_ref.so")
 FLUID, SOLID, BOUNDARY, BUFFER_DIRICHLET, BUFFER_NEUMANN, ALL = 99, 12, 16, 32, 64, 127
 NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
 WENDLAND, CUBIC, QUINTIC = 0, 1, 2
-F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP = range(14)
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP, F_PSI0 = range(15)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -70,6 +70,7 @@ def _load(kind):
     L.orc_ns_helmholtz.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]
     L.orc_pb_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.orc_ns_correct.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp]
+    L.orc_pb_residual.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
     L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
     L.orc_diag_get.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_spmv.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
@@ -151,6 +152,12 @@ class Oracle:
 
     def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
         self._ck(self.L.orc_pb_jacobian(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma), "pb_jacobian")
+
+    def pb_residual(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0, extra_f=None):
+        f = np.zeros(self.nlocal); ex = None if extra_f is None else np.ascontiguousarray(extra_f, dtype=np.float64)
+        self._ck(self.L.orc_pb_residual(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma,
+                                        None if ex is None else _d(ex), _d(f)), "pb_residual")
+        return f
 
     def ns_correct(self, dt, dp, anti=True, incremental_pressure=True):
         dp = np.ascontiguousarray(dp, dtype=np.float64); assert dp.size == self.nlocal

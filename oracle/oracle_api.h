@@ -25,7 +25,8 @@ enum { ORC_F_VFRAC = 0,   /* 1  */  ORC_F_GC = 1,       /* 9: dim x dim column-m
        ORC_F_NORMAL = 3,  /* 3  */  ORC_F_PND = 4,      /* 1 */
        ORC_F_DENSITY = 5, ORC_F_VISCOSITY = 6, ORC_F_PRESSURE = 7,
        ORC_F_VELOCITY = 8,/* 3  */  ORC_F_VSTAR = 9,    /* 3 */  ORC_F_FORCE = 10, /* 3 */
-       ORC_F_EPS = 11,    ORC_F_PSI = 12, ORC_F_DP = 13 /* 1: pressure increment, owned + ghost */, ORC_F_COUNT = 14 };
+       ORC_F_EPS = 11,    ORC_F_PSI = 12, ORC_F_DP = 13 /* 1: pressure increment, owned + ghost */,
+       ORC_F_PSI0 = 14, /* 1: atom->psi0 */ ORC_F_COUNT = 15 };
 
 typedef struct orc_problem orc_problem;
 
@@ -56,6 +57,11 @@ int orc_ns_helmholtz(orc_problem *p, double dt, double theta, int anti, int morr
                      int incremental_pressure, const double *g, double *b);
 /* functor_poisson_boltzmann_jacobian.h:35-107 (A.is_filled kept between calls) */
 int orc_pb_jacobian(orc_problem *p, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+/* functor_poisson_boltzmann_f.h:58-88 (psi, psi0, eps from the fields) + functor_poisson_boltzmann_extra_f.h:76-90 with the
+ * caller's precomputed source extra_f[nlocal] (NULL: none); psi is forward-communicated first (pair_isph_corrected.cpp:446-450);
+ * f[nlocal] out */
+int orc_pb_residual(orc_problem *p, int morris_holmes, int linearized, double ezcb, double psiref, double gamma,
+                    const double *extra_f, double *f);
 /* the block right after the Poisson solve, pair_isph.cpp:1017-1031: forward_comm(DeltaP), computeZeroMeanPressure(dp)
  * (:422-464, when incremental pressure is used), correctVelocity (functor_correct_velocity.h:52-78, pair_isph_corrected.cpp
  * :1019-1034) incl. forward_comm(Vstar), correctPressure (functor_correct_pressure.h:29-43).  dp_owned[nlocal] = the solution. */

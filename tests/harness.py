@@ -13,7 +13,7 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     o = O.Oracle(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"], kind=kind)
     o.set_field(O.F_DENSITY, F["density"]); o.set_field(O.F_VISCOSITY, F["viscosity"]); o.set_field(O.F_PRESSURE, F["pressure"])
     o.set_field(O.F_VSTAR, F["velocity"]); o.set_field(O.F_VELOCITY, F["velocity"]); o.set_field(O.F_FORCE, F["force"])
-    o.set_field(O.F_EPS, F["eps"]); o.set_field(O.F_PSI, F["psi"])
+    o.set_field(O.F_EPS, F["eps"]); o.set_field(O.F_PSI, F["psi"]); o.set_field(O.F_PSI0, F["psi0"])
     o.compute_pre(normals=cs["has_solid"])
     out = dict(vfrac=o.get_field(O.F_VFRAC), gc=o.get_field(O.F_GC), lc=o.get_field(O.F_LC))
     if cs["has_solid"]:
@@ -24,6 +24,8 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     out["diag_poisson"], out["sld_poisson"] = o.diagonals(); o.invalidate_matrix()
     b0 = np.asfortranarray(F["velocity"][:nl, :dim])
     out["b_helmholtz"] = o.ns_helmholtz(cs["dt"], cs["theta"], b0, anti=anti, morris_holmes=mh); out["A_helmholtz"] = o.matrix(); o.invalidate_matrix()
+    out["pb_f"] = o.pb_residual(morris_holmes=mh, extra_f=F["pb_extra"][:nl])                     # PB residual: before the Jacobian (no matrix needed)
+    out["pb_f_lin"] = o.pb_residual(morris_holmes=mh, linearized=True, gamma=0.1)
     o.pb_jacobian(morris_holmes=mh); out["A_pb"] = o.matrix()
     o.set_field(O.F_PSI, np.cos(P["xw"][:, 0])); o.pb_jacobian(morris_holmes=mh); out["A_pb2"] = o.matrix()
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = o.spmv(x)
@@ -39,7 +41,7 @@ def cuda_context(P, F, device=0):
     c.set_particles(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"])
     c.field_set(isph.F_DENSITY, F["density"]); c.field_set(isph.F_VISCOSITY, F["viscosity"]); c.field_set(isph.F_PRESSURE, F["pressure"])
     c.field_set(isph.F_VSTAR, F["velocity"]); c.field_set(isph.F_VELOCITY, F["velocity"]); c.field_set(isph.F_FORCE, F["force"])
-    c.field_set(isph.F_EPS, F["eps"]); c.field_set(isph.F_PSI, F["psi"])
+    c.field_set(isph.F_EPS, F["eps"]); c.field_set(isph.F_PSI, F["psi"]); c.field_set(isph.F_PSI0, F["psi0"])
     return c
 
 
@@ -59,6 +61,8 @@ def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
     c.create_load(None, dim); c.load_set(np.asfortranarray(F["velocity"][:nl, :dim]))
     c.ns_helmholtz(cs["dt"], cs["theta"], anti=anti, morris_holmes=mh)
     out["b_helmholtz"] = c.load_get(dim); out["A_helmholtz"] = c.matrix_get(); c.matrix_invalidate()
+    out["pb_f"] = c.pb_residual(morris_holmes=mh, extra_f=F["pb_extra"][:nl])
+    out["pb_f_lin"] = c.pb_residual(morris_holmes=mh, linearized=True, gamma=0.1)
     c.pb_jacobian(morris_holmes=mh); out["A_pb"] = c.matrix_get()
     c.field_set(isph.F_PSI, np.cos(P["xw"][:, 0])); c.pb_jacobian(morris_holmes=mh); out["A_pb2"] = c.matrix_get()
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = c.matrix_multiply(x)

@@ -42,6 +42,8 @@ def make_case(name):
     F["force"] = 0.01 * np.stack([np.cos(xw[:, 0]), np.sin(xw[:, 1]), np.zeros(len(xw))], axis=1)
     F["eps"] = 1.0 + 0.2 * np.cos(xw[:, 0])
     F["psi"] = np.sin(xw[:, 0]) * np.cos(xw[:, 1])
+    F["psi0"] = 0.3 + 0.1 * np.cos(xw[:, 0])                                     # prescribed potential of solid / boundary particles
+    F["pb_extra"] = -2.0 * np.sin(xw[:, 0]) * np.cos(xw[:, 1]) - np.sinh(np.sin(xw[:, 0]) * np.cos(xw[:, 1]))   # poisson-boltzmann-harmonic.xml:14-30
     P["case"] = dict(name=name, kinds=c["kinds"], kernel=c.get("kernel", 0), has_solid=bool(slab), dt=0.05 * dx / 0.1, theta=0.5,
                      h_min=(0.8 * 1.5 * dx) if slab else None)
     return P, F

@@ -48,3 +48,13 @@ def test_product_does_not_link_the_oracle(isph):
             assert "oracle" not in open(os.path.join(src, fn)).read().replace("oracle/krylov_oracle.cpp", "").replace("oracle/", "ORACLE_DOC/") or True
     py = open(os.path.join(isph.HERE, "__init__.py")).read()
     assert "import oracle" not in py and "libisph_oracle" not in py
+
+
+def test_field_tables_agree_with_the_header(isph):
+    """The Python binding's field table, the header's enum and the oracle's enum must list the same fields."""
+    import re
+    txt = open(isph.HEADER).read()
+    count = int(re.search(r"ISPH_F_COUNT\s*=\s*(\d+)", txt).group(1))
+    assert len(isph.FIELD_NCOMP) == count == isph.F_PSI0 + 1
+    orc = open(os.path.join(os.path.dirname(isph.HERE), "oracle", "oracle_api.h")).read()
+    assert int(re.search(r"ORC_F_COUNT\s*=\s*(\d+)", orc).group(1)) == count

@@ -157,3 +157,37 @@ def test_helmholtz_three_rhs_cg_chebyshev():
     for k in range(dim):
         assert np.linalg.norm(x[:, k] - xs[k]) / np.linalg.norm(xs[k]) <= 1e-8
     c.close()
+
+
+@pytest.mark.parametrize("name,prec", [("jitter2d", O.PREC_JACOBI), ("jitter3d", O.PREC_ILU0)])
+def test_poisson_boltzmann_newton_matches_cpu_newton(name, prec):
+    """BASELINE config 5 in miniature: the Newton iteration NOX runs for computePoissonBoltzmann (full steps, NormF 1e-8 AND
+    NormUpdate 1e-5, solver_nox_impl.h:76-160) with computeF / computeJacobian / the Jacobian solve on the device, against the
+    same loop built from the CPU oracle's pieces (manufactured source of sph-script/poisson-boltzmann-harmonic.xml)."""
+    import harness
+    P, F = make_case(name); cs = P["case"]; nl = P["nlocal"]; ex = F["pb_extra"][:nl].copy()
+    o = O.Oracle(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"], kind="port")
+    o.set_field(O.F_EPS, F["eps"]); o.set_field(O.F_PSI0, F["psi0"]); o.compute_pre(); rp, col = o.graph()
+    colL = O.tags_to_local(col, P["tag"][:nl]); prm = O.krylov_params(precond=prec, row_gid=P["tag"][:nl])
+    psi = np.zeros(nl + P["nghost"]); nup = 0.0; lin = 0; k = 0
+    while True:
+        o.set_field(O.F_PSI, psi); f = o.pb_residual(extra_f=ex); nf = np.linalg.norm(f) / np.sqrt(nl)
+        if (k > 0 and nf <= 1e-8 and nup <= 1e-5) or k >= 100:
+            break
+        o.pb_jacobian(); A = o.matrix()
+        dx, info = O.krylov_solve(rp, colL, A, -f, params=prm); assert info["converged"]; lin += info["iters"]
+        psi[:nl] += dx; nup = np.linalg.norm(dx) / np.sqrt(nl); k += 1
+    o.close()
+    assert 2 <= k < 20                                           # a genuinely nonlinear solve that converges quadratically
+    c = harness.cuda_context(P, F)
+    c.field_set(isph.F_PSI, np.zeros(nl + P["nghost"]))
+    c.compute_pre(); c.graph_build(); c.create_solution(None, 1); c.create_load(None, 1)
+    configure(c, O.SOLVER_GMRES, prec)
+    st = c.pb_newton(extra_f=ex)
+    psi_gpu = c.field_get(isph.F_PSI)
+    c.close()
+    assert st["converged"] and st["newton_iters"] == k and abs(st["linear_iters"] - lin) <= 2 * k, (st, k, lin)
+    assert st["normf"] <= 1e-8
+    assert np.linalg.norm(psi_gpu[:nl] - psi[:nl]) / np.linalg.norm(psi[:nl]) <= 1e-8
+    ghost_owner = P["tag"][nl:] - 1                              # single rank: tags are 1-based owned indices
+    assert np.array_equal(psi_gpu[nl:], psi_gpu[ghost_owner])    # psi forwarded to the ghosts after the solve (pair_isph.cpp:595-598)

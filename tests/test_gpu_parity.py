@@ -27,6 +27,7 @@ def _compare(a, b, has_solid):
     assert scaled_err(a["b_poisson"], b["b_poisson"]) <= VAL_TOL
     assert scaled_err(a["b_helmholtz"], b["b_helmholtz"]) <= VAL_TOL
     assert relerr(a["diag_poisson"], b["diag_poisson"]) <= VAL_TOL
+    assert scaled_err(a["pb_f"], b["pb_f"]) <= VAL_TOL and scaled_err(a["pb_f_lin"], b["pb_f_lin"]) <= VAL_TOL      # Poisson-Boltzmann residual
     assert scaled_err(a["spmv_y"], b["spmv_y"]) <= 1e-13
     # post-solve block: zero-mean dp, corrected velocity (owned + ghosts), corrected pressure
     assert scaled_err(a["corr_dp"], b["corr_dp"]) <= VAL_TOL and scaled_err(a["corr_vstar"], b["corr_vstar"]) <= VAL_TOL and scaled_err(a["corr_p"], b["corr_p"]) <= VAL_TOL
