@@ -44,6 +44,9 @@ WORKLOADS = {
     # BASELINE configs[2]: velocity Helmholtz (I - theta dt nu lap) v* = rhs, dim right-hand sides one after another, CG + Chebyshev
     "c3": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="Chebyshev", solver="Block CG", strong=True, system="helmholtz", theta=0.5,
                desc="BASELINE configs[2]: 3-D velocity Helmholtz (functor_incomp_navier_stokes_helmholtz), 8M particles, 3 right-hand sides, CG + Chebyshev(1), x0 = v^n, fixed global size (strong scaling)"),
+    # BASELINE configs[4]: Poisson-Boltzmann Newton-Krylov (full-step Newton, NormF 1e-8 AND NormUpdate 1e-5), manufactured source
+    "c5": dict(dim=3, n=160, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True, system="pb",
+               desc="BASELINE configs[4]: 3-D Poisson-Boltzmann electrostatics, 4M particles (160^3), Newton iteration with device-resident computeF / computeJacobian and GMRES(50)+Jacobi Jacobian solves, manufactured source of poisson-boltzmann-harmonic.xml, psi0 = 0, fixed global size (strong scaling)"),
     # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
     "p8m": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True,
                 desc="north_star target: 3-D 8M-particle (200^3) pressure Poisson, flexible GMRES(50)+Jacobi, fixed global size (strong scaling)"),
@@ -207,7 +210,10 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory(); return t, t.numpy()
     hx = pin(P["x"]); htype = pin(P["type"]); htag = pin(P["tag"]); hneigh = pin(P["neigh"]); hnoff = pin(P["noff"]); hil = pin(P["ilist"])
     hv = pin(F["vstar"]); hrho = pin(F["density"]); hsol = pin(np.zeros(nl))
-    helm = w.get("system") == "helmholtz"
+    helm = w.get("system") == "helmholtz"; pbs = w.get("system") == "pb"
+    if pbs:
+        xw_ = P["xw"]; s_ = np.sin(xw_[:, 0]) * np.cos(xw_[:, 1])
+        hex_ = pin((-2.0 * s_ - np.sinh(s_))[:nl]); hpsi = pin(np.zeros(len(xw_))); heps = pin(np.ones(len(xw_))); hsol = pin(np.zeros(len(xw_)))
     if helm:
         hnu = pin(F["viscosity"]); hvn = pin(np.asfortranarray(F["vstar"][:nl, :dim]).reshape(-1, order="F")); hsol = pin(np.zeros((nl, dim), order="F").reshape(-1, order="F"))
 
@@ -228,11 +234,28 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         c.field_set(isph.F_VSTAR, hv[1]); c.field_set(isph.F_DENSITY, hrho[1])
         if helm:
             c.field_set(isph.F_VELOCITY, hv[1]); c.field_set(isph.F_VISCOSITY, hnu[1])
+        if pbs:
+            c.field_set(isph.F_EPS, heps[1]); c.field_set(isph.F_PSI0, hpsi[1])
     h2d_bytes = hx[1].nbytes + htype[1].nbytes + htag[1].nbytes + hneigh[1].nbytes + hnoff[1].nbytes + hil[1].nbytes + hv[1].nbytes + hrho[1].nbytes
+    if pbs:
+        h2d_bytes += heps[1].nbytes + 2 * hpsi[1].nbytes + hex_[1].nbytes   # eps, psi0, psi (initial guess), source
     if helm:
         h2d_bytes += hv[1].nbytes + hnu[1].nbytes + 2 * hvn[1].nbytes      # + load and initial guess (both = v^n) written every step
     d2h_bytes = hsol[1].nbytes
-    solve_label = "Helmholtz" if helm else "Poisson"
+    solve_label = "Helmholtz" if helm else ("PoissonBoltzmannJacobian" if pbs else "Poisson")
+
+    def pb_step():
+        """pair_isph.cpp:572-600: Newton iteration for psi (initial guess written every step, result read back)"""
+        c.graph_invalidate()
+        c.compute_pre()
+        c.graph_build()
+        c.create_solution(None, 1); c.create_load(None, 1)
+        c.field_set(isph.F_PSI, hpsi[1])
+        c.set_matrix_is_singular(False)
+        r = c.pb_newton(extra_f=hex_[1])
+        c.call("isph_field_get", isph.F_PSI, isph._d(hsol[1]))
+        c.matrix_invalidate()
+        return dict(iters=r["linear_iters"], relres=r["normf"], converged=r["converged"], newton_iters=r["newton_iters"])
 
     def helmholtz_step():
         """pair_isph.cpp:924-982: x = b = v^n (transposed view), computeHelmholtz, solveHelmholtz (dim right-hand sides)"""
@@ -264,6 +287,8 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
 
     if helm:
         device_step = helmholtz_step
+    if pbs:
+        device_step = pb_step
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,7 +316,8 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     ms_dev = e0.elapsed_time(e1) / steps
     spmv_ms, spmv_cnt = c.profile_spmv_get(); c.profile_spmv(False)
     launches = (c.launches - launches0) // steps
-    timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "compute" + solve_label, "precondCreate", "solve" + solve_label)}
+    timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "precondCreate", "solve" + solve_label) +
+              (("computeFPoissonBoltzmann", "computeJacobianPoissonBoltzmann") if pbs else ("compute" + solve_label,))}
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
     barrier()
@@ -332,7 +358,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=wname, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
-                            iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"],
+                            iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"], **({"newton_iters": st["newton_iters"]} if pbs else {}),
                             l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),
                 e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
                 gpu_launches=int(launches), clocks=clocks,
@@ -341,7 +367,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                               share_of_step=spmv_ms / steps / ms_dev,
                               note="per-launch time from CUDA events on the launching stream; at n_gpus > 1 it includes the NVLink import of the halo"),
                 breakdown_ms=timers, ms_per_iter=solve_ms / max(st["iters"], 1))
-    if w["prec"] == "point relaxation" and w["solver"] == "Block GMRES":
+    if w["prec"] == "point relaxation" and w["solver"] == "Block GMRES" and not pbs:
         kb = krylov_bytes_per_solve(nl, nnz, st["iters"], st.get("second_passes", st["iters"]))
         sg = kb / (solve_ms * 1e-3) / 1e9
         line["solve_roofline"] = dict(bound="hbm", what="whole GMRES(50)+Jacobi solve on one GPU of the job: SpMV + Gram-Schmidt sweeps + solution update (DESIGN.md §3), rank 0's rows",

@@ -8,6 +8,7 @@ GLOBAL problem: graph bit-exact, values <= 1e-12, iteration counts +-2, solution
   1. pressure Poisson, NullSpace, flexible GMRES(50) + Jacobi                       (BASELINE configs[1])
   2. the same system with block-Jacobi ILU(0), one open block per rank (= Ifpack overlap 0 on an MPI run)   (configs[3])
   3. velocity Helmholtz, 3 right-hand sides one after another, CG + Chebyshev(2)     (configs[2]; SpMM with a 3-vector import)
+  4. Poisson-Boltzmann Newton iteration (computeF / computeJacobian / GMRES + Jacobi Jacobian solves)      (configs[4])
 tests/test_gpu_multi.py wraps this for pytest when >= 2 GPUs are visible.
 """
 import importlib
@@ -62,7 +63,13 @@ def main():
     x3 = np.asfortranarray(np.zeros((nl, dim))); c.create_solution(x3, dim); c.set_matrix_is_singular(False); c.set_initial_solution(isph.INIT_ZERO)
     c.solver_param("Solver Type", "Block CG"); c.precond_param("Precond Type", "Chebyshev"); c.precond_param("chebyshev: degree", 2)
     st3 = c.solve(True, "Helmholtz")
-    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, Ah=Ah, bh=bh, x3=x3, st3=st3)
+    # 4. Poisson-Boltzmann: Newton iteration from psi = 0 with the manufactured source
+    s_ = np.sin(xw[:, 0]) * np.cos(xw[:, 1]); ex = (-2.0 * s_ - np.sinh(s_))[:nl].copy()
+    c.matrix_invalidate(); c.field_set(isph.F_EPS, 1.0 + 0.2 * np.cos(xw[:, 0])); c.field_set(isph.F_PSI0, 0.3 + 0.0 * s_); c.field_set(isph.F_PSI, 0.0 * s_)
+    c.create_solution(None, 1); c.create_load(None, 1); c.set_matrix_is_singular(False)
+    c.solver_param("Solver Type", "Block GMRES"); c.precond_param("Precond Type", "point relaxation")
+    st4 = c.pb_newton(extra_f=ex); psi4 = c.field_get(isph.F_PSI)[:nl].copy()
+    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
     allr = [None] * world
     dist.gather_object(mine, allr if rank == 0 else None, 0)
     ok = True
@@ -115,6 +122,24 @@ def main():
         its3 = allr[0]["st3"]["iters"]
         print(f"  Helmholtz CG+Chebyshev(2) x{dim}: values/b max err {worst3:.2e}; iters gpu {its3} vs oracle {its3o}; x rel diff {x3err:.2e}; converged {allr[0]['st3']['converged']}")
         ok = ok and worst3 <= 1e-12 and abs(its3 - its3o) <= 2 * dim and x3err <= 1e-7 and allr[0]["st3"]["converged"]
+        # 4. Poisson-Boltzmann Newton on the global problem, built from the oracle's pieces (same stopping rule)
+        sg = np.sin(xg[:, 0]) * np.cos(xg[:, 1]); exg = (-2.0 * sg - np.sinh(sg))[:n].copy()
+        o.set_field(O.F_EPS, 1.0 + 0.2 * np.cos(xg[:, 0])); o.set_field(O.F_PSI0, 0.3 + 0.0 * sg)
+        psi = np.zeros(len(xg)); nup = 0.0; lin = 0; kn = 0; prm4 = O.krylov_params(precond=O.PREC_JACOBI, row_gid=G["tag"][:n])
+        while True:
+            o.set_field(O.F_PSI, psi); fv = o.pb_residual(extra_f=exg); nf = np.linalg.norm(fv) / np.sqrt(n)
+            if (kn > 0 and nf <= 1e-8 and nup <= 1e-5) or kn >= 100:
+                break
+            o.invalidate_matrix() if kn == 0 else None
+            o.pb_jacobian(); Aj = o.matrix()
+            dxk, ik = O.krylov_solve(grp, colL, Aj, -fv, params=prm4); lin += ik["iters"]
+            psi[:n] += dxk; nup = np.linalg.norm(dxk) / np.sqrt(n); kn += 1
+        psid = np.zeros(n)
+        for d in allr:
+            psid[row_of_tag[d["tag"]]] = d["psi4"]
+        s4 = allr[0]["st4"]; p4err = np.linalg.norm(psid - psi[:n]) / np.linalg.norm(psi[:n])
+        print(f"  Poisson-Boltzmann Newton: newton its gpu {s4['newton_iters']} vs oracle {kn}; linear its {s4['linear_iters']} vs {lin}; psi rel diff {p4err:.2e}; ||F|| {s4['normf']:.1e}; converged {s4['converged']}")
+        ok = ok and s4["converged"] and s4["newton_iters"] == kn and abs(s4["linear_iters"] - lin) <= 2 * kn and p4err <= 1e-8
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
     c.close()
     flag = torch.tensor([1 if ok else 0]); dist.broadcast(flag, 0)
