@@ -20,8 +20,8 @@ KIND_FLUID, KIND_SOLID, KIND_BOUNDARY, KIND_BUFFER_DIRICHLET, KIND_BUFFER_NEUMAN
 NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
 WENDLAND, CUBIC, QUINTIC = 0, 1, 2
 INIT_RANDOM, INIT_ZERO, INIT_VALUE = 0, 1, 2
-F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP, F_PSI0 = range(15)
-FIELD_NCOMP = (1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1)
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP, F_PSI0, F_SIGMA, F_PHI = range(17)
+FIELD_NCOMP = (1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1, 1, 1)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -182,6 +182,12 @@ class Context:
     def ns_helmholtz(self, dt, theta, anti=True, morris_holmes=False, incremental_pressure=True, g=(0.0, 0.0, 0.0)):
         gg = np.asarray(g, dtype=np.float64)
         self.call("isph_ns_helmholtz", C.c_double(dt), C.c_double(theta), int(anti), int(morris_holmes), int(incremental_pressure), _d(gg))
+
+    def applied_electric_potential(self):
+        self.call("isph_applied_electric_potential")
+
+    def solute_transport(self, dt, theta, dcoeff):
+        self.call("isph_solute_transport", C.c_double(dt), C.c_double(theta), C.c_double(dcoeff))
 
     def pb_residual(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0, extra_f=None):
         f = np.zeros(self.nlocal); ex = None if extra_f is None else np.ascontiguousarray(extra_f, dtype=np.float64)

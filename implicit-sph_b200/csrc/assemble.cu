@@ -47,8 +47,9 @@ __device__ __forceinline__ double kern_dval(const PairTab *T, int ti, int tj, do
 }
 
 __device__ __forceinline__ double sph_op(bool anti, double fi, double fj) { return anti ? (fi + fj) : (fj - fi); }      // functor.h:9-20
-__device__ __forceinline__ bool fyes1(int m0, int ik) { return (ik & m0) != 0; }                                          // filter.h:49-51
-__device__ __forceinline__ bool fyes2(int m0, int m1, int ik, int jk) { return (ik & m0) && (jk & m1); }                  // filter.h:52-55
+// FilterBinary (filter.h:49-55) ; with ISPH_FILTER_MATCH in m0: FilterMatchBinary (filter.h:101-107), i == kind, j & mask
+__device__ __forceinline__ bool fyes1(int m0, int ik) { return (m0 & ISPH_FILTER_MATCH) ? ik == (m0 & 0xff) : (ik & m0) != 0; }
+__device__ __forceinline__ bool fyes2(int m0, int m1, int ik, int jk) { return fyes1(m0, ik) && (jk & m1); }
 
 struct Dev {                         // everything a row kernel needs, passed by value
   int n, dim; const long long *slice_off; const int *row_len, *diag_k, *atom, *col; double *val;
@@ -481,6 +482,33 @@ __global__ void k_pb_rows(Dev d, bool linearized, double kappasq, double gamma, 
   const int kd = d.diag_k[row]; if (kd >= 0) d.val[base + 32ll * kd] = diag;
 }
 
+// FunctorOuterAppliedElectricPotential::operator() + exitFor, functor_applied_electric_potential.h:64-96
+__global__ void k_aep_rows(Dev d, const double *phi, double *diagonal, double *b) {
+  ROW_SETUP(d)
+  (void)rlen;
+  const int kd = d.diag_k[row];
+  double diag = kd < 0 ? 0.0 : d.val[base + 32ll * kd];                          // ExtractDiagonalCopy in enterFor, :58
+  double bi = 0.0;
+  if (ikind == ISPH_KIND_SOLID) diag = 1.0;
+  else if (ikind == ISPH_KIND_BUFFER_NEUMANN || ikind == ISPH_KIND_BUFFER_DIRICHLET) { diag = 1.0; bi = phi[i]; }
+  b[i] = bi; diagonal[i] = diag;
+  if (kd >= 0) d.val[base + 32ll * kd] = diag;
+}
+// FunctorOuterSoluteTransport::operator() + exitFor, functor_solute_transport.h:100-134 (after enterFor's Scale(-theta))
+__global__ void k_solute_rows(Dev d, const double *w, double *diagonal, double *sld, double *b, int *bad_kind) {
+  ROW_SETUP(d)
+  (void)rlen;
+  const int kd = d.diag_k[row];
+  const double s = kd < 0 ? 0.0 : d.val[base + 32ll * kd];
+  sld[row] = s;
+  double diag = diagonal[i];
+  if (ikind == ISPH_KIND_BUFFER_DIRICHLET || ikind == ISPH_KIND_BUFFER_NEUMANN || ikind == ISPH_KIND_SOLID) diag = 1.0;
+  else if (ikind == ISPH_KIND_FLUID) { diag = 1.0 + s; b[i] += w[i]; }
+  else *bad_kind = 1;                                                             // :123-124 "Particle types are not supported"
+  diagonal[i] = diag;
+  if (kd >= 0) d.val[base + 32ll * kd] = diag;
+}
+
 // FunctorOuterPoissonBoltzmannF::operator() (functor_poisson_boltzmann_f.h:58-88) on top of the matrix-free corrected
 // Laplacian Corrected::FunctorOuterLaplacianHelper::operator() (functor_laplacian.h:67-277; scalar field, alpha = -1,
 // material = eps, filter (Fluid, All)).  The reference's Jacobian is NOT the exact derivative of this residual next to
@@ -618,7 +646,7 @@ static Dev make_dev(Ctx *c, bool need_graph = true) {
 #define LGRID(c) ceil_div((c)->inum, 128), 128, 0, (c)->stream
 
 void forward_comm(Ctx *c, int field) {
-  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
+  static const int nc[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1, 1, 1};
   if (c->nghost == 0) return;
   if (c->nranks > 1) halo_forward_field(c, field, nc[field]);      // ghosts owned by other ranks
   k_forward<<<ceil_div(c->nghost, 256), 256, 0, c->stream>>>(c->col_of_atom.p, c->nlocal, c->nall, nc[field], c->field[field].p); ++c->launches;
@@ -745,6 +773,34 @@ void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, d
   }
   k_pb_rows<<<GRID(c)>>>(d, linearized, kappasq, gamma, c->field[ISPH_F_PSI].p, c->A.diagonal.p, c->A.sld.p); ++c->launches;
   c->toc("computeJacobianPoissonBoltzmann");
+}
+
+void applied_electric_potential(Ctx *c) {
+  Dev d = make_dev(c);
+  ISPH_REQUIRE(c->A.is_filled == 0, "FunctorAppliedElectricPotential:: A is already filled");     // functor_applied_electric_potential.h:43-44
+  ISPH_REQUIRE(c->b_nvec == 1 && c->bs.p, "isph_applied_electric_potential: create the load vector first");
+  c->tic("computeAppliedElectricPotential");
+  assemble_laplacian(c, -1.0, c->field[ISPH_F_SIGMA].p, false, false, ISPH_KIND_FLUID | ISPH_FILTER_MATCH, ISPH_KIND_FLUID);   // :49-57
+  k_aep_rows<<<GRID(c)>>>(d, c->field[ISPH_F_PHI].p, c->A.diagonal.p, c->bs.p); ++c->launches;
+  c->toc("computeAppliedElectricPotential");
+}
+
+void solute_transport(Ctx *c, double dt, double theta, double dcoeff) {
+  Dev d = make_dev(c);
+  ISPH_REQUIRE(c->A.is_filled == 0, "FunctorSoluteTransport:: A is already filled");              // functor_solute_transport.h:56-57
+  ISPH_REQUIRE(c->b_nvec == 1 && c->bs.p, "isph_solute_transport: the load vector must hold the concentration");
+  c->tic("computeSoluteTransportSpecies");
+  c->wk.ensure((size_t)c->nall + (size_t)c->ld * 3); c->flag.ensure(16);
+  double *w = c->wk.p + c->nall;
+  assemble_laplacian(c, dt * dcoeff, nullptr, false, false, ISPH_KIND_FLUID | ISPH_FILTER_MATCH, ISPH_KIND_FLUID - ISPH_KIND_BUFFER_NEUMANN);   // :62-70
+  spmv(c, c->bs.p, w, 1, c->ld, c->ld);                                                          // :88     w = A c^n
+  k_scale_vec<<<ceil_div(c->nlocal, 256), 256, 0, c->stream>>>(w, 1.0 - theta, c->nlocal, c->ld, 1); ++c->launches;              // :89
+  matrix_scale(c, -theta);                                                                       // :92
+  CUDA_CHECK(cudaMemsetAsync(c->flag.p + 7, 0, sizeof(int), c->stream));
+  k_solute_rows<<<GRID(c)>>>(d, w, c->A.diagonal.p, c->A.sld.p, c->bs.p, c->flag.p + 7); ++c->launches;
+  int bad = 0; CUDA_CHECK(cudaMemcpyAsync(&bad, c->flag.p + 7, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->toc("computeSoluteTransportSpecies");
+  ISPH_REQUIRE(!bad, "FunctorSoluteTransport:: Particle types are not supported");
 }
 
 // PairISPH_Corrected::computeF, pair_isph_corrected.cpp:438-485: psi is communicated to the ghosts, then the functor runs

@@ -19,7 +19,7 @@ void Ctx::toc(const char *name) {      // no host synchronisation here: the elap
   cudaEventRecord(t.b, stream); t.open = false; t.pending = true;
 }
 
-static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
+static const int FIELD_NC[ISPH_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1, 1, 1};
 
 static void ensure_fields(Ctx *c) {
   for (int f = 0; f < ISPH_F_COUNT; ++f) {
@@ -254,6 +254,8 @@ int isph_assemble_gradient_dot(isph_ctx *ctx, double alpha, int vf, int f0, int 
 int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int mh) { API_BEGIN(ctx) ns_poisson(c, dt, anti != 0, singular, mh != 0); API_END }
 int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int mh, int incp, const double *g) { API_BEGIN(ctx) ns_helmholtz(c, dt, theta, anti != 0, mh != 0, incp != 0, g); API_END }
 int isph_pb_jacobian(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma) { API_BEGIN(ctx) pb_jacobian(c, mh != 0, lin != 0, ezcb, psiref, gamma); API_END }
+int isph_applied_electric_potential(isph_ctx *ctx) { API_BEGIN(ctx) applied_electric_potential(c); API_END }
+int isph_solute_transport(isph_ctx *ctx, double dt, double theta, double dcoeff) { API_BEGIN(ctx) solute_transport(c, dt, theta, dcoeff); API_END }
 // extra source (functor_poisson_boltzmann_extra_f.h) staged on the device, indexed by owned atom
 static const double *stage_extra(Ctx *c, const double *extra_f) {
   if (!extra_f) return nullptr;

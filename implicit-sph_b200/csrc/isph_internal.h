@@ -159,6 +159,8 @@ void ns_poisson(Ctx *c, double dt, bool anti, int singular, bool mh);
 void ns_helmholtz(Ctx *c, double dt, double theta, bool anti, bool mh, bool incp, const double *g);
 void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma);
 void ns_correct(Ctx *c, double dt, bool anti, bool incp, const double *dp_owned_host);
+void applied_electric_potential(Ctx *c);
+void solute_transport(Ctx *c, double dt, double theta, double dcoeff);
 void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f);
 void forward_comm(Ctx *c, int field);
 

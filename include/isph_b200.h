@@ -39,7 +39,8 @@ enum { ISPH_F_VFRAC = 0,   /* 1 */ ISPH_F_GC = 1,       /* 9: dim x dim column-m
        ISPH_F_DENSITY = 5, ISPH_F_VISCOSITY = 6, ISPH_F_PRESSURE = 7,
        ISPH_F_VELOCITY = 8,/* 3 */ ISPH_F_VSTAR = 9,    /* 3 */ ISPH_F_FORCE = 10, /* 3 */
        ISPH_F_EPS = 11, ISPH_F_PSI = 12, ISPH_F_DP = 13 /* 1: pressure increment dp, owned + ghost */,
-       ISPH_F_PSI0 = 14 /* 1: prescribed (normalised) potential of solid / boundary particles, atom->psi0 */, ISPH_F_COUNT = 15 };
+       ISPH_F_PSI0 = 14 /* 1: prescribed (normalised) potential of solid / boundary particles, atom->psi0 */, 
+       ISPH_F_SIGMA = 15 /* 1: electric conductivity, atom->sigma */, ISPH_F_PHI = 16 /* 1: applied electric potential, atom->phi */, ISPH_F_COUNT = 17 };
 
 /* ---- context ------------------------------------------------------------------------------------------------
  * replaces: SolverLin(MPI_Comm&) solver_lin.h:28, PrecondWrapper(MPI_Comm) precond.h:26 (one communicator per
@@ -103,6 +104,7 @@ int isph_matrix_invalidate(isph_ctx *ctx);                                 /* A.
 int isph_graph_invalidate(isph_ctx *ctx);
 /* Corrected::FunctorOuterLaplacianMatrix<Pair,Anti>[_MorrisHolmes], functor_laplacian_matrix.h:56-328, including the
  * PutScalar(0.0) that precedes it at every call site.  material_field < 0: material == 1. */
+#define ISPH_FILTER_MATCH 0x100   /* OR into filter_i: FilterMatchBinary (filter.h:84-108): i must EQUAL the kind, j & mask */
 int isph_assemble_laplacian(isph_ctx *ctx, double alpha, int material_field, int anti, int morris_holmes,
                             int filter_i, int filter_j);
 /* FunctorOuterGradientDotOperatorMatrix, functor_gradient_dot_operator_matrix.h:36-79 (SumInto) */
@@ -122,6 +124,16 @@ int isph_pb_jacobian(isph_ctx *ctx, int morris_holmes, int linearized, double ez
  * vstar -= dt/rho grad(dp), then forward_comm(Vstar)), correctPressure (functor_correct_pressure.h:29-43).  dp = the device
  * solution of the last solve, or dp_owned[nlocal] when given.  Results: fields ISPH_F_DP, ISPH_F_VSTAR, ISPH_F_PRESSURE. */
 int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incremental_pressure, const double *dp_owned);
+/* FunctorOuterAppliedElectricPotential (functor_applied_electric_potential.h:34-96; call site pair_isph_corrected.cpp:598-617,
+ * pair_isph.cpp:628-663): A = Laplacian(alpha = -1, material = sigma, FilterMatchBinary(Fluid, Fluid)); A.diagonal = diag(A);
+ * b = 0; Solid rows: diagonal 1; buffer rows: diagonal 1, b = phi; ReplaceDiagonalValues.  Fields ISPH_F_SIGMA, ISPH_F_PHI;
+ * b = the load vector (one column). */
+int isph_applied_electric_potential(isph_ctx *ctx);
+/* FunctorOuterSoluteTransport (functor_solute_transport.h:47-134; call site pair_isph_corrected.cpp:843-861, pair_isph.cpp:811-835):
+ * A = Laplacian(alpha = dt * dcoeff, FilterMatchBinary(Fluid, Fluid - BufferNeumann)); w = (1 - theta) A c^n; A *= -theta;
+ * scaled_laplace_diagonal = diag(A); Fluid rows: diagonal 1 + sld, b += w; Solid / buffer rows: diagonal 1.  The load vector
+ * (one column) holds the concentration c^n on entry and the right-hand side on return. */
+int isph_solute_transport(isph_ctx *ctx, double dt, double theta, double dcoeff);
 /* PairISPH_Corrected::computeF (pair_isph_corrected.cpp:438-485): forward_comm(psi), then FunctorOuterPoissonBoltzmannF
  * (functor_poisson_boltzmann_f.h:58-88; fields ISPH_F_PSI, ISPH_F_PSI0, ISPH_F_EPS) on the matrix-free corrected Laplacian
  * (functor_laplacian.h:67-277), plus the caller-evaluated source of FunctorOuterPoissonBoltzmannExtraF

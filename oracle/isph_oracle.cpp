@@ -62,8 +62,9 @@ struct KernelFn {                          // kernel.h:9-24 ; kernel_{wendland,c
 };
 
 inline double sph_op(bool anti, double fi, double fj) { return anti ? (fi + fj) : (fj - fi); }   // functor.h:9-20
-inline bool fyes1(int m0, int ik) { return (ik & m0) != 0; }                                       // filter.h:49-51
-inline bool fyes2(int m0, int m1, int ik, int jk) { return (ik & m0) && (jk & m1); }               // filter.h:52-55
+// FilterBinary, filter.h:49-55 ; with ORC_FILTER_MATCH in m0: FilterMatchBinary, filter.h:101-107 (i == kind, j & mask)
+inline bool fyes1(int m0, int ik) { return (m0 & ORC_FILTER_MATCH) ? ik == (m0 & 0xff) : (ik & m0) != 0; }
+inline bool fyes2(int m0, int m1, int ik, int jk) { return fyes1(m0, ik) && (jk & m1); }
 
 }  // namespace
 
@@ -112,7 +113,7 @@ extern "C" {
 const char *orc_name(void) { return "C++ restatement (oracle port)"; }
 
 int orc_field_ncomp(int fl) {
-  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
+  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1, 1, 1};
   return (fl >= 0 && fl < ORC_F_COUNT) ? nc[fl] : -1;
 }
 
@@ -597,6 +598,45 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
     }
   }
   replace_diag(q, q->diagonal);                                                                       // :105
+  return 0;
+}
+
+// FunctorOuterAppliedElectricPotential, functor_applied_electric_potential.h:34-96
+int orc_applied_electric_potential(orc_problem *q, double *b) {
+  if (!q->have_graph || q->is_filled) return -1;
+  std::fill(q->val.begin(), q->val.end(), 0.0);                                                       // :47
+  laplacian_matrix(q, -1.0, q->f[ORC_F_SIGMA].data(), false, false, ORC_FLUID | ORC_FILTER_MATCH, ORC_FLUID);   // :49-57
+  extract_diag(q, q->diagonal);                                                                       // :58
+  const double *phi = q->f[ORC_F_PHI].data();
+  for (int ii = 0; ii < q->inum; ++ii) {                                                              // :64-88
+    const int i = q->ilist[ii], ikind = q->kind(q->type[i]);
+    b[i] = 0.0;
+    if (ikind == ORC_SOLID) q->diagonal[i] = 1.0;
+    else if (ikind == ORC_BUFFER_NEUMANN || ikind == ORC_BUFFER_DIRICHLET) { q->diagonal[i] = 1.0; b[i] = phi[i]; }
+  }
+  replace_diag(q, q->diagonal);                                                                       // :94
+  return 0;
+}
+
+static void spmv_rows(const Q *q, const double *x, double *y, int nvec);
+
+// FunctorOuterSoluteTransport, functor_solute_transport.h:47-134
+int orc_solute_transport(orc_problem *q, double dt, double theta, double dcoeff, double *b) {
+  if (!q->have_graph || q->is_filled) return -1;
+  std::fill(q->val.begin(), q->val.end(), 0.0);                                                       // :60
+  laplacian_matrix(q, dt * dcoeff, nullptr, false, false, ORC_FLUID | ORC_FILTER_MATCH, ORC_FLUID - ORC_BUFFER_NEUMANN);   // :62-70
+  std::vector<double> w(q->nlocal, 0.0);
+  spmv_rows(q, b, w.data(), 1);                                                                       // :88
+  for (auto &v : w) v *= (1.0 - theta);                                                               // :89
+  for (auto &v : q->val) v *= -theta;                                                                 // :92
+  extract_diag(q, q->sld);                                                                            // :93
+  for (int ii = 0; ii < q->inum; ++ii) {                                                              // :100-126
+    const int i = q->ilist[ii], ikind = q->kind(q->type[i]);
+    if (ikind == ORC_BUFFER_DIRICHLET || ikind == ORC_BUFFER_NEUMANN || ikind == ORC_SOLID) q->diagonal[i] = 1.0;
+    else if (ikind == ORC_FLUID) { q->diagonal[i] = 1.0 + q->sld[i]; b[i] += w[i]; }
+    else return -1;
+  }
+  replace_diag(q, q->diagonal);                                                                       // :132
   return 0;
 }
 

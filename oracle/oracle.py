@@ -19,7 +19,7 @@ REF_SO = os.path.join(HERE, "_ref", "libisph_ref.so")
 FLUID, SOLID, BOUNDARY, BUFFER_DIRICHLET, BUFFER_NEUMANN, ALL = 99, 12, 16, 32, 64, 127
 NOT_SINGULAR, NULLSPACE, PINZERO, DOUBLEDIAG = 0, 1, 2, 3
 WENDLAND, CUBIC, QUINTIC = 0, 1, 2
-F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP, F_PSI0 = range(15)
+F_VFRAC, F_GC, F_LC, F_NORMAL, F_PND, F_DENSITY, F_VISCOSITY, F_PRESSURE, F_VELOCITY, F_VSTAR, F_FORCE, F_EPS, F_PSI, F_DP, F_PSI0, F_SIGMA, F_PHI = range(17)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -70,6 +70,8 @@ def _load(kind):
     L.orc_ns_helmholtz.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]
     L.orc_pb_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.orc_ns_correct.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp]
+    L.orc_applied_electric_potential.argtypes = [C.c_void_p, _dp]
+    L.orc_solute_transport.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp]
     L.orc_pb_residual.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
     L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
     L.orc_diag_get.argtypes = [C.c_void_p, _dp, _dp]
@@ -152,6 +154,12 @@ class Oracle:
 
     def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
         self._ck(self.L.orc_pb_jacobian(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma), "pb_jacobian")
+
+    def applied_electric_potential(self):
+        b = np.zeros(self.nlocal); self._ck(self.L.orc_applied_electric_potential(self.p, _d(b)), "applied_electric_potential"); return b
+
+    def solute_transport(self, dt, theta, dcoeff, conc):
+        b = np.array(conc, dtype=np.float64)[:self.nlocal].copy(); self._ck(self.L.orc_solute_transport(self.p, dt, theta, dcoeff, _d(b)), "solute_transport"); return b
 
     def pb_residual(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0, extra_f=None):
         f = np.zeros(self.nlocal); ex = None if extra_f is None else np.ascontiguousarray(extra_f, dtype=np.float64)

@@ -15,6 +15,7 @@ extern "C" {
 #endif
 
 /* particle kinds, pair_isph.h:113-123 */
+#define ORC_FILTER_MATCH 0x100   /* FilterMatchBinary, filter.h:84-108 */
 enum { ORC_FLUID = 99, ORC_SOLID = 12, ORC_BOUNDARY = 16, ORC_BUFFER_DIRICHLET = 32, ORC_BUFFER_NEUMANN = 64, ORC_ALL = 127 };
 /* SingularPoisson, pair_isph.h:133-137 */
 enum { ORC_NOT_SINGULAR = 0, ORC_NULLSPACE = 1, ORC_PINZERO = 2, ORC_DOUBLEDIAG = 3 };
@@ -26,7 +27,7 @@ enum { ORC_F_VFRAC = 0,   /* 1  */  ORC_F_GC = 1,       /* 9: dim x dim column-m
        ORC_F_DENSITY = 5, ORC_F_VISCOSITY = 6, ORC_F_PRESSURE = 7,
        ORC_F_VELOCITY = 8,/* 3  */  ORC_F_VSTAR = 9,    /* 3 */  ORC_F_FORCE = 10, /* 3 */
        ORC_F_EPS = 11,    ORC_F_PSI = 12, ORC_F_DP = 13 /* 1: pressure increment, owned + ghost */,
-       ORC_F_PSI0 = 14, /* 1: atom->psi0 */ ORC_F_COUNT = 15 };
+       ORC_F_PSI0 = 14, /* 1: atom->psi0 */ ORC_F_SIGMA = 15, ORC_F_PHI = 16, ORC_F_COUNT = 17 };
 
 typedef struct orc_problem orc_problem;
 
@@ -57,6 +58,10 @@ int orc_ns_helmholtz(orc_problem *p, double dt, double theta, int anti, int morr
                      int incremental_pressure, const double *g, double *b);
 /* functor_poisson_boltzmann_jacobian.h:35-107 (A.is_filled kept between calls) */
 int orc_pb_jacobian(orc_problem *p, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+/* functor_applied_electric_potential.h:34-96 (sigma, phi from the fields); b[nlocal] out */
+int orc_applied_electric_potential(orc_problem *p, double *b);
+/* functor_solute_transport.h:47-134; b[nlocal]: in c^n, out rhs */
+int orc_solute_transport(orc_problem *p, double dt, double theta, double dcoeff, double *b);
 /* functor_poisson_boltzmann_f.h:58-88 (psi, psi0, eps from the fields) + functor_poisson_boltzmann_extra_f.h:76-90 with the
  * caller's precomputed source extra_f[nlocal] (NULL: none); psi is forward-communicated first (pair_isph_corrected.cpp:446-450);
  * f[nlocal] out */

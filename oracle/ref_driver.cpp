@@ -44,6 +44,8 @@ namespace LAMMPS_NS { Utils util; }
 #include "functor_incomp_navier_stokes_poisson.h"
 #include "functor_poisson_boltzmann_jacobian.h"
 #include "functor_poisson_boltzmann_f.h"
+#include "functor_applied_electric_potential.h"
+#include "functor_solute_transport.h"
 #include "functor_correct_velocity.h"
 #include "functor_correct_pressure.h"
 
@@ -54,7 +56,7 @@ using namespace LAMMPS_NS;
 namespace {
 
 struct MockPair;
-struct MockAtom { double *vfrac, **x, *density, *viscosity, *pressure, **v, **f, *eps, *psi, *psi0; int *type, *tag, *part; int nlocal, nghost; };
+struct MockAtom { double *vfrac, **x, *density, *viscosity, *pressure, **v, **f, *eps, *psi, *psi0, *sigma, *phi; int *type, *tag, *part; int nlocal, nghost; };
 struct MockList { int inum, *ilist, *numneigh, **firstneigh; };
 struct MockDomain { int dimension; };
 struct MockError { void all(const char *, int, const char *msg) { throw std::runtime_error(msg); } };
@@ -124,7 +126,7 @@ typedef MockPair P;
 struct orc_problem {
   int dim, nlocal, nghost, nall, ntypes;
   Arr2<double> x, v, f, vstar, normal, Gc, Lc, cutsq, h;
-  std::vector<double> vfrac, density, viscosity, pressure, eps, psi, psi0, pnd, work, work3, dpv;
+  std::vector<double> vfrac, density, viscosity, pressure, eps, psi, psi0, sigma, phi, pnd, work, work3, dpv;
   std::vector<int> type, tag, ilist, numneigh, neigh; std::vector<int *> firstneigh;
   MockAtom atom; MockList list; MockDomain domain; MockError error; MockComm comm; MockPair pair;
   KernelFunction *kernel;
@@ -140,7 +142,7 @@ extern "C" {
 const char *orc_name(void) { return "reference functors (IMPLICIT-SPH/functor_*.h) + stand-in Epetra"; }
 
 int orc_field_ncomp(int f) {
-  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1};
+  static const int nc[ORC_F_COUNT] = {1, 9, 6, 3, 1, 1, 1, 1, 3, 3, 3, 1, 1, 1, 1, 1, 1};
   return (f >= 0 && f < ORC_F_COUNT) ? nc[f] : -1;
 }
 
@@ -155,7 +157,7 @@ orc_problem *orc_create(int dim, int nlocal, int nghost, const double *x, const 
   q->Gc.init(nall, 9); q->Lc.init(nall, 6);
   memcpy(q->x.d.data(), x, sizeof(double) * 3 * nall);
   q->vfrac.assign(nall, 0.0); q->density.assign(nall, 1.0); q->viscosity.assign(nall, 0.0); q->pressure.assign(nall, 0.0);
-  q->eps.assign(nall, 1.0); q->psi.assign(nall, 0.0); q->psi0.assign(nall, 0.0); q->dpv.assign(nall, 0.0); q->pnd.assign(nall, 0.0); q->work.assign(nall, 0.0); q->work3.assign((size_t)nall * 3, 0.0);
+  q->eps.assign(nall, 1.0); q->psi.assign(nall, 0.0); q->psi0.assign(nall, 0.0); q->sigma.assign(nall, 1.0); q->phi.assign(nall, 0.0); q->dpv.assign(nall, 0.0); q->pnd.assign(nall, 0.0); q->work.assign(nall, 0.0); q->work3.assign((size_t)nall * 3, 0.0);
   q->type.assign(type, type + nall); q->tag.assign(tag, tag + nall);
   q->ilist.assign(ilist, ilist + inum);
   q->neigh.assign(neigh, neigh + noff[inum]);
@@ -164,7 +166,7 @@ orc_problem *orc_create(int dim, int nlocal, int nghost, const double *x, const 
 
   MockPair &p = q->pair;
   q->atom = MockAtom{q->vfrac.data(), q->x.ptr(), q->density.data(), q->viscosity.data(), q->pressure.data(), q->v.ptr(), q->f.ptr(),
-                     q->eps.data(), q->psi.data(), q->psi0.data(), q->type.data(), q->tag.data(), nullptr, nlocal, nghost};
+                     q->eps.data(), q->psi.data(), q->psi0.data(), q->sigma.data(), q->phi.data(), q->type.data(), q->tag.data(), nullptr, nlocal, nghost};
   q->list = MockList{inum, q->ilist.data(), q->numneigh.data(), q->firstneigh.data()};
   q->domain.dimension = dim; q->comm.me = 0; q->comm.owner = &p;
   p.atom = &q->atom; p.list = &q->list; p.domain = &q->domain; p.error = &q->error; p.comm = &q->comm;
@@ -208,7 +210,7 @@ static double *field_ptr(orc_problem *q, int f) {
   case ORC_F_VFRAC: return q->vfrac.data(); case ORC_F_GC: return q->Gc.d.data(); case ORC_F_LC: return q->Lc.d.data();
   case ORC_F_NORMAL: return q->normal.d.data(); case ORC_F_PND: return q->pnd.data(); case ORC_F_DENSITY: return q->density.data();
   case ORC_F_VISCOSITY: return q->viscosity.data(); case ORC_F_PRESSURE: return q->pressure.data(); case ORC_F_VELOCITY: return q->v.d.data();
-  case ORC_F_VSTAR: return q->vstar.d.data(); case ORC_F_FORCE: return q->f.d.data(); case ORC_F_EPS: return q->eps.data(); case ORC_F_PSI: return q->psi.data(); case ORC_F_DP: return q->dpv.data(); case ORC_F_PSI0: return q->psi0.data();
+  case ORC_F_VSTAR: return q->vstar.d.data(); case ORC_F_FORCE: return q->f.d.data(); case ORC_F_EPS: return q->eps.data(); case ORC_F_PSI: return q->psi.data(); case ORC_F_DP: return q->dpv.data(); case ORC_F_PSI0: return q->psi0.data(); case ORC_F_SIGMA: return q->sigma.data(); case ORC_F_PHI: return q->phi.data();
   }
   return nullptr;
 }
@@ -296,6 +298,24 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
     // bindings: pair_isph_corrected.cpp:110-115 ; call :489-523
     if (!mh) { FunctorOuterPoissonBoltzmannJacobian<P, FunctorOuterLaplacianMatrixSymmetric> f(&p, p.atom->psi, p.atom->eps); PairFor(f, f.getNumberOfWork()); }
     else { FunctorOuterPoissonBoltzmannJacobian<P, FunctorOuterLaplacianMatrixSymmetric_MorrisHolmes> f(&p, p.atom->psi, p.atom->eps); PairFor(f, f.getNumberOfWork()); }
+  })
+}
+
+int orc_applied_electric_potential(orc_problem *q, double *b) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    // binding: pair_isph_corrected.cpp:142-144 ; call :604-611 (normal is passed but unused by the functor)
+    FunctorOuterAppliedElectricPotential<P, FunctorOuterLaplacianMatrixSymmetric> f(&p, p.atom->sigma, p.atom->phi, p.normal, b);
+    PairFor(f, f.getNumberOfWork());
+  })
+}
+int orc_solute_transport(orc_problem *q, double dt, double theta, double dcoeff, double *b) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    std::fill(q->work.begin(), q->work.end(), 0.0);                                // clearCommArray(WorkScalar), pair_isph_corrected.cpp:850
+    // binding: pair_isph_corrected.cpp:136-139 ; call :852-857
+    FunctorOuterSoluteTransport<P, FunctorOuterLaplacianMatrixSymmetric, FunctorOuterGradientOperator> f(&p, p.atom->v, false, dt, theta, dcoeff, b, q->work.data());
+    PairFor(f, f.getNumberOfWork());
   })
 }
 

@@ -14,6 +14,7 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     o.set_field(O.F_DENSITY, F["density"]); o.set_field(O.F_VISCOSITY, F["viscosity"]); o.set_field(O.F_PRESSURE, F["pressure"])
     o.set_field(O.F_VSTAR, F["velocity"]); o.set_field(O.F_VELOCITY, F["velocity"]); o.set_field(O.F_FORCE, F["force"])
     o.set_field(O.F_EPS, F["eps"]); o.set_field(O.F_PSI, F["psi"]); o.set_field(O.F_PSI0, F["psi0"])
+    o.set_field(O.F_SIGMA, F["sigma"]); o.set_field(O.F_PHI, F["phi"])
     o.compute_pre(normals=cs["has_solid"])
     out = dict(vfrac=o.get_field(O.F_VFRAC), gc=o.get_field(O.F_GC), lc=o.get_field(O.F_LC))
     if cs["has_solid"]:
@@ -24,6 +25,8 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     out["diag_poisson"], out["sld_poisson"] = o.diagonals(); o.invalidate_matrix()
     b0 = np.asfortranarray(F["velocity"][:nl, :dim])
     out["b_helmholtz"] = o.ns_helmholtz(cs["dt"], cs["theta"], b0, anti=anti, morris_holmes=mh); out["A_helmholtz"] = o.matrix(); o.invalidate_matrix()
+    out["b_aep"] = o.applied_electric_potential(); out["A_aep"] = o.matrix(); o.invalidate_matrix()      # applied electric potential,
+    out["b_solute"] = o.solute_transport(cs["dt"], cs["theta"], 0.7, F["conc"]); out["A_solute"] = o.matrix(); o.invalidate_matrix()   # solute transport
     out["pb_f"] = o.pb_residual(morris_holmes=mh, extra_f=F["pb_extra"][:nl])                     # PB residual: before the Jacobian (no matrix needed)
     out["pb_f_lin"] = o.pb_residual(morris_holmes=mh, linearized=True, gamma=0.1)
     o.pb_jacobian(morris_holmes=mh); out["A_pb"] = o.matrix()
@@ -42,6 +45,7 @@ def cuda_context(P, F, device=0):
     c.field_set(isph.F_DENSITY, F["density"]); c.field_set(isph.F_VISCOSITY, F["viscosity"]); c.field_set(isph.F_PRESSURE, F["pressure"])
     c.field_set(isph.F_VSTAR, F["velocity"]); c.field_set(isph.F_VELOCITY, F["velocity"]); c.field_set(isph.F_FORCE, F["force"])
     c.field_set(isph.F_EPS, F["eps"]); c.field_set(isph.F_PSI, F["psi"]); c.field_set(isph.F_PSI0, F["psi0"])
+    c.field_set(isph.F_SIGMA, F["sigma"]); c.field_set(isph.F_PHI, F["phi"])
     return c
 
 
@@ -61,6 +65,9 @@ def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
     c.create_load(None, dim); c.load_set(np.asfortranarray(F["velocity"][:nl, :dim]))
     c.ns_helmholtz(cs["dt"], cs["theta"], anti=anti, morris_holmes=mh)
     out["b_helmholtz"] = c.load_get(dim); out["A_helmholtz"] = c.matrix_get(); c.matrix_invalidate()
+    c.create_load(None, 1); c.applied_electric_potential(); out["b_aep"] = c.load_get(1)[:, 0]; out["A_aep"] = c.matrix_get(); c.matrix_invalidate()
+    c.create_load(None, 1); c.load_set(F["conc"][:nl]); c.solute_transport(cs["dt"], cs["theta"], 0.7)
+    out["b_solute"] = c.load_get(1)[:, 0]; out["A_solute"] = c.matrix_get(); c.matrix_invalidate()
     out["pb_f"] = c.pb_residual(morris_holmes=mh, extra_f=F["pb_extra"][:nl])
     out["pb_f_lin"] = c.pb_residual(morris_holmes=mh, linearized=True, gamma=0.1)
     c.pb_jacobian(morris_holmes=mh); out["A_pb"] = c.matrix_get()

@@ -20,6 +20,7 @@ CASES = {
     "solid3d":     dict(dim=3, N=10, jitter=0.03, rs2=12, kinds=(0, FLUID, SOLID), slab=3),
     "quintic2d":   dict(dim=2, N=20, jitter=0.04, rs2=12, kinds=(0, FLUID), kernel=2),
     "cubic3d":     dict(dim=3, N=9,  jitter=0.03, rs2=12, kinds=(0, FLUID), kernel=1),
+    "buffer2d":    dict(dim=2, N=24, jitter=0.04, rs2=12, kinds=(0, FLUID, 32), slab=3),                 # type 2 = BufferDirichlet rows (applied potential / solute transport branches)
     "tgv128":      dict(dim=2, N=128, jitter=0.0, rs2=9,  kinds=(0, FLUID), origin=0.5),     # BASELINE C1 particle set
 }
 
@@ -42,10 +43,14 @@ def make_case(name):
     F["force"] = 0.01 * np.stack([np.cos(xw[:, 0]), np.sin(xw[:, 1]), np.zeros(len(xw))], axis=1)
     F["eps"] = 1.0 + 0.2 * np.cos(xw[:, 0])
     F["psi"] = np.sin(xw[:, 0]) * np.cos(xw[:, 1])
+    F["sigma"] = 1.0 + 0.3 * np.sin(xw[:, 0])                                     # electric conductivity
+    F["phi"] = np.cos(xw[:, 1]) + 0.1 * np.sin(2 * xw[:, 0])                      # applied potential (buffer rows: Dirichlet data)
+    F["conc"] = 0.5 + 0.2 * np.sin(xw[:, 0]) * np.cos(xw[:, 1])                   # solute concentration c^n
     F["psi0"] = 0.3 + 0.1 * np.cos(xw[:, 0])                                     # prescribed potential of solid / boundary particles
     F["pb_extra"] = -2.0 * np.sin(xw[:, 0]) * np.cos(xw[:, 1]) - np.sinh(np.sin(xw[:, 0]) * np.cos(xw[:, 1]))   # poisson-boltzmann-harmonic.xml:14-30
-    P["case"] = dict(name=name, kinds=c["kinds"], kernel=c.get("kernel", 0), has_solid=bool(slab), dt=0.05 * dx / 0.1, theta=0.5,
-                     h_min=(0.8 * 1.5 * dx) if slab else None)
+    has_solid = bool(slab) and SOLID in c["kinds"]
+    P["case"] = dict(name=name, kinds=c["kinds"], kernel=c.get("kernel", 0), has_solid=has_solid, dt=0.05 * dx / 0.1, theta=0.5,
+                     h_min=(0.8 * 1.5 * dx) if has_solid else None)
     return P, F
 
 

@@ -55,6 +55,6 @@ def test_field_tables_agree_with_the_header(isph):
     import re
     txt = open(isph.HEADER).read()
     count = int(re.search(r"ISPH_F_COUNT\s*=\s*(\d+)", txt).group(1))
-    assert len(isph.FIELD_NCOMP) == count == isph.F_PSI0 + 1
+    assert len(isph.FIELD_NCOMP) == count == isph.F_PHI + 1
     orc = open(os.path.join(os.path.dirname(isph.HERE), "oracle", "oracle_api.h")).read()
     assert int(re.search(r"ORC_F_COUNT\s*=\s*(\d+)", orc).group(1)) == count

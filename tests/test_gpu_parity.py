@@ -21,9 +21,10 @@ def _compare(a, b, has_solid):
     assert scaled_err(a["lc"][:nl], b["lc"][:nl]) <= 1e-11          # 6x6 pivoted LU per particle: conditioning, not op order
     if has_solid:
         assert scaled_err(a["normal"], b["normal"]) <= 1e-11 and relerr(a["pnd"], b["pnd"]) <= VAL_TOL
-    for k in ("A_poisson", "A_helmholtz", "A_pb", "A_pb2"):
+    for k in ("A_poisson", "A_helmholtz", "A_pb", "A_pb2", "A_aep", "A_solute"):
         e = relerr(a[k], b[k])
-        assert e <= (VAL_TOL if k == "A_poisson" or k == "A_helmholtz" else 1e-10), (k, e)
+        assert e <= (1e-10 if k in ("A_pb", "A_pb2") else VAL_TOL), (k, e)
+    assert scaled_err(a["b_aep"], b["b_aep"]) <= VAL_TOL and scaled_err(a["b_solute"], b["b_solute"]) <= VAL_TOL
     assert scaled_err(a["b_poisson"], b["b_poisson"]) <= VAL_TOL
     assert scaled_err(a["b_helmholtz"], b["b_helmholtz"]) <= VAL_TOL
     assert relerr(a["diag_poisson"], b["diag_poisson"]) <= VAL_TOL
@@ -45,7 +46,7 @@ def test_assembly_parity_fluid(name, anti):
 
 
 @pytest.mark.parametrize("name,anti,singular,mh", [("solid2d", False, 1, True), ("solid2d", True, 0, True), ("solid3d", False, 2, False),
-                                                   ("solid3d", True, 1, True), ("jitter2d", True, 3, False)])
+                                                   ("solid3d", True, 1, True), ("jitter2d", True, 3, False), ("buffer2d", False, 1, False)])
 def test_assembly_parity_boundaries(name, anti, singular, mh):
     import harness
     P, F = make_case(name)
