@@ -81,7 +81,7 @@ struct Halo {
   int nhalo = 0, nsend = 0;
   std::vector<int> recv_count, recv_off, send_count, send_off;
   DevBuf<int> send_idx, itmp, itmp2; DevBuf<long long> owner_tab; DevBuf<double> sendbuf, fieldbuf;
-  // fused halo + SpMV
+  // device-resident exchange plan (halo kernels, push from the producer)
   DevBuf<HaloDev> d_plan; bool plan_ok = false;
   DevBuf<int> row_sp, row_sd, row_cur; DevBuf<char> cubtmp; bool rows_ok = false;      // per-row send list (push from the producer)
 };
@@ -242,7 +242,7 @@ void halo_setup(Ctx *c) {
     if (!ipc_share(c, h, h->hbox, h->hpeer, h->hopened)) { cudaFree(h->hbox); h->hbox = nullptr; h->hcap = 0; }
   }
   h->plan_ok = false;
-  if (h->p2p && h->hbox) {                                       // device copy of the plan for the fused halo + SpMV kernel
+  if (h->p2p && h->hbox) {                                       // device copy of the plan for the halo kernels
     HaloDev hd; memset(&hd, 0, sizeof(hd));
     for (int p = 0; p < R; ++p) { hd.peer[p] = h->hpeer[p]; hd.send_off[p] = h->send_off[p]; hd.dst_off[p] = h->dst_off[p]; hd.recv_cnt[p] = h->recv_count[p]; }
     for (int p = R; p <= ISPH_MAX_RANKS; ++p) hd.send_off[p] = h->send_off[R];
