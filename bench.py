@@ -183,12 +183,13 @@ FULL_ITERS = {"p8m": 452, "c2": 188, "c4": 81}          # GMRES iterations of th
 def krylov_bytes_per_solve(n, nnz, iters, second, m=50):
     """Algorithmic HBM bytes of one flexible GMRES(m)+Jacobi solve on one GPU: per Arnoldi step with basis
     size nv: SpMV 12 nnz + 20 n; pass-0 coefficients 8 n (nv+2); first update 8 n (nv+3); and, when the DGKS test asks for
-    it (`second` of the `iters` steps), pass-1 coefficients 8 n (nv+1) and the second update inside the closing sweep
-    8 n nv; closing sweep (normalise + Jacobi) 8 n 4.  The x update at the end of a cycle: 8 n (ncol + 2)."""
+    it (`second` of the `iters` steps), pass-1 coefficients — 8 n (nv+1) for nv <= 8, nothing extra for nv > 8 where they
+    are formed in the same sweep as the first update — and the second update inside the closing sweep 8 n nv; closing
+    sweep (normalise + Jacobi) 8 n 4.  The x update at the end of a cycle: 8 n (ncol + 2)."""
     tot = 0.0; frac2 = second / max(iters, 1)
     for it in range(iters):
         nv = it % m + 1
-        tot += 12.0 * nnz + 20.0 * n + 8.0 * n * ((nv + 2) + (nv + 3) + 4) + frac2 * 8.0 * n * ((nv + 1) + nv)
+        tot += 12.0 * nnz + 20.0 * n + 8.0 * n * ((nv + 2) + (nv + 3) + 4) + frac2 * 8.0 * n * ((nv + 1 if nv <= 8 else 0) + nv)
     cycles = (iters + m - 1) // m
     tot += cycles * 8.0 * n * (min(iters, m) + 2)
     return tot

@@ -195,6 +195,108 @@ k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   }
 }
 
+// First Gram-Schmidt update AND second-pass coefficients in ONE sweep over the basis (the two kernels above read V twice):
+//   w1 = y - (n.y) n - sum_k h_k V_k ,  h2[k] = V_k . w1 ,  h2[nv] = w1.w1
+// The block walks its row chunk in tiles of UT rows.  Warp q owns the basis vectors k = q, q+8, ... (<= KPW of them): it
+// loads their tile values ONCE into registers, contributes its partial sum of h_k V_k to shared memory, the first UT threads
+// finish w1 for the tile (written back, kept in shared memory), and every warp then forms its vectors' dot products with w1
+// from the SAME registers.  Traffic 8 n (nv + 3) instead of 8 n (2 nv + 4).  The dots are only formed when the DGKS test
+// (known from the pass-0 message) asks for a second pass.  Used for nv > 8; shorter bases keep the two streaming kernels.
+static const int KPW = 7;                                       // 8 warps x 7 vectors >= 51 basis vectors
+template <int HV> __global__ void __launch_bounds__(VB, HV == 1 ? 3 : 2)     // HV = 64-row halves per tile
+k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
+             double *S, double *partials, unsigned *counter, P2PRed pr) {
+  constexpr int UT = 64 * HV;
+  __shared__ __align__(16) double s_part[VB / 32][UT];
+  __shared__ __align__(16) double s_w1[UT];
+  __shared__ double s_h[64], s_red[UT / 32];
+  __shared__ bool s_go, s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_go = dgks_second(S, nv, nvec != nullptr);
+  if (tid < nv) s_h[tid] = S[S_H + tid];
+  __syncthreads();
+  const bool go = s_go;
+  const double proj = nvec ? S[S_H + nv + 1] : 0.0;
+  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + UT - 1) / UT * UT;
+  const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk);
+  double acc[KPW], nrm = 0.0;
+#pragma unroll
+  for (int q = 0; q < KPW; ++q) acc[q] = 0.0;
+  for (int t0 = r0; t0 < r1; t0 += UT) {
+    // the tile's w (and n) values are requested together with the basis values: one memory latency per tile, not two
+    double wv = 0.0, nn = 0.0;
+    if (tid < UT && t0 + tid < r1) { wv = w[t0 + tid]; if (nvec) nn = nvec[t0 + tid]; }
+    double2 v[KPW][HV], p[HV];
+#pragma unroll
+    for (int hf = 0; hf < HV; ++hf) p[hf] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < KPW; ++q) {
+      const int k = warp + (VB / 32) * q;
+#pragma unroll
+      for (int hf = 0; hf < HV; ++hf) {
+        const int i = t0 + 64 * hf + 2 * lane;                   // this lane's rows: two in each half of the tile
+        v[q][hf] = make_double2(0.0, 0.0);
+        if (k < nv) {
+          const double *vk = V + (size_t)k * ld + i;
+          if (i + 1 < r1) v[q][hf] = *reinterpret_cast<const double2 *>(vk); else if (i < r1) v[q][hf].x = vk[0];
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < KPW; ++q) {
+      const int k = warp + (VB / 32) * q;
+      if (k < nv) { const double h = s_h[k];
+#pragma unroll
+        for (int hf = 0; hf < HV; ++hf) { p[hf].x += h * v[q][hf].x; p[hf].y += h * v[q][hf].y; } }
+    }
+#pragma unroll
+    for (int hf = 0; hf < HV; ++hf) *reinterpret_cast<double2 *>(&s_part[warp][64 * hf + 2 * lane]) = p[hf];
+    __syncthreads();
+    if (tid < UT) {
+      double w1 = 0.0;
+      if (t0 + tid < r1) {
+        w1 = wv - proj * nn;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < VB / 32; ++q) s += s_part[q][tid];
+        w1 -= s; w[t0 + tid] = w1; nrm += w1 * w1;
+      }
+      s_w1[tid] = w1;
+    }
+    __syncthreads();
+    if (go) {
+#pragma unroll
+      for (int hf = 0; hf < HV; ++hf) {
+        const double2 ww = *reinterpret_cast<const double2 *>(&s_w1[64 * hf + 2 * lane]);
+#pragma unroll
+        for (int q = 0; q < KPW; ++q) { acc[q] += v[q][hf].x * ww.x; acc[q] += v[q][hf].y * ww.y; }
+      }
+    }
+  }
+  if (!go) return;                                               // block-uniform: the DGKS decision is the same everywhere (and on every rank)
+  double *mine = partials + (size_t)blockIdx.x * 64;
+#pragma unroll
+  for (int q = 0; q < KPW; ++q) { const double s = warp_sum(acc[q]); const int k = warp + (VB / 32) * q; if (lane == 0 && k < nv) mine[k] = s; }
+  if (tid < UT) { const double s = warp_sum(nrm); if (lane == 0) s_red[warp] = s; }
+  __syncthreads();
+  if (tid == 0) { double t = 0.0; for (int q = 0; q < UT / 32; ++q) t += s_red[q]; mine[63] = t; }
+  __threadfence(); __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int k = warp; k < 64; k += VB / 32) {
+      if (!(k < nv || k == 63)) continue;
+      double s = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
+      s = warp_sum(s);
+      if (lane == 0) S[S_H2 + (k == 63 ? nv : k)] = s;
+    }
+    if (tid == 0) *counter = 0u;
+    if (pr.nranks > 1) { __threadfence(); p2p_allreduce_block(pr, S + S_H2, nv + 1); }
+  }
+}
+
 // Hessenberg column j: DGKS bookkeeping, Givens rotations, implicit residual (BlockGmresIter::updateLSQR); one warp:
 // lanes stage the column and the rotations in shared memory, lane 0 runs the (inherently sequential) recurrence there
 __device__ void givens_step(double *S, int j, bool singular, double *host_res, int slot) {
@@ -435,6 +537,10 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   const double *nvp = c->is_singular ? c->nullvec.p : nullptr;
   const DiagPrec dp = diag_prec_of(c, use_prec); const bool jacobi_fused = dp.on;
   const int sing = c->is_singular ? 1 : 0;
+  static const bool fuse_ud = getenv("ISPH_NO_FUSE_UD") == nullptr;
+  static const int ud_hv = getenv("ISPH_UD_HV") ? atoi(getenv("ISPH_UD_HV")) : 2;            // 64-row halves per tile of the fused sweep
+  static const int udcap = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : (ud_hv == 1 ? 444 : 296);       // 148 SMs x resident CTAs
+  const int gud = std::max(1, std::min(udcap, ceil_div(n, 64 * ud_hv)));
   std::vector<cudaEvent_t> ev(m);
   for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   int iters = 0, restarts = 0; bool converged = false, first = true; double scale = 0.0, res = 0.0;
@@ -459,8 +565,17 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
       dbg(c, "prologue");
       { ProfScope ps(c, "op_apply"); spmv(c, zj, vn, 1, ld, ld); } dbg(c, "op_apply");          // y = A z_j ; the PoissonProjection tail rides on the Gram-Schmidt sweep
       { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); } dbg(c, "multidot0");
-      { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S); ++c->launches; } dbg(c, "update0");
-      { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); } dbg(c, "multidot1");
+      if (fuse_ud && j + 1 > 8) {                                // one sweep: first update + second-pass coefficients
+        ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c);
+        if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);      // flag word 14
+        else k_update_dot<2><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);
+        ++c->launches;
+        if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_H2, j + 2);
+      } else {
+        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S); ++c->launches; }
+        { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
+      }
+      dbg(c, "update0/dot1");
       ++iters;
       if (j + 1 < m) {                                           // second update + normalisation + next preconditioned vector + Givens, one sweep
         ProfScope ps(c, "finish");
