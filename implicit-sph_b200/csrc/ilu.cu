@@ -1,5 +1,7 @@
-// Block-Jacobi ILU(0): Ifpack::Create("ILU", A, overlap 0) with "fact: level-of-fill" 0 (precond_ifpack.h:50-75 is the
-// call site; Ifpack_ILU itself is third-party and restated in oracle/krylov_oracle.cpp).
+// Block-Jacobi ILU(k): Ifpack::Create("ILU", A, overlap 0) with "fact: level-of-fill" k (precond_ifpack.h:50-75 is the
+// call site; Ifpack_ILU itself is third-party and restated in oracle/krylov_oracle.cpp).  k = 0 (BASELINE's ILU(0)) is
+// the all-device path; for k > 0 (the reference's own default is 1, precond_ifpack.h:38) the level-of-fill pattern comes
+// from a host pass (isph_iluk_symbolic_host, Ifpack_IlukGraph's level rule) and the same numeric kernels run on it.
 //   * block = the set of rows one Ifpack/MPI rank would own ("block_of_row", default: all local rows); columns outside
 //     the row's block are dropped (Ifpack_LocalFilter), so blocks are independent;
 //   * factors in Ifpack's form: L unit-lower (l_ij = a_ij / d_j), D stored inverted, U unit-upper scaled by 1/d_i;
@@ -14,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <queue>
 
 namespace cg = cooperative_groups;
 #define ILU_TB 1024
@@ -22,7 +25,7 @@ namespace isph {
 
 struct IluData {
   int n = 0; long long nnz = 0; int nlev_l = 0, nlev_u = 0, maxw_l = 0, maxw_u = 0;
-  DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt, lev, hist; DevBuf<double> fv, dinv, y; DevBuf<char> tmp;
+  DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt, lev, hist, rp0, ci0; DevBuf<double> fv, fv0, dinv, y; DevBuf<char> tmp;
   int grid_f = 1, grid_s = 1, maxlen = 0, tb_f = ILU_TB; bool sync_free = true; size_t smem_f = 0; DevBuf<int> fault;
 };
 
@@ -45,6 +48,19 @@ __global__ void k_ilu_fill(const long long *slice_off, const int *row_len, const
     prev = cc;
   }
   dpos[row] = dp;
+}
+
+// values of the block-restricted matrix scattered into the (larger) level-of-fill pattern; fill entries start at zero
+__global__ void k_ilu_expand(const int *rp0, const int *ci0, const double *fv0, const int *rp1, const int *ci1, int n, double *fv1, int *dpos1) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
+  int a = rp0[row], dp = -1; const int ae = rp0[row + 1];
+  for (int q = rp1[row]; q < rp1[row + 1]; ++q) {
+    const int cc = ci1[q];
+    while (a < ae && ci0[a] < cc) ++a;
+    fv1[q] = (a < ae && ci0[a] == cc) ? fv0[a] : 0.0;
+    if (cc == row) dp = q;
+  }
+  dpos1[row] = dp;
 }
 
 // ---- numeric factorisation, one warp per row, levels separated by grid barriers ------------------------------------
@@ -224,6 +240,31 @@ static void level_sets(int n, const std::vector<int> &rp, const std::vector<int>
   for (int i = 0; i < n; ++i) order[pos[lev[i]]++] = i;
 }
 
+// Level-of-fill pattern, Ifpack_IlukGraph's rule: entries of the matrix have level 0; eliminating row i with pivot row k
+// creates (i,j) for every strictly-upper (k,j) with level(i,k) + level(k,j) + 1, kept when that is <= fill.  Rows ascending,
+// pivots of a row in ascending column order (a heap holds the pending lower columns), levels of finished rows kept per entry.
+static void iluk_symbolic(int n, const int *rp, const int *ci, int fill, std::vector<int> &frp, std::vector<int> &fci) {
+  std::vector<unsigned char> flev; std::vector<int> ubeg(n, 0), lev(n, -1), touched;
+  std::priority_queue<int, std::vector<int>, std::greater<int>> pend;
+  frp.assign(1, 0); fci.clear(); fci.reserve((size_t)rp[n] * (fill + 1));
+  for (int i = 0; i < n; ++i) {
+    touched.clear();
+    for (int q = rp[i]; q < rp[i + 1]; ++q) { const int cc = ci[q]; if (lev[cc] < 0) { lev[cc] = 0; touched.push_back(cc); if (cc < i) pend.push(cc); } }
+    while (!pend.empty()) {
+      const int k = pend.top(); pend.pop(); const int lk = lev[k];
+      for (int u = ubeg[k]; u < frp[k + 1]; ++u) {
+        const int nl = lk + flev[u] + 1; if (nl > fill) continue;
+        const int j = fci[u];
+        if (lev[j] < 0) { lev[j] = nl; touched.push_back(j); if (j < i) pend.push(j); } else if (nl < lev[j]) lev[j] = nl;
+      }
+    }
+    std::sort(touched.begin(), touched.end());
+    ubeg[i] = (int)fci.size();
+    for (int cc : touched) { if (cc <= i) ++ubeg[i]; fci.push_back(cc); flev.push_back((unsigned char)lev[cc]); lev[cc] = -1; }
+    frp.push_back((int)fci.size());
+  }
+}
+
 static int coop_grid(Ctx *c, const void *fn, int max_width) {
   int per_sm = 0, sms = 0;
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ILU_TB, 0));
@@ -249,9 +290,21 @@ void ilu_create(Ctx *c) {
   std::vector<int> rp(n + 1);
   CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
   I.nnz = rp[n]; I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
-  I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
   I.sync_free = !getenv("ISPH_ILU_BARRIER"); I.fault.ensure(4); CUDA_CHECK(cudaMemsetAsync(I.fault.p, 0, 4 * sizeof(int), c->stream));
   k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
+  if (c->pp.fill > 0) {                                          // level-of-fill pattern (host), values expanded on the device
+    std::vector<int> ci0(I.nnz), frp, fci;
+    CUDA_CHECK(cudaMemcpyAsync(ci0.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    iluk_symbolic(n, rp.data(), ci0.data(), c->pp.fill, frp, fci);
+    std::swap(I.rp0, I.rp); std::swap(I.ci0, I.ci); std::swap(I.fv0, I.fv);               // level-0 arrays become the source of the expansion
+    I.nnz = frp[n]; I.rp.ensure(n + 1); I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
+    CUDA_CHECK(cudaMemcpyAsync(I.rp.p, frp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.ci.p, fci.data(), sizeof(int) * I.nnz, cudaMemcpyHostToDevice, c->stream));
+    k_ilu_expand<<<ceil_div(n, 128), 128, 0, c->stream>>>(I.rp0.p, I.ci0.p, I.fv0.p, I.rp.p, I.ci.p, n, I.fv.p, I.dpos.p); ++c->launches;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));               // frp / fci are host temporaries
+    rp = frp;
+  }
+  I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
   // dependency levels + level sets, on the device (no download of the pattern)
   I.order_l.ensure(n); I.order_u.ensure(n); I.lev.ensure(n); I.hist.ensure(n + 2); I.lptr_l.ensure(n + 2); I.lptr_u.ensure(n + 2);
   bool device_ok = !getenv("ISPH_ILU_HOST_LEVELS");
@@ -339,7 +392,20 @@ void ilu_apply(Ctx *c, const double *r, double *z) {
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
-  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
+  I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.rp0.release(); I.ci0.release(); I.fv0.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
 }
 
 }  // namespace isph
+
+extern "C" {
+// Pure host code (no CUDA): the level-of-fill pattern of ILU(k) for a CSR pattern with ascending columns (CPU-side test
+// hook).  Returns ISPH_FAILURE when `cap` is too small; *nnz_out is set either way.
+int isph_iluk_symbolic_host(int n, const int *rowptr, const int *col, int fill, int *rowptr_out, int *col_out, long long cap, long long *nnz_out) {
+  if (n < 0 || !rowptr || !col || fill < 0 || fill > 255 || !nnz_out) return ISPH_FAILURE;
+  std::vector<int> frp, fci; isph::iluk_symbolic(n, rowptr, col, fill, frp, fci);
+  *nnz_out = (long long)fci.size();
+  if (!rowptr_out || !col_out || cap < (long long)fci.size()) return ISPH_FAILURE;
+  memcpy(rowptr_out, frp.data(), sizeof(int) * (n + 1)); memcpy(col_out, fci.data(), sizeof(int) * fci.size());
+  return ISPH_SUCCESS;
+}
+}

@@ -68,11 +68,12 @@ void precond_create(Ctx *c) {
   Matrix &A = c->A; ISPH_REQUIRE(A.built, ">> A is null");                      // precond_ifpack.h:52
   const int n = A.n, ld = c->ld; const std::string &t = c->pp.type;
   c->tic("precondCreate");
-  ISPH_REQUIRE(c->pp.overlap == 0, "Overlap Level > 0 is not implemented (block-Jacobi / overlap 0 only)");
+  // with one rank and one block there is nothing to overlap with: Ifpack's "Overlap Level" (default 1, precond_ifpack.h:37) is a no-op
+  ISPH_REQUIRE(c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks), "Overlap Level > 0 across ranks / blocks is not implemented (block-Jacobi, overlap 0)");
   if (t == "none") c->prec_kind = 0;
   else if (t == "point relaxation" || t == "point relaxation stand-alone" || t == "Jacobi") { ISPH_REQUIRE(c->pp.relax_type == "Jacobi", "relaxation: type must be Jacobi"); c->prec_kind = 1; }
   else if (t == "Chebyshev") c->prec_kind = 2;
-  else if (t == "ILU") { ISPH_REQUIRE(c->pp.fill == 0, "fact: level-of-fill > 0 is not implemented (ILU(0) only)"); c->prec_kind = 3; }
+  else if (t == "ILU") { ISPH_REQUIRE(c->pp.fill >= 0 && c->pp.fill <= 255, "fact: level-of-fill must be in 0..255"); c->prec_kind = 3; }
   else ISPH_REQUIRE(false, "Precond Type not supported: " + t);
   if (c->prec_kind == 1 || c->prec_kind == 2) {
     c->invdiag.ensure(ld); c->cv.ensure(ld); c->cw.ensure(ld);

@@ -177,6 +177,10 @@ int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v);
 int isph_precond_set_param_str(isph_ctx *ctx, const char *name, const char *v);
 int isph_precond_set_blocks(isph_ctx *ctx, const int *block_of_row /*[nlocal] or NULL = one block*/);
 int isph_precond_create(isph_ctx *ctx);     /* PrecondWrapper::create(), precond_ifpack.h:50-75 */
+/* Pure host code (no CUDA): level-of-fill pattern of Ifpack_ILU ("fact: level-of-fill" k, precond_ifpack.h:38) for a CSR
+ * pattern with ascending columns — the host pass behind ILU(k), k > 0; exported so that CPU-only tests can drive it.
+ * ISPH_FAILURE when cap is too small (*nnz_out holds the size needed). */
+int isph_iluk_symbolic_host(int n, const int *rowptr, const int *col, int fill, int *rowptr_out, int *col_out, long long cap, long long *nnz_out);
 int isph_precond_free(isph_ctx *ctx);       /* PrecondWrapper::free() */
 int isph_precond_apply(isph_ctx *ctx, const double *r, double *z);        /* ApplyInverse, host vectors (tests) */
 /* SolverLin_Belos::solveProblem(prec, name): use_prec != 0 creates and frees the preconditioner around the solve */

@@ -14,8 +14,9 @@
 // initial residual, test `<= tol`, restart every `Num Blocks`, stop at Maximum Iterations / Maximum Restarts.
 // BlockCGSolMgr with block size 1 — standard PCG, test ||r||_2 / ||r_0||_2 before every iteration.
 // Ifpack semantics restated: point relaxation (Jacobi, zero start), Ifpack_Chebyshev (ApplyInverse recurrence with
-// alpha = lmax/ratio, beta = 1.1 lmax; lmax from a 10-step power method on D^-1 A), Ifpack_ILU level 0 on the local
-// block (overlap 0: off-block columns dropped), row-wise IKJ, L unit-lower, D stored inverted, U unit-upper scaled.
+// alpha = lmax/ratio, beta = 1.1 lmax; lmax from a 10-step power method on D^-1 A), Ifpack_ILU with level-of-fill k on
+// the local block (overlap 0: off-block columns dropped): pattern from Ifpack_IlukGraph's level rule
+// level(i,j) = min_k level(i,k) + level(k,j) + 1 <= k, then row-wise IKJ, L unit-lower, D stored inverted, U unit-upper scaled.
 // Deviation (documented in DESIGN.md): Epetra's Random() start vector of the power method is replaced by a
 // deterministic per-row hash, identically here and in the CUDA path.
 #include <vector>
@@ -23,6 +24,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <map>
 #include "krylov_oracle.h"
 
 namespace {
@@ -55,7 +57,7 @@ struct Precond {
   std::vector<double> invdiag;
   double lmax;
   // ILU(0): factors stored on A's pattern restricted to the row's block
-  std::vector<double> fv, dinv; std::vector<int> diagpos; const int *blk;
+  std::vector<double> fv, dinv; std::vector<int> diagpos, frp, fci; const int *blk;
   std::vector<double> V, W;
 
   void setup(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
@@ -84,25 +86,42 @@ struct Precond {
       }
       V.assign(n, 0.0); W.assign(n, 0.0);
     }
-    if (type == ORC_PREC_ILU0) {                           // Ifpack_ILU::Compute, level-of-fill 0, relax 0, athresh 0, rthresh 1
-      fv.assign(A_.v, A_.v + A_.rp[n]); dinv.assign(n, 0.0); diagpos.assign(n, -1);
-      std::vector<int> colflag(n, -1);
+    if (type == ORC_PREC_ILU0) {                           // Ifpack_ILU::Compute, level-of-fill p->ilu_fill, relax 0, athresh 0, rthresh 1
       auto inblk = [&](int i, int c) { return c >= 0 && (!blk || blk[c] == blk[i]); };
-      for (int i = 0; i < n; ++i) for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] == i) diagpos[i] = q;
+      // pattern: Ifpack_IlukGraph::ConstructFilledGraph.  Level 0 = entries of A inside the row's block; a fill entry (i,j)
+      // created through pivot k gets level(i,k) + level(k,j) + 1 and is kept when that is <= fill.
+      const int fill = p->ilu_fill;
+      frp.assign(1, 0); fci.clear(); fv.clear(); std::vector<int> flev;
+      std::vector<int> ubeg(n, 0);                            // first strictly-upper entry of every finished row
       for (int i = 0; i < n; ++i) {
-        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (inblk(i, A_.ci[q])) colflag[A_.ci[q]] = q;
-        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) {     // columns ascending => strictly-lower part first
-          const int j = A_.ci[q]; if (!inblk(i, j) || j >= i) continue;
+        std::map<int, std::pair<int, double>> row;            // col -> (level, value)
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) { const int c = A_.ci[q]; if (!inblk(i, c)) continue; auto it = row.find(c); if (it == row.end()) row[c] = {0, A_.v[q]}; else it->second.second += A_.v[q]; }
+        if (fill > 0) for (auto it = row.begin(); it != row.end() && it->first < i; ++it) {
+          const int k = it->first, lk = it->second.first;
+          for (int u = ubeg[k]; u < frp[k + 1]; ++u) { const int nl = lk + flev[u] + 1; if (nl > fill) continue;
+            auto jt = row.find(fci[u]); if (jt == row.end()) row[fci[u]] = {nl, 0.0}; else if (nl < jt->second.first) jt->second.first = nl; }
+        }
+        ubeg[i] = (int)fci.size();
+        for (auto &e : row) { if (e.first <= i) ++ubeg[i]; fci.push_back(e.first); flev.push_back(e.second.first); fv.push_back(e.second.second); }
+        frp.push_back((int)fci.size());
+      }
+      dinv.assign(n, 0.0); diagpos.assign(n, -1);
+      std::vector<int> colflag(n, -1);
+      for (int i = 0; i < n; ++i) for (int q = frp[i]; q < frp[i + 1]; ++q) if (fci[q] == i) diagpos[i] = q;
+      for (int i = 0; i < n; ++i) {                           // numeric phase on the filled pattern
+        for (int q = frp[i]; q < frp[i + 1]; ++q) colflag[fci[q]] = q;
+        for (int q = frp[i]; q < frp[i + 1]; ++q) {           // columns ascending => strictly-lower part first
+          const int j = fci[q]; if (j >= i) continue;
           const double multiplier = fv[q];
           fv[q] *= dinv[j];
-          for (int u = A_.rp[j]; u < A_.rp[j + 1]; ++u) { const int k = A_.ci[u]; if (!inblk(j, k) || k <= j) continue;
+          for (int u = frp[j]; u < frp[j + 1]; ++u) { const int k = fci[u]; if (k <= j) continue;
             const int kk = colflag[k]; if (kk > -1) fv[kk] -= multiplier * fv[u]; }
         }
         double d = fv[diagpos[i]];
         d = 1.0 / d;
         dinv[i] = d;
-        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) { const int k = A_.ci[q]; if (inblk(i, k) && k > i) fv[q] *= d; }
-        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] >= 0) colflag[A_.ci[q]] = -1;
+        for (int q = frp[i]; q < frp[i + 1]; ++q) if (fci[q] > i) fv[q] *= d;
+        for (int q = frp[i]; q < frp[i + 1]; ++q) colflag[fci[q]] = -1;
       }
     }
   }
@@ -131,10 +150,9 @@ struct Precond {
       }
       break; }
     case ORC_PREC_ILU0: {                                   // Ifpack_ILU::ApplyInverse: L (unit) solve, D^-1 scale, U (unit) solve
-      auto inblk = [&](int i, int c) { return c >= 0 && (!blk || blk[c] == blk[i]); };
-      for (int i = 0; i < n; ++i) { double s = r[i]; for (int q = A->rp[i]; q < A->rp[i + 1]; ++q) { const int j = A->ci[q]; if (inblk(i, j) && j < i) s -= fv[q] * z[j]; } z[i] = s; }
+      for (int i = 0; i < n; ++i) { double s = r[i]; for (int q = frp[i]; q < frp[i + 1]; ++q) { const int j = fci[q]; if (j < i) s -= fv[q] * z[j]; } z[i] = s; }
       for (int i = 0; i < n; ++i) z[i] *= dinv[i];
-      for (int i = n - 1; i >= 0; --i) { double s = z[i]; for (int q = A->rp[i]; q < A->rp[i + 1]; ++q) { const int j = A->ci[q]; if (inblk(i, j) && j > i) s -= fv[q] * z[j]; } z[i] = s; }
+      for (int i = n - 1; i >= 0; --i) { double s = z[i]; for (int q = frp[i]; q < frp[i + 1]; ++q) { const int j = fci[q]; if (j > i) s -= fv[q] * z[j]; } z[i] = s; }
       break; }
     }
   }
@@ -156,7 +174,7 @@ void orc_krylov_default_params(orc_krylov_params *p) {
   memset(p, 0, sizeof(*p));
   p->solver = ORC_SOLVER_GMRES; p->flexible = 1; p->num_blocks = 50; p->max_iters = 500; p->max_restarts = 15; p->tol = 1.0e-8;   // solver_lin_belos.h:231-240
   p->precond = ORC_PREC_NONE; p->jacobi_sweeps = 1; p->jacobi_damping = 1.0; p->min_diag = 0.0;
-  p->cheb_degree = 1; p->cheb_ratio = 30.0; p->cheb_lambda_max = -1.0; p->cheb_eig_iters = 10; p->row_gid = 0;
+  p->cheb_degree = 1; p->cheb_ratio = 30.0; p->cheb_lambda_max = -1.0; p->cheb_eig_iters = 10; p->row_gid = 0; p->ilu_fill = 0;
 }
 
 int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,

@@ -23,6 +23,7 @@ typedef struct {
   double cheb_lambda_max;/* "chebyshev: max eigenvalue" (<=0: power method) */
   int cheb_eig_iters;    /* "chebyshev: eigenvalue max iterations" */
   const int *row_gid;    /* global id per row for the power-method start vector (NULL: row+1) */
+  int ilu_fill;          /* "fact: level-of-fill" (Ifpack_IlukGraph level rule) */
 } orc_krylov_params;
 
 void orc_krylov_default_params(orc_krylov_params *p);

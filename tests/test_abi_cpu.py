@@ -58,3 +58,42 @@ def test_field_tables_agree_with_the_header(isph):
     assert len(isph.FIELD_NCOMP) == count == isph.F_PHI + 1
     orc = open(os.path.join(os.path.dirname(isph.HERE), "oracle", "oracle_api.h")).read()
     assert int(re.search(r"ORC_F_COUNT\s*=\s*(\d+)", orc).group(1)) == count
+
+
+def _dense_levels(pattern, fill):
+    """Level-of-fill by definition (sum rule) on a dense level matrix — independent of both restatements."""
+    import numpy as np
+    n = pattern.shape[0]; INF = 10 ** 6
+    lev = np.where(pattern, 0, INF)
+    for k in range(n):
+        for i in range(k + 1, n):
+            if lev[i, k] <= fill:
+                cand = lev[i, k] + lev[k, k + 1:] + 1
+                lev[i, k + 1:] = np.where((cand < lev[i, k + 1:]) & (cand <= fill), cand, lev[i, k + 1:])
+    return lev <= fill
+
+
+@pytest.mark.parametrize("fill", [0, 1, 2, 3])
+def test_iluk_symbolic_pattern_matches_the_definition(isph, fill):
+    """Host pass behind ILU(k) (Ifpack 'fact: level-of-fill', precond_ifpack.h:38): pattern == dense level-of-fill pattern."""
+    import numpy as np
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    e = np.ones(6); T = sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1])
+    mats = [sp.csr_matrix(sp.kron(sp.eye(6), T) + sp.kron(T, sp.eye(6))), sp.csr_matrix(sp.random(40, 40, 0.08, random_state=3) + sp.eye(40))]
+    L = isph.lib()
+    for A in mats:
+        A.sort_indices(); n = A.shape[0]
+        want = _dense_levels(A.toarray() != 0, fill)
+        rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        nnz = ctypes.c_longlong()
+        ip = ctypes.POINTER(ctypes.c_int)
+        assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), fill, None, None, ctypes.c_longlong(0), ctypes.byref(nnz)) == -1
+        assert nnz.value == want.sum()
+        rpo = np.zeros(n + 1, dtype=np.int32); cio = np.zeros(nnz.value, dtype=np.int32)
+        assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), fill, rpo.ctypes.data_as(ip), cio.ctypes.data_as(ip),
+                                         ctypes.c_longlong(nnz.value), ctypes.byref(nnz)) == 0
+        got = np.zeros((n, n), dtype=bool)
+        for i in range(n):
+            cols = cio[rpo[i]:rpo[i + 1]]; assert np.all(np.diff(cols) > 0); got[i, cols] = True
+        assert np.array_equal(got, want)

@@ -191,3 +191,40 @@ def test_poisson_boltzmann_newton_matches_cpu_newton(name, prec):
     assert np.linalg.norm(psi_gpu[:nl] - psi[:nl]) / np.linalg.norm(psi[:nl]) <= 1e-8
     ghost_owner = P["tag"][nl:] - 1                              # single rank: tags are 1-based owned indices
     assert np.array_equal(psi_gpu[nl:], psi_gpu[ghost_owner])    # psi forwarded to the ghosts after the solve (pair_isph.cpp:595-598)
+
+
+@pytest.mark.parametrize("fill", [1, 2])
+def test_gmres_iluk_external_matrix(fill):
+    """Ifpack ILU with 'fact: level-of-fill' k > 0 and the reference's default 'Overlap Level' 1 (precond_ifpack.h:37-38; a no-op on
+    one rank): host level-of-fill pattern + the ILU(0) numeric kernels on it, against the oracle's ILU(k)."""
+    A = lap2d(40, 0.05, 0.4); n = A.shape[0]
+    b = np.random.default_rng(0).standard_normal(n)
+    prm = O.krylov_params(precond=O.PREC_ILU0, ilu_fill=fill)
+    xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=prm)
+    zo, _ = O.precond_apply(A.indptr, A.indices, A.data, b, prm)
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    configure(c, O.SOLVER_GMRES, O.PREC_ILU0); c.precond_param("fact: level-of-fill", fill); c.precond_param("Overlap Level", 1)
+    c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "ext")
+    check(st, info, x, xo, sol_tol=1e-7)
+    c.precond_create(); z = c.precond_apply(b); c.precond_free()
+    assert np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max()
+    c.close()
+
+
+def test_c1_tgv128_gmres_ifpack_default_ilu1():
+    """BASELINE config 1 particle set with Ifpack's OWN defaults (ILU, level-of-fill 1, overlap 1: precond_ifpack.h:30-44)."""
+    import harness
+    P, F = make_case("tgv128"); cs = P["case"]; nl = P["nlocal"]
+    ref = harness.run_oracle(P, F, "port")
+    col = O.tags_to_local(ref["col"], P["tag"][:nl]); mask = np.ones(nl, dtype=np.int32)
+    xo, info = O.krylov_solve(ref["rowptr"], col, ref["A_poisson"], ref["b_poisson"].copy(), params=O.krylov_params(precond=O.PREC_ILU0, ilu_fill=1, row_gid=P["tag"][:nl]),
+                              null_mask=mask, use_null=True)
+    c = harness.cuda_context(P, F)
+    c.compute_pre(); c.graph_build(); c.create_load(None, 1); c.ns_poisson(cs["dt"])
+    x = np.zeros(nl); c.create_solution(x, 1)
+    c.set_null_vector_mask(mask); c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO)
+    configure(c, O.SOLVER_GMRES, O.PREC_ILU0); c.precond_param("fact: level-of-fill", 1); c.precond_param("Overlap Level", 1)
+    st = c.solve(True, "Poisson"); c.close()
+    check(st, info, x, xo, sol_tol=1e-5)

@@ -103,3 +103,41 @@ def test_singular_neumann_problem_with_null_space_projection():
     bp = b - b.mean()
     assert np.linalg.norm(bp - A @ x) / np.linalg.norm(bp) < 1e-7
     assert abs(info["b"].sum()) < 1e-10 * np.abs(b).sum()                        # b was projected in place (solver_lin_belos.h:141-143)
+
+
+@pytest.mark.parametrize("fill", [1, 2, 3])
+@pytest.mark.parametrize("blocked", [False, True])
+def test_iluk_factors_match_a_dense_level_of_fill_factorisation(fill, blocked):
+    """Ifpack 'fact: level-of-fill' k (the reference's own default is 1, precond_ifpack.h:38): pattern by the level sum rule on a
+    dense level matrix, IKJ elimination restricted to it, Ifpack's scaled-U form — computed densely, independent of the oracle."""
+    A = lap2d(7, 0.05, 0.4); n = A.shape[0]; rp, ci, v = csr(A)
+    blocks = (np.arange(n) % 7 >= 3).astype(np.int32) if blocked else None
+    D = A.toarray().astype(float); INF = 10 ** 6
+    lev = np.where(D != 0, 0, INF)
+    if blocked:
+        same = blocks[:, None] == blocks[None, :]; lev = np.where(same, lev, INF); D = np.where(same, D, 0.0)
+    for k in range(n):
+        for i in range(k + 1, n):
+            if lev[i, k] <= fill:
+                cand = lev[i, k] + lev[k, k + 1:] + 1
+                lev[i, k + 1:] = np.where((cand < lev[i, k + 1:]) & (cand <= fill), cand, lev[i, k + 1:])
+    pat = lev <= fill
+    F = np.where(pat, D, 0.0); dinv = np.zeros(n)
+    for i in range(n):
+        for j in range(i):
+            if pat[i, j]:
+                m = F[i, j]; F[i, j] = m * dinv[j]
+                upd = pat[i, j + 1:] & pat[j, j + 1:]
+                F[i, j + 1:] -= np.where(upd, m * F[j, j + 1:], 0.0)
+        dinv[i] = 1.0 / F[i, i]; F[i, i + 1:] *= dinv[i]
+    r = np.random.default_rng(0).standard_normal(n); z = r.copy()
+    for i in range(n):
+        z[i] -= F[i, :i] @ z[:i]
+    z *= dinv
+    for i in range(n - 1, -1, -1):
+        z[i] -= F[i, i + 1:] @ z[i + 1:]
+    zo, _ = O.precond_apply(rp, ci, v, r, O.krylov_params(precond=O.PREC_ILU0, ilu_fill=fill), blocks=blocks)
+    assert np.abs(zo - z).max() <= 1e-13 * np.abs(z).max()
+    # more fill => a better preconditioner on this matrix
+    its = [O.krylov_solve(rp, ci, v, r, params=O.krylov_params(precond=O.PREC_ILU0, ilu_fill=f))[1]["iters"] for f in (0, fill)]
+    assert its[1] <= its[0]
