@@ -12,6 +12,7 @@
 //   * getLoadMultiVector()->Values() becomes loadSet()/loadGet() because b lives in HBM.
 #pragma once
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include "isph_b200.h"
@@ -32,7 +33,9 @@ class PrecondWrapper_B200 {
   virtual ~PrecondWrapper_B200() {}
   // setMatrix(Epetra_CrsMatrix*) : the matrix is the context's device matrix; kept for call-site compatibility
   virtual void setMatrix(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
-  // setParameters(NULL) loads the wrapper defaults of precond_ifpack.h:30-44 restricted to what BASELINE names (fill 0, overlap 0)
+  // setParameters(NULL) loads the wrapper defaults of precond_ifpack.h:30-44 restricted to what BASELINE names (fill 0, overlap 0).
+  // The reference's own values (level-of-fill 1, overlap 1) can be set explicitly: level-of-fill k > 0 is supported, overlap > 0
+  // only where it is a no-op (one rank, one block).
   virtual void setParameters() { set("Precond Type", "ILU"); set("Overlap Level", 0); set("fact: level-of-fill", 0); }
   int set(const char *name, int v) { return isph_precond_set_param_int(_ctx, name, v); }
   int set(const char *name, double v) { return isph_precond_set_param_double(_ctx, name, v); }
@@ -93,6 +96,52 @@ class SolverLin_B200 {
   static int rc(int r) { return r == ISPH_SUCCESS ? LAMMPS_SUCCESS : LAMMPS_FAILURE; }
   isph_ctx *_ctx;
   bool _is_singular;
+};
+
+// SolverNOX<PairISPH> as PairISPH::computePoissonBoltzmann uses it (pair_isph.cpp:572-600, solver_nox.h, solver_nox_impl.h:26-200):
+// the Newton iteration with the reference's default lists (line search "Full Step", NormF 1e-8 AND NormUpdate 1e-5, 100
+// iterations) runs on the device (isph_pb_newton); computeF / computeJacobian are no longer host callbacks.
+class SolverNonlinear_B200 {
+ public:
+  enum SolutionInitType { Random, Zero, Value };                // solver_nox.h SolutionInitType
+  enum JacobianType { Analytic, MatrixFree };                   // only Analytic (pair_isph.cpp:373) is provided
+
+  explicit SolverNonlinear_B200(isph_ctx *ctx) : _ctx(ctx), _psi(NULL), _nlocal(0), _nall(0), _mh(0), _lin(0), _ezcb(0.5), _psiref(1.0), _gamma(0.0),
+                                                 _extra(NULL), _max_newton(100), _tol_f(1.0e-8), _tol_update(1.0e-5), _newton(0), _linear(0), _normf(0.0) {}
+  void setNodalMap(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
+  void setJacobianMatrix(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
+  // createSolutionVector(atom->psi): a View like the reference's; the ghost part (nall - nlocal values) is refreshed on return
+  int createSolutionVector(double *psi, int nlocal, int nall) { _psi = psi; _nlocal = nlocal; _nall = nall; return LAMMPS_SUCCESS; }
+  void setInitialSolution(SolutionInitType init, double val = 0.0) {
+    if (!_psi) return;
+    unsigned long long s = 37482ull;                            // seed of pair_isph.cpp:1454 ; Epetra's generator itself is not restated
+    for (int i = 0; i < _nall; ++i) {
+      if (init == Zero) _psi[i] = 0.0; else if (init == Value) _psi[i] = val;
+      else { s = s * 6364136223846793005ull + 1442695040888963407ull; _psi[i] = 2.0 * ((double)(s >> 11) * (1.0 / 9007199254740992.0)) - 1.0; }
+    }
+  }
+  void setParameters() {}                                       // "Full Step" Newton: what isph_pb_newton does
+  void setConvergenceTests(int max_iters = 100, double normf = 1.0e-8, double normupdate = 1.0e-5) { _max_newton = max_iters; _tol_f = normf; _tol_update = normupdate; }
+  // pair->pb.* (pair_isph.h) and the evaluated pb.extra_f expression (functor_poisson_boltzmann_extra_f.h), per owned particle or NULL
+  void setPoissonBoltzmann(bool morris_holmes, bool linearized, double ezcb, double psiref, double gamma, const double *extra_f) {
+    _mh = morris_holmes; _lin = linearized; _ezcb = ezcb; _psiref = psiref; _gamma = gamma; _extra = extra_f;
+  }
+  int solveProblem(PrecondWrapper_B200 *prec = NULL, const char *name = NULL) {
+    if (!_psi) return LAMMPS_FAILURE;
+    if (name != NULL) std::printf(">> isph_b200::Label - %s\n", name);
+    int conv = 0;
+    if (isph_field_set(_ctx, ISPH_F_PSI, _psi) != ISPH_SUCCESS ||
+        isph_solver_create_solution_multivector(_ctx, NULL, _nlocal, 1) != ISPH_SUCCESS || isph_solver_create_load_multivector(_ctx, NULL, _nlocal, 1) != ISPH_SUCCESS ||
+        isph_pb_newton(_ctx, _mh, _lin, _ezcb, _psiref, _gamma, _extra, _max_newton, _tol_f, _tol_update, prec != NULL ? 1 : 0, &_newton, &_linear, &_normf, &conv) != ISPH_SUCCESS ||
+        isph_field_get(_ctx, ISPH_F_PSI, _psi) != ISPH_SUCCESS) { std::fprintf(stderr, ">> isph_b200 error: %s\n", isph_last_error(_ctx)); return LAMMPS_FAILURE; }
+    std::printf(">> isph_b200::Status - %s %s (%d Newton / %d linear iterations, ||F|| = %.3e)\n", conv ? "Passed!" : "Failed to converge!", name ? name : " ", _newton, _linear, _normf);
+    return LAMMPS_SUCCESS;                                       // non-convergence is reported, not an error (as for the linear solver)
+  }
+  int newtonIterations() const { return _newton; }
+  int linearIterations() const { return _linear; }
+ protected:
+  isph_ctx *_ctx; double *_psi; int _nlocal, _nall; int _mh, _lin; double _ezcb, _psiref, _gamma; const double *_extra;
+  int _max_newton; double _tol_f, _tol_update; int _newton, _linear; double _normf;
 };
 
 }  // namespace isph_b200
