@@ -1,0 +1,57 @@
+"""CPU-side checks of bench.py's contract pieces that do not need a GPU: the reference arm's JSON line, the traffic model
+behind `solve_roofline`, the brick decomposition used for N = 1, 2, 4, 8, and the loud failure without a CUDA device."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-n", "16"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None and line["scaling"] == "strong"
+    assert line["config"]["workload"] == "p8m" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["full_workload_estimate"]["iters"] == 452 and line["full_workload_estimate"]["value"] < line["value"]   # fewer iterations on the sample
+
+
+def test_b200_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_solve_traffic_model():
+    bench = importlib.import_module("bench")
+    n, nnz = 1000, 100000
+    one = bench.krylov_bytes_per_solve(n, nnz, 1, 1)             # nv = 1: SpMV + (3 + 4 + 4 + 2 + 1) n doubles + x update (1 + 2) n
+    assert one == 12.0 * nnz + 20.0 * n + 8.0 * n * (3 + 4 + 4 + 2 + 1) + 8.0 * n * 3
+    full = bench.krylov_bytes_per_solve(n, nnz, 50, 50)          # one full cycle: fused sweep for nv > 8
+    want = sum(12.0 * nnz + 20.0 * n + 8.0 * n * ((nv + 2) + (nv + 3) + 4 + (nv + 1 if nv <= 8 else 0) + nv) for nv in range(1, 51)) + 8.0 * n * 52
+    assert abs(full - want) <= 1e-9 * want
+    assert bench.krylov_bytes_per_solve(n, nnz, 50, 0) < full    # no second passes => less traffic
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_bricks_tile_the_global_lattice(world):
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    dim = 3; ng = (8, 8, 8); grid = lat.brick_grid(world, dim)
+    assert int(np.prod(grid)) == world
+    seen = np.zeros(ng, dtype=np.int32)
+    for r in range(world):
+        lo, nloc = lat.brick_of_rank(r, grid, ng)
+        seen[lo[0]:lo[0] + nloc[0], lo[1]:lo[1] + nloc[1], lo[2]:lo[2] + nloc[2]] += 1
+    assert np.all(seen == 1)
