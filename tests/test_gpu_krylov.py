@@ -228,3 +228,21 @@ def test_c1_tgv128_gmres_ifpack_default_ilu1():
     configure(c, O.SOLVER_GMRES, O.PREC_ILU0); c.precond_param("fact: level-of-fill", 1); c.precond_param("Overlap Level", 1)
     st = c.solve(True, "Poisson"); c.close()
     check(st, info, x, xo, sol_tol=1e-5)
+
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_known_answer_poisson_boltzmann_convergence_table_on_the_device(N):
+    """The reference's recorded err.psi.norm2 (sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt) reproduced by the CUDA
+    path alone: pre-computation, graph, computeF / computeJacobian and the Newton iteration all on the device."""
+    from test_oracle_cpu import PB_TABLE, pb_harmonic_problem
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    P, s, ex = pb_harmonic_problem(lat, N); nl = P["nlocal"]
+    c = isph.Context(); c.set_particles(P)
+    c.field_set(isph.F_EPS, np.ones(len(s))); c.field_set(isph.F_PSI0, np.zeros(len(s))); c.field_set(isph.F_PSI, np.zeros(len(s)))
+    c.compute_pre(); c.graph_build(); c.create_solution(None, 1); c.create_load(None, 1)
+    configure(c, O.SOLVER_GMRES, O.PREC_ILU0, **{"Convergence Tolerance": 1e-12, "Maximum Iterations": 2000})
+    st = c.pb_newton(extra_f=ex, tol_f=1e-12, tol_update=1e-6)
+    psi = c.field_get(isph.F_PSI)[:nl]; c.close()
+    err = np.sqrt(np.mean((psi - s[:nl]) ** 2))
+    assert st["converged"] and st["newton_iters"] < 10
+    assert abs(err - PB_TABLE[N]) <= 1e-10 * PB_TABLE[N], (err, PB_TABLE[N])

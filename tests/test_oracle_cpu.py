@@ -76,3 +76,36 @@ def test_row_sums_and_symmetry_properties(oracle_mod):
     assert np.abs(rs).max() <= 1e-12 * np.abs(out["A_poisson"]).max()          # pure-Neumann Laplacian: zero row sums
     rs = np.add.reduceat(out["A_helmholtz"], out["rowptr"][:-1])
     assert np.abs(rs - 1.0).max() <= 1e-12                                      # I - theta dt nu lap: unit row sums
+
+
+# sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt: the reference's own recorded output of
+# poisson-boltzmann-harmonic-2d.lmp + poisson-boltzmann-harmonic.xml (periodic square lattice, Wendland, h = 1.5 dx, eps = 1,
+# ezcb = 0.5, psiref = 1, manufactured source; err.psi.norm2 = sqrt(mean((psi - sin x cos y)^2)), fix_isph_error.cpp:300-313)
+PB_TABLE = {16: 1.479161878614346e-02, 32: 3.706069041498665e-03, 64: 9.269711306933226e-04}
+
+
+def pb_harmonic_problem(lattice, N):
+    dx = 2 * np.pi / N
+    P = lattice.make_brick(2, (N, N), dx)
+    xw = P["xw"]; s = np.sin(xw[:, 0]) * np.cos(xw[:, 1])
+    return P, s, (-2.0 * s - np.sinh(s))[:P["nlocal"]].copy()
+
+
+@pytest.mark.parametrize("N", sorted(PB_TABLE))
+def test_known_answer_poisson_boltzmann_convergence_table(N, oracle_mod, lattice):
+    """End-to-end known answer of the reference itself: volumes, gradient/Laplacian corrections, the Poisson-Boltzmann residual
+    and Jacobian functors and the Newton iteration reproduce the recorded discretisation error to ~1e-14 relative."""
+    O = oracle_mod
+    P, s, ex = pb_harmonic_problem(lattice, N); nl = P["nlocal"]
+    o = O.Oracle(P, kind="port"); o.set_field(O.F_EPS, np.ones(len(s))); o.compute_pre(); rp, col = o.graph()
+    colL = O.tags_to_local(col, P["tag"][:nl]); prm = O.krylov_params(precond=O.PREC_ILU0, tol=1e-12, max_iters=2000)
+    psi = np.zeros(len(s)); k = 0
+    while True:
+        o.set_field(O.F_PSI, psi); f = o.pb_residual(extra_f=ex)
+        if (k > 0 and np.linalg.norm(f) / np.sqrt(nl) <= 1e-12) or k >= 30:
+            break
+        o.pb_jacobian(); dx_, info = O.krylov_solve(rp, colL, o.matrix(), -f, params=prm); psi[:nl] += dx_; k += 1
+    o.close()
+    err = np.sqrt(np.mean((psi[:nl] - s[:nl]) ** 2))
+    assert k < 10 and abs(err - PB_TABLE[N]) <= 1e-12 * PB_TABLE[N], (k, err, PB_TABLE[N])
+    assert abs(np.sqrt(np.mean(s[:nl] ** 2)) - 0.5) < 1e-14              # sol.psi.norm2 of the same table
