@@ -55,3 +55,14 @@ def test_bricks_tile_the_global_lattice(world):
         lo, nloc = lat.brick_of_rank(r, grid, ng)
         seen[lo[0]:lo[0] + nloc[0], lo[1]:lo[1] + nloc[1], lo[2]:lo[2] + nloc[2]] += 1
     assert np.all(seen == 1)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """Driver contract for N > 1: launched with torchrun, rank 0 alone runs the CPU arm and prints the line; the other ranks exit 0."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-n", "12"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0]); assert line["impl"] == "reference" and line["n_gpus"] == 2
