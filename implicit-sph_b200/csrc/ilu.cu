@@ -17,6 +17,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <queue>
+#include <thread>
 
 namespace cg = cooperative_groups;
 #define ILU_TB 1024
@@ -243,7 +244,34 @@ static void level_sets(int n, const std::vector<int> &rp, const std::vector<int>
 // Level-of-fill pattern, Ifpack_IlukGraph's rule: entries of the matrix have level 0; eliminating row i with pivot row k
 // creates (i,j) for every strictly-upper (k,j) with level(i,k) + level(k,j) + 1, kept when that is <= fill.  Rows ascending,
 // pivots of a row in ascending column order (a heap holds the pending lower columns), levels of finished rows kept per entry.
+// Level 1 (Ifpack's default) needs no levels of earlier rows: (i,j) is a level-1 entry iff some level-0 pivot k < min(i,j) has
+// (i,k) and (k,j) in the matrix, so every row's pattern is the union of its own row and the upper parts of its lower
+// neighbours' ORIGINAL rows — rows are independent and are formed by host threads.
+static void ilu1_symbolic_parallel(int n, const int *rp, const int *ci, std::vector<int> &frp, std::vector<int> &fci) {
+  unsigned T = std::thread::hardware_concurrency(); T = std::max(1u, std::min(T, 32u)); if (n < 4096) T = 1;
+  std::vector<std::vector<int>> cols(T), lens(T);
+  auto work = [&](unsigned t) {
+    const int r0 = (int)((long long)n * t / T), r1 = (int)((long long)n * (t + 1) / T);
+    std::vector<int> mark(n, -1), touched;
+    for (int i = r0; i < r1; ++i) {
+      touched.clear();
+      for (int q = rp[i]; q < rp[i + 1]; ++q) { const int cc = ci[q]; if (mark[cc] != i) { mark[cc] = i; touched.push_back(cc); } }
+      for (int q = rp[i]; q < rp[i + 1]; ++q) {
+        const int k = ci[q]; if (k >= i) continue;
+        for (int u = rp[k]; u < rp[k + 1]; ++u) { const int j = ci[u]; if (j > k && mark[j] != i) { mark[j] = i; touched.push_back(j); } }
+      }
+      std::sort(touched.begin(), touched.end());
+      cols[t].insert(cols[t].end(), touched.begin(), touched.end()); lens[t].push_back((int)touched.size());
+    }
+  };
+  std::vector<std::thread> th; for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0); for (auto &x : th) x.join();
+  frp.assign(1, 0); fci.clear();
+  for (unsigned t = 0; t < T; ++t) { for (int l : lens[t]) frp.push_back(frp.back() + l); fci.insert(fci.end(), cols[t].begin(), cols[t].end()); }
+}
+
 static void iluk_symbolic(int n, const int *rp, const int *ci, int fill, std::vector<int> &frp, std::vector<int> &fci) {
+  if (fill == 1) { ilu1_symbolic_parallel(n, rp, ci, frp, fci); return; }
   std::vector<unsigned char> flev; std::vector<int> ubeg(n, 0), lev(n, -1), touched;
   std::priority_queue<int, std::vector<int>, std::greater<int>> pend;
   frp.assign(1, 0); fci.clear(); fci.reserve((size_t)rp[n] * (fill + 1));

@@ -97,3 +97,21 @@ def test_iluk_symbolic_pattern_matches_the_definition(isph, fill):
         for i in range(n):
             cols = cio[rpo[i]:rpo[i + 1]]; assert np.all(np.diff(cols) > 0); got[i, cols] = True
         assert np.array_equal(got, want)
+
+
+def test_ilu1_symbolic_threaded_matches_the_sparse_product(isph):
+    """Level-of-fill 1 on a matrix large enough for the threaded host pass: pattern(A) | pattern(strict_lower(A) @ strict_upper(A))."""
+    import numpy as np
+    import scipy.sparse as sp
+    n1 = 72; e = np.ones(n1); T = sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1])
+    A = sp.csr_matrix(sp.kron(sp.eye(n1), T) + sp.kron(T, sp.eye(n1)) + sp.random(n1 * n1, n1 * n1, 3e-4, random_state=1)); A.sort_indices(); n = A.shape[0]
+    assert n >= 4096
+    B = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
+    want = sp.csr_matrix(((B + sp.tril(B, -1) @ sp.triu(B, 1)) != 0).astype(np.int8)); want.sort_indices()
+    L = isph.lib(); ip = ctypes.POINTER(ctypes.c_int)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32); nnz = ctypes.c_longlong()
+    L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), 1, None, None, ctypes.c_longlong(0), ctypes.byref(nnz))
+    assert nnz.value == want.nnz
+    rpo = np.zeros(n + 1, dtype=np.int32); cio = np.zeros(nnz.value, dtype=np.int32)
+    assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), 1, rpo.ctypes.data_as(ip), cio.ctypes.data_as(ip), ctypes.c_longlong(nnz.value), ctypes.byref(nnz)) == 0
+    assert np.array_equal(rpo, want.indptr) and np.array_equal(cio, want.indices)
