@@ -136,3 +136,38 @@ def test_two_rank_partition_matches_global_oracle(dim, nglobal, jitter, rs2, ora
             assert d["b"][li] == b[gi] and d["vf"][li] == vf[gi]
             assert abs(d["y"][li] - yg[gi]) <= 1e-13 * max(1.0, abs(yg[gi]))
     assert seen == P["nlocal"]
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_halo_plan_for_four_and_eight_bricks(world, lattice):
+    """The host planner on the 2x2x1 / 2x2x2 brick layouts bench.py uses at 4 / 8 GPUs (in-process: the planner is a pure function):
+    every remote ghost gets a halo column, slots are grouped by owner in (owner, tag) order, and the request list of rank r for
+    peer p names exactly the owner-local particles whose tags r's slots carry."""
+    isph = importlib.import_module("implicit-sph_b200"); L = isph.lib(); ip = C.POINTER(C.c_int)
+    dim = 3; grid = lattice.brick_grid(world, dim); ng_ = tuple(8 * g for g in grid); dx = 2 * np.pi / ng_[0]
+    bricks = []
+    for r in range(world):
+        lo, nloc = lattice.brick_of_rank(r, grid, ng_)
+        bricks.append(lattice.make_brick(dim, ng_, dx, lo=lo, nloc=nloc, rs2=12, jitter=0.03))
+    mt = max(int(P["tag"].max()) for P in bricks) + 1
+    own_rank = -np.ones(mt, dtype=np.int32); own_idx = -np.ones(mt, dtype=np.int32)
+    for r, P in enumerate(bricks):
+        t = P["tag"][:P["nlocal"]]; assert np.all(own_rank[t] < 0); own_rank[t] = r; own_idx[t] = np.arange(len(t), dtype=np.int32)
+    assert np.count_nonzero(own_rank >= 0) == int(np.prod(ng_))                      # every particle owned exactly once
+    recv = np.zeros((world, world), dtype=np.int64)
+    for r, P in enumerate(bricks):
+        nl, ngh = P["nlocal"], P["nghost"]
+        gt = np.ascontiguousarray(P["tag"][nl:], dtype=np.int32); g_owner = np.ascontiguousarray(own_rank[gt]); g_idx = np.ascontiguousarray(own_idx[gt])
+        gcol = np.zeros(ngh, dtype=np.int32); rcount = np.zeros(world, dtype=np.int32); req = np.zeros(max(ngh, 1), dtype=np.int32); nh = C.c_int()
+        assert L.isph_halo_plan_host(world, r, nl, ngh, gt.ctypes.data_as(ip), g_owner.ctypes.data_as(ip), g_idx.ctypes.data_as(ip),
+                                     gcol.ctypes.data_as(ip), rcount.ctypes.data_as(ip), req.ctypes.data_as(ip), C.byref(nh)) == 0
+        nhalo = nh.value; roff = np.concatenate([[0], np.cumsum(rcount)]); recv[r] = rcount
+        rem = g_owner != r
+        assert roff[-1] == nhalo == len(np.unique(gt[rem])) and rcount[r] == 0       # one slot per distinct remote tag
+        assert np.all(gcol[~rem] == g_idx[~rem]) and np.all((gcol[rem] >= nl) & (gcol[rem] < nl + nhalo))
+        slot_tag = np.zeros(nhalo, dtype=np.int64); slot_tag[gcol[rem] - nl] = gt[rem]
+        for p in range(world):
+            st = slot_tag[roff[p]:roff[p + 1]]
+            assert np.all(own_rank[st] == p) and np.all(np.diff(st) > 0)              # grouped by owner, ascending tag inside a group
+            assert np.array_equal(bricks[p]["tag"][req[roff[p]:roff[p + 1]]], st)     # the request names the right particles on the owner
+    assert np.array_equal(recv > 0, (recv > 0).T)                                    # exchanges are pairwise in both directions
