@@ -115,3 +115,31 @@ def test_ilu1_symbolic_threaded_matches_the_sparse_product(isph):
     rpo = np.zeros(n + 1, dtype=np.int32); cio = np.zeros(nnz.value, dtype=np.int32)
     assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), 1, rpo.ctypes.data_as(ip), cio.ctypes.data_as(ip), ctypes.c_longlong(nnz.value), ctypes.byref(nnz)) == 0
     assert np.array_equal(rpo, want.indptr) and np.array_equal(cio, want.indices)
+
+
+def test_host_entry_points_edge_cases(isph):
+    """Empty and degenerate inputs of the two pure-host entry points (no GPU needed)."""
+    import numpy as np
+    L = isph.lib(); ip = ctypes.POINTER(ctypes.c_int)
+    z = np.zeros(1, dtype=np.int32); rc = np.zeros(2, dtype=np.int32); nh = ctypes.c_int(-1)
+    # no ghosts at all: empty plan
+    assert L.isph_halo_plan_host(2, 0, 5, 0, z.ctypes.data_as(ip), z.ctypes.data_as(ip), z.ctypes.data_as(ip), z.ctypes.data_as(ip),
+                                 rc.ctypes.data_as(ip), z.ctypes.data_as(ip), ctypes.byref(nh)) == 0
+    assert nh.value == 0 and rc.tolist() == [0, 0]
+    # a ghost whose tag no rank owns: loud failure, not a silent column
+    gt = np.array([7], dtype=np.int32); go = np.array([-1], dtype=np.int32); gi = np.array([-1], dtype=np.int32); gc = np.zeros(1, dtype=np.int32)
+    assert L.isph_halo_plan_host(2, 0, 5, 1, gt.ctypes.data_as(ip), go.ctypes.data_as(ip), gi.ctypes.data_as(ip), gc.ctypes.data_as(ip),
+                                 rc.ctypes.data_as(ip), z.ctypes.data_as(ip), ctypes.byref(nh)) == -1
+    # two ghost copies of the same remote particle share one halo column
+    gt = np.array([9, 9], dtype=np.int32); go = np.array([1, 1], dtype=np.int32); gi = np.array([3, 3], dtype=np.int32); gc = np.zeros(2, dtype=np.int32); rq = np.zeros(2, dtype=np.int32)
+    assert L.isph_halo_plan_host(2, 0, 5, 2, gt.ctypes.data_as(ip), go.ctypes.data_as(ip), gi.ctypes.data_as(ip), gc.ctypes.data_as(ip),
+                                 rc.ctypes.data_as(ip), rq.ctypes.data_as(ip), ctypes.byref(nh)) == 0
+    assert nh.value == 1 and gc.tolist() == [5, 5] and rc.tolist() == [0, 1] and rq[0] == 3
+    # level-of-fill pattern: a diagonal matrix stays diagonal at any level; bad arguments are refused
+    n = 6; rp = np.arange(n + 1, dtype=np.int32); ci = np.arange(n, dtype=np.int32); nnz = ctypes.c_longlong()
+    for fill in (0, 1, 3):
+        rpo = np.zeros(n + 1, dtype=np.int32); cio = np.zeros(n, dtype=np.int32)
+        assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), fill, rpo.ctypes.data_as(ip), cio.ctypes.data_as(ip), ctypes.c_longlong(n), ctypes.byref(nnz)) == 0
+        assert nnz.value == n and np.array_equal(rpo, rp) and np.array_equal(cio, ci)
+    assert L.isph_iluk_symbolic_host(n, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), -1, None, None, ctypes.c_longlong(0), ctypes.byref(nnz)) == -1
+    assert L.isph_iluk_symbolic_host(n, None, ci.ctypes.data_as(ip), 0, None, None, ctypes.c_longlong(0), ctypes.byref(nnz)) == -1
