@@ -173,6 +173,14 @@ def run_reference(args, w, lat):
         line["full_workload_estimate"] = dict(value=rows_full / sec_full / 1e6, unit="Mrow/s", ms_per_step=sec_full * 1e3, iters=full_iters,
                                               how="rows_full x (assembly s/row + iters_full x solve s/(row x iteration)), both measured on the sample; iters_full = the "
                                                   "iteration count of the full workload (B200 run; the oracle matches it within +-2 on the parity cases)")
+    # BASELINE configs[1] beside the headline line, as in the B200 arm: the CPU arm runs the FULL 1M-particle workload here
+    # (no sampling), so configs1_c2 of the two arms is a same-workload comparison
+    if args.workload == "p8m" and not args.no_secondary:
+        w2 = dict(WORKLOADS["c2"]); n2 = args.cpu_n or w2["n"]
+        P2, F2, dt2 = make_problem(w2, n2, lat)
+        t = time.perf_counter(); r2 = cpu_step(O, P2, F2, dt2, w2, threads); sec2 = time.perf_counter() - t
+        line["configs1_c2"] = dict(workload=w2["desc"], rows=P2["nlocal"], value=P2["nlocal"] / sec2 / 1e6, unit="Mrow/s", ms_per_step=sec2 * 1e3, iters=r2["iters"],
+                                   sample="full workload" if n2 == w2["n"] else f"{n2}^3 sample", assemble_ms=r2["assemble_s"] * 1e3, solve_ms=r2["solve_s"] * 1e3)
     print(json.dumps(line))
 
 
