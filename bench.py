@@ -345,6 +345,12 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     else:
         solve_ms = timers["solve" + solve_label]
     nnz = c.nnz
+    halo = None
+    if world > 1:
+        try:
+            halo = c.halo_counts()
+        except Exception:                                    # reporting only: never let it take the benchmark line down
+            halo = None
     if world > 1:
         t = torch.tensor([float(nnz), float(nl)], dtype=torch.float64); dist.all_reduce(t); nnz_g, rows_g = t.tolist()
     else:
@@ -376,6 +382,13 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                               share_of_step=spmv_ms / steps / ms_dev,
                               note="per-launch time from CUDA events on the launching stream; at n_gpus > 1 it includes the NVLink import of the halo"),
                 breakdown_ms=timers, ms_per_iter=solve_ms / max(st["iters"], 1))
+    if halo is not None:                                     # NVLink side of the roofline (rank 0's brick): bytes that leave this GPU per operator apply
+        spmv_per_s = spmv_cnt / max(steps, 1) / max(ms_dev * 1e-3, 1e-12)
+        line["nvlink"] = dict(what="halo import of one SpMV on rank 0 (NVLink peer stores, 8 B per value) and the two all-reduces of an Arnoldi step (<= 53 doubles to each peer)",
+                              send_values_per_spmv=halo["nsend"], recv_values_per_spmv=halo["nhalo"], peers=halo["npeers"],
+                              bytes_sent_per_spmv=8 * halo["nsend"], bytes_sent_per_second=8.0 * halo["nsend"] * spmv_per_s,
+                              peak_gbs_per_direction=900.0, frac_of_nvlink_peak=8.0 * halo["nsend"] * spmv_per_s / 900e9,
+                              note="0.1 % of the local SpMV traffic: the exchange is latency-, not bandwidth-bound (DESIGN.md §6)")
     if w["prec"] == "point relaxation" and w["solver"] == "Block GMRES" and not pbs:
         kb = krylov_bytes_per_solve(nl, nnz, st["iters"], st.get("second_passes", st["iters"]))
         sg = kb / (solve_ms * 1e-3) / 1e9

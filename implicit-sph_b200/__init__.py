@@ -307,6 +307,10 @@ class Context:
     def timer_reset(self):
         self.call("isph_timer_reset")
 
+    def halo_counts(self):
+        a = C.c_int(); b = C.c_int(); p = C.c_int(); self.call("isph_halo_counts", C.byref(a), C.byref(b), C.byref(p))
+        return dict(nhalo=a.value, nsend=b.value, npeers=p.value)
+
     @property
     def launches(self):
         return int(self.L.isph_kernel_launches(self.h))

@@ -391,6 +391,9 @@ int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged,
   API_BEGIN(ctx) if (iters) *iters = c->last_iters; if (relres) *relres = c->last_relres; if (converged) *converged = c->last_converged; if (lmax) *lmax = c->last_lmax; API_END
 }
 
+int isph_halo_counts(isph_ctx *ctx, int *nhalo, int *nsend, int *npeers) {
+  API_BEGIN(ctx) int a = 0, b = 0, p = 0; halo_counts(c, &a, &b, &p); if (nhalo) *nhalo = a; if (nsend) *nsend = b; if (npeers) *npeers = p; API_END
+}
 long long isph_solver_second_passes(isph_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->last_second_passes : -1; }
 
 double isph_timer_ms(isph_ctx *ctx, const char *name) { if (!ctx || !name) return -1.0; Ctx *c = reinterpret_cast<Ctx *>(ctx); auto it = c->timers.find(name); if (it == c->timers.end()) return 0.0; timer_flush(it->second); return it->second.ms; }

@@ -280,6 +280,11 @@ void halo_wait_unstage(Ctx *c, double *x, unsigned long long seq) {
 }
 
 int halo_ncols(Ctx *c) { return c->nlocal + (c->halo ? c->halo->nhalo : 0); }
+void halo_counts(Ctx *c, int *nhalo, int *nsend, int *npeers) {
+  *nhalo = *nsend = *npeers = 0; if (!c->halo) return;
+  *nhalo = c->halo->nhalo; *nsend = c->halo->nsend;
+  for (size_t p = 0; p < c->halo->send_count.size(); ++p) if (c->halo->send_count[p] > 0) ++*npeers;
+}
 
 // Halo import for an SpMV (Epetra_Import): the off-rank entries of x land behind its owned rows.
 void halo_exchange(Ctx *c, double *x, int nvec, int ldx) {

@@ -199,5 +199,6 @@ void halo_allreduce(Ctx *c, double *d_buf, int count);
 void halo_forward_field(Ctx *c, int field, int ncomp);
 void halo_destroy(Ctx *c);
 int halo_ncols(Ctx *c);
+void halo_counts(Ctx *c, int *nhalo, int *nsend, int *npeers);
 
 }  // namespace isph

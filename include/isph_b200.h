@@ -192,6 +192,9 @@ long long isph_solver_second_passes(isph_ctx *ctx);
 /* ---- timers (the reference's Teuchos::Time scopes, utils.cpp:16-43): "computePoisson", "solvePoisson", ... ----- */
 double isph_timer_ms(isph_ctx *ctx, const char *name);    /* accumulated device time (CUDA events) */
 int isph_timer_reset(isph_ctx *ctx);
+/* halo plan of this rank (after isph_atoms_set with nranks > 1): values received / sent per vector import and the number of
+ * peers sent to; 8 * nsend bytes leave this GPU over NVLink per SpMV */
+int isph_halo_counts(isph_ctx *ctx, int *nhalo, int *nsend, int *npeers);
 long long isph_kernel_launches(isph_ctx *ctx);            /* number of kernels this context has launched */
 /* per-launch CUDA-event timing of the SpMV kernel inside whatever runs next (solve, assembly): enable, run, read */
 int isph_profile_spmv(isph_ctx *ctx, int enable);
