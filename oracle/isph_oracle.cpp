@@ -1,8 +1,12 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle ("port"): a plain C++ restatement of the reference's
 // graph / pre-computation / operator-assembly algorithms for the linear-solve hot path.
 // Every function cites the reference file:line it follows (paths relative to /root/reference/IMPLICIT-SPH).
-// It is pinned against oracle/_ref (the reference's own functor headers compiled here) by
-// tests/test_oracle_vs_ref.py and by the fixtures under tests/golden/ that were generated from _ref.
+// PARITY PINNED (this half of the oracle): (1) bit-identical to oracle/_ref — the reference's own functor headers compiled
+// here — on every case of tests/test_oracle_cpu.py and on the fixtures under tests/golden/ that were generated from _ref;
+// (2) against the reference's own recorded outputs (sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt): total volume
+// to 13 digits and, end to end through volumes / corrections / Poisson-Boltzmann residual / Jacobian / Newton iteration, the
+// recorded err.psi.norm2 at N = 16, 32, 64 to <= 1e-14 relative.  (The Krylov half, krylov_oracle.cpp, restates un-vendored
+// Trilinos code and stays "parity unpinned".)
 // Nothing in the product path (implicit-sph_b200/) may call into this file.
 //
 // Arithmetic notes: built with -ffp-contract=off; expressions keep the reference's operation order because
