@@ -86,7 +86,7 @@ def test_row_sums_and_symmetry_properties(oracle_mod):
 # sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt: the reference's own recorded output of
 # poisson-boltzmann-harmonic-2d.lmp + poisson-boltzmann-harmonic.xml (periodic square lattice, Wendland, h = 1.5 dx, eps = 1,
 # ezcb = 0.5, psiref = 1, manufactured source; err.psi.norm2 = sqrt(mean((psi - sin x cos y)^2)), fix_isph_error.cpp:300-313)
-PB_TABLE = {16: 1.479161878614346e-02, 32: 3.706069041498665e-03, 64: 9.269711306933226e-04}
+PB_TABLE = {16: 1.479161878614346e-02, 32: 3.706069041498665e-03, 64: 9.269711306933226e-04, 128: 2.317702568247343e-04}
 
 
 def pb_harmonic_problem(lattice, N):
