@@ -605,6 +605,21 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
   return 0;
 }
 
+// Corrected::FunctorOuterGradient (functor_gradient.h:80-169) on a scalar field, alpha = 1: grad_i = sum_j (G_i r_ij) dW/dr / r V_j coeff op(f_i, f_j)
+int orc_scalar_gradient(orc_problem *q, int field, int anti, int mh, int f0, int f1, double *grad) {
+  if (orc_field_ncomp(field) != 1) return -1;
+  q->forward(field);
+  const double *fld = q->f[field].data(); const int dim = q->dim;
+  std::fill(grad, grad + (size_t)3 * q->nlocal, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii]; double g[3] = {};
+    grad_like_loop(q, ii, anti != 0, mh != 0, f0, f1, [&](int j, int k2, double gitmp, double vjtmp) { const double ijtmp = gitmp * vjtmp; g[k2] += ijtmp * (sph_op(anti != 0, fld[i], fld[j])); });
+    for (int k = 0; k < dim; ++k) grad[3 * (size_t)i + k] = g[k] * 1.0;
+  }
+  return 0;
+}
+
 // FunctorOuterAppliedElectricPotential, functor_applied_electric_potential.h:34-96
 int orc_applied_electric_potential(orc_problem *q, double *b) {
   if (!q->have_graph || q->is_filled) return -1;

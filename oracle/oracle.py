@@ -71,6 +71,7 @@ def _load(kind):
     L.orc_pb_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.orc_ns_correct.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp]
     L.orc_applied_electric_potential.argtypes = [C.c_void_p, _dp]
+    L.orc_scalar_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
     L.orc_solute_transport.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp]
     L.orc_pb_residual.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
     L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
@@ -154,6 +155,9 @@ class Oracle:
 
     def pb_jacobian(self, morris_holmes=False, linearized=False, ezcb=0.5, psiref=1.0, gamma=0.0):
         self._ck(self.L.orc_pb_jacobian(self.p, int(morris_holmes), int(linearized), ezcb, psiref, gamma), "pb_jacobian")
+
+    def scalar_gradient(self, field, anti=False, morris_holmes=False, filter_i=FLUID, filter_j=127):
+        g = np.zeros((self.nlocal, 3)); self._ck(self.L.orc_scalar_gradient(self.p, field, int(anti), int(morris_holmes), filter_i, filter_j, _d(g)), "scalar_gradient"); return g
 
     def applied_electric_potential(self):
         b = np.zeros(self.nlocal); self._ck(self.L.orc_applied_electric_potential(self.p, _d(b)), "applied_electric_potential"); return b

@@ -58,6 +58,10 @@ int orc_ns_helmholtz(orc_problem *p, double dt, double theta, int anti, int morr
                      int incremental_pressure, const double *g, double *b);
 /* functor_poisson_boltzmann_jacobian.h:35-107 (A.is_filled kept between calls) */
 int orc_pb_jacobian(orc_problem *p, int morris_holmes, int linearized, double ezcb, double psiref, double gamma);
+/* Corrected::FunctorOuterGradient<Pair, anti>(field, alpha = 1, grad) with FilterBinary(filter_i, filter_j) — the matrix-free
+ * corrected gradient of a scalar per-particle field (functor_gradient.h:80-169), as PairISPH_Corrected::computePsiGradient
+ * calls it (pair_isph_corrected.cpp:528-553; psi, (Fluid, All)); the field is forward-communicated first; grad[nlocal][3] out */
+int orc_scalar_gradient(orc_problem *p, int field, int anti, int morris_holmes, int filter_i, int filter_j, double *grad);
 /* functor_applied_electric_potential.h:34-96 (sigma, phi from the fields); b[nlocal] out */
 int orc_applied_electric_potential(orc_problem *p, double *b);
 /* functor_solute_transport.h:47-134; b[nlocal]: in c^n, out rhs */

@@ -301,6 +301,21 @@ int orc_pb_jacobian(orc_problem *q, int mh, int linearized, double ezcb, double 
   })
 }
 
+int orc_scalar_gradient(orc_problem *q, int field, int anti, int mh, int f0, int f1, double *grad) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    double *fld = field_ptr(q, field); if (!fld || orc_field_ncomp(field) != 1) throw std::runtime_error("scalar field expected");
+    if (field == ORC_F_PSI) { p.comm_variable = MockPair::Psi; p.comm_forward = 1; p.comm->forward_comm_pair(&p); }
+    else for (int g = 0; g < q->nghost; ++g) { const int o = p.owner_of_ghost[g]; if (o >= 0) fld[q->nlocal + g] = fld[o]; }
+    Arr2<double> out; out.init(q->nall, 3);
+    FilterBinary filter; filter.setPairYes(f0, f1);
+    // bindings: functor_gradient.h:15-16, functor_boundary_morris_holmes.h ; call pair_isph_corrected.cpp:537-549
+    if (mh) { FunctorOuterGradient_MorrisHolmes<P> f(&p, fld, 1.0, out.ptr()); f.setFilter(&filter); PairFor(f, f.getNumberOfWork()); }
+    else if (anti) { FunctorOuterGradient<P, true> f(&p, fld, 1.0, out.ptr()); f.setFilter(&filter); PairFor(f, f.getNumberOfWork()); }
+    else { FunctorOuterGradient<P, false> f(&p, fld, 1.0, out.ptr()); f.setFilter(&filter); PairFor(f, f.getNumberOfWork()); }
+    memcpy(grad, out.d.data(), sizeof(double) * 3 * q->nlocal);
+  })
+}
 int orc_applied_electric_potential(orc_problem *q, double *b) {
   ORC_TRY({
     MockPair &p = q->pair; using namespace Corrected;

@@ -72,6 +72,20 @@ def test_port_matches_ref_library_when_present(name, anti, sing, mh, oracle_mod)
             assert relerr(a[k], b[k]) <= 1e-13, k
 
 
+@pytest.mark.parametrize("name,anti,mh", [("jitter2d", False, False), ("jitter3d", True, False), ("solid2d", False, True)])
+def test_scalar_gradient_port_matches_ref_library_when_present(name, anti, mh, oracle_mod):
+    """Corrected::FunctorOuterGradient (functor_gradient.h:80-169) on a scalar field: the restatement is bit-identical to the
+    reference's own functor."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    O = oracle_mod; P, F = make_case(name); cs = P["case"]; res = {}
+    for kind in ("ref", "port"):
+        o = O.Oracle(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"], kind=kind)
+        o.set_field(O.F_PSI, F["psi"]); o.compute_pre(normals=cs["has_solid"])
+        res[kind] = o.scalar_gradient(O.F_PSI, anti=anti, morris_holmes=mh); o.close()
+    assert np.array_equal(res["ref"], res["port"]) and np.abs(res["port"]).max() > 0
+
+
 def test_row_sums_and_symmetry_properties(oracle_mod):
     """Size-independent properties of the operators (also asserted on the GPU at full size)."""
     import harness
@@ -87,6 +101,9 @@ def test_row_sums_and_symmetry_properties(oracle_mod):
 # poisson-boltzmann-harmonic-2d.lmp + poisson-boltzmann-harmonic.xml (periodic square lattice, Wendland, h = 1.5 dx, eps = 1,
 # ezcb = 0.5, psiref = 1, manufactured source; err.psi.norm2 = sqrt(mean((psi - sin x cos y)^2)), fix_isph_error.cpp:300-313)
 PB_TABLE = {16: 1.479161878614346e-02, 32: 3.706069041498665e-03, 64: 9.269711306933226e-04, 128: 2.317702568247343e-04}
+
+
+PB_GRAD_TABLE = {16: 4.719682089799385e-02, 32: 1.198133743842115e-02, 64: 3.006646113179593e-03}     # err.psi.grad.norm2, same file
 
 
 def pb_harmonic_problem(lattice, N):
@@ -113,4 +130,9 @@ def test_known_answer_poisson_boltzmann_convergence_table(N, oracle_mod, lattice
     o.close()
     err = np.sqrt(np.mean((psi[:nl] - s[:nl]) ** 2))
     assert k < 10 and abs(err - PB_TABLE[N]) <= 1e-12 * PB_TABLE[N], (k, err, PB_TABLE[N])
+    if N in PB_GRAD_TABLE:       # computePsiGradient (pair_isph_corrected.cpp:528-553): the matrix-free corrected gradient of the solution
+        o = O.Oracle(P, kind="port"); o.compute_pre(); o.set_field(O.F_PSI, psi); g = o.scalar_gradient(O.F_PSI); o.close()
+        xw = P["xw"][:nl]; ge = np.stack([np.cos(xw[:, 0]) * np.cos(xw[:, 1]), -np.sin(xw[:, 0]) * np.sin(xw[:, 1])], axis=1)
+        gerr = np.sqrt(np.mean(((g[:, :2] - ge) ** 2).sum(axis=1)))
+        assert abs(gerr - PB_GRAD_TABLE[N]) <= 1e-12 * PB_GRAD_TABLE[N], (gerr, PB_GRAD_TABLE[N])
     assert abs(np.sqrt(np.mean(s[:nl] ** 2)) - 0.5) < 1e-14              # sol.psi.norm2 of the same table
