@@ -5,7 +5,9 @@
 // here — on every case of tests/test_oracle_cpu.py and on the fixtures under tests/golden/ that were generated from _ref;
 // (2) against the reference's own recorded outputs (sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt): total volume
 // to 13 digits and, end to end through volumes / corrections / Poisson-Boltzmann residual / Jacobian / Newton iteration, the
-// recorded err.psi.norm2 at N = 16, 32, 64, 128 to <= 1e-12 relative (observed 3e-15 .. 7e-15).  (The Krylov half, krylov_oracle.cpp, restates un-vendored
+// recorded err.psi.norm2 at N = 16, 32, 64, 128 to <= 1e-12 relative (observed 3e-15 .. 7e-15), the recorded gradient errors, and —
+// for solid walls, normals, the Morris-Holmes mirror and the linearized equation — the six recorded errors and the volumes of
+// sph-script/conv-channel-edl-potential-2d-morrisholmes-rev722.txt (2e-15 .. 2e-12).  (The Krylov half, krylov_oracle.cpp, restates un-vendored
 // Trilinos code and stays "parity unpinned".)
 // Nothing in the product path (implicit-sph_b200/) may call into this file.
 //

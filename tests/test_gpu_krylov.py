@@ -246,3 +246,21 @@ def test_known_answer_poisson_boltzmann_convergence_table_on_the_device(N):
     err = np.sqrt(np.mean((psi - s[:nl]) ** 2))
     assert st["converged"] and st["newton_iters"] < 10
     assert abs(err - PB_TABLE[N]) <= 1e-10 * PB_TABLE[N], (err, PB_TABLE[N])
+
+
+@pytest.mark.parametrize("boundary", ["MorrisHolmes", "ConstExtension"])
+def test_known_answer_channel_edl_table_on_the_device(boundary):
+    """The reference's recorded channel-EDL errors (sph-script/conv-channel-edl-potential-2d-morrisholmes-rev722.txt, N = 32 and 64)
+    from the CUDA path alone: solid walls, normals / number density, Morris-Holmes mirror, linearized Poisson-Boltzmann Newton."""
+    from test_oracle_cpu import EDL_TABLE, edl_channel_problem
+    lat = importlib.import_module("implicit-sph_b200.lattice"); mh = boundary == "MorrisHolmes"
+    for N in (32, 64):
+        P, h, exact = edl_channel_problem(lat, N); nl = P["nlocal"]; fluid = P["type"][:nl] != 2
+        c = isph.Context(); c.set_particles(P, kinds=(0, isph.KIND_FLUID, isph.KIND_SOLID, isph.KIND_FLUID), h=h, h_min=h, morris_safe=0.0)
+        c.field_set(isph.F_EPS, np.ones(len(exact))); c.field_set(isph.F_PSI0, np.ones(len(exact))); c.field_set(isph.F_PSI, np.zeros(len(exact)))
+        c.compute_pre(normals=True); c.graph_build(); c.create_solution(None, 1); c.create_load(None, 1)
+        configure(c, O.SOLVER_GMRES, O.PREC_ILU0, **{"Convergence Tolerance": 1e-13, "Maximum Iterations": 3000})
+        st = c.pb_newton(morris_holmes=mh, linearized=True, ezcb=50.0, psiref=1.0, tol_f=1e-11, tol_update=1.0)
+        psi = c.field_get(isph.F_PSI)[:nl]; c.close()
+        err = np.sqrt(np.mean((psi[fluid] - exact[:nl][fluid]) ** 2)); want = EDL_TABLE[(boundary, N)]
+        assert st["converged"] and st["newton_iters"] <= 3 and abs(err - want) <= 1e-9 * want, (N, st, err, want)

@@ -136,3 +136,49 @@ def test_known_answer_poisson_boltzmann_convergence_table(N, oracle_mod, lattice
         gerr = np.sqrt(np.mean(((g[:, :2] - ge) ** 2).sum(axis=1)))
         assert abs(gerr - PB_GRAD_TABLE[N]) <= 1e-12 * PB_GRAD_TABLE[N], (gerr, PB_GRAD_TABLE[N])
     assert abs(np.sqrt(np.mean(s[:nl] ** 2)) - 0.5) < 1e-14              # sol.psi.norm2 of the same table
+
+
+# sph-script/conv-channel-edl-potential-2d-morrisholmes-rev722.txt ("Wendland Kernel h = 1.2dx, cut over h = 2.0"): the reference's
+# recorded output of channel-edl-potential-2d.lmp at that revision — a periodic strip of round(0.2 N) x (N + 12) particles on
+# `lattice sq dx origin 0.5 0.5`, |y| < 1 fluid (types 1 and 3), six layers of solid wall (type 2, psi0 = 1) on either side,
+# h_min = h, eps = 1, ezcb = 50, psiref = 1, LINEARIZED Poisson-Boltzmann, analytic psi = cosh(kappa y) / cosh(kappa), kappa = 10;
+# err.psi.norm2 = sqrt(mean over the fluid particles of (psi - analytic)^2).  Two sections: MorrisHolmes and ConstExtension.
+EDL_TABLE = {("MorrisHolmes", 32): 9.116361684603088e-03, ("MorrisHolmes", 64): 2.472541432093094e-03, ("MorrisHolmes", 128): 5.863480602005782e-04,
+             ("ConstExtension", 32): 5.759847249691673e-02, ("ConstExtension", 64): 3.251980384017656e-02, ("ConstExtension", 128): 1.714795402048308e-02}
+EDL_VOLUME = {32: 7.367736289630282e-01, 64: 7.981714313766128e-01, 128: 7.981714313766139e-01}      # "total volume" (fluid particles)
+EDL_SOLNORM = {32: 2.165346849657311e-01, 64: 2.218003136662599e-01, 128: 2.231527086946378e-01}    # "sol.psi.norm2"
+
+
+def edl_channel_problem(lattice, N, hfac=1.2):
+    r = 1.0; dx = 2 * r / N; nx = int(round(N * 0.2)); wall = 6
+
+    def type_fn(wx, wy, wz):
+        y = (wy + 0.5) * dx - (r + wall * dx)
+        return np.where(np.abs(y) < r, np.where(np.abs(y) < r - 2 * hfac * dx, 1, 3), 2).astype(np.int32)
+    P = lattice.make_brick(2, (nx, N + 2 * wall), dx, rs2=9, origin=0.5, type_fn=type_fn)
+    y = P["xw"][:, 1] - (r + wall * dx)
+    return P, hfac * dx, np.cosh(10.0 * y) / np.cosh(10.0)
+
+
+@pytest.mark.parametrize("boundary,N", sorted(EDL_TABLE))
+def test_known_answer_channel_edl_table(boundary, N, oracle_mod, lattice):
+    """Solid walls end to end against the reference's recorded numbers: particle kinds, h_min table, interface normals and particle
+    number density (FunctorOuterNormal), the Morris-Holmes mirror coefficient, the linearized Poisson-Boltzmann residual and
+    Jacobian with and without the mirror, Newton + ILU/GMRES."""
+    O = oracle_mod; mh = boundary == "MorrisHolmes"
+    P, h, exact = edl_channel_problem(lattice, N); nl = P["nlocal"]; fluid = P["type"][:nl] != 2
+    o = O.Oracle(P, kinds=(0, O.FLUID, O.SOLID, O.FLUID), h=h, h_min=h, morris_safe=0.0, kind="port")
+    o.set_field(O.F_EPS, np.ones(len(exact))); o.set_field(O.F_PSI0, np.ones(len(exact)))
+    o.compute_pre(normals=True); rp, col = o.graph(); colL = O.tags_to_local(col, P["tag"][:nl])
+    vol = o.get_field(O.F_VFRAC)[:nl][fluid].sum()
+    assert abs(vol - EDL_VOLUME[N]) <= 1e-13 * EDL_VOLUME[N] and abs(np.sqrt(np.mean(exact[:nl][fluid] ** 2)) - EDL_SOLNORM[N]) <= 1e-14
+    psi = np.zeros(len(exact)); k = 0; prm = O.krylov_params(precond=O.PREC_ILU0, tol=1e-13, max_iters=3000)
+    while True:
+        o.set_field(O.F_PSI, psi); f = o.pb_residual(morris_holmes=mh, linearized=True, ezcb=50.0, psiref=1.0)
+        if (k > 0 and np.linalg.norm(f) / np.sqrt(nl) <= 1e-11) or k >= 10:
+            break
+        o.pb_jacobian(morris_holmes=mh, linearized=True, ezcb=50.0, psiref=1.0)
+        d, info = O.krylov_solve(rp, colL, o.matrix(), -f, params=prm); psi[:nl] += d; k += 1
+    o.close()
+    err = np.sqrt(np.mean((psi[:nl][fluid] - exact[:nl][fluid]) ** 2)); want = EDL_TABLE[(boundary, N)]
+    assert k <= 2 and abs(err - want) <= 1e-10 * want, (k, err, want)            # observed 2e-15 .. 2e-12
