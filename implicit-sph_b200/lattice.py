@@ -124,3 +124,41 @@ def tgv_velocity(xw: np.ndarray, U: float = 0.1) -> np.ndarray:
     v[:, 0] = U * np.sin(xw[:, 0]) * np.cos(xw[:, 1])
     v[:, 1] = -U * np.cos(xw[:, 0]) * np.sin(xw[:, 1])
     return v
+
+
+def make_cloud(dim, n, box, reach, seed=7, min_sep=0.0, type_fn=None):
+    """A non-lattice particle set in the same LAMMPS shape: `n` owned particles uniformly random in the periodic box
+    [0, box)^dim (rejected below `min_sep` of an earlier one), ghosts = every periodic image within `reach` of the box, and a
+    full neighbor list holding, for each owned particle, all atoms (owned or ghost) within `reach` in an order unrelated to
+    position — rows have ragged lengths.  `reach` must be >= the pair cutoff; the functors' own rsq < cutsq test decides."""
+    rng = np.random.default_rng(seed)
+    pts = []
+    while len(pts) < n:
+        p = rng.uniform(0.0, box, size=3); p[dim:] = 0.0
+        if min_sep > 0.0 and pts:
+            d = np.abs(np.asarray(pts) - p); d = np.minimum(d, box - d); d[:, dim:] = 0.0
+            if (np.sqrt((d ** 2).sum(axis=1)) < min_sep).any():
+                continue
+        pts.append(p)
+    own = np.asarray(pts)
+    shifts = [s for s in np.ndindex(*(3,) * dim)]
+    gx, gt = [], []
+    for s in shifts:
+        sh = np.zeros(3); sh[:dim] = (np.asarray(s) - 1) * box
+        if not sh.any():
+            continue
+        img = own + sh
+        near = np.all((img[:, :dim] > -reach) & (img[:, :dim] < box + reach), axis=1)
+        gx.append(img[near]); gt.append(np.nonzero(near)[0])
+    ghost = np.concatenate(gx) if gx else np.zeros((0, 3)); gtag = np.concatenate(gt) if gt else np.zeros(0, dtype=np.int64)
+    x = np.concatenate([own, ghost]); tag = np.concatenate([np.arange(n), gtag]).astype(np.int32) + 1
+    xw = np.concatenate([own, own[gtag]])
+    neigh, noff = [], [0]
+    for i in range(n):
+        d = x - own[i]; r2 = (d ** 2).sum(axis=1)
+        j = np.nonzero((r2 < reach * reach) & (np.arange(len(x)) != i))[0]
+        neigh.append(rng.permutation(j)); noff.append(noff[-1] + len(j))
+    typ = np.ones(len(x), dtype=np.int32) if type_fn is None else np.asarray(type_fn(xw), dtype=np.int32)
+    return dict(dim=dim, nlocal=n, nghost=len(ghost), x=np.ascontiguousarray(x), xw=xw, type=typ, tag=tag,
+                ilist=np.arange(n, dtype=np.int32), noff=np.asarray(noff, dtype=np.int64), neigh=np.concatenate(neigh).astype(np.int32),
+                gidx=(tag - 1).astype(np.int64), dx=box / n ** (1.0 / dim), nglobal=(n,), lo=(0,) * dim, nloc=(n,))

@@ -186,3 +186,25 @@ def test_known_answer_channel_edl_table(boundary, N, oracle_mod, lattice):
     o.close()
     err = np.sqrt(np.mean((psi[:nl][fluid] - exact[:nl][fluid]) ** 2)); want = EDL_TABLE[(boundary, N)]
     assert k <= 3 and abs(err - want) <= 1e-10 * want, (k, err, want)            # observed 2e-15 .. 2e-12
+
+
+@pytest.mark.parametrize("dim,n", [(2, 500), (3, 700)])
+def test_port_matches_ref_on_a_random_cloud(dim, n, oracle_mod, lattice):
+    """Ragged input: uniformly random particles (not a lattice), rows of very different lengths, neighbor lists in an order
+    unrelated to position — graph, pre-computation, Poisson system, Poisson-Boltzmann residual and corrected gradient of the
+    restatement are bit-identical to the reference's own functors."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    O = oracle_mod; box = 2 * np.pi; dx = box / n ** (1.0 / dim); h = 1.5 * dx
+    P = lattice.make_cloud(dim, n, box, reach=2 * h * 1.05, min_sep=0.45 * dx)
+    jn = np.diff(P["noff"]); assert jn.max() >= 1.4 * jn.min()                 # genuinely ragged
+    res = {}
+    for kind in ("ref", "port"):
+        o = O.Oracle(P, h=h, kind=kind); xw = P["xw"]
+        o.set_field(O.F_PSI, np.sin(xw[:, 0]) * np.cos(xw[:, 1])); o.set_field(O.F_EPS, 1 + 0.2 * np.cos(xw[:, 0]))
+        v = lattice.tgv_velocity(xw); o.set_field(O.F_VSTAR, v); o.set_field(O.F_VELOCITY, v)
+        o.compute_pre(); rp, col = o.graph(); b = o.ns_poisson(0.05); A = o.matrix(); o.invalidate_matrix()
+        res[kind] = (rp, col, b, A, o.pb_residual(), o.scalar_gradient(O.F_PSI), o.get_field(O.F_VFRAC), o.get_field(O.F_GC), o.get_field(O.F_LC)); o.close()
+    for a, b_ in zip(res["ref"], res["port"]):
+        assert np.array_equal(a, b_)
+    rs = np.add.reduceat(res["port"][3], res["port"][0][:-1]); assert np.abs(rs).max() <= 1e-11 * np.abs(res["port"][3]).max()   # still a pure-Neumann Laplacian
