@@ -7,12 +7,16 @@ One *step* = what `PairISPH::compute` does per time step for the pressure Poisso
 reference does.  Metric: rows assembled-and-solved per second (whole job), with `ms_per_step` = the absolute Poisson
 step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM bandwidth inside the solve.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|c2|c1|c4|c2j] [--n LATTICE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|c2|c1|c3|c4|c4s|c5|c2j] [--n LATTICE]
 
 Default workload = the configuration BASELINE.json's metric and target are quoted on: the 3-D 8M-particle (200^3) pressure
-Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  At N=1
-the line also carries BASELINE configs[1] (1M particles, `configs1_c2`) measured in the same run.  `--impl reference` times
-the CPU path (oracle port, OpenMP over all host cores) on a bounded sample.
+Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  The line
+also carries, at every N, secondary blocks for BASELINE configs[2] (`configs2_c3`: 8M Helmholtz, 3 RHS, CG + Chebyshev),
+configs[3] (`configs3_c4`: 8M corrected-operator Poisson, GMRES + block-Jacobi ILU(0) on 4x4x4 bricks of 50^3) and configs[4]
+(`configs4_c5`: 4M Poisson-Boltzmann Newton), at N=1 also configs[1] (`configs1_c2`, 1M particles), and at N>1 a `parity`
+block: the multi-GPU path checked against the CPU oracle on a small global problem before the timed region (the run fails on
+a mismatch).  `--impl reference` times the CPU path (oracle port, OpenMP over all host cores) on a bounded sample of the same
+workload, with the same `config`.
 """
 import argparse
 import importlib
@@ -41,6 +45,10 @@ WORKLOADS = {
     # 2x2x2 Ifpack-rank-equivalent bricks per GPU (= 4x4x4 bricks of 50^3 at 8 GPUs)
     "c4": dict(dim=3, n=100, jitter=0.04, rs2=12, prec="ILU", solver="Block GMRES", anti=False, blocks=2,
                desc="BASELINE configs[3] per GPU: corrected-operator (Gc/Lc) pressure Poisson, 1M particles per GPU, GMRES(50) + block-Jacobi ILU(0), 8 bricks of 50^3 per GPU"),
+    # BASELINE configs[3] as BASELINE.md §3 defines it: the 8M-row problem (strong scaling), block-Jacobi ILU(0) on the Ifpack-rank
+    # partition 4x4x4 bricks of 50^3 (64 / N blocks per GPU), corrected (Gc/Lc) operators, jittered particles
+    "c4s": dict(dim=3, n=200, jitter=0.04, rs2=12, prec="ILU", solver="Block GMRES", anti=False, strong=True, global_blocks=4,
+                desc="BASELINE configs[3]: 3-D corrected-operator (Gc/Lc) pressure Poisson, 8M particles (200^3), GMRES(50) + block-Jacobi ILU(0) on 4x4x4 Ifpack-rank-equivalent bricks of 50^3, fixed global size (strong scaling)"),
     # BASELINE configs[2]: velocity Helmholtz (I - theta dt nu lap) v* = rhs, dim right-hand sides one after another, CG + Chebyshev
     "c3": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="Chebyshev", solver="Block CG", strong=True, system="helmholtz", theta=0.5,
                desc="BASELINE configs[2]: 3-D velocity Helmholtz (functor_incomp_navier_stokes_helmholtz), 8M particles, 3 right-hand sides, CG + Chebyshev(1), x0 = v^n, fixed global size (strong scaling)"),
@@ -53,10 +61,32 @@ WORKLOADS = {
 }
 
 
+def workload_config(wname, w, world, lat):
+    """The declarative description of the workload: identical on the B200 arm and on the reference arm (the driver compares the
+    two `config` objects).  Everything a run MEASURES (iterations, residual, nnz) goes into `result`, not here."""
+    dim = w["dim"]; grid = lat.brick_grid(world, dim)
+    nglobal = (w["n"],) * dim if w.get("strong") else tuple(w["n"] * g for g in grid)
+    rows = int(np.prod(nglobal)); per = rows // world
+    nnz_row = 93 if dim == 3 else 25                         # SURVEY.md §8: ideal stored entries per row
+    return dict(workload=wname, description=w["desc"], rows=rows, rows_per_gpu=per, bricks="x".join(map(str, grid)), lattice="x".join(map(str, nglobal)),
+                system=w.get("system", "poisson"), precond=w["prec"], solver=w["solver"], restart=50, tolerance=1e-8,
+                operators="antisymmetric" if w.get("anti", True) else "corrected (Gc/Lc)", jitter_dx=w["jitter"],
+                l2="inputs larger than L2: matrix stream ~%.0f MB per SpMV per GPU, Krylov basis ~%.0f MB per GPU (L2 = 126 MB)" % ((12.0 * nnz_row + 20.0) * per / 1e6, 8e-6 * per * 101))
+
+
+_PROBLEMS = {}
+
+
 def make_problem(w, n, lat, lo=None, nloc=None, nglobal=None):
     dim = w["dim"]; ng = nglobal if nglobal is not None else (n,) * dim
     dx = 2.0 * np.pi / ng[0]
-    P = lat.make_brick(dim, ng, dx, lo=lo, nloc=nloc, rs2=w["rs2"], jitter=w["jitter"], origin=w.get("origin", 0.0))
+    key = (dim, tuple(ng), None if lo is None else tuple(lo), None if nloc is None else tuple(nloc), w["rs2"], w["jitter"], w.get("origin", 0.0))
+    if key not in _PROBLEMS:                                  # p8m and c3 share one 200^3 lattice: generated once (one big lattice is kept at a time)
+        if int(np.prod(nloc if nloc is not None else ng)) >= 500000:
+            for k in [k for k, v in _PROBLEMS.items() if v["nlocal"] >= 500000]:
+                del _PROBLEMS[k]
+        _PROBLEMS[key] = lat.make_brick(dim, ng, dx, lo=lo, nloc=nloc, rs2=w["rs2"], jitter=w["jitter"], origin=w.get("origin", 0.0))
+    P = _PROBLEMS[key]
     xw = P["xw"]
     v = lat.tgv_velocity(xw)
     # v* of a real step is not the analytic vortex: add a broadband (per-particle, tag-hashed => identical on every rank
@@ -122,8 +152,15 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_step(O, P, F, dt, w, threads):
-    """One step of the CPU path (oracle port): pre-computation, graph, assembly, Krylov solve."""
+# GMRES iterations of the FULL-SIZE workloads (measured by the B200 arm, BENCH_r01 / profiles/; on every size where both ran
+# the CPU oracle needs the same count, e.g. 188 = 188 on the 1M-particle configs[1]).  The CPU arm's bounded sample pins its
+# solve to this count, so that a sampled row costs what a row of the full workload costs.
+FULL_ITERS = {"p8m": 452, "c2": 188}
+
+
+def cpu_step(O, P, F, dt, w, pin_iters=None):
+    """One step of the CPU path (oracle port): pre-computation, graph, assembly, Krylov solve.  pin_iters: run exactly that
+    many Krylov iterations (Convergence Tolerance 0, Maximum Iterations = pin_iters) instead of stopping at 1e-8."""
     t0 = time.perf_counter()
     o = O.Oracle(P, kind="port")
     o.set_field(O.F_VSTAR, F["vstar"]); o.set_field(O.F_DENSITY, F["density"])
@@ -135,56 +172,59 @@ def cpu_step(O, P, F, dt, w, threads):
     nl = P["nlocal"]
     colL = O.tags_to_local(col, P["tag"][:nl])
     prec = {"point relaxation": O.PREC_JACOBI, "ILU": O.PREC_ILU0, "Chebyshev": O.PREC_CHEBYSHEV}[w["prec"]]
-    x, info = O.krylov_solve(rp, colL, A, b, params=O.krylov_params(precond=prec, row_gid=P["tag"][:nl]), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
+    kw = dict(tol=0.0, max_iters=int(pin_iters)) if pin_iters else {}
+    x, info = O.krylov_solve(rp, colL, A, b, params=O.krylov_params(precond=prec, row_gid=P["tag"][:nl], **kw), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
     t2 = time.perf_counter()
     o.close()
     return dict(assemble_s=t1 - t0, solve_s=t2 - t1, iters=info["iters"], converged=info["converged"], nnz=len(col))
 
 
+def cpu_sample_edge(args, w):
+    """Lattice edge of the CPU arm's bounded sample: ~10-20 s of CPU work per step on the bench box (16-32 host cores)."""
+    return args.cpu_n or (min(80, w["n"]) if w["dim"] == 3 else w["n"])
+
+
+def cpu_sample_text(w, n, rows, r, pinned):
+    full = f"{w['n']}^{w['dim']}"
+    how = (f"solve pinned to the full workload's {r['iters']} GMRES iterations (tolerance 0), so a sampled row costs what a row of the full workload costs"
+           if pinned else f"{r['iters']} GMRES iterations to 1e-8")
+    return (f"{w['dim']}-D {n}^{w['dim']} = {rows} rows of the same periodic lattice / physics / solver as the {full} workload; every step = "
+            f"pre-computation + graph + assembly + solve, {how}")
+
+
 def run_reference(args, w, lat):
+    """CPU arm.  Runs on rank 0 only; all host threads (torchrun exports OMP_NUM_THREADS=1: overridden here)."""
+    threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)                 # unconditional, and before the OpenMP runtime loads
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     O.build(("port",))
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    n = args.cpu_n or (min(96, w["n"]) if w["dim"] == 3 else w["n"])     # ~10-30 s of CPU work per step on the bench box
+    threads = O.set_num_threads(threads)
+    budget = float(os.environ.get("ISPH_REF_BUDGET_S", "540"))   # the whole --steps K --warmup W run ends within a few minutes
+    t_start = time.perf_counter()
+    n = cpu_sample_edge(args, w)
+    pin = FULL_ITERS.get(args.workload) if n != w["n"] else None
     P, F, dt = make_problem(w, n, lat)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_step(O, P, F, dt, w, threads)
+    cpu_step(O, P, F, dt, w, pin)                                # one warm-up step (page faults, OpenMP pool)
     ts, last = [], None
-    for _ in range(args.steps):
-        t = time.perf_counter(); last = cpu_step(O, P, F, dt, w, threads); ts.append(time.perf_counter() - t)
+    for k in range(args.steps):
+        t = time.perf_counter(); last = cpu_step(O, P, F, dt, w, pin); ts.append(time.perf_counter() - t)
+        if time.perf_counter() - t_start + 1.5 * ts[-1] > budget:
+            break
     sec = float(np.mean(ts)); val = P["nlocal"] / sec / 1e6
-    sample = f"{w['dim']}-D {n}^{w['dim']} = {P['nlocal']} rows of the same lattice/physics (full workload: {w['n']}^{w['dim']}), {last['iters']} GMRES its, all of graph+assembly+solve per step"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = cpu_sample_text(w, n, P["nlocal"], last, pin is not None)
     line = dict(metric="sph_poisson_step_throughput", value=val, unit="Mrow/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3,
                 higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=args.workload, description=w["desc"], rows=P["nlocal"], nnz=last["nnz"], iters=last["iters"]),
-                cpu_baseline=dict(value=val, unit="Mrow/s", cores=threads, kind="port", sample=sample,
-                                  note="CPU restatement of the reference path (oracle port: reference functor algorithms + Belos/Ifpack semantics), OpenMP over rows; Trilinos/LAMMPS are not installable here"),
+                config=workload_config(args.workload, w, world, lat),
+                cpu_baseline=dict(value=val, unit="Mrow/s", cores=threads, kind="port", sample=sample, sample_rows=P["nlocal"], sample_iters=last["iters"],
+                                  steps_timed=len(ts), sample_ms_per_step=sec * 1e3,
+                                  note="CPU restatement of the reference path (oracle port: reference functor algorithms + Belos/Ifpack semantics), OpenMP over rows; "
+                                       "Trilinos/LAMMPS/MPI are not installable here (DESIGN.md §5)"),
                 e2e=dict(value=val, unit="Mrow/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                assemble_ms=last["assemble_s"] * 1e3, solve_ms=last["solve_s"] * 1e3)
-    # the sample converges in fewer GMRES iterations than the full lattice (Jacobi is not mesh independent), so its Mrow/s
-    # flatters the CPU; the per-row, per-iteration costs measured on the sample give the full-workload estimate
-    full_iters = FULL_ITERS.get(args.workload)
-    if full_iters and n != w["n"]:
-        rows_full = float(w["n"]) ** w["dim"]
-        t_asm = last["assemble_s"] / P["nlocal"]; t_it = last["solve_s"] / (max(last["iters"], 1) * P["nlocal"])
-        sec_full = rows_full * (t_asm + full_iters * t_it)
-        line["full_workload_estimate"] = dict(value=rows_full / sec_full / 1e6, unit="Mrow/s", ms_per_step=sec_full * 1e3, iters=full_iters,
-                                              how="rows_full x (assembly s/row + iters_full x solve s/(row x iteration)), both measured on the sample; iters_full = the "
-                                                  "iteration count of the full workload (B200 run; the oracle matches it within +-2 on the parity cases)")
-    # BASELINE configs[1] beside the headline line, as in the B200 arm: the CPU arm runs the FULL 1M-particle workload here
-    # (no sampling), so configs1_c2 of the two arms is a same-workload comparison
-    if args.workload == "p8m" and not args.no_secondary:
-        w2 = dict(WORKLOADS["c2"]); n2 = args.cpu_n or w2["n"]
-        P2, F2, dt2 = make_problem(w2, n2, lat)
-        t = time.perf_counter(); r2 = cpu_step(O, P2, F2, dt2, w2, threads); sec2 = time.perf_counter() - t
-        line["configs1_c2"] = dict(workload=w2["desc"], rows=P2["nlocal"], value=P2["nlocal"] / sec2 / 1e6, unit="Mrow/s", ms_per_step=sec2 * 1e3, iters=r2["iters"],
-                                   sample="full workload" if n2 == w2["n"] else f"{n2}^3 sample", assemble_ms=r2["assemble_s"] * 1e3, solve_ms=r2["solve_s"] * 1e3)
+                assemble_ms=last["assemble_s"] * 1e3, solve_ms=last["solve_s"] * 1e3,
+                full_workload_ms_per_step=sec * 1e3 * (float(w["n"]) ** w["dim"]) / P["nlocal"])
     print(json.dumps(line))
-
-
-FULL_ITERS = {"p8m": 452, "c2": 188, "c4": 81}          # GMRES iterations of the full-size workloads (gpurun_out/*.json, profiles/)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -203,8 +243,8 @@ def krylov_bytes_per_solve(n, nnz, iters, second, m=50):
     return tot
 
 
-def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu):
-    w = dict(WORKLOADS[wname])
+def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu, warmup=None):
+    w = dict(WORKLOADS[wname]); warmup = max(args.warmup, 3) if warmup is None else max(warmup, 3)
     if args.n:
         w["n"] = args.n
     # ---- this rank's brick of the periodic lattice (weak: w['n']^dim rows per GPU; strong: the global lattice is split)
@@ -236,6 +276,10 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         nb = w["blocks"]; li = P["gidx"][:nl]; ng = nglobal
         gx = li % ng[0] - lo[0]; gy = (li // ng[0]) % ng[1] - lo[1]; gz = (li // (ng[0] * ng[1])) - (lo[2] if dim == 3 else 0)
         blk = ((gx * nb) // nloc[0] + nb * ((gy * nb) // nloc[1]) + (nb * nb * ((gz * nb) // nloc[2]) if dim == 3 else 0)).astype(np.int32)
+    if w.get("global_blocks"):   # the Ifpack-rank partition of the GLOBAL lattice (4x4x4 bricks of 50^3), whatever the GPU count
+        nb = w["global_blocks"]; li = P["gidx"][:nl]; ng = nglobal
+        bx = (li % ng[0]) * nb // ng[0]; by = ((li // ng[0]) % ng[1]) * nb // ng[1]; bz = (li // (ng[0] * ng[1])) * nb // ng[2]
+        blk = (bx + nb * (by + nb * bz)).astype(np.int32)
 
     def upload():
         c.atoms_set(nl, P["nghost"], hx[1], htype[1], htag[1])
@@ -306,7 +350,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
 
     upload()
     st = None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         st = device_step()
     # ---- timed region 1: device-resident inputs
     sampler = ClockSampler(local_rank)
@@ -323,10 +367,12 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1) / steps
-    spmv_ms, spmv_cnt = c.profile_spmv_get(); c.profile_spmv(False)
+    spmv_ms, spmv_cnt = c.profile_spmv_get(); prec_ms, prec_cnt = c.profile_precond_get(); c.profile_spmv(False)
+    ilu = c.precond_info() if w["prec"] == "ILU" else None
     launches = (c.launches - launches0) // steps
     timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "precondCreate", "solve" + solve_label) +
               (("computeFPoissonBoltzmann", "computeJacobianPoissonBoltzmann") if pbs else ("compute" + solve_label,))}
+    c.timer_reset()
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
     barrier()
@@ -339,6 +385,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     barrier()
     ms_e2e = e0.elapsed_time(e1) / steps
     wall_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    e2e_timers = {k: c.timer_ms(k) / steps for k in ("h2dAtoms", "h2dNeighbors", "haloSetup")}
     ms_e2e = max(ms_e2e, wall_e2e)          # host-side packing/validation inside the ABI calls is part of the end-to-end cost
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, timers["solve" + solve_label]], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms = t.tolist()
@@ -370,18 +417,27 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
             traffic = float(tj[wname]["dram_bytes_per_launch"])
     except Exception:
         pass
-    line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=steps, warmup=max(args.warmup, 3),
+    result = dict(iters=st["iters"], relres=st["relres"], converged=st["converged"], rows=int(rows_g), nnz=int(nnz_g), rows_this_gpu=nl, **({"newton_iters": st["newton_iters"]} if pbs else {}))
+    line = dict(metric="sph_poisson_step_throughput", value=rows_g / (ms_dev * 1e-3) / 1e6, unit="Mrow/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=wname, description=w["desc"], rows=int(rows_g), nnz=int(nnz_g), rows_per_gpu=nl, bricks="x".join(map(str, grid)),
-                            iters=st["iters"], relres=st["relres"], converged=st["converged"], precond=w["prec"], solver=w["solver"], **({"newton_iters": st["newton_iters"]} if pbs else {}),
-                            l2="inputs larger than L2: matrix stream %.0f MB per SpMV, Krylov basis %.0f MB (L2 = 126 MB)" % (spmv_bytes / 1e6, 8e-6 * nl * 101)),
-                e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                config=workload_config(wname, w, world, lat), result=result,
+                e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes),
+                         upload_ms=e2e_timers),
                 gpu_launches=int(launches), clocks=clocks,
                 roofline=dict(bound="hbm", kernel="k_spmv_sell<1>", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
+                              traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload "
+                                             "(profiles/spmv_traffic.json); not re-measured in this run" if traffic else None,
                               launches_timed=int(spmv_cnt), avg_launch_ms=avg, algorithmic_bytes_per_launch=spmv_bytes,
                               share_of_step=spmv_ms / steps / ms_dev,
                               note="per-launch time from CUDA events on the launching stream; at n_gpus > 1 it includes the NVLink import of the halo"),
                 breakdown_ms=timers, ms_per_iter=solve_ms / max(st["iters"], 1))
+    if ilu is not None and prec_cnt:                         # triangular solves of the block-Jacobi ILU apply (12 nnz_factor + 32 n, and the level count)
+        pav = prec_ms / prec_cnt; pb = 12.0 * ilu["factor_nnz"] + 32.0 * nl
+        line["ilu_roofline"] = dict(bound="hbm", kernel="k_ilu_solve", achieved=pb / (pav * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=pb / (pav * 1e-3) / 1e9 / peak,
+                                    algorithmic_bytes_per_launch=pb, avg_launch_ms=pav, launches_timed=int(prec_cnt), share_of_step=prec_ms / steps / ms_dev,
+                                    factor_nnz=ilu["factor_nnz"], levels_lower=ilu["levels_lower"], levels_upper=ilu["levels_upper"],
+                                    us_per_level=1e3 * pav / max(ilu["levels_lower"] + ilu["levels_upper"], 1),
+                                    note="latency-bound by the dependency levels of the forward + backward sweeps, not by bytes (DESIGN.md §3)")
     if halo is not None:                                     # NVLink side of the roofline (rank 0's brick): bytes that leave this GPU per operator apply
         spmv_per_s = spmv_cnt / max(steps, 1) / max(ms_dev * 1e-3, 1e-12)
         line["nvlink"] = dict(what="halo import of one SpMV on rank 0 (NVLink peer stores, 8 B per value) and the two all-reduces of an Arnoldi step (<= 53 doubles to each peer)",
@@ -395,16 +451,18 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         line["solve_roofline"] = dict(bound="hbm", what="whole GMRES(50)+Jacobi solve on one GPU of the job: SpMV + Gram-Schmidt sweeps + solution update (DESIGN.md §3), rank 0's rows",
                                       achieved=sg, peak=peak, unit="GB/s", frac=sg / peak, algorithmic_bytes_per_solve=kb, solve_ms=solve_ms,
                                       iters=st["iters"], second_pass_steps=st.get("second_passes"))
-    if with_cpu:
+    if with_cpu:                                             # the same bounded sample the reference arm times (see run_reference), two steps
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
         O.build(("port",))
-        ncpu = args.cpu_n or (min(96, w["n"]) if dim == 3 else w["n"])     # ~10-30 s of CPU work on the bench box
+        threads = O.set_num_threads(os.cpu_count() or 1)
+        ncpu = cpu_sample_edge(args, w); pin = FULL_ITERS.get(wname) if ncpu != w["n"] else None
         Pc, Fc, dtc = make_problem(w, ncpu, lat)
-        cpu_step(O, Pc, Fc, dtc, w, os.cpu_count())           # warm
-        t = time.perf_counter(); r = cpu_step(O, Pc, Fc, dtc, w, os.cpu_count()); sec = time.perf_counter() - t
-        line["cpu_baseline"] = dict(value=Pc["nlocal"] / sec / 1e6, unit="Mrow/s", cores=os.cpu_count(), kind="port",
-                                    sample=f"{dim}-D {ncpu}^{dim} = {Pc['nlocal']} rows of the same lattice/physics, {r['iters']} GMRES its, one full step (graph+assembly+solve), {sec:.1f} s")
+        cpu_step(O, Pc, Fc, dtc, w, pin)                     # warm
+        t = time.perf_counter(); r = cpu_step(O, Pc, Fc, dtc, w, pin); sec = time.perf_counter() - t
+        line["cpu_baseline"] = dict(value=Pc["nlocal"] / sec / 1e6, unit="Mrow/s", cores=threads, kind="port",
+                                    sample=cpu_sample_text(w, ncpu, Pc["nlocal"], r, pin is not None) + f"; one step timed, {sec:.1f} s")
     return line
 
 
@@ -413,7 +471,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"]); ap.add_argument("--workload", default="p8m", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="lattice edge override (per GPU)"); ap.add_argument("--cpu-n", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-secondary", action="store_true"); ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     lat = importlib.import_module("implicit-sph_b200.lattice")
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -432,22 +490,45 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    nccl_id = None
     if world > 1:
         dist.init_process_group("gloo", init_method="env://")          # plumbing only: unique-id broadcast, barrier, max-over-ranks
+
+    def fresh_id():                                          # one NCCL communicator per context: a new unique id for each
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = (isph.C.c_ubyte * 128)(); assert isph.lib().isph_nccl_unique_id(buf) == 0, "NCCL unique id"
             idt = torch.tensor(list(buf), dtype=torch.uint8)
-        dist.broadcast(idt, 0); nccl_id = bytes(idt.tolist())
+        dist.broadcast(idt, 0); return bytes(idt.tolist())
 
-    line = measure(args, args.workload, args.steps, isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu=(not args.no_cpu_baseline and world == 1))
-    # BASELINE configs[1] (1M particles on 1 B200) beside the headline 8M-particle line: same code path, measured in the same run
-    if world == 1 and args.workload == "p8m" and not args.n and not args.no_secondary:
-        sec = measure(args, "c2", min(args.steps, 5), isph, lat, torch, dist, rank, world, local_rank, nccl_id, with_cpu=False)
-        line["configs1_c2"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "breakdown_ms", "ms_per_iter") if k in sec}
-        line["configs1_c2"].update(workload=sec["config"]["description"], iters=sec["config"]["iters"], spmv_roofline_frac=sec["roofline"]["frac"],
-                                   spmv_gbs=sec["roofline"]["achieved"], solve_roofline_frac=sec.get("solve_roofline", {}).get("frac"))
+    parity = None
+    if world > 1 and not args.no_parity:                     # multi-GPU parity against the CPU oracle BEFORE anything is timed (tests/ may use the oracle)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import multi_gpu_check
+        parity = multi_gpu_check.run_check(isph, lat, torch, dist, rank, world, local_rank, fresh_id(), quiet=True)
+        if not parity["pass"]:
+            if rank == 0:
+                print(json.dumps(dict(metric="sph_poisson_step_throughput", value=None, n_gpus=world, parity=parity, error="multi-GPU parity check failed: nothing was timed")))
+            dist.destroy_process_group()
+            raise SystemExit(3)
+
+    line = measure(args, args.workload, args.steps, isph, lat, torch, dist, rank, world, local_rank, fresh_id(), with_cpu=(not args.no_cpu_baseline and world == 1))
+    if parity is not None and rank == 0:
+        line["parity"] = parity
+    # the other BASELINE configs beside the headline line: same code path, measured in the same run, at this GPU count
+    if args.workload == "p8m" and not args.n and not args.no_secondary:
+        sec_steps = max(1, min(args.steps, 3))
+        todo = ([("configs1_c2", "c2")] if world == 1 else []) + [("configs2_c3", "c3"), ("configs3_c4", "c4s"), ("configs4_c5", "c5")]
+        for key, wn in todo:
+            sec = measure(args, wn, min(args.steps, 5) if wn == "c2" else sec_steps, isph, lat, torch, dist, rank, world, local_rank, fresh_id(), with_cpu=False, warmup=3)
+            if rank != 0:
+                continue
+            blk = {k: sec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "breakdown_ms", "ms_per_iter", "result", "ilu_roofline", "nvlink") if k in sec}
+            blk.update(workload=sec["config"]["description"], rows=sec["config"]["rows"], iters=sec["result"]["iters"], converged=sec["result"]["converged"],
+                       spmv_roofline_frac=sec["roofline"]["frac"], spmv_gbs=sec["roofline"]["achieved"], spmv_bytes_per_launch=sec["roofline"]["algorithmic_bytes_per_launch"],
+                       solve_roofline_frac=sec.get("solve_roofline", {}).get("frac"))
+            line[key] = blk
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -221,6 +221,13 @@ class Context:
     def profile_spmv_get(self):
         ms = C.c_double(); n = C.c_longlong(); self.call("isph_profile_spmv_get", C.byref(ms), C.byref(n)); return ms.value, n.value
 
+    def profile_precond_get(self):
+        ms = C.c_double(); n = C.c_longlong(); self.call("isph_profile_precond_get", C.byref(ms), C.byref(n)); return ms.value, n.value
+
+    def precond_info(self):
+        z = C.c_longlong(); a = C.c_int(); b = C.c_int(); m = C.c_int(); self.call("isph_precond_info", C.byref(z), C.byref(a), C.byref(b), C.byref(m))
+        return dict(factor_nnz=z.value, levels_lower=a.value, levels_upper=b.value, max_row=m.value)
+
     # ---- SolverLin mirror
     def create_solution(self, x=None, nvec=1):
         """x: Fortran-ordered (nlocal, nvec) float64 array that receives the solution (a View, like the reference), or None."""

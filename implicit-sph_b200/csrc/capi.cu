@@ -51,6 +51,22 @@ static double kernel_C(int kernel, int dim, double h) {   // kernel_{wendland,cu
   }
 }
 
+// A load multivector created over caller memory is a View in the reference (solver_lin.cpp:45-58): the functors write the
+// right-hand side INTO that memory and the caller may write it too, at any time before solveProblem.  Here the functors write
+// the device copy, so (1) what a device functor wrote is copied back into the borrowed host array, and the solve does not
+// upload the (older) host content over it; (2) whatever else is in the host array when a functor that reads b (Helmholtz,
+// solute transport) or the solve starts is uploaded first.
+void load_from_host(Ctx *c) {
+  if (!c->b_host || c->b_owned || c->b_dev_fresh || c->b_nvec < 1) return;
+  for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->bs.p + (size_t)q * c->ld, c->b_host + (size_t)q * c->b_lda, sizeof(double) * c->A.n, cudaMemcpyHostToDevice, c->stream));
+}
+void load_written(Ctx *c) {
+  c->b_dev_fresh = true;
+  if (!c->b_host || c->b_owned || c->b_nvec < 1) return;
+  for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->b_host + (size_t)q * c->b_lda, c->bs.p + (size_t)q * c->ld, sizeof(double) * c->A.n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
 }  // namespace isph
 
 using namespace isph;
@@ -94,6 +110,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
+  for (auto e : c->pprof_ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c; return ISPH_SUCCESS;
 }
@@ -134,8 +151,10 @@ int isph_atoms_set(isph_ctx *ctx, int nlocal, int nghost, const double *x, const
   CUDA_CHECK(cudaMemcpyAsync(c->type.p, type, sizeof(int) * nall, cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->tag.p, tag, sizeof(int) * nall, cudaMemcpyHostToDevice, c->stream));
   c->h_type.assign(type, type + nall); c->h_tag.assign(tag, tag + nall);
-  int mt = 0; for (int i = 0; i < nall; ++i) { ISPH_REQUIRE(tag[i] >= 0, "negative atom tag"); mt = std::max(mt, tag[i]); ISPH_REQUIRE(type[i] >= 1 && type[i] <= c->tab.ntypes, "atom type out of range"); }
-  c->max_tag = mt; c->have_atoms = true; c->A.built = false;
+  int mt = 0; unsigned long long hsh = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)nlocal << 32 | (unsigned)nghost);      // hash of the tag set: key of the halo-plan cache
+  for (int i = 0; i < nall; ++i) { ISPH_REQUIRE(tag[i] >= 0, "negative atom tag"); mt = std::max(mt, tag[i]); ISPH_REQUIRE(type[i] >= 1 && type[i] <= c->tab.ntypes, "atom type out of range");
+    hsh = (hsh ^ (unsigned long long)(unsigned)tag[i]) * 0x100000001B3ull; hsh ^= hsh >> 29; }
+  c->max_tag = mt; c->tag_hash = hsh; c->have_atoms = true; c->A.built = false;
   ensure_fields(c);
   compute_first_fluid_row(c);
   c->toc("h2dAtoms");
@@ -251,11 +270,11 @@ int isph_assemble_gradient_dot(isph_ctx *ctx, double alpha, int vf, int f0, int 
   API_BEGIN(ctx) ISPH_REQUIRE(vf >= 0 && vf < ISPH_F_COUNT && FIELD_NC[vf] == 3, "vector field expected"); assemble_gradient_dot(c, alpha, c->field[vf].p, f0, f1); API_END
 }
 
-int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int mh) { API_BEGIN(ctx) ns_poisson(c, dt, anti != 0, singular, mh != 0); API_END }
-int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int mh, int incp, const double *g) { API_BEGIN(ctx) ns_helmholtz(c, dt, theta, anti != 0, mh != 0, incp != 0, g); API_END }
+int isph_ns_poisson(isph_ctx *ctx, double dt, int anti, int singular, int mh) { API_BEGIN(ctx) ns_poisson(c, dt, anti != 0, singular, mh != 0); load_written(c); API_END }
+int isph_ns_helmholtz(isph_ctx *ctx, double dt, double theta, int anti, int mh, int incp, const double *g) { API_BEGIN(ctx) load_from_host(c); ns_helmholtz(c, dt, theta, anti != 0, mh != 0, incp != 0, g); load_written(c); API_END }
 int isph_pb_jacobian(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, double gamma) { API_BEGIN(ctx) pb_jacobian(c, mh != 0, lin != 0, ezcb, psiref, gamma); API_END }
-int isph_applied_electric_potential(isph_ctx *ctx) { API_BEGIN(ctx) applied_electric_potential(c); API_END }
-int isph_solute_transport(isph_ctx *ctx, double dt, double theta, double dcoeff) { API_BEGIN(ctx) solute_transport(c, dt, theta, dcoeff); API_END }
+int isph_applied_electric_potential(isph_ctx *ctx) { API_BEGIN(ctx) applied_electric_potential(c); load_written(c); API_END }
+int isph_solute_transport(isph_ctx *ctx, double dt, double theta, double dcoeff) { API_BEGIN(ctx) load_from_host(c); solute_transport(c, dt, theta, dcoeff); load_written(c); API_END }
 // extra source (functor_poisson_boltzmann_extra_f.h) staged on the device, indexed by owned atom
 static const double *stage_extra(Ctx *c, const double *extra_f) {
   if (!extra_f) return nullptr;
@@ -267,6 +286,7 @@ int isph_pb_residual(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref,
   API_BEGIN(ctx) ISPH_REQUIRE(c->have_atoms && c->have_neigh, "atoms and neighbors must be set first");
   double *df; if (c->b_nvec >= 1 && c->bs.p) df = c->bs.p; else { c->wk.ensure((size_t)c->nall + (size_t)c->nlocal); df = c->wk.p + c->nall; }
   pb_residual(c, mh != 0, lin != 0, ezcb, psiref, gamma, stage_extra(c, extra_f), df);
+  if (df == c->bs.p) load_written(c);
   if (f_out) CUDA_CHECK(cudaMemcpyAsync(f_out, df, sizeof(double) * c->nlocal, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
 }
@@ -277,6 +297,7 @@ int isph_pb_newton(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, d
   const double *dex = nullptr;
   if (extra_f) { c->pb_extra.ensure(c->nlocal); CUDA_CHECK(cudaMemcpyAsync(c->pb_extra.p, extra_f, sizeof(double) * c->nlocal, cudaMemcpyHostToDevice, c->stream)); dex = c->pb_extra.p; }
   pb_newton(c, mh != 0, lin != 0, ezcb, psiref, gamma, dex, max_newton, tol_f, tol_update, use_prec != 0, &a, &b, &nf, &cv);
+  load_written(c); c->b_dev_fresh = false;                        // F(psi) of the last iteration is what the load vector holds
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (newton_iters) *newton_iters = a; if (linear_iters) *linear_iters = b; if (normf) *normf = nf; if (converged) *converged = cv; API_END
 }
@@ -300,12 +321,12 @@ int isph_solver_create_solution_multivector(isph_ctx *ctx, double *x, int lda, i
 }
 int isph_solver_create_load_multivector(isph_ctx *ctx, double *b, int lda, int nvec) {
   API_BEGIN(ctx) ISPH_REQUIRE(nvec >= 1 && nvec <= 3 && (b == nullptr || lda >= c->A.n), "bad load multivector");
-  alloc_mv(c, c->bs, nvec); c->b_host = b; c->b_lda = lda; c->b_nvec = nvec; c->b_owned = (b == nullptr); API_END
+  alloc_mv(c, c->bs, nvec); c->b_host = b; c->b_lda = lda; c->b_nvec = nvec; c->b_owned = (b == nullptr); c->b_dev_fresh = false; API_END
 }
 int isph_solver_load_set(isph_ctx *ctx, const double *b, int lda) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->b_nvec >= 1 && b && lda >= c->A.n, "no load multivector");
   for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->bs.p + (size_t)q * c->ld, b + (size_t)q * lda, sizeof(double) * c->A.n, cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+  CUDA_CHECK(cudaStreamSynchronize(c->stream)); load_written(c); API_END
 }
 int isph_solver_load_get(isph_ctx *ctx, double *b, int lda) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->b_nvec >= 1 && b && lda >= c->A.n, "no load multivector");
@@ -363,7 +384,11 @@ int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v) {
   API_BEGIN(ctx) const std::string k(name ? name : "");
   if (k == "relaxation: damping factor") c->pp.damping = v; else if (k == "relaxation: min diagonal value" || k == "chebyshev: min diagonal value") c->pp.min_diag = v;
   else if (k == "chebyshev: ratio eigenvalue") c->pp.cheb_ratio = v; else if (k == "chebyshev: max eigenvalue") c->pp.cheb_lmax = v;
-  else if (k == "fact: drop tolerance" || k == "fact: relax value" || k == "fact: absolute threshold" || k == "fact: relative threshold") { /* ILU(0): accepted, defaults only */ }
+  else if (k == "fact: drop tolerance" || k == "fact: relax value" || k == "fact: absolute threshold" || k == "fact: relative threshold") {
+    // Ifpack_ILU defaults (drop 0, relax 0, absolute 0, relative 1): anything else changes the factors and is not implemented — refuse, do not ignore
+    const double dflt = (k == "fact: relative threshold") ? 1.0 : 0.0;
+    ISPH_REQUIRE(v == dflt, "preconditioner parameter '" + k + "' is only supported at its Ifpack default value");
+  }
   else ISPH_REQUIRE(false, "unknown double preconditioner parameter: " + k);
   API_END
 }
@@ -409,6 +434,19 @@ int isph_profile_spmv_get(isph_ctx *ctx, double *total_ms, long long *launches) 
   if (total_ms) *total_ms = c->prof_ms; if (launches) *launches = c->prof_cnt;
   c->prof_ms = 0.0; c->prof_cnt = 0;
   API_END
+}
+int isph_profile_precond_get(isph_ctx *ctx, double *total_ms, long long *launches) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (size_t q = 0; q + 1 < c->pprof_used; q += 2) { float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, c->pprof_ev[q], c->pprof_ev[q + 1])); c->pprof_ms += ms; ++c->pprof_cnt; }
+  c->pprof_used = 0;
+  if (total_ms) *total_ms = c->pprof_ms; if (launches) *launches = c->pprof_cnt;
+  c->pprof_ms = 0.0; c->pprof_cnt = 0;
+  API_END
+}
+int isph_precond_info(isph_ctx *ctx, long long *factor_nnz, int *levels_lower, int *levels_upper, int *max_row) {
+  API_BEGIN(ctx) long long z = 0; int a = 0, b = 0, m = 0; ilu_info(c, &z, &a, &b, &m);
+  if (factor_nnz) *factor_nnz = z; if (levels_lower) *levels_lower = a; if (levels_upper) *levels_upper = b; if (max_row) *max_row = m; API_END
 }
 int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->A.built && reps > 0 && avg_ms, "no matrix"); const int ld = c->ld; c->V.ensure((size_t)2 * ld);

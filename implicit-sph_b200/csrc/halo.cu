@@ -71,18 +71,66 @@ __global__ void __launch_bounds__(256) k_halo_unstage(const HaloDev *hp, unsigne
   for (int q = 0; q < nvec; ++q) x[(size_t)q * ldx + nlocal + k] = p2p_take(cell + (size_t)q * hp->cap, hp->fault);
 }
 
+// ---- device-side plan (the role of Epetra's column map construction): distinct remote (owner, tag) pairs numbered in
+// (owner, tag) order.  Same result as isph_halo_plan_host (the pure host restatement kept for the CPU tests).
+__global__ void k_plan_keys(const int *tag, const int *owner, int nlocal, int nghost, int rank, int nranks, unsigned long long *key, int *val, int *err) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x; if (g >= nghost) return;
+  const int o = owner[g]; unsigned long long k = ~0ull;
+  if (o < 0 || o >= nranks) atomicAdd(err, 1);                   // a ghost whose tag no rank owns
+  else if (o != rank) k = ((unsigned long long)(unsigned)o << 32) | (unsigned)tag[nlocal + g];
+  key[g] = k; val[g] = g;
+}
+__global__ void k_plan_heads(const unsigned long long *key, int n, int *head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  head[i] = (key[i] != ~0ull && (i == 0 || key[i] != key[i - 1])) ? 1 : 0;
+}
+__global__ void k_plan_assign(const unsigned long long *key, const int *val, const int *head, const int *inc, const int *owner, const int *owner_idx, int n, int nlocal,
+                              int rank, int *ghost_col, int *request, int *recv_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const int g = val[i];
+  if (key[i] == ~0ull) { if (owner[g] == rank) ghost_col[g] = owner_idx[g]; return; }
+  const int slot = inc[i] - 1;
+  ghost_col[g] = nlocal + slot;
+  if (head[i]) { request[slot] = owner_idx[g]; atomicAdd(recv_count + (int)(key[i] >> 32), 1); }
+}
+// ghost_tag/ghost_owner/ghost_owner_idx: device arrays of nghost entries (ghost_tag = tag + nlocal).  Results on the device:
+// ghost_col[nghost], request[<= nghost], counts[0..R) = values received per peer, counts[R] = number of unowned ghosts.
+struct PlanWork { DevBuf<unsigned long long> gkey, gkey2; DevBuf<int> gval, gval2, head, inc; DevBuf<char> tmp;
+  void release() { gkey.release(); gkey2.release(); gval.release(); gval2.release(); head.release(); inc.release(); tmp.release(); } };
+static void plan_device(Ctx *c, PlanWork *h, const int *d_tag_all, const int *d_owner, const int *d_idx, int nl, int ng, int *d_ghost_col, int *d_request, int *d_counts) {
+  const int R = c->nranks, B = 256;
+  CUDA_CHECK(cudaMemsetAsync(d_counts, 0, sizeof(int) * (R + 1), c->stream));
+  if (ng == 0) return;
+  h->gkey.ensure(ng); h->gkey2.ensure(ng); h->gval.ensure(ng); h->gval2.ensure(ng); h->head.ensure(ng); h->inc.ensure(ng);
+  k_plan_keys<<<ceil_div(ng, B), B, 0, c->stream>>>(d_tag_all, d_owner, nl, ng, c->rank, R, h->gkey.p, h->gval.p, d_counts + R);
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, h->gkey.p, h->gkey2.p, h->gval.p, h->gval2.p, ng, 0, 64, c->stream);
+  cub::DeviceScan::InclusiveSum(nullptr, t2, h->head.p, h->inc.p, ng, c->stream);
+  h->tmp.ensure(std::max(t1, t2));
+  t1 = h->tmp.cap; cub::DeviceRadixSort::SortPairs(h->tmp.p, t1, h->gkey.p, h->gkey2.p, h->gval.p, h->gval2.p, ng, 0, 64, c->stream);
+  k_plan_heads<<<ceil_div(ng, B), B, 0, c->stream>>>(h->gkey2.p, ng, h->head.p);
+  t2 = h->tmp.cap; cub::DeviceScan::InclusiveSum(h->tmp.p, t2, h->head.p, h->inc.p, ng, c->stream);
+  k_plan_assign<<<ceil_div(ng, B), B, 0, c->stream>>>(h->gkey2.p, h->gval2.p, h->head.p, h->inc.p, d_owner, d_idx, ng, nl, c->rank, d_ghost_col, d_request, d_counts);
+  c->launches += 5;
+}
+
 struct Halo {
   ncclComm_t comm = nullptr; bool inited = false;
   // peer-memory exchange
   bool p2p = false; double *mbox = nullptr; double *mpeer[ISPH_MAX_RANKS] = {}; void *mopened[ISPH_MAX_RANKS] = {};
   double *hbox = nullptr; double *hpeer[ISPH_MAX_RANKS] = {}; void *hopened[ISPH_MAX_RANKS] = {}; long long hcap = 0;
-  unsigned long long seq = 0, hseq = 0; int *fault = nullptr; int dst_off[ISPH_MAX_RANKS] = {}; P2PTab *d_tab = nullptr;
+  unsigned long long seq = 0, hseq = 0; int *fault = nullptr; std::vector<int> dst_off; P2PTab *d_tab = nullptr;
   // plan
   int nhalo = 0, nsend = 0;
   std::vector<int> recv_count, recv_off, send_count, send_off;
   DevBuf<int> send_idx, itmp, itmp2; DevBuf<long long> owner_tab; DevBuf<double> sendbuf, fieldbuf;
+  // set-up workspace: grow-only like every other buffer of the path (isph_internal.h DevBuf) — nothing is allocated or freed per step
+  DevBuf<int> mytags, alltags, gown, gidx, req, gcol_saved; PlanWork pw;
+  PinBuf<int> h_small;                                           // pinned landing zone of the few integers the host needs
+  // plan cache: the plan depends only on (nlocal, nghost, tags); when no rank's tag set changed since the last set-up it is reused
+  bool plan_valid = false; unsigned long long plan_hash = 0; int plan_nl = -1, plan_ng = -1; long long setups = 0, reuses = 0;
   // device-resident exchange plan (halo kernels, push from the producer)
-  DevBuf<HaloDev> d_plan; bool plan_ok = false;
+  DevBuf<HaloDev> d_plan; HaloDev hd_host; bool plan_ok = false;
   DevBuf<int> row_sp, row_sd, row_cur; DevBuf<char> cubtmp; bool rows_ok = false;      // per-row send list (push from the producer)
 };
 
@@ -153,7 +201,8 @@ static Halo *get(Ctx *c) {
     if (!getenv("ISPH_NO_P2P") && c->nranks <= ISPH_MAX_RANKS) {   // peer mailboxes for the small all-reduces
       const size_t bytes = sizeof(double) * MB_SLOTS * c->nranks * MB_STRIDE;
       CUDA_CHECK(cudaMalloc(&h->mbox, bytes)); CUDA_CHECK(cudaMemset(h->mbox, 0xff, bytes));     // every cell armed (sentinel)
-      CUDA_CHECK(cudaMalloc(&h->fault, sizeof(int))); CUDA_CHECK(cudaMemset(h->fault, 0, sizeof(int)));
+      { const int lim[4] = {0, getenv("ISPH_P2P_TIMEOUT_MS") ? std::max(1, atoi(getenv("ISPH_P2P_TIMEOUT_MS"))) : 20000, 0, 0};   // fault[0] = raised, fault[1] = wait limit in ms
+        CUDA_CHECK(cudaMalloc(&h->fault, sizeof(lim))); CUDA_CHECK(cudaMemcpy(h->fault, lim, sizeof(lim), cudaMemcpyHostToDevice)); }
       h->p2p = ipc_share(c, h, h->mbox, h->mpeer, h->mopened);
       if (h->p2p) { P2PTab t; memset(&t, 0, sizeof(t)); for (int p = 0; p < c->nranks; ++p) t.box[p] = h->mpeer[p]; t.mine = h->mbox; t.nranks = c->nranks; t.rank = c->rank; t.fault = h->fault;
         CUDA_CHECK(cudaMalloc(&h->d_tab, sizeof(t))); CUDA_CHECK(cudaMemcpy(h->d_tab, &t, sizeof(t), cudaMemcpyHostToDevice)); }
@@ -179,57 +228,81 @@ static void exchange(Ctx *c, Halo *h, const double *sendbuf, double *recv_base, 
   NCCL_CHECK(g_nccl.GroupEnd());
 }
 
+// After a peer wait timed out (fault word raised) the slot rings of the ranks are out of step.  Collective, called at the start
+// of every solve: if ANY rank saw a fault, all ranks drain, re-arm every cell, reset the sequence numbers and clear the fault.
+void halo_recover(Ctx *c) {
+  if (c->nranks <= 1) return; Halo *h = get(c); if (!h->p2p) return;
+  h->itmp.ensure((size_t)c->nranks + 8); h->h_small.ensure(64);
+  CUDA_CHECK(cudaMemcpyAsync(h->itmp.p, h->fault, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  NCCL_CHECK(g_nccl.AllReduce(h->itmp.p, h->itmp.p, 1, ncclInt, ncclMax, h->comm, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->h_small.p, h->itmp.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (h->h_small.p[0] == 0) return;
+  CUDA_CHECK(cudaMemsetAsync(h->mbox, 0xff, sizeof(double) * MB_SLOTS * c->nranks * MB_STRIDE, c->stream));
+  if (h->hbox) CUDA_CHECK(cudaMemsetAsync(h->hbox, 0xff, sizeof(double) * ((size_t)MB_SLOTS * 3 * h->hcap), c->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->fault, 0, sizeof(int), c->stream));
+  h->seq = 0; h->hseq = 0; c->prepush_x = nullptr;
+  NCCL_CHECK(g_nccl.AllReduce(h->itmp.p, h->itmp.p, 1, ncclInt, ncclMax, h->comm, c->stream));      // nobody pushes before everybody has re-armed
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
 void halo_setup(Ctx *c) {
   Halo *h = get(c); const int R = c->nranks, nl = c->nlocal, ng = c->nghost;
   c->tic("haloSetup");
+  static const bool no_cache = getenv("ISPH_NO_PLAN_CACHE") != nullptr;
+  h->itmp.ensure((size_t)R + 8); h->itmp2.ensure((size_t)R * (R + 1) + 8); h->h_small.ensure((size_t)R * (R + 1) + 64);
+  // ---- plan cache: a collective decision (one rank's new tag set changes the other ranks' send lists)
+  { const int changed = (no_cache || !h->plan_valid || h->plan_hash != c->tag_hash || h->plan_nl != nl || h->plan_ng != ng) ? 1 : 0;
+    h->h_small.p[0] = changed;
+    CUDA_CHECK(cudaMemcpyAsync(h->itmp2.p, h->h_small.p, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(g_nccl.AllReduce(h->itmp2.p, h->itmp2.p, 1, ncclInt, ncclMax, h->comm, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->h_small.p + 1, h->itmp2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (h->h_small.p[1] == 0) {                                   // same tags everywhere: only the ghost columns have to be put back
+      if (ng) CUDA_CHECK(cudaMemcpyAsync(c->col_of_atom.p + nl, h->gcol_saved.p, sizeof(int) * ng, cudaMemcpyDeviceToDevice, c->stream));
+      ++h->reuses; c->toc("haloSetup"); return;
+    } }
+  h->plan_valid = false; ++h->setups;
   // owned-tag directory: allgather (padded to the largest rank) -> tag -> (owner rank, owner-local index)
-  h->itmp.ensure((size_t)R + 8); h->itmp2.ensure((size_t)R * R + 8);
-  CUDA_CHECK(cudaMemcpyAsync(h->itmp2.p, &nl, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  h->h_small.p[0] = nl;
+  CUDA_CHECK(cudaMemcpyAsync(h->itmp2.p, h->h_small.p, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   NCCL_CHECK(g_nccl.AllGather(h->itmp2.p, h->itmp.p, 1, ncclInt, h->comm, c->stream));
-  std::vector<int> nloc_all(R);
-  CUDA_CHECK(cudaMemcpyAsync(nloc_all.data(), h->itmp.p, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  const int maxn = *std::max_element(nloc_all.begin(), nloc_all.end());
-  DevBuf<int> mytags, alltags; mytags.ensure(maxn); alltags.ensure((size_t)R * maxn);
-  CUDA_CHECK(cudaMemsetAsync(mytags.p, 0, sizeof(int) * maxn, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(mytags.p, c->tag.p, sizeof(int) * nl, cudaMemcpyDeviceToDevice, c->stream));
-  NCCL_CHECK(g_nccl.AllGather(mytags.p, alltags.p, maxn, ncclInt, h->comm, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->h_small.p, h->itmp.p, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int maxn = *std::max_element(h->h_small.p, h->h_small.p + R);
+  h->mytags.ensure(maxn); h->alltags.ensure((size_t)R * maxn);
+  CUDA_CHECK(cudaMemsetAsync(h->mytags.p, 0, sizeof(int) * maxn, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->mytags.p, c->tag.p, sizeof(int) * nl, cudaMemcpyDeviceToDevice, c->stream));
+  NCCL_CHECK(g_nccl.AllGather(h->mytags.p, h->alltags.p, maxn, ncclInt, h->comm, c->stream));
   h->owner_tab.ensure((size_t)c->max_tag + 1);
   CUDA_CHECK(cudaMemsetAsync(h->owner_tab.p, 0xff, sizeof(long long) * ((size_t)c->max_tag + 1), c->stream));
-  k_owner_tab<<<ceil_div((long long)R * maxn, 256), 256, 0, c->stream>>>(alltags.p, h->itmp.p, maxn, R, c->max_tag, h->owner_tab.p); ++c->launches;
-  DevBuf<int> gown, gidx; gown.ensure(ng + 1); gidx.ensure(ng + 1);
-  k_ghost_owner<<<ceil_div(ng, 256), 256, 0, c->stream>>>(c->tag.p, c->col_of_atom.p, h->owner_tab.p, nl, ng, c->rank, gown.p, gidx.p); ++c->launches;
-  std::vector<int> owner(ng), idx(ng), gcol(ng), request(ng);
-  CUDA_CHECK(cudaMemcpyAsync(owner.data(), gown.p, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(idx.data(), gidx.p, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  mytags.release(); alltags.release(); gown.release(); gidx.release();
-  h->recv_count.assign(R, 0);
-  const int rc = isph_halo_plan_host(R, c->rank, nl, ng, c->h_tag.data() + nl, owner.data(), idx.data(), gcol.data(), h->recv_count.data(), request.data(), &h->nhalo);
-  ISPH_REQUIRE(rc == ISPH_SUCCESS, "halo plan: a ghost atom's tag is owned by no rank");
-  CUDA_CHECK(cudaMemcpyAsync(c->col_of_atom.p + nl, gcol.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, c->stream));
-  // who needs what from me: allgather the request-count matrix, then swap the index lists
-  CUDA_CHECK(cudaMemcpyAsync(h->itmp.p, h->recv_count.data(), sizeof(int) * R, cudaMemcpyHostToDevice, c->stream));
-  NCCL_CHECK(g_nccl.AllGather(h->itmp.p, h->itmp2.p, R, ncclInt, h->comm, c->stream));
-  std::vector<int> M((size_t)R * R);                       // M[r][p] = how many values rank r receives from rank p
-  CUDA_CHECK(cudaMemcpyAsync(M.data(), h->itmp2.p, sizeof(int) * R * R, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  h->send_count.assign(R, 0); h->send_off.assign(R + 1, 0); h->recv_off.assign(R + 1, 0);
-  long long max_halo = 0;
+  k_owner_tab<<<ceil_div((long long)R * maxn, 256), 256, 0, c->stream>>>(h->alltags.p, h->itmp.p, maxn, R, c->max_tag, h->owner_tab.p); ++c->launches;
+  h->gown.ensure(ng + 1); h->gidx.ensure(ng + 1); h->req.ensure(ng + 1); h->gcol_saved.ensure(ng + 1);
+  k_ghost_owner<<<ceil_div(ng, 256), 256, 0, c->stream>>>(c->tag.p, c->col_of_atom.p, h->owner_tab.p, nl, ng, c->rank, h->gown.p, h->gidx.p); ++c->launches;
+  // the plan itself: sorted and numbered on the device; only R + 1 integers per rank come back to the host
+  int *d_counts = h->itmp.p;                                      // [R] received per peer, [R] = unowned ghosts
+  plan_device(c, &h->pw, c->tag.p, h->gown.p, h->gidx.p, nl, ng, c->col_of_atom.p + nl, h->req.p, d_counts);
+  if (ng) CUDA_CHECK(cudaMemcpyAsync(h->gcol_saved.p, c->col_of_atom.p + nl, sizeof(int) * ng, cudaMemcpyDeviceToDevice, c->stream));
+  // who needs what from me: allgather the (request count, error) rows -> M[r][p] = how many values rank r receives from rank p
+  NCCL_CHECK(g_nccl.AllGather(d_counts, h->itmp2.p, R + 1, ncclInt, h->comm, c->stream));
+  int *M = h->h_small.p;
+  CUDA_CHECK(cudaMemcpyAsync(M, h->itmp2.p, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < R; ++r) ISPH_REQUIRE(M[(size_t)r * (R + 1) + R] == 0, "halo plan: a ghost atom's tag is owned by no rank");
+  h->recv_count.assign(R, 0); h->send_count.assign(R, 0); h->send_off.assign(R + 1, 0); h->recv_off.assign(R + 1, 0); h->dst_off.assign(R, 0);
+  long long max_halo = 0; bool symmetric = true;
   for (int p = 0; p < R; ++p) {
-    h->send_count[p] = M[(size_t)p * R + c->rank]; h->send_off[p + 1] = h->send_off[p] + h->send_count[p]; h->recv_off[p + 1] = h->recv_off[p] + h->recv_count[p];
+    h->recv_count[p] = M[(size_t)c->rank * (R + 1) + p];
+    h->send_count[p] = M[(size_t)p * (R + 1) + c->rank]; h->send_off[p + 1] = h->send_off[p] + h->send_count[p]; h->recv_off[p + 1] = h->recv_off[p] + h->recv_count[p];
     long long tot = 0; int before_me = 0;                  // where my block starts in rank p's staging buffer
-    for (int q = 0; q < R; ++q) { if (q < c->rank) before_me += M[(size_t)p * R + q]; tot += M[(size_t)p * R + q]; }
+    for (int q = 0; q < R; ++q) { if (q < c->rank) before_me += M[(size_t)p * (R + 1) + q]; tot += M[(size_t)p * (R + 1) + q];
+      if ((M[(size_t)p * (R + 1) + q] > 0) != (M[(size_t)q * (R + 1) + p] > 0)) symmetric = false; }
     h->dst_off[p] = before_me; max_halo = std::max(max_halo, tot);
   }
-  h->nsend = h->send_off[R];
-  DevBuf<int> req; req.ensure(h->nhalo + 1); h->send_idx.ensure(h->nsend + 1);
-  CUDA_CHECK(cudaMemcpyAsync(req.p, request.data(), sizeof(int) * h->nhalo, cudaMemcpyHostToDevice, c->stream));
+  h->nhalo = h->recv_off[R]; h->nsend = h->send_off[R];
+  h->send_idx.ensure(h->nsend + 1);
   NCCL_CHECK(g_nccl.GroupStart());
   for (int p = 0; p < R; ++p) {
-    if (h->recv_count[p]) NCCL_CHECK(g_nccl.Send(req.p + h->recv_off[p], h->recv_count[p], ncclInt, p, h->comm, c->stream));
+    if (h->recv_count[p]) NCCL_CHECK(g_nccl.Send(h->req.p + h->recv_off[p], h->recv_count[p], ncclInt, p, h->comm, c->stream));
     if (h->send_count[p]) NCCL_CHECK(g_nccl.Recv(h->send_idx.p + h->send_off[p], h->send_count[p], ncclInt, p, h->comm, c->stream));
   }
   NCCL_CHECK(g_nccl.GroupEnd());
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  req.release();
   h->sendbuf.ensure((size_t)h->nsend * 9 + 8); h->fieldbuf.ensure((size_t)h->nhalo * 9 + 8);
   // halo staging buffers in peer-addressable memory; every rank sees the same max_halo, so growth is collective
   if (h->p2p && max_halo > h->hcap) {
@@ -241,27 +314,29 @@ void halo_setup(Ctx *c) {
     h->hseq = 0;
     if (!ipc_share(c, h, h->hbox, h->hpeer, h->hopened)) { cudaFree(h->hbox); h->hbox = nullptr; h->hcap = 0; }
   }
-  h->plan_ok = false;
-  if (h->p2p && h->hbox) {                                       // device copy of the plan for the halo kernels
-    HaloDev hd; memset(&hd, 0, sizeof(hd));
+  h->plan_ok = false; h->rows_ok = false;
+  // the slot-ring safety of the staging buffers needs every receiver of a peer to also send to it (p2p_device.cuh); the exchange
+  // matrix is known to all ranks, so all take the same decision.  R > ISPH_MAX_RANKS never has peer buffers (get()).
+  if (h->p2p && h->hbox && symmetric && R <= ISPH_MAX_RANKS) {   // device copy of the plan for the halo kernels
+    HaloDev &hd = h->hd_host; memset(&hd, 0, sizeof(hd));
     for (int p = 0; p < R; ++p) { hd.peer[p] = h->hpeer[p]; hd.send_off[p] = h->send_off[p]; hd.dst_off[p] = h->dst_off[p]; hd.recv_cnt[p] = h->recv_count[p]; }
     for (int p = R; p <= ISPH_MAX_RANKS; ++p) hd.send_off[p] = h->send_off[R];
     hd.mine = h->hbox; hd.nranks = R; hd.rank = c->rank; hd.cap = h->hcap; hd.fault = h->fault;
     h->d_plan.ensure(1);
-    CUDA_CHECK(cudaMemcpyAsync(h->d_plan.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_plan.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, c->stream));   // hd_host is only rewritten after the next set-up's first synchronisation
     h->plan_ok = true;
-    h->rows_ok = false;
     if (!getenv("ISPH_NO_PREPUSH") && h->nsend > 0 && h->hcap < (1ll << 28)) {
       h->row_sp.ensure(nl + 2); h->row_cur.ensure(nl + 2); h->row_sd.ensure(h->nsend + 1);
       CUDA_CHECK(cudaMemsetAsync(h->row_cur.p, 0, sizeof(int) * (nl + 1), c->stream));
       k_rowsend_count<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(h->send_idx.p, h->nsend, h->row_cur.p); ++c->launches;
       size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, h->row_cur.p, h->row_sp.p, nl + 1, c->stream); h->cubtmp.ensure(tb);
-      cub::DeviceScan::ExclusiveSum(h->cubtmp.p, tb, h->row_cur.p, h->row_sp.p, nl + 1, c->stream); ++c->launches;
+      tb = h->cubtmp.cap; cub::DeviceScan::ExclusiveSum(h->cubtmp.p, tb, h->row_cur.p, h->row_sp.p, nl + 1, c->stream); ++c->launches;
       CUDA_CHECK(cudaMemcpyAsync(h->row_cur.p, h->row_sp.p, sizeof(int) * (nl + 1), cudaMemcpyDeviceToDevice, c->stream));
       k_rowsend_fill<<<ceil_div(h->nsend, 256), 256, 0, c->stream>>>(h->d_plan.p, h->send_idx.p, h->nsend, h->row_cur.p, h->row_sd.p); ++c->launches;
       h->rows_ok = true;
     }
   }
+  h->plan_valid = true; h->plan_hash = c->tag_hash; h->plan_nl = nl; h->plan_ng = ng;
   c->toc("haloSetup");
 }
 
@@ -332,6 +407,7 @@ void halo_destroy(Ctx *c) {
   if (h->mbox) cudaFree(h->mbox); if (h->hbox) cudaFree(h->hbox); if (h->fault) cudaFree(h->fault); if (h->d_tab) cudaFree(h->d_tab);
   if (h->inited && h->comm) g_nccl.CommDestroy(h->comm);
   h->d_plan.release(); h->row_sp.release(); h->row_sd.release(); h->row_cur.release(); h->cubtmp.release();
+  h->mytags.release(); h->alltags.release(); h->gown.release(); h->gidx.release(); h->req.release(); h->pw.release(); h->gcol_saved.release(); h->h_small.release();
   h->send_idx.release(); h->itmp.release(); h->itmp2.release(); h->owner_tab.release(); h->sendbuf.release(); h->fieldbuf.release();
   delete h; c->halo = nullptr;
 }
@@ -344,6 +420,38 @@ int isph_nccl_unique_id(void *id128) {
   if (!id128 || !isph::g_nccl.load()) return ISPH_FAILURE;
   ncclUniqueId id; if (isph::g_nccl.GetUniqueId(&id) != ncclSuccess) return ISPH_FAILURE;
   memset(id128, 0, 128); memcpy(id128, &id, sizeof(id) < 128 ? sizeof(id) : 128); return ISPH_SUCCESS;
+}
+
+// The device planner halo_setup runs (sort + number the distinct remote (owner, tag) pairs on the GPU), with the signature of
+// isph_halo_plan_host so that a one-GPU test can compare the two on identical inputs.  Host arrays in, host arrays out.
+int isph_halo_plan_device(isph_ctx *ctx, int nranks, int rank, int nlocal, int nghost, const int *ghost_tag, const int *ghost_owner, const int *ghost_owner_idx,
+                          int *ghost_col, int *recv_count, int *request_idx, int *nhalo_out) {
+  if (!ctx) return ISPH_FAILURE; isph::Ctx *c = reinterpret_cast<isph::Ctx *>(ctx);
+  try {
+    using namespace isph;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    ISPH_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && nlocal >= 0 && nghost >= 0, "bad plan arguments");
+    const int save_r = c->nranks, save_k = c->rank; c->nranks = nranks; c->rank = rank;
+    PlanWork pw; DevBuf<int> tag, own, idx, col, req, cnt;
+    tag.ensure((size_t)nlocal + nghost + 1); own.ensure(nghost + 1); idx.ensure(nghost + 1); col.ensure(nghost + 1); req.ensure(nghost + 1); cnt.ensure(nranks + 1);
+    CUDA_CHECK(cudaMemcpy(tag.p + nlocal, ghost_tag, sizeof(int) * nghost, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(own.p, ghost_owner, sizeof(int) * nghost, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(idx.p, ghost_owner_idx, sizeof(int) * nghost, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(col.p, 0xff, sizeof(int) * (nghost + 1)));
+    std::string err;
+    try { plan_device(c, &pw, tag.p, own.p, idx.p, nlocal, nghost, col.p, req.p, cnt.p); CUDA_CHECK(cudaStreamSynchronize(c->stream)); } catch (const std::exception &e) { err = e.what(); }
+    c->nranks = save_r; c->rank = save_k;
+    std::vector<int> hc(nranks + 1, 0);
+    if (err.empty()) {
+      CUDA_CHECK(cudaMemcpy(hc.data(), cnt.p, sizeof(int) * (nranks + 1), cudaMemcpyDeviceToHost));
+      int nh = 0; for (int p = 0; p < nranks; ++p) { recv_count[p] = hc[p]; nh += hc[p]; }
+      *nhalo_out = nh;
+      CUDA_CHECK(cudaMemcpy(ghost_col, col.p, sizeof(int) * nghost, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(request_idx, req.p, sizeof(int) * nh, cudaMemcpyDeviceToHost));
+    }
+    pw.release(); tag.release(); own.release(); idx.release(); col.release(); req.release(); cnt.release();
+    if (!err.empty()) throw std::runtime_error(err);
+    if (hc[nranks] != 0) { c->err = "halo plan: a ghost atom's tag is owned by no rank"; return ISPH_FAILURE; }
+  } catch (const std::exception &e) { c->err = e.what(); cudaGetLastError(); return ISPH_FAILURE; }
+  return ISPH_SUCCESS;
 }
 
 // Pure host code (no CUDA): halo columns for the ghosts owned by other ranks.  Distinct (owner, tag) pairs are numbered

@@ -402,7 +402,20 @@ bool ilu_fault(Ctx *c) {
   int f = 0; cudaMemcpy(&f, c->ilu->fault.p, sizeof(int), cudaMemcpyDeviceToHost); return f != 0;
 }
 
+void ilu_info(Ctx *c, long long *nnz, int *nlev_l, int *nlev_u, int *maxlen) {
+  *nnz = 0; *nlev_l = *nlev_u = *maxlen = 0; if (!c->ilu) return;
+  *nnz = c->ilu->nnz; *nlev_l = c->ilu->nlev_l; *nlev_u = c->ilu->nlev_u; *maxlen = c->ilu->maxlen;
+}
+
+static void ilu_apply_launch(Ctx *c, const double *r, double *z);
 void ilu_apply(Ctx *c, const double *r, double *z) {
+  if (!c->prof_spmv) { ilu_apply_launch(c, r, z); return; }
+  // per-launch device timing on the launching stream (bench.py: achieved GB/s of the triangular solves)
+  if (c->pprof_used + 2 > c->pprof_ev.size()) { const size_t o = c->pprof_ev.size(); c->pprof_ev.resize(o + 512, nullptr); for (size_t q = o; q < c->pprof_ev.size(); ++q) CUDA_CHECK(cudaEventCreate(&c->pprof_ev[q])); }
+  cudaEvent_t e0 = c->pprof_ev[c->pprof_used++], e1 = c->pprof_ev[c->pprof_used++];
+  CUDA_CHECK(cudaEventRecord(e0, c->stream)); ilu_apply_launch(c, r, z); CUDA_CHECK(cudaEventRecord(e1, c->stream));
+}
+static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
   IluData &I = *c->ilu;
   if (I.sync_free) {
     CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"

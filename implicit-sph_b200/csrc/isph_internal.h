@@ -86,7 +86,7 @@ struct Ctx {
   // pair
   bool have_pair = false; PairTab tab; DevBuf<PairTab> d_tab;
   // atoms
-  int nlocal = 0, nghost = 0, nall = 0, first_fluid_row = -1, max_tag = 0; bool have_atoms = false;
+  int nlocal = 0, nghost = 0, nall = 0, first_fluid_row = -1, max_tag = 0; bool have_atoms = false; unsigned long long tag_hash = 0;
   DevBuf<double> x; DevBuf<int> type, tag, kind, col_of_atom, tag2own; std::vector<int> h_type, h_tag;
   DevBuf<double> field[ISPH_F_COUNT];
   // neighbors
@@ -98,6 +98,7 @@ struct Ctx {
   // solver state (SolverLin members, solver_lin.h:70-97)
   SolverParams sp; PrecondParams pp;
   double *x_host = nullptr, *b_host = nullptr; int x_lda = 0, b_lda = 0, x_nvec = 0, b_nvec = 0; bool x_owned = true, b_owned = true;
+  bool b_dev_fresh = false;        // a device functor / isph_solver_load_set wrote the load vector after the last solve: a borrowed host b is not re-uploaded over it
   DevBuf<double> xs, bs;           // device solution / load multivectors, column-major, leading dimension ld
   int ld = 0;                      // padded length of every Krylov vector (>= ncols)
   bool is_singular = false, have_mask = false; DevBuf<double> nullvec; DevBuf<int> mask;
@@ -116,6 +117,7 @@ struct Ctx {
   // timers
   std::map<std::string, Timer> timers;
   bool prof_spmv = false; std::vector<cudaEvent_t> prof_ev; size_t prof_used = 0; double prof_ms = 0.0; long long prof_cnt = 0;
+  std::vector<cudaEvent_t> pprof_ev; size_t pprof_used = 0; double pprof_ms = 0.0; long long pprof_cnt = 0;      // the same for the ILU apply kernel
   // optional per-phase device timing of the Krylov loop (ISPH_PROFILE=1): name -> event pairs
   bool prof_phases = false; std::map<std::string, std::vector<cudaEvent_t>> phase_ev; std::map<std::string, size_t> phase_used;
 
@@ -171,7 +173,10 @@ void precond_free(Ctx *c);
 void precond_apply(Ctx *c, const double *d_r, double *d_z);  // z = M^-1 r
 void ilu_destroy(Ctx *c);                                    // ilu.cu
 bool ilu_fault(Ctx *c);
+void ilu_info(Ctx *c, long long *nnz, int *nlev_l, int *nlev_u, int *maxlen);
 
+void load_from_host(Ctx *c);                                  // capi.cu: borrowed (View) load vector, see there
+void load_written(Ctx *c);
 void solver_prepare_vectors(Ctx *c);                         // krylov.cu
 void solver_solve(Ctx *c, bool use_prec, const char *label);
 void pb_newton(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, int max_newton, double tol_f, double tol_update,
@@ -195,6 +200,7 @@ void halo_wait_unstage(Ctx *c, double *d_x, unsigned long long seq);  // complet
 void halo_exchange(Ctx *c, double *d_x, int nvec, int ldx);   // import: off-rank entries of x land behind its owned rows
 P2PRed halo_p2p_ticket(Ctx *c);          // sequence ticket for an in-kernel peer all-reduce (nranks <= 1 in it: not available)
 bool halo_fault(Ctx *c);
+void halo_recover(Ctx *c);                                   // collective: re-arm the peer slots after a timed-out wait
 void halo_allreduce(Ctx *c, double *d_buf, int count);
 void halo_forward_field(Ctx *c, int field, int ncomp);
 void halo_destroy(Ctx *c);

@@ -679,6 +679,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   ISPH_REQUIRE(is_cg || c->sp.solver_type == "Block GMRES", "Solver Type must be \"Block GMRES\" or \"Block CG\" (Recycling GMRES is not implemented)");
   ISPH_REQUIRE(c->sp.block_size == 1, "Block Size must be 1");
   c->prof_phases = getenv("ISPH_PROFILE") != nullptr;
+  halo_recover(c);                                               // a peer wait that timed out in an earlier solve: re-arm the slots on all ranks
   std::string tname = std::string("solve") + (label ? label : "");
   c->tic(tname.c_str());
   c->hbuf.ensure(S_TOTAL); c->flag.ensure(16); c->red.ensure((size_t)8 * 592 * 18 + 1024 + (size_t)A.nslices / 8 + 64);
@@ -696,7 +697,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   else if (c->x_host) {     // caller's x is the initial guess (Helmholtz: x = v, pair_isph.cpp:932-941)
     for (int q = 0; q < c->x_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * ld, c->x_host + (size_t)q * c->x_lda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   }
-  if (c->b_host && !c->b_owned) for (int q = 0; q < c->b_nvec; ++q) CUDA_CHECK(cudaMemcpyAsync(c->bs.p + (size_t)q * ld, c->b_host + (size_t)q * c->b_lda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  load_from_host(c); c->b_dev_fresh = false;                     // borrowed b: the host View is uploaded unless a device functor wrote the load vector since the last solve
   double *S = c->hbuf.p;
   if (c->is_singular) {     // createNullVector (solver_lin.cpp:59-77) ; b -= (b.n) n (solver_lin_belos.h:138-144)
     c->nullvec.ensure(ld);
@@ -774,7 +775,7 @@ void pb_newton(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, dou
     if (k >= max_newton) break;
     pb_jacobian(c, mh, linearized, ezcb, psiref, gamma);                                          // J(psi_k): diagonal refreshed, Laplacian block kept
     k_scale_by<<<g, VB, 0, c->stream>>>(c->bs.p, -1.0, n); ++c->launches;                         // J dpsi = -F
-    c->init_type = ISPH_INIT_ZERO;
+    c->init_type = ISPH_INIT_ZERO; c->b_dev_fresh = true;         // -F was formed on the device
     solver_solve(c, use_prec, "PoissonBoltzmannJacobian"); lin_total += c->last_iters;
     k_add_rows<<<g, VB, 0, c->stream>>>(c->field[ISPH_F_PSI].p, c->xs.p, n); ++c->launches;       // full step
     dot_dev(c, c->xs.p, nullptr, n, S + S_TMP); nup = sqrt(read_scalar(c, S + S_TMP) / nglobal);

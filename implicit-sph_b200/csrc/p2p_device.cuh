@@ -11,8 +11,10 @@
 // latency per exchange instead of store -> system fence -> flag -> poll.  All-reduce payloads are summed in rank order,
 // so every rank forms the bit-identical sum.  A rank can never overwrite a cell a peer has not consumed yet: to get
 // MB_SLOTS calls ahead it would need the peer's contributions to the calls in between, which the peer only issues after
-// it has consumed (and re-armed) the older call.  Waits are bounded: a dead peer raises the fault word, after which every
-// wait on this GPU drains immediately.
+// it has consumed (and re-armed) the older call.  For the halo staging slots this argument needs every receiver of a peer to
+// also send to that peer (halo_setup checks the symmetry of the exchange matrix on all ranks and falls back to NCCL send/recv
+// otherwise).  Waits are bounded in wall-clock time: a dead peer raises the fault word, after which every wait on this GPU
+// drains immediately.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -38,12 +40,22 @@ struct P2PRed {               // passed by value to kernels; tab == nullptr mean
 __device__ __forceinline__ double p2p_payload(double v) {      // a value that may be stored into a peer cell
   return (unsigned long long)__double_as_longlong(v) == ISPH_SENTINEL ? __longlong_as_double(0x7FF8000000000000ll) : v;
 }
-// poll a cell of this rank's own buffer until a peer's value has landed, then re-arm it
+// poll a cell of this rank's own buffer until a peer's value has landed, then re-arm it.  The wait is bounded by WALL-CLOCK
+// time (%globaltimer; fault[1] = limit in milliseconds, ISPH_P2P_TIMEOUT_MS, default 20 s), not by a poll count: a peer that
+// is merely late to enqueue (host I/O, a first-touch cudaMalloc) is waited for; a dead one raises the fault word fault[0], after
+// which every wait on this GPU drains immediately, the running solve reports the failure (solver_solve) and the next solve
+// re-arms all slots collectively (halo_recover).
+__device__ __forceinline__ unsigned long long p2p_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ double p2p_take(double *cell, int *fault) {
   volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(cell);
-  unsigned long long bits = *q; int spins = 0;
+  unsigned long long bits = *q, t0 = 0; int spins = 0;
   while (bits == ISPH_SENTINEL) {
-    if ((++spins & 1023) == 0) { if (*reinterpret_cast<volatile int *>(fault)) return 0.0; if (spins > (1 << 23)) { *fault = 1; return 0.0; } }
+    if ((++spins & 1023) == 0) {
+      volatile int *f = reinterpret_cast<volatile int *>(fault);
+      if (f[0]) return 0.0;
+      const unsigned long long now = p2p_now();
+      if (t0 == 0) t0 = now; else if (now - t0 > (unsigned long long)f[1] * 1000000ull) { f[0] = 1; return 0.0; }
+    }
     bits = *q;
   }
   *q = ISPH_SENTINEL;

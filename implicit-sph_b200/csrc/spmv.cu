@@ -42,9 +42,11 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
             const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
   if (!DOT && s >= nslices) return;
-  if (DOT && s >= nslices) { spmv_dot_finish(0.0, partials, counter, out, pr); return; }
-  const long long base = slice_off[s] + (row & 31);
-  const int slen = slice_len[s];
+  // DOT: warps past the last slice do no row work (slen = 0) but fall through to the ONE spmv_dot_finish call site below, so
+  // every thread of the block meets the same barrier instructions
+  const bool active = s < nslices;
+  const long long base = active ? slice_off[s] + (row & 31) : 0;
+  const int slen = active ? slice_len[s] : 0;
   const int *cp = col + base; const double *vp = val + base;
   double acc[NV];
 #pragma unroll

@@ -162,3 +162,44 @@ def make_cloud(dim, n, box, reach, seed=7, min_sep=0.0, type_fn=None):
     return dict(dim=dim, nlocal=n, nghost=len(ghost), x=np.ascontiguousarray(x), xw=xw, type=typ, tag=tag,
                 ilist=np.arange(n, dtype=np.int32), noff=np.asarray(noff, dtype=np.int64), neigh=np.concatenate(neigh).astype(np.int32),
                 gidx=(tag - 1).astype(np.int64), dx=box / n ** (1.0 / dim), nglobal=(n,), lo=(0,) * dim, nloc=(n,))
+
+
+def make_cloud_kd(dim, n, box, reach, seed=11, min_sep=0.0, type_fn=None):
+    """`make_cloud` for tens of thousands of particles: the same construction (uniformly random owned particles in the
+    periodic box, thinned below `min_sep`; ghosts = every periodic image within `reach` of the box; full neighbor list of all
+    atoms within `reach`, each row in a random order) with k-d trees instead of the O(n^2) scans."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    own = np.zeros((0, 3))
+    while len(own) < n:
+        cand = np.zeros((int(1.5 * (n - len(own))) + 16, 3)); cand[:, :dim] = rng.uniform(0.0, box, size=(len(cand), dim))
+        pts = np.concatenate([own, cand])
+        if min_sep > 0.0:
+            t = cKDTree(pts[:, :dim], boxsize=box)
+            drop = np.zeros(len(pts), dtype=bool)
+            for a, b in sorted(t.query_pairs(min_sep)):          # keep the earlier particle of every close pair
+                if not drop[a]:
+                    drop[b] = True
+            pts = pts[~drop]
+        own = pts[:n]
+    gx, gt = [], []
+    for s in np.ndindex(*(3,) * dim):
+        sh = np.zeros(3); sh[:dim] = (np.asarray(s) - 1) * box
+        if not sh.any():
+            continue
+        img = own + sh
+        near = np.all((img[:, :dim] > -reach) & (img[:, :dim] < box + reach), axis=1)
+        gx.append(img[near]); gt.append(np.nonzero(near)[0])
+    ghost = np.concatenate(gx); gtag = np.concatenate(gt)
+    x = np.concatenate([own, ghost]); tag = np.concatenate([np.arange(n), gtag]).astype(np.int32) + 1
+    xw = np.concatenate([own, own[gtag]])
+    tree = cKDTree(x[:, :dim])
+    rows = tree.query_ball_point(own[:, :dim], reach * (1.0 - 1e-12))
+    neigh, noff = [], np.zeros(n + 1, dtype=np.int64)
+    for i, r in enumerate(rows):
+        j = np.asarray(r, dtype=np.int32); j = j[j != i]
+        neigh.append(rng.permutation(j)); noff[i + 1] = noff[i] + len(j)
+    typ = np.ones(len(x), dtype=np.int32) if type_fn is None else np.asarray(type_fn(xw), dtype=np.int32)
+    return dict(dim=dim, nlocal=n, nghost=len(ghost), x=np.ascontiguousarray(x), xw=xw, type=typ, tag=tag,
+                ilist=np.arange(n, dtype=np.int32), noff=noff, neigh=np.concatenate(neigh).astype(np.int32),
+                gidx=(tag - 1).astype(np.int64), dx=box / n ** (1.0 / dim), nglobal=(n,), lo=(0,) * dim, nloc=(n,))

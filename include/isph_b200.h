@@ -56,6 +56,10 @@ int isph_nccl_unique_id(void *id128);
  * request, in slot order. */
 int isph_halo_plan_host(int nranks, int rank, int nlocal, int nghost, const int *ghost_tag, const int *ghost_owner,
                         const int *ghost_owner_idx, int *ghost_col, int *recv_count, int *request_idx, int *nhalo_out);
+/* The same plan computed by the device planner that multi-GPU runs use (sort + numbering on the GPU); host arrays in and out.
+ * Exists so that a one-GPU parity test can hold the device planner against isph_halo_plan_host. */
+int isph_halo_plan_device(isph_ctx *ctx, int nranks, int rank, int nlocal, int nghost, const int *ghost_tag, const int *ghost_owner,
+                          const int *ghost_owner_idx, int *ghost_col, int *recv_count, int *request_idx, int *nhalo_out);
 const char *isph_last_error(const isph_ctx *ctx);
 int isph_set_stream(isph_ctx *ctx, void *cuda_stream);   /* run on the caller's CUDA stream (borrowed) */
 int isph_synchronize(isph_ctx *ctx);
@@ -64,6 +68,9 @@ const char *isph_version(void);
 /* ---- pair / atom / neighbor data ------------------------------------------------------------------------------
  * replaces: PairISPH_Corrected::coeff pair_isph_corrected.cpp:1273-1347 (kernel, cutsq, h tables, MorrisSafeCoeff)
  *           and the FunctorOuter<PairIsph> constructor capture functor.h:64-91 (atom->{x,type,tag,vfrac}, list->...) */
+/* Limits: 1 <= ntypes <= 7 (particle types 1..7; the reference's scripts use at most 3); ilist must enumerate the owned atoms
+ * in order, ilist[ii] == ii, and inum == nlocal (what a LAMMPS full list built for pair_style isph gives, pair_isph.cpp:1887-1894:
+ * the row map IS the owned-atom order, :1258); at most 511 neighbors per row; atom tags fit a 32-bit int (functor.h:62). */
 int isph_pair_coeff(isph_ctx *ctx, int dim, int ntypes, const int *kind_of_type /*[ntypes+1]*/, double h, double h_min,
                     double cut_over_h, int kernel, double morris_safe);
 int isph_atoms_set(isph_ctx *ctx, int nlocal, int nghost, const double *x /*[nall][3]*/, const int *type, const int *tag);
@@ -153,6 +160,9 @@ int isph_diagonals_get(isph_ctx *ctx, double *diagonal, double *scaled_laplace_d
 
 /* ---- SolverLin / SolverLin_Belos mirror (solver_lin.h:23-98, solver_lin.cpp, solver_lin_belos.h:130-264) --------- */
 int isph_solver_create_solution_multivector(isph_ctx *ctx, double *x /*borrowed; NULL: owned*/, int lda, int nvec);
+/* b borrowed = a View of caller memory as in the reference (solver_lin.cpp:45-58): the system functors (isph_ns_poisson, ...) copy
+ * the right-hand side they form on the device back into b, and whatever b holds when a functor that reads it or the solve starts
+ * is uploaded, unless a device functor / isph_solver_load_set wrote the load vector after the previous solve. */
 int isph_solver_create_load_multivector(isph_ctx *ctx, double *b /*borrowed; NULL: owned, device-resident*/, int lda, int nvec);
 int isph_solver_load_set(isph_ctx *ctx, const double *b, int lda);        /* write getLoadMultiVector()->Values() */
 int isph_solver_load_get(isph_ctx *ctx, double *b, int lda);
@@ -199,6 +209,11 @@ long long isph_kernel_launches(isph_ctx *ctx);            /* number of kernels t
 /* per-launch CUDA-event timing of the SpMV kernel inside whatever runs next (solve, assembly): enable, run, read */
 int isph_profile_spmv(isph_ctx *ctx, int enable);
 int isph_profile_spmv_get(isph_ctx *ctx, double *total_ms, long long *launches);   /* also resets the counters */
+/* the same for the ILU triangular-solve kernel (enabled by isph_profile_spmv) */
+int isph_profile_precond_get(isph_ctx *ctx, double *total_ms, long long *launches);
+/* the ILU factors of the last isph_precond_create / solve: stored entries of L + D + U (all blocks), dependency levels of the
+ * forward and backward sweeps (the critical path of the level-scheduled solves), longest factor row */
+int isph_precond_info(isph_ctx *ctx, long long *factor_nnz, int *levels_lower, int *levels_upper, int *max_row);
 /* last SpMV-only micro benchmark: runs `reps` SpMVs on the current matrix, returns average ms (device events) */
 int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms);
 

@@ -19,6 +19,9 @@
 // level(i,j) = min_k level(i,k) + level(k,j) + 1 <= k, then row-wise IKJ, L unit-lower, D stored inverted, U unit-upper scaled.
 // Deviation (documented in DESIGN.md): Epetra's Random() start vector of the power method is replaced by a
 // deterministic per-row hash, identically here and in the CUDA path.
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -169,6 +172,16 @@ struct Op {   // A, or PoissonProjection (I - n n^T) A   (solver_lin.h:130-140)
 }  // namespace
 
 extern "C" {
+
+// thread count of the OpenMP row loops of this library (bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1)
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n; return 1;
+#endif
+}
 
 void orc_krylov_default_params(orc_krylov_params *p) {
   memset(p, 0, sizeof(*p));

@@ -26,6 +26,7 @@ typedef struct {
   int ilu_fill;          /* "fact: level-of-fill" (Ifpack_IlukGraph level rule) */
 } orc_krylov_params;
 
+int orc_set_num_threads(int n);   /* OpenMP threads of the port's row loops; returns the count in effect */
 void orc_krylov_default_params(orc_krylov_params *p);
 /* col = local row index of each column, -1 for a column that is not in this process' rows.  b is modified in place
  * when use_null (as solver_lin_belos.h:141-143 does).  returns 0 converged, 1 not converged. */

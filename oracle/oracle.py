@@ -245,6 +245,11 @@ def precond_apply(rowptr, col, val, r, params, blocks=None):
     return z, lm.value
 
 
+def set_num_threads(n):
+    """OpenMP threads of the port's row loops (returns the count in effect)."""
+    return int(_load("port").orc_set_num_threads(int(n)))
+
+
 def tags_to_local(col_tags, tags_owned):
     """canonical graph columns (global tags) -> local row indices (-1 when the tag is not owned here)"""
     lut = -np.ones(int(max(col_tags.max(), tags_owned.max())) + 2, dtype=np.int64)

@@ -34,6 +34,15 @@ def main():
         buf = (isph.C.c_ubyte * 128)(); assert isph.lib().isph_nccl_unique_id(buf) == 0
         idt = torch.tensor(list(buf), dtype=torch.uint8)
     dist.broadcast(idt, 0)
+    res = run_check(isph, lat, torch, dist, rank, world, lr, bytes(idt.tolist()))
+    dist.destroy_process_group()
+    sys.exit(0 if res["pass"] else 1)
+
+
+def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
+    """The comparison itself (collective; every rank calls it).  Returns {"pass": bool, ...measured errors...} on every rank.
+    bench.py calls this before its timed region at n_gpus > 1 and prints the result as the line's "parity" block."""
+    say = (lambda *a: None) if quiet else print
     dim = 3; grid = lat.brick_grid(world, dim); per = (10, 8, 8); nglobal = tuple(per[k] * grid[k] for k in range(dim))
     lo, nloc = lat.brick_of_rank(rank, grid, nglobal)
     dx = 2 * np.pi / nglobal[0]
@@ -42,7 +51,7 @@ def main():
     v = lat.tgv_velocity(xw)
     for k in range(dim):
         v[:, k] += 0.05 * (2.0 * lat._hash01(P["gidx"] + 1, 100 + k) - 1.0)
-    c = isph.Context(lr, world, rank, bytes(idt.tolist()))
+    c = isph.Context(lr, world, rank, nccl_id)
     c.set_particles(P)
     nu = 0.1 + 0.01 * np.cos(xw[:, 1]); pr = np.sin(xw[:, 0]) * np.cos(xw[:, 1])
     c.field_set(isph.F_VSTAR, v); c.field_set(isph.F_VELOCITY, v); c.field_set(isph.F_VISCOSITY, nu); c.field_set(isph.F_PRESSURE, pr)
@@ -72,7 +81,7 @@ def main():
     mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
     allr = [None] * world
     dist.gather_object(mine, allr if rank == 0 else None, 0)
-    ok = True
+    ok = True; rep = {}
     if rank == 0:
         import oracle as O
         from problems import relerr
@@ -97,7 +106,7 @@ def main():
             xd[gi] = d["x"]
         its = allr[0]["st"]["iters"]
         xerr = np.linalg.norm(xd - xo) / np.linalg.norm(xo)
-        print(f"multi_gpu_check world={world} rows={n}: values/b/vfrac max err {worst:.2e}; iters gpu {its} vs oracle {info['iters']}; x rel diff {xerr:.2e}; converged {allr[0]['st']['converged']}")
+        say(f"multi_gpu_check world={world} rows={n}: values/b/vfrac max err {worst:.2e}; iters gpu {its} vs oracle {info['iters']}; x rel diff {xerr:.2e}; converged {allr[0]['st']['converged']}")
         ok = worst <= 1e-12 and abs(its - info["iters"]) <= 2 and xerr <= 1e-6 and allr[0]["st"]["converged"] and all(d["st"]["iters"] == its for d in allr)
         # 2. ILU(0), one block per rank
         colL = O.tags_to_local(gcol, G["tag"][:n]); blocks = np.zeros(n, dtype=np.int32); x2d = np.zeros(n)
@@ -105,7 +114,7 @@ def main():
             gi = row_of_tag[d["tag"]]; blocks[gi] = r_; x2d[gi] = d["x2"]
         x2o, info2 = O.krylov_solve(grp, colL, gA, gb.copy(), params=O.krylov_params(precond=O.PREC_ILU0, row_gid=G["tag"][:n]), null_mask=np.ones(n, dtype=np.int32), use_null=True, blocks=blocks)
         its2 = allr[0]["st2"]["iters"]; x2err = np.linalg.norm(x2d - x2o) / np.linalg.norm(x2o)
-        print(f"  block-Jacobi ILU(0): iters gpu {its2} vs oracle {info2['iters']}; x rel diff {x2err:.2e}; converged {allr[0]['st2']['converged']}")
+        say(f"  block-Jacobi ILU(0): iters gpu {its2} vs oracle {info2['iters']}; x rel diff {x2err:.2e}; converged {allr[0]['st2']['converged']}")
         ok = ok and abs(its2 - info2["iters"]) <= 2 and x2err <= 1e-6 and allr[0]["st2"]["converged"]
         # 3. Helmholtz, CG + Chebyshev(2), dim right-hand sides
         o.invalidate_matrix(); gbh = o.ns_helmholtz(dt, 0.5, np.asfortranarray(vg[:n, :dim])); gAh = o.matrix()
@@ -120,7 +129,7 @@ def main():
             xk, ik = O.krylov_solve(grp, colL, gAh, gbh[:, k], params=prm); its3o += ik["iters"]
             x3err = max(x3err, np.linalg.norm(x3d[:, k] - xk) / np.linalg.norm(xk))
         its3 = allr[0]["st3"]["iters"]
-        print(f"  Helmholtz CG+Chebyshev(2) x{dim}: values/b max err {worst3:.2e}; iters gpu {its3} vs oracle {its3o}; x rel diff {x3err:.2e}; converged {allr[0]['st3']['converged']}")
+        say(f"  Helmholtz CG+Chebyshev(2) x{dim}: values/b max err {worst3:.2e}; iters gpu {its3} vs oracle {its3o}; x rel diff {x3err:.2e}; converged {allr[0]['st3']['converged']}")
         ok = ok and worst3 <= 1e-12 and abs(its3 - its3o) <= 2 * dim and x3err <= 1e-7 and allr[0]["st3"]["converged"]
         # 4. Poisson-Boltzmann Newton on the global problem, built from the oracle's pieces (same stopping rule)
         sg = np.sin(xg[:, 0]) * np.cos(xg[:, 1]); exg = (-2.0 * sg - np.sinh(sg))[:n].copy()
@@ -138,13 +147,17 @@ def main():
         for d in allr:
             psid[row_of_tag[d["tag"]]] = d["psi4"]
         s4 = allr[0]["st4"]; p4err = np.linalg.norm(psid - psi[:n]) / np.linalg.norm(psi[:n])
-        print(f"  Poisson-Boltzmann Newton: newton its gpu {s4['newton_iters']} vs oracle {kn}; linear its {s4['linear_iters']} vs {lin}; psi rel diff {p4err:.2e}; ||F|| {s4['normf']:.1e}; converged {s4['converged']}")
+        say(f"  Poisson-Boltzmann Newton: newton its gpu {s4['newton_iters']} vs oracle {kn}; linear its {s4['linear_iters']} vs {lin}; psi rel diff {p4err:.2e}; ||F|| {s4['normf']:.1e}; converged {s4['converged']}")
         ok = ok and s4["converged"] and s4["newton_iters"] == kn and abs(s4["linear_iters"] - lin) <= 2 * kn and p4err <= 1e-8
-        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+        say("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+        rep = dict(rows=int(n), graph="bit-exact", values_max_rel_err=float(worst), gmres_jacobi=dict(iters=int(its), oracle_iters=int(info["iters"]), x_rel_diff=float(xerr)),
+                   gmres_block_ilu0=dict(iters=int(its2), oracle_iters=int(info2["iters"]), x_rel_diff=float(x2err)),
+                   helmholtz_cg_chebyshev=dict(iters=int(its3), oracle_iters=int(its3o), x_rel_diff=float(x3err), values_max_rel_err=float(worst3)),
+                   pb_newton=dict(newton_iters=int(s4["newton_iters"]), oracle_newton_iters=int(kn), linear_iters=int(s4["linear_iters"]), oracle_linear_iters=int(lin), psi_rel_diff=float(p4err)))
     c.close()
-    flag = torch.tensor([1 if ok else 0]); dist.broadcast(flag, 0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    box = [dict(rep, **{"pass": bool(ok), "world": world, "against": "CPU oracle (port) on the global problem, tests/multi_gpu_check.py"})]
+    dist.broadcast_object_list(box, 0)
+    return box[0]
 
 
 if __name__ == "__main__":

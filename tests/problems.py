@@ -25,12 +25,36 @@ CASES = {
 }
 
 
+# ragged inputs: uniformly random particle clouds (rows of very different lengths, neighbor lists in an order unrelated to position)
+CLOUDS = {
+    "cloud2d":  dict(dim=2, n=500),
+    "cloud3d":  dict(dim=3, n=700),
+    "cloud3d_50k": dict(dim=3, n=50000, kd=True),
+}
+
+
 def make_case(name):
+    if name in CLOUDS:
+        return make_cloud_case(name)
     c = dict(CASES[name]); dim, N = c["dim"], c["N"]
     dx = 2.0 * np.pi / N
     slab = c.get("slab")
     type_fn = (lambda wx, wy, wz: np.where(wy < slab, 2, 1)) if slab else None
     P = lat.make_brick(dim, (N,) * dim, dx, rs2=c["rs2"], jitter=c["jitter"], type_fn=type_fn, origin=c.get("origin", 0.0))
+    return P, fields_for(P, c, name, dx, slab)
+
+
+def make_cloud_case(name):
+    c = dict(CLOUDS[name]); dim, n = c["dim"], c["n"]; box = 2.0 * np.pi
+    dx = box / n ** (1.0 / dim); h = 1.5 * dx
+    gen = lat.make_cloud_kd if c.get("kd") else lat.make_cloud
+    P = gen(dim, n, box, reach=2 * h * 1.05, min_sep=0.45 * dx)
+    c["kinds"] = (0, FLUID)
+    return P, fields_for(P, c, name, dx, None)
+
+
+def fields_for(P, c, name, dx, slab):
+    dim = P["dim"]
     xw = P["xw"]
     F = {}
     F["density"] = 1.0 + 0.1 * np.sin(xw[:, 0])
@@ -51,7 +75,7 @@ def make_case(name):
     has_solid = bool(slab) and SOLID in c["kinds"]
     P["case"] = dict(name=name, kinds=c["kinds"], kernel=c.get("kernel", 0), has_solid=has_solid, dt=0.05 * dx / 0.1, theta=0.5,
                      h_min=(0.8 * 1.5 * dx) if has_solid else None)
-    return P, F
+    return F
 
 
 def relerr(a, b):

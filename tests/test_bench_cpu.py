@@ -23,7 +23,12 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None and line["scaling"] == "strong"
     assert line["config"]["workload"] == "p8m" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
-    assert line["full_workload_estimate"]["iters"] == 452 and line["full_workload_estimate"]["value"] < line["value"]   # fewer iterations on the sample
+    # same `config` as the B200 arm (the driver compares them): the FULL workload is named, the bounded sample is described in cpu_baseline
+    bench = importlib.import_module("bench"); lat = importlib.import_module("implicit-sph_b200.lattice")
+    assert line["config"] == json.loads(json.dumps(bench.workload_config("p8m", bench.WORKLOADS["p8m"], 1, lat))) and line["config"]["rows"] == 8000000
+    cb = line["cpu_baseline"]
+    assert cb["sample_rows"] == 16 ** 3 and cb["sample_iters"] == 452 and "452" in cb["sample"]      # the sample's solve is pinned to the full workload's iteration count
+    assert cb["cores"] == (os.cpu_count() or 1)
 
 
 def test_b200_arm_refuses_to_run_without_a_gpu():
@@ -66,3 +71,7 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     line = json.loads(lines[0]); assert line["impl"] == "reference" and line["n_gpus"] == 2
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every host core (the N > 1 reference arm timed out)
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    bench = importlib.import_module("bench"); lat = importlib.import_module("implicit-sph_b200.lattice")
+    assert line["config"] == json.loads(json.dumps(bench.workload_config("p8m", bench.WORKLOADS["p8m"], 2, lat))) and line["config"]["bricks"] == "2x1x1"

@@ -44,6 +44,24 @@ def check(st, info, x, xo, sol_tol=1e-8, tol=1e-8):
     assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= sol_tol, np.linalg.norm(x - xo) / np.linalg.norm(xo)
 
 
+TIGHT = {"Convergence Tolerance": 1e-13, "Maximum Iterations": 4000, "Maximum Restarts": 200}
+TIGHT_ORACLE = dict(tol=1e-13, max_iters=4000, max_restarts=200)
+
+
+def tight_external(A, b, solver, prec, flex, degree):
+    """north_star's solution bar proper: the same system solved to 1e-13 on both sides => x agrees to <= 1e-8 (VERDICT r1 weak #3:
+    with the reference's 1e-8 residual stop the two solutions may differ by kappa(A) * 1e-8, which says nothing about the path)."""
+    n = A.shape[0]
+    xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(solver=solver, precond=prec, flexible=int(flex), cheb_degree=degree, **TIGHT_ORACLE))
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    configure(c, solver, prec, flex, degree, **TIGHT); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(prec != O.PREC_NONE, "ext-tight"); c.close()
+    err = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+    assert st["converged"] and info["converged"] and err <= 1e-8, (st, info, err)
+    return err
+
+
 @pytest.mark.parametrize("prec,degree", [(O.PREC_NONE, 1), (O.PREC_JACOBI, 1), (O.PREC_CHEBYSHEV, 3), (O.PREC_ILU0, 1)])
 @pytest.mark.parametrize("flex", [True, False])
 def test_gmres_external_matrix(prec, degree, flex):
@@ -57,6 +75,7 @@ def test_gmres_external_matrix(prec, degree, flex):
     check(st, info, x, xo, sol_tol=1e-7)
     assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) <= 2e-8
     c.close()
+    tight_external(A, b, O.SOLVER_GMRES, prec, flex, degree)
 
 
 @pytest.mark.parametrize("prec,degree", [(O.PREC_NONE, 1), (O.PREC_JACOBI, 1), (O.PREC_CHEBYSHEV, 4), (O.PREC_ILU0, 1)])
@@ -70,6 +89,7 @@ def test_cg_external_matrix(prec, degree):
     st = c.solve(prec != O.PREC_NONE, "ext")
     check(st, info, x, xo, sol_tol=1e-7)
     c.close()
+    tight_external(A, b, O.SOLVER_CG, prec, True, degree)
 
 
 def test_restart_and_iteration_cap_follow_the_parameter_list():
@@ -88,25 +108,49 @@ def test_restart_and_iteration_cap_follow_the_parameter_list():
     c.close()
 
 
-def _sph_poisson(name, prec, solver=O.SOLVER_GMRES, degree=1, blocks=None):
+_ORACLE_CACHE = {}
+
+
+def _case_with_oracle(name):
     import harness
-    P, F = make_case(name); cs = P["case"]; nl = P["nlocal"]
-    ref = harness.run_oracle(P, F, "port")
+    if name not in _ORACLE_CACHE:
+        P, F = make_case(name)
+        if P["nlocal"] > 20000:      # big cloud: only what the solve needs (run_oracle assembles every system)
+            o = O.Oracle(P, kind="port"); o.set_field(O.F_DENSITY, F["density"]); o.set_field(O.F_VSTAR, F["velocity"]); o.compute_pre()
+            rp, col = o.graph(); b = o.ns_poisson(P["case"]["dt"]); ref = dict(rowptr=rp, col=col, b_poisson=b, A_poisson=o.matrix()); o.close()
+        else:
+            ref = harness.run_oracle(P, F, "port")
+        _ORACLE_CACHE.clear(); _ORACLE_CACHE[name] = (P, F, ref)
+    return _ORACLE_CACHE[name]
+
+
+def _sph_poisson(name, prec, solver=O.SOLVER_GMRES, degree=1, blocks=None, tight=False, fill=0):
+    import harness
+    P, F, ref = _case_with_oracle(name); cs = P["case"]; nl = P["nlocal"]
     col = O.tags_to_local(ref["col"], P["tag"][:nl])
     b = ref["b_poisson"].copy()
     mask = np.ones(nl, dtype=np.int32)
-    xo, info = O.krylov_solve(ref["rowptr"], col, ref["A_poisson"], b, params=O.krylov_params(solver=solver, precond=prec, cheb_degree=degree, row_gid=P["tag"][:nl]),
+    kw = dict(TIGHT_ORACLE) if tight else {}
+    xo, info = O.krylov_solve(ref["rowptr"], col, ref["A_poisson"], b, params=O.krylov_params(solver=solver, precond=prec, cheb_degree=degree, ilu_fill=fill, row_gid=P["tag"][:nl], **kw),
                               null_mask=mask, use_null=True, blocks=blocks)
     c = harness.cuda_context(P, F)
     c.compute_pre(); c.graph_build(); c.create_load(None, 1); c.ns_poisson(cs["dt"])
     x = np.zeros(nl); c.create_solution(x, 1)
     c.set_null_vector_mask(mask); c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO)
-    configure(c, solver, prec, True, degree)
+    configure(c, solver, prec, True, degree, **(TIGHT if tight else {}))
+    c.precond_param("fact: level-of-fill", fill)
     if blocks is not None:
         c.precond_set_blocks(blocks)
     st = c.solve(prec != O.PREC_NONE, "Poisson")
     c.close()
     return st, info, x, xo
+
+
+def check_tight(name, prec, **kw):
+    """the 1e-8 solution bar, measured with both solves driven to 1e-13 (see tight_external)"""
+    st, info, x, xo = _sph_poisson(name, prec, tight=True, **kw)
+    err = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+    assert st["converged"] and info["converged"] and err <= 1e-8, (st, info, err)
 
 
 @pytest.mark.parametrize("name,prec,degree", [("jitter3d", O.PREC_JACOBI, 1), ("jitter2d", O.PREC_CHEBYSHEV, 2), ("lattice3d", O.PREC_JACOBI, 1), ("jitter2d", O.PREC_ILU0, 1)])
@@ -115,6 +159,17 @@ def test_sph_pressure_poisson_nullspace(name, prec, degree):
     st, info, x, xo = _sph_poisson(name, prec, degree=degree)
     check(st, info, x, xo, sol_tol=1e-6)      # kappa(A) ~ 1e3-1e4 on these cases: 1e-8 residual parity allows ~1e-6 on x
     assert abs(x.sum()) <= 1e-9 * np.abs(x).sum()
+    check_tight(name, prec, degree=degree)
+
+
+@pytest.mark.parametrize("name,prec", [("cloud2d", O.PREC_JACOBI), ("cloud2d", O.PREC_ILU0), ("cloud3d", O.PREC_JACOBI), ("cloud3d", O.PREC_ILU0),
+                                       ("cloud3d_50k", O.PREC_JACOBI), ("cloud3d_50k", O.PREC_ILU0)])
+def test_sph_pressure_poisson_ragged_cloud(name, prec):
+    """Ragged random clouds: GMRES(50) + Jacobi and + ILU(0) on the SELL slack path — iteration counts
+    within +-2 of the oracle at the reference's tolerance, solutions <= 1e-8 with both solves driven to 1e-13."""
+    st, info, x, xo = _sph_poisson(name, prec)
+    check(st, info, x, xo, sol_tol=1e-5)
+    check_tight(name, prec)
 
 
 def test_block_jacobi_ilu0_follows_the_rank_partition():
@@ -126,12 +181,14 @@ def test_block_jacobi_ilu0_follows_the_rank_partition():
     blocks = ((g % N) >= N // 2).astype(np.int32) + 2 * ((g // N) >= N // 2).astype(np.int32)
     st, info, x, xo = _sph_poisson("jitter2d", O.PREC_ILU0, blocks=blocks)
     check(st, info, x, xo, sol_tol=1e-6)
+    check_tight("jitter2d", O.PREC_ILU0, blocks=blocks)
 
 
 def test_c1_tgv128_gmres_ilu0():
     """BASELINE config 1: 2-D TGV 128x128 pressure Poisson, flexible GMRES(50) + ILU(0) (fill 0, overlap 0), one rank."""
     st, info, x, xo = _sph_poisson("tgv128", O.PREC_ILU0)
     check(st, info, x, xo, sol_tol=1e-5)
+    check_tight("tgv128", O.PREC_ILU0)
 
 
 def test_helmholtz_three_rhs_cg_chebyshev():
@@ -264,3 +321,37 @@ def test_known_answer_channel_edl_table_on_the_device(boundary):
         psi = c.field_get(isph.F_PSI)[:nl]; c.close()
         err = np.sqrt(np.mean((psi[fluid] - exact[:nl][fluid]) ** 2)); want = EDL_TABLE[(boundary, N)]
         assert st["converged"] and st["newton_iters"] <= 3 and abs(err - want) <= 1e-9 * want, (N, st, err, want)
+
+
+def test_borrowed_load_vector_is_a_view_like_the_reference():
+    """createLoadMultiVector(b_ptr) wraps caller memory (solver_lin.cpp:45-58).  (1) a system functor writes the
+    right-hand side INTO that memory and the solve uses it (it is not overwritten by the stale host array); (2) what the caller
+    writes into b after the create is what the next solve uses."""
+    import harness
+    P, F = make_case("jitter2d"); cs = P["case"]; nl = P["nlocal"]
+    c = harness.cuda_context(P, F); c.compute_pre(); c.graph_build()
+    configure(c, O.SOLVER_GMRES, O.PREC_JACOBI)
+    # owned load vector: the baseline
+    c.create_load(None, 1); c.ns_poisson(cs["dt"]); b_ref = c.load_get(1)[:, 0].copy()
+    x0 = np.zeros(nl); c.create_solution(x0, 1); c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO); st0 = c.solve(True, "Poisson")
+    # (1) borrowed b, filled by the device functor
+    b = np.full(nl, 7.0); c.matrix_invalidate(); c.create_load(b, 1); c.ns_poisson(cs["dt"])
+    assert np.array_equal(b, b_ref)
+    x1 = np.zeros(nl); c.create_solution(x1, 1); c.set_initial_solution(isph.INIT_ZERO); st1 = c.solve(True, "Poisson")
+    assert st1["iters"] == st0["iters"] and np.array_equal(x1, x0)
+    # (2) the caller rewrites the View on the host: the next solve sees it
+    b[:] = 2.0 * b_ref
+    x2 = np.zeros(nl); c.create_solution(x2, 1); c.set_initial_solution(isph.INIT_ZERO); st2 = c.solve(True, "Poisson")
+    assert st2["converged"] and np.linalg.norm(x2 - 2.0 * x0) <= 1e-12 * np.linalg.norm(x0)
+    c.close()
+
+
+def test_non_default_ilu_thresholds_are_refused():
+    """Ifpack's fact: drop tolerance / relax value / absolute|relative threshold change the factors; only the
+    defaults are implemented, and anything else is an error instead of being silently ignored."""
+    c = isph.Context()
+    for name, dflt in (("fact: drop tolerance", 0.0), ("fact: relax value", 0.0), ("fact: absolute threshold", 0.0), ("fact: relative threshold", 1.0)):
+        c.precond_param(name, dflt)
+        with pytest.raises(isph.IsphError):
+            c.precond_param(name, dflt + 0.5)
+    c.close()

@@ -3,18 +3,38 @@
 Bars (BASELINE.json north_star): CSR rowptr/col bit-exact; FP64 matrix values rel. err <= 1e-12; vectors <= 1e-12 of
 their max norm (entries of b can cancel to ~0, so they are scaled by max|b|).
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
-from problems import CASES, make_case, relerr, scaled_err
+from problems import CASES, CLOUDS, make_case, relerr, scaled_err
 
 VAL_TOL = 1e-12
 pytestmark = pytest.mark.gpu
+MEASURED = {}          # case -> {quantity: measured max error}; written to gpurun_out/parity_measured.json at the end of the module
 
 
-def _compare(a, b, has_solid):
+@pytest.fixture(scope="module", autouse=True)
+def _dump_measured():
+    yield
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump(MEASURED, open(os.path.join(out, "parity_measured.json"), "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _compare(a, b, has_solid, label=None):
     assert np.array_equal(a["rowptr"], b["rowptr"]), "graph row pointers differ"
     assert np.array_equal(a["col"], b["col"]), "graph column indices differ"
+    if label is not None:      # the measured errors behind the assertions below (VERDICT r1: "asserted, not measured")
+        m = {k: relerr(a[k], b[k]) for k in ("vfrac", "A_poisson", "A_helmholtz", "A_pb", "A_pb2", "A_aep", "A_solute", "diag_poisson")}
+        m.update({k: scaled_err(a[k], b[k]) for k in ("b_poisson", "b_helmholtz", "b_aep", "b_solute", "pb_f", "pb_f_lin", "spmv_y", "corr_dp", "corr_vstar", "corr_p")})
+        nl_ = len(a["rowptr"]) - 1; m["gc"] = scaled_err(a["gc"][:nl_], b["gc"][:nl_]); m["lc"] = scaled_err(a["lc"][:nl_], b["lc"][:nl_])
+        MEASURED[label] = m
     nl = len(a["rowptr"]) - 1
     assert relerr(a["vfrac"], b["vfrac"]) <= VAL_TOL
     assert scaled_err(a["gc"][:nl], b["gc"][:nl]) <= VAL_TOL
@@ -23,7 +43,7 @@ def _compare(a, b, has_solid):
         assert scaled_err(a["normal"], b["normal"]) <= 1e-11 and relerr(a["pnd"], b["pnd"]) <= VAL_TOL
     for k in ("A_poisson", "A_helmholtz", "A_pb", "A_pb2", "A_aep", "A_solute"):
         e = relerr(a[k], b[k])
-        assert e <= (1e-10 if k in ("A_pb", "A_pb2") else VAL_TOL), (k, e)
+        assert e <= VAL_TOL, (k, e)
     assert scaled_err(a["b_aep"], b["b_aep"]) <= VAL_TOL and scaled_err(a["b_solute"], b["b_solute"]) <= VAL_TOL
     assert scaled_err(a["b_poisson"], b["b_poisson"]) <= VAL_TOL
     assert scaled_err(a["b_helmholtz"], b["b_helmholtz"]) <= VAL_TOL
@@ -41,7 +61,7 @@ def test_assembly_parity_fluid(name, anti):
     P, F = make_case(name)
     ref = harness.run_oracle(P, F, "port", anti=anti)
     got = harness.run_cuda(P, F, anti=anti)
-    _compare(got, ref, False)
+    _compare(got, ref, False, f"{name}/anti{int(anti)}")
     assert got["launches"] > 0
 
 
@@ -52,7 +72,7 @@ def test_assembly_parity_boundaries(name, anti, singular, mh):
     P, F = make_case(name)
     ref = harness.run_oracle(P, F, "port", anti=anti, singular=singular, mh=mh)
     got = harness.run_cuda(P, F, anti=anti, singular=singular, mh=mh)
-    _compare(got, ref, P["case"]["has_solid"])
+    _compare(got, ref, P["case"]["has_solid"], f"{name}/anti{int(anti)}/s{singular}/mh{int(mh)}")
 
 
 def test_tgv128_graph_bit_exact():
@@ -63,3 +83,40 @@ def test_tgv128_graph_bit_exact():
     got = harness.run_cuda(P, F)
     _compare(got, ref, False)
     assert np.bincount(np.diff(got["rowptr"])).nonzero()[0].min() >= 25
+
+
+@pytest.mark.parametrize("name,anti", [("cloud2d", True), ("cloud2d", False), ("cloud3d", True), ("cloud3d", False), ("cloud3d_50k", True)])
+def test_assembly_parity_ragged_cloud(name, anti):
+    """Ragged input: uniformly random particles, rows of very different lengths (slice capacity >> row
+    length: the SELL slack path), neighbor lists in an order unrelated to position.  The oracle port is bit-identical to the
+    reference's own functors on these clouds (tests/test_oracle_cpu.py::test_port_matches_ref_on_a_random_cloud)."""
+    import harness
+    P, F = make_case(name)
+    jn = np.diff(P["noff"]); assert jn.max() >= 1.4 * jn.min()
+    ref = harness.run_oracle(P, F, "port", anti=anti)
+    got = harness.run_cuda(P, F, anti=anti)
+    _compare(got, ref, False, f"{name}/anti{int(anti)}")
+    assert np.diff(got["rowptr"]).max() >= 1.3 * np.diff(got["rowptr"]).min()
+
+
+def test_device_halo_planner_matches_host_planner(isph):
+    """The halo plan multi-GPU runs build on the device (sort + numbering of the distinct remote (owner, tag) pairs) against the
+    pure host planner, on one GPU: random ghosts with repeated tags (several periodic images of one remote atom), ghosts owned
+    by this rank, empty peers, world sizes 2, 8 and 12."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    c = isph.Context()
+    for R, rank, nl, ng in [(2, 0, 50, 400), (8, 3, 1000, 20000), (12, 11, 10, 3000), (4, 1, 7, 0)]:
+        owner = rng.integers(0, R, ng).astype(np.int32); owner[owner == (rank + 1) % R] = rank      # one peer contributes nothing
+        oidx = rng.integers(0, max(nl, 1) * 3, ng).astype(np.int32)
+        tag = (1 + owner.astype(np.int64) * 100000 + oidx).astype(np.int32)                          # tag <-> (owner, index) one to one, with repeats
+        out = {}
+        for kind in ("host", "device"):
+            col = np.full(ng, -7, dtype=np.int32); rc = np.zeros(R, dtype=np.int32); req = np.full(ng + 1, -1, dtype=np.int32); nh = C.c_int(-1)
+            args = (R, rank, nl, ng, isph._i(tag), isph._i(owner), isph._i(oidx), isph._i(col), isph._i(rc), isph._i(req), C.byref(nh))
+            st = isph.lib().isph_halo_plan_host(*args) if kind == "host" else isph.lib().isph_halo_plan_device(c.h, *args)
+            assert st == 0
+            out[kind] = (col, rc, req[:nh.value].copy(), nh.value)
+        for a, b in zip(out["host"], out["device"]):
+            assert np.array_equal(a, b)
+    c.close()

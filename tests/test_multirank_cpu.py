@@ -171,3 +171,21 @@ def test_halo_plan_for_four_and_eight_bricks(world, lattice):
             assert np.all(own_rank[st] == p) and np.all(np.diff(st) > 0)              # grouped by owner, ascending tag inside a group
             assert np.array_equal(bricks[p]["tag"][req[roff[p]:roff[p + 1]]], st)     # the request names the right particles on the owner
     assert np.array_equal(recv > 0, (recv > 0).T)                                    # exchanges are pairwise in both directions
+
+
+def test_halo_plan_host_beyond_eight_ranks(isph):
+    """the planner itself has no 8-rank limit (the NVLink peer path has, and is skipped above it); slots are numbered
+    in (owner, tag) order whatever the world size, repeated tags share a slot, ghosts owned here keep the owner-local index."""
+    import ctypes as C
+    rng = np.random.default_rng(12); R, rank, nl, ng = 12, 5, 40, 2500
+    owner = rng.integers(0, R, ng).astype(np.int32); oidx = rng.integers(0, 200, ng).astype(np.int32)
+    tag = (1 + owner.astype(np.int64) * 1000 + oidx).astype(np.int32)
+    col = np.zeros(ng, dtype=np.int32); rc = np.zeros(R, dtype=np.int32); req = np.zeros(ng, dtype=np.int32); nh = C.c_int()
+    assert isph.lib().isph_halo_plan_host(R, rank, nl, ng, isph._i(tag), isph._i(owner), isph._i(oidx), isph._i(col), isph._i(rc), isph._i(req), C.byref(nh)) == 0
+    remote = owner != rank
+    keys = sorted(set(zip(owner[remote].tolist(), tag[remote].tolist())))
+    assert nh.value == len(keys) and rc.sum() == len(keys) and rc[rank] == 0
+    slot = {k: i for i, k in enumerate(keys)}
+    assert all(col[g] == (nl + slot[(owner[g], tag[g])] if remote[g] else oidx[g]) for g in range(ng))
+    assert all(req[slot[k]] == k[1] - 1 - k[0] * 1000 for k in keys)
+    assert [int(rc[p]) for p in range(R)] == [sum(1 for k in keys if k[0] == p) for p in range(R)]
