@@ -262,7 +262,12 @@ __global__ void k_forward(const int *col_of_atom, int nlocal, int nall, int nc, 
 // ---- operator rows -------------------------------------------------------------------------------------------
 // Corrected::FunctorOuterLaplacianMatrix<Pair,ANTI>[_MorrisHolmes]::operator(), functor_laplacian_matrix.h:72-316
 // (iblock < 0, normal == NULL), fused with the PutScalar(0) that precedes it at every call site.
-template <int DIM, bool ANTI> __global__ void __launch_bounds__(128, 8)
+// FAITHFUL: the two neighbour sums every entry of the row depends on (gm = sum_j G e_ij dW V_j op(m_i,m_j), ci = sum_j a_ij e_ij,
+// :153-190) are accumulated in the NEIGHBOR LIST's own order, as the reference does, in a pre-pass over the list; the per-entry
+// work stays on the (column-ordered) matrix.  Without it the sums are reassociated, which is invisible relative to the row
+// (1.5e-15 of the row maximum) but reaches 2e-12 RELATIVE on entries of particles that sit next to the cutoff (|a_ij| ~ 1e-8 of
+// the diagonal) on random clouds — measured: tests/test_gpu_parity.py::test_assembly_parity_ragged_cloud, gpurun_out/parity_measured.json.
+template <int DIM, bool ANTI, bool FAITHFUL> __global__ void __launch_bounds__(128, 8)
 k_laplacian_rows(Dev d, double alpha, const double *material, bool mh, int f0, int f1) {
   ROW_SETUP(d)
   if (!fyes1(f0, ikind)) {                                                        // :88-96 (row left at zero)
@@ -276,6 +281,39 @@ k_laplacian_rows(Dev d, double alpha, const double *material, bool mh, int f0, i
   const bool self_coeff = fyes2(f0, f1, ikind, ikind);
   double gm[3] = {0, 0, 0}, ci[3] = {0, 0, 0}, diag = 0.0;
   int kself = -1;
+  if (FAITHFUL) {                                                                 // gm / ci in list order (the reference's summation order)
+    const long long nb = d.noff[row], ne = d.noff[row + 1];
+    for (long long p = nb; p < ne; ++p) {
+      const int j = d.neigh[p] & ISPH_NEIGHMASK, jtype = d.type[j];
+      PAIR_GEOM(d, DIM)
+      if (!(rsq < d.T->cutsq[itype][jtype])) continue;
+      const int jkind = d.kind[j];
+      const double m_j = material ? material[j] : 1.0;
+      const double r = sqrt(rsq) + ISPH_EPS_R, dwdr = kern_dval(d.T, itype, jtype, r);
+      double eij[3] = {0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) eij[q] = rij[q] / r;
+      const double vf = (ANTI ? sqrt(vf_i * d.vfrac[j]) : d.vfrac[j]), vjtmp = dwdr * vf;
+#pragma unroll
+      for (int k2 = 0; k2 < DIM; ++k2) {
+        double gitmp = 0.0;
+#pragma unroll
+        for (int k1 = 0; k1 < DIM; ++k1) gitmp += G[k2 * DIM + k1] * eij[k1];
+        const double ijtmp = gitmp * vjtmp;
+        if (ikind & jkind) gm[k2] += ijtmp * (sph_op(ANTI, m_i, m_j));
+      }
+      if (!ANTI) {
+        double aij = 0.0; int op = 0;
+#pragma unroll
+        for (int k2 = 0; k2 < DIM; ++k2)
+#pragma unroll
+          for (int k1 = 0; k1 < (k2 + 1); ++k1, ++op) aij += L[op] * eij[k1] * eij[k2] * (k1 == k2 ? 1.0 : 2.0);
+        aij *= 2.0 * dwdr * vf;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) ci[q] += aij * eij[q];
+      }
+    }
+  }
   for (int k = 0; k < rlen; ++k) {                                                // pass 1, :127-195
     const int j = d.atom[base + 32ll * k];
     if (j == i) { kself = k; continue; }
@@ -295,7 +333,7 @@ k_laplacian_rows(Dev d, double alpha, const double *material, bool mh, int f0, i
 #pragma unroll
       for (int k1 = 0; k1 < DIM; ++k1) gitmp += G[k2 * DIM + k1] * eij[k1];
       const double ijtmp = gitmp * vjtmp;
-      if (ikind & jkind) gm[k2] += ijtmp * (sph_op(ANTI, m_i, m_j));
+      if (!FAITHFUL && (ikind & jkind)) gm[k2] += ijtmp * (sph_op(ANTI, m_i, m_j));
     }
     double aij = 0.0; int op = 0;
 #pragma unroll
@@ -303,7 +341,7 @@ k_laplacian_rows(Dev d, double alpha, const double *material, bool mh, int f0, i
 #pragma unroll
       for (int k1 = 0; k1 < (k2 + 1); ++k1, ++op) aij += L[op] * eij[k1] * eij[k2] * (k1 == k2 ? 1.0 : 2.0);
     aij *= 2.0 * dwdr * vf;
-    if (!ANTI) {
+    if (!ANTI && !FAITHFUL) {
 #pragma unroll
       for (int q = 0; q < DIM; ++q) ci[q] += aij * eij[q];
     }
@@ -683,8 +721,12 @@ void compute_normals(Ctx *c) {
 
 void assemble_laplacian(Ctx *c, double alpha, const double *mat, bool anti, bool mh, int f0, int f1) {
   Dev d = make_dev(c);
-  if (d.dim == 2) { if (anti) k_laplacian_rows<2, true><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); else k_laplacian_rows<2, false><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); }
-  else { if (anti) k_laplacian_rows<3, true><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); else k_laplacian_rows<3, false><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); }
+  // list-order neighbour sums (bit-faithful; default) or everything on the column-ordered matrix (ISPH_ASM_REASSOC=1: ~1/3 less work, entries next to the cutoff then differ by up to ~2e-12 relative)
+  static const bool reassoc = getenv("ISPH_ASM_REASSOC") != nullptr;
+#define LAP(DIM_, ANTI_) do { if (reassoc) k_laplacian_rows<DIM_, ANTI_, false><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); else k_laplacian_rows<DIM_, ANTI_, true><<<GRID(c)>>>(d, alpha, mat, mh, f0, f1); } while (0)
+  if (d.dim == 2) { if (anti) LAP(2, true); else LAP(2, false); }
+  else { if (anti) LAP(3, true); else LAP(3, false); }
+#undef LAP
   ++c->launches;
   matrix_merge_duplicates(c);
   c->A.is_filled = 1;                                                              // exitFor, functor_laplacian_matrix.h:322-326

@@ -110,6 +110,7 @@ template <int G> __global__ void __launch_bounds__(VB, G == 16 ? 2 : (G == 8 ? 3
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
            double *S, int pass, double *partials, unsigned *counters, P2PRed pr) {
   __shared__ bool go;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fused update sweep that follows may start its prologue (it waits for this grid before it reads S / w)
   if (pass == 1) { if (threadIdx.x == 0) go = dgks_second(S, nv, nvec != nullptr); __syncthreads(); if (!go) return; }
   const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
   const bool with_n = (pass == 0 && nvec != nullptr && g == 0);
@@ -286,6 +287,118 @@ k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   if (s_last) {
     __threadfence();
     for (int k = warp; k < 64; k += VB / 32) {
+      if (!(k < nv || k == 63)) continue;
+      double s = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
+      s = warp_sum(s);
+      if (lane == 0) S[S_H2 + (k == 63 ? nv : k)] = s;
+    }
+    if (tid == 0) *counter = 0u;
+    if (pr.nranks > 1) { __threadfence(); p2p_allreduce_block(pr, S + S_H2, nv + 1); }
+  }
+}
+
+// ---- the same fused sweep as a TMA pipeline (default for nv > 8) -----------------------------------------------------------
+// w1 = y - (n.y) n - sum_k h_k V_k ,  h2[k] = V_k . w1 ,  h2[nv] = w1.w1        (one read of the basis, as above)
+// k_update_dot stages every tile through registers and meets two block barriers per tile with nothing in flight behind them
+// (ncu: 24 % warp occupancy, barrier + long-scoreboard stalls: profiles/r01_prof_update_dot_c2_ncu.txt).  Here the tile's
+// nv basis segments (+ y and n) are brought into shared memory by the bulk-copy engine (cp.async.bulk, one copy per vector
+// segment of TT rows = 1 KB, completion counted by an mbarrier per stage), NS stages deep: while the 4 warps of the CTA work on
+// tile i (thread-per-row update, then warp-per-vector dots out of the SAME shared-memory tile) the copies of tiles i+1 .. i+NS-1
+// are in flight, so the barriers no longer drain the memory pipeline.  With programmatic dependent launch the kernel starts
+// while the pass-0 reduction kernel is still finishing its all-reduce and pre-issues the basis copies of its first stages
+// (they do not depend on that kernel) before it waits for the coefficients.
+static const int TT = 128;                                       // rows per tile = threads per CTA
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(TT)
+k_update_dot_tma(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, int ns,
+                 double *S, double *partials, unsigned *counter, P2PRed pr) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ __align__(8) unsigned long long full[4];
+  __shared__ __align__(16) double s_w1[TT];
+  __shared__ double s_h[64], s_red[TT / 32];
+  __shared__ bool s_go, s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nrow = nv + (nvec ? 2 : 1);                          // segments per stage: nv basis vectors, y, [n]
+  const size_t stage_doubles = (size_t)nrow * TT;
+  double *stage0 = reinterpret_cast<double *>(dsm);
+  int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + TT - 1) / TT * TT;
+  const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk), ntiles = (r1 - r0 + TT - 1) / TT;
+  if (tid == 0) { for (int q = 0; q < ns; ++q) mbar_init(&full[q], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  // one thread feeds the copy engine: basis segments first (they are not written by the preceding kernels), then y (and n)
+  auto issue = [&](int tile, bool basis, bool rest) {
+    const int q = tile % ns, t0 = r0 + tile * TT, rows = min(TT, r1 - t0);
+    const unsigned bytes = (unsigned)(((rows + 1) & ~1) * 8);    // 16-byte granules; the row padding of ld (a multiple of 32) covers an odd tail
+    double *dst = stage0 + (size_t)q * stage_doubles;
+    if (basis) { mbar_expect_tx(&full[q], bytes * (unsigned)nrow);
+      for (int k = 0; k < nv; ++k) bulk_g2s(dst + (size_t)k * TT, V + (size_t)k * ld + t0, bytes, &full[q]); }
+    if (rest) { bulk_g2s(dst + (size_t)nv * TT, w + t0, bytes, &full[q]); if (nvec) bulk_g2s(dst + (size_t)(nv + 1) * TT, nvec + t0, bytes, &full[q]); }
+  };
+  const int pre = min(ns, ntiles);
+  if (tid == 0) for (int t = 0; t < pre; ++t) issue(t, true, false);
+  asm volatile("griddepcontrol.wait;" ::: "memory");             // everything below reads what the pass-0 kernel produced (coefficients, y)
+  if (tid == 0) { for (int t = 0; t < pre; ++t) issue(t, false, true); s_go = dgks_second(S, nv, nvec != nullptr); }
+  if (tid < nv) s_h[tid] = S[S_H + tid];
+  __syncthreads();
+  const bool go = s_go;
+  const double proj = nvec ? S[S_H + nv + 1] : 0.0;
+  constexpr int KW = 13;                                         // 4 warps x 13 vectors >= 51 basis vectors
+  double acc[KW], nrm = 0.0;
+#pragma unroll
+  for (int q = 0; q < KW; ++q) acc[q] = 0.0;
+  for (int it = 0; it < ntiles; ++it) {
+    const int q = it % ns, t0 = r0 + it * TT, rows = min(TT, r1 - t0);
+    const double *sv = stage0 + (size_t)q * stage_doubles;
+    mbar_wait(&full[q], (unsigned)((it / ns) & 1));
+    double w1 = 0.0;
+    if (tid < rows) {                                            // thread-per-row update out of shared memory (conflict-free: consecutive rows)
+      double s0 = 0.0, s1 = 0.0; int k = 0;
+      for (; k + 2 <= nv; k += 2) { s0 += s_h[k] * sv[(size_t)k * TT + tid]; s1 += s_h[k + 1] * sv[(size_t)(k + 1) * TT + tid]; }
+      if (k < nv) s0 += s_h[k] * sv[(size_t)k * TT + tid];
+      w1 = sv[(size_t)nv * TT + tid]; if (nvec) w1 -= proj * sv[(size_t)(nv + 1) * TT + tid];
+      w1 -= (s0 + s1); w[t0 + tid] = w1; nrm += w1 * w1;
+    }
+    if (go) {
+      s_w1[tid] = w1;
+      __syncthreads();
+      double ww[TT / 32];
+#pragma unroll
+      for (int i = 0; i < TT / 32; ++i) ww[i] = s_w1[lane + 32 * i];      // rows past the tile's end carry w1 = 0 ...
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        const int k = warp + (TT / 32) * j;
+        if (k < nv) {
+          const double *vk = sv + (size_t)k * TT;
+#pragma unroll
+          for (int i = 0; i < TT / 32; ++i) { const int r = lane + 32 * i; if (r < rows) acc[j] += vk[r] * ww[i]; }     // ... and their (stale) basis cells are never read
+        }
+      }
+    }
+    __syncthreads();                                             // every warp is done with stage q (and with s_w1)
+    if (tid == 0 && it + ns < ntiles) issue(it + ns, true, true);
+  }
+  if (!go) return;                                               // block-uniform: the DGKS decision is the same everywhere (and on every rank)
+  double *mine = partials + (size_t)blockIdx.x * 64;
+#pragma unroll
+  for (int j = 0; j < KW; ++j) { const double s = warp_sum(acc[j]); const int k = warp + (TT / 32) * j; if (lane == 0 && k < nv) mine[k] = s; }
+  { const double s = warp_sum(nrm); if (lane == 0) s_red[warp] = s; }
+  __syncthreads();
+  if (tid == 0) { double t = 0.0; for (int q = 0; q < TT / 32; ++q) t += s_red[q]; mine[63] = t; }
+  __threadfence(); __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int k = warp; k < 64; k += TT / 32) {
       if (!(k < nv || k == 63)) continue;
       double s = 0.0;
       for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
@@ -524,6 +637,24 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + (nv_ ? 2 : 1) : nv + 1);
 }
 
+// fused update + second-pass sweep, bulk-copy pipeline; launched with programmatic stream serialization so that its prologue
+// (barrier init, first basis copies) overlaps the tail (last-block reduction, peer all-reduce) of the pass-0 kernel before it
+static void launch_update_dot_tma(Ctx *c, const double *V, int ld, int nv, double *w, const double *nvp, int n, double *S, unsigned *counter, P2PRed pr) {
+  static const int grid_env = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : 0, ns_env = getenv("ISPH_UD_STAGES") ? atoi(getenv("ISPH_UD_STAGES")) : 0;
+  static const bool pdl = getenv("ISPH_NO_PDL") == nullptr;
+  static int sms = 0; static bool attr_set = false;
+  if (!attr_set) { CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    CUDA_CHECK(cudaFuncSetAttribute(k_update_dot_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr_set = true; }
+  const size_t stage = (size_t)(nv + (nvp ? 2 : 1)) * TT * sizeof(double);
+  int ns = ns_env ? ns_env : (int)((size_t)(106 * 1024) / stage); ns = std::max(2, std::min(4, ns));      // two CTAs of <= 106 KB per SM
+  const int grid = std::max(1, std::min(grid_env ? grid_env : 2 * sms, ceil_div(n, TT)));
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = stage * ns; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_update_dot_tma, V, ld, nv, w, nvp, n, ns, S, c->red.p, counter, pr));
+}
+
 static void dbg(Ctx *c, const char *what) {      // ISPH_DEBUG_SYNC=1: synchronise after every phase and name the one that faulted
   static const bool on = getenv("ISPH_DEBUG_SYNC") != nullptr; if (!on) return;
   cudaError_t e = cudaStreamSynchronize(c->stream); if (e == cudaSuccess) e = cudaGetLastError();
@@ -538,6 +669,7 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   const DiagPrec dp = diag_prec_of(c, use_prec); const bool jacobi_fused = dp.on;
   const int sing = c->is_singular ? 1 : 0;
   static const bool fuse_ud = getenv("ISPH_NO_FUSE_UD") == nullptr;
+  static const bool ud_tma = !(getenv("ISPH_UD_TMA") && atoi(getenv("ISPH_UD_TMA")) == 0);      // TMA-pipelined sweep (default) vs the register-tile kernel
   static const int ud_hv = getenv("ISPH_UD_HV") ? atoi(getenv("ISPH_UD_HV")) : 2;            // 64-row halves per tile of the fused sweep
   static const int udcap = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : (ud_hv == 1 ? 444 : 296);       // 148 SMs x resident CTAs
   const int gud = std::max(1, std::min(udcap, ceil_div(n, 64 * ud_hv)));
@@ -567,7 +699,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
       { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); } dbg(c, "multidot0");
       if (fuse_ud && j + 1 > 8) {                                // one sweep: first update + second-pass coefficients
         ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c);
-        if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);      // flag word 14
+        if (ud_tma) launch_update_dot_tma(c, V, ld, j + 1, vn, nvp, n, S, cnt + 6, pr);                                        // flag word 14
+        else if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);
         else k_update_dot<2><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);
         ++c->launches;
         if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_H2, j + 2);

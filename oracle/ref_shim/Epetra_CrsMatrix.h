@@ -184,4 +184,14 @@ public:
   }
   const Epetra_Map &RowMap() const { return *g_->map_; }
   const Epetra_CrsGraph &Graph() const { return *g_; }
+  // local-index read access used by the Epetra-typed adapter (include/solver_lin_b200_epetra.h): single-process stand-in, every
+  // column id is owned locally, local column id = LID of the global id
+  int NumMyRows() const { return g_->map_->NumMyElements(); }
+  int MaxNumEntries() const { return g_->MaxNumIndices(); }
+  int ExtractMyRowCopy(int lrow, int len, int &n, double *values, int *indices) const {
+    if (lrow < 0 || lrow >= NumMyRows()) return -1;
+    n = g_->rowptr[lrow + 1] - g_->rowptr[lrow]; if (n > len) return -2;
+    for (int k = 0; k < n; ++k) { values[k] = val[g_->rowptr[lrow] + k]; indices[k] = g_->map_->LID(g_->col[g_->rowptr[lrow] + k]); }
+    return 0;
+  }
 };
