@@ -209,6 +209,21 @@ class Context:
             dp = np.ascontiguousarray(dp, dtype=np.float64); assert dp.size == self.nlocal
         self.call("isph_ns_correct", C.c_double(dt), int(anti), int(incremental_pressure), _d(dp))
 
+    def pair_fixed(self, fixed_of_type):
+        a = np.ascontiguousarray(fixed_of_type, dtype=np.int32); self.call("isph_pair_fixed", _i(a))
+
+    def advance_time(self, dt, anti=True):
+        self.call("isph_advance_time", C.c_double(dt), int(anti))
+
+    def atoms_get_x(self):
+        x = np.empty((self.nall, 3)); self.call("isph_atoms_get_x", _d(x)); return x
+
+    def boundary_navier_slip(self, beta):
+        self.call("isph_boundary_navier_slip", C.c_double(beta))
+
+    def boundary_dirichlet(self):
+        self.call("isph_boundary_dirichlet")
+
     def matrix_invalidate(self):
         self.call("isph_matrix_invalidate")
 

@@ -665,6 +665,112 @@ __global__ void k_correct_pressure(double *p, const double *dp, int nall, int in
   if (incp) p[i] += dp[i]; else p[i] = dp[i];
 }
 
+
+// ---- advanceTime (PairISPH_Corrected::advanceTime, pair_isph_corrected.cpp:1183-1194) -------------------------
+// FunctorOuterAdvanceTimeBegin::operator(), functor_advance_time_begin.h:52-72: dp_i = grad(p)_i . 0.5 dt (v^{n+1}_i + v^n_i) on rows of
+// fluid kind (0 elsewhere); the gradient functor carries FilterBinary(Fluid, Fluid) and alpha = 1
+template <int DIM, bool ANTI> __global__ void __launch_bounds__(128)
+k_advance_begin(Dev d, double dt, const double *v, const double *vnp1, const double *p, double *dp) {
+  ROW_SETUP(d)
+  double dx[3] = {0, 0, 0}, g[3] = {0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) dx[q] = 0.5 * dt * (vnp1[3 * (size_t)i + q] + v[3 * (size_t)i + q]);
+  grad_like_loop<DIM, ANTI>(d, i, itype, ikind, xi0, xi1, xi2, base, rlen, false, ISPH_KIND_FLUID, ISPH_KIND_FLUID,
+    [&](int j, int k2, double gitmp, double vjtmp) { const double ijtmp = gitmp * vjtmp; g[k2] += ijtmp * (sph_op(ANTI, p[i], p[j])); });
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) { g[q] *= 1.0; s += g[q] * dx[q]; }
+  dp[i] = fyes1(ISPH_KIND_FLUID, ikind) ? s : 0.0;
+}
+// FunctorOuterAdvanceTimeEnd::operator() over owned AND ghost atoms, functor_advance_time_end.h:48-66
+struct FixedTab { int f[ISPH_MAXT]; };
+__global__ void k_advance_end(int nall, int dim, double dt, const int *type, FixedTab fixed, double *v, const double *vnp1, double *p, const double *dp, double *x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nall) return;
+  if (fixed.f[type[i]]) { for (int k = 0; k < dim; ++k) v[3 * (size_t)i + k] = vnp1[3 * (size_t)i + k]; return; }
+  p[i] += dp[i];
+  for (int k = 0; k < dim; ++k) {
+    const double delta = 0.5 * dt * (vnp1[3 * (size_t)i + k] + v[3 * (size_t)i + k]);
+    x[3 * (size_t)i + k] += delta; v[3 * (size_t)i + k] = vnp1[3 * (size_t)i + k];
+  }
+}
+
+// ---- boundary-condition row modifiers of computeHelmholtz (pair_isph_corrected.cpp:918-934) --------------------
+// Corrected::FunctorOuterBoundaryNavierSlip::operator(), functor_boundary_navier_slip.h:54-174 (iblock < 0, add_neumann_term): for
+// rows of fluid / buffer kind, robin_j = beta dW/dr / r V_j / rho_i (n_i + n_j) . (G_i r_ij) is summed into the entries of the
+// solid neighbours and -sum_j robin_j into the diagonal (SumIntoGlobalValues)
+template <int DIM> __global__ void __launch_bounds__(128) k_navier_slip_rows(Dev d, double beta, const double *rho, int *bad_kind) {
+  ROW_SETUP(d)
+  if (ikind == ISPH_KIND_SOLID) return;
+  if (!(ikind == ISPH_KIND_FLUID || ikind == ISPH_KIND_BUFFER_DIRICHLET || ikind == ISPH_KIND_BUFFER_NEUMANN)) { *bad_kind = 1; return; }
+  double G[DIM * DIM]; for (int q = 0; q < DIM * DIM; ++q) G[q] = d.Gc[9 * (size_t)i + q];
+  double robin_at_i = 0.0; int kself = -1;
+  for (int k = 0; k < rlen; ++k) {
+    const int j = d.atom[base + 32ll * k];
+    if (j == i) { kself = k; continue; }
+    const int jtype = d.type[j];
+    if (d.kind[j] != ISPH_KIND_SOLID) continue;
+    PAIR_GEOM(d, DIM)
+    const double r = sqrt(rsq) + ISPH_EPS_R, dwdr = kern_dval(d.T, itype, jtype, r);
+    double tmp = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < DIM; ++k2) {
+      double a = 0.0;
+#pragma unroll
+      for (int k1 = 0; k1 < DIM; ++k1) a += G[k2 * DIM + k1] * rij[k1];
+      tmp += (d.normal[3 * (size_t)i + k2] + d.normal[3 * (size_t)j + k2]) * a;
+    }
+    const double robin_at_j = beta * dwdr / r * d.vfrac[j] / rho[i] * tmp;
+    d.val[base + 32ll * k] += robin_at_j;
+    robin_at_i -= robin_at_j;
+  }
+  if (kself >= 0) d.val[base + 32ll * kself] += robin_at_i;
+}
+// Corrected::FunctorOuterBoundaryDirichlet::operator(), functor_boundary_dirichlet.h:47-150: a fluid row with a solid particle within h is
+// REPLACED by the least-squares extrapolation stencil along its normal over the neighbours within h (zero for the other in-cut
+// neighbours, 1 on the diagonal) and its right-hand side entries are zeroed.  The two sums (mean normal coordinate, xterm) are taken
+// over the neighbor list in its own order, as the reference does; the per-entry values are written on the matrix.
+template <int DIM> __global__ void __launch_bounds__(128) k_dirichlet_rows(Dev d, double *b, int ldb, int *bad_kind) {
+  ROW_SETUP(d)
+  if (ikind == ISPH_KIND_SOLID) return;
+  if (ikind != ISPH_KIND_FLUID) { *bad_kind = 1; return; }
+  const long long nb = d.noff[row], ne = d.noff[row + 1];
+  int n_solid = 0, natoms_cut = 0; double xn_av = 0.0;
+  const double *n_i = d.normal + 3 * (size_t)i;
+  for (long long p = nb; p < ne; ++p) {
+    const int j = d.neigh[p] & ISPH_NEIGHMASK, jtype = d.type[j];
+    PAIR_GEOM(d, DIM)
+    const double hij = d.T->h[itype][jtype];
+    if (rsq < hij * hij) {                                                        // pow(h, 2): exactly h * h
+      n_solid += (d.kind[j] == ISPH_KIND_SOLID);
+      double xn_j = 0.0;
+      for (int k = 0; k < DIM; ++k) xn_j += d.x[3 * (size_t)j + k] * n_i[k];
+      xn_av += xn_j; ++natoms_cut;
+    }
+  }
+  if (n_solid <= 0) return;
+  double xn_i = 0.0;
+  xn_i += xi0 * n_i[0]; xn_i += xi1 * n_i[1]; if (DIM == 3) xn_i += xi2 * n_i[2];
+  xn_av /= natoms_cut;
+  double xterm = 0.0;
+  for (long long p = nb; p < ne; ++p) {
+    const int j = d.neigh[p] & ISPH_NEIGHMASK, jtype = d.type[j];
+    PAIR_GEOM(d, DIM)
+    const double hij = d.T->h[itype][jtype];
+    if (rsq < hij * hij) { double xn_j = 0.0; for (int k = 0; k < DIM; ++k) xn_j += d.x[3 * (size_t)j + k] * n_i[k]; xterm += xn_j * (xn_j - xn_av); }
+  }
+  for (int k = 0; k < rlen; ++k) {
+    const int j = d.atom[base + 32ll * k];
+    if (j == i) { d.val[base + 32ll * k] = 1.0; continue; }
+    const int jtype = d.type[j];
+    PAIR_GEOM(d, DIM)
+    const double hij = d.T->h[itype][jtype];
+    double v = 0.0;
+    if (rsq < hij * hij) { double xn_j = 0.0; for (int kk = 0; kk < DIM; ++kk) xn_j += d.x[3 * (size_t)j + kk] * n_i[kk]; v = -(xn_i - xn_av) * (xn_j - xn_av) / xterm - 1.0 / natoms_cut; }
+    d.val[base + 32ll * k] = v;
+  }
+  for (int k = 0; k < DIM; ++k) b[(size_t)k * ldb + i] = 0.0;
+}
+
 __global__ void k_recip(const double *a, double *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = 1.0 / a[i]; }
 __global__ void k_mul(const double *a, const double *b, double *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = a[i] * b[i]; }
 __global__ void k_scale_vec(double *a, double s, int n, int ld, int nvec) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) for (int q = 0; q < nvec; ++q) a[(size_t)q * ld + i] *= s; }
@@ -856,6 +962,43 @@ void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, d
   else k_pb_residual<3><<<LGRID(c)>>>(d, mh, linearized, kappasq, gamma, psi, psi0, eps, d_extra, d_f);
   ++c->launches;
   c->toc("computeFPoissonBoltzmann");
+}
+
+void advance_time(Ctx *c, double dt, bool anti) {
+  Dev d = make_dev(c);
+  c->tic("advanceTime");
+  double *v = c->field[ISPH_F_VELOCITY].p, *p = c->field[ISPH_F_PRESSURE].p, *dp = c->field[ISPH_F_DP].p; const double *vnp1 = c->field[ISPH_F_VSTAR].p;
+#define AB(D, AN) k_advance_begin<D, AN><<<GRID(c)>>>(d, dt, v, vnp1, p, dp)
+  if (d.dim == 2) { if (anti) AB(2, true); else AB(2, false); } else { if (anti) AB(3, true); else AB(3, false); }
+#undef AB
+  ++c->launches;
+  forward_comm(c, ISPH_F_DP);                                                                     // functor_advance_time_begin.h:74-78
+  FixedTab ft; for (int t = 0; t < ISPH_MAXT; ++t) ft.f[t] = c->fixed_of_type[t];
+  k_advance_end<<<ceil_div(c->nall, 256), 256, 0, c->stream>>>(c->nall, d.dim, dt, c->type.p, ft, v, vnp1, p, dp, c->x.p); ++c->launches;
+  c->A.built = false; c->A.is_filled = 0;                                                         // the particles moved: graph and matrix belong to the old positions
+  c->toc("advanceTime");
+}
+
+static void check_kind_flag(Ctx *c, const char *what) {
+  int bad = 0; CUDA_CHECK(cudaMemcpyAsync(&bad, c->flag.p + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  ISPH_REQUIRE(bad == 0, std::string(what) + ":: Particle types are not supported");
+}
+void boundary_navier_slip(Ctx *c, double beta) {
+  Dev d = make_dev(c);
+  if (beta == 0.0) return;                                                                        // pair_isph_corrected.cpp:922
+  c->flag.ensure(16); CUDA_CHECK(cudaMemsetAsync(c->flag.p + 5, 0, sizeof(int), c->stream));
+  if (d.dim == 2) k_navier_slip_rows<2><<<GRID(c)>>>(d, beta, c->field[ISPH_F_DENSITY].p, c->flag.p + 5);
+  else k_navier_slip_rows<3><<<GRID(c)>>>(d, beta, c->field[ISPH_F_DENSITY].p, c->flag.p + 5);
+  ++c->launches;
+  check_kind_flag(c, "FunctorBoundaryNavierSlip");
+}
+void boundary_dirichlet(Ctx *c) {
+  Dev d = make_dev(c);
+  ISPH_REQUIRE(c->b_nvec == d.dim && c->bs.p, "isph_boundary_dirichlet: the load multivector must have dim columns");
+  c->flag.ensure(16); CUDA_CHECK(cudaMemsetAsync(c->flag.p + 5, 0, sizeof(int), c->stream));
+  if (d.dim == 2) k_dirichlet_rows<2><<<GRID(c)>>>(d, c->bs.p, c->ld, c->flag.p + 5); else k_dirichlet_rows<3><<<GRID(c)>>>(d, c->bs.p, c->ld, c->flag.p + 5);
+  ++c->launches;
+  check_kind_flag(c, "FunctorBoundaryDirichlet");
 }
 
 }  // namespace isph

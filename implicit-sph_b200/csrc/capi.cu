@@ -301,6 +301,16 @@ int isph_pb_newton(isph_ctx *ctx, int mh, int lin, double ezcb, double psiref, d
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (newton_iters) *newton_iters = a; if (linear_iters) *linear_iters = b; if (normf) *normf = nf; if (converged) *converged = cv; API_END
 }
+int isph_pair_fixed(isph_ctx *ctx, const int *fixed_of_type) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->have_pair && fixed_of_type, "isph_pair_coeff first"); for (int t = 0; t < ISPH_MAXT; ++t) c->fixed_of_type[t] = (t <= c->tab.ntypes) ? (fixed_of_type[t] != 0) : 0; API_END
+}
+int isph_advance_time(isph_ctx *ctx, double dt, int anti) { API_BEGIN(ctx) advance_time(c, dt, anti != 0); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END }
+int isph_atoms_get_x(isph_ctx *ctx, double *x) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->have_atoms && x, "atoms not set");
+  CUDA_CHECK(cudaMemcpyAsync(x, c->x.p, sizeof(double) * 3 * c->nall, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+}
+int isph_boundary_navier_slip(isph_ctx *ctx, double beta) { API_BEGIN(ctx) boundary_navier_slip(c, beta); API_END }
+int isph_boundary_dirichlet(isph_ctx *ctx) { API_BEGIN(ctx) boundary_dirichlet(c); load_written(c); API_END }
 int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incp, const double *dp) { API_BEGIN(ctx) ns_correct(c, dt, anti != 0, incp != 0, dp); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END }
 int isph_diagonals_get(isph_ctx *ctx, double *d, double *s) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->A.built, "no matrix");

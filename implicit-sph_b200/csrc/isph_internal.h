@@ -84,7 +84,7 @@ struct Ctx {
   std::string err;
   long long launches = 0;
   // pair
-  bool have_pair = false; PairTab tab; DevBuf<PairTab> d_tab;
+  bool have_pair = false; PairTab tab; DevBuf<PairTab> d_tab; int fixed_of_type[ISPH_MAXT] = {};   // pinfo[1] ("fixed" particle types), pair_isph.cpp:165-167
   // atoms
   int nlocal = 0, nghost = 0, nall = 0, first_fluid_row = -1, max_tag = 0; bool have_atoms = false; unsigned long long tag_hash = 0;
   DevBuf<double> x; DevBuf<int> type, tag, kind, col_of_atom, tag2own; std::vector<int> h_type, h_tag;
@@ -163,6 +163,9 @@ void pb_jacobian(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, d
 void ns_correct(Ctx *c, double dt, bool anti, bool incp, const double *dp_owned_host);
 void applied_electric_potential(Ctx *c);
 void solute_transport(Ctx *c, double dt, double theta, double dcoeff);
+void advance_time(Ctx *c, double dt, bool anti);
+void boundary_navier_slip(Ctx *c, double beta);
+void boundary_dirichlet(Ctx *c);
 void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f);
 void forward_comm(Ctx *c, int field);
 

@@ -11,6 +11,7 @@
 //   * with several ranks the partial results are summed with one ncclAllReduce per reduction (halo.cu).
 // No tensor cores: nothing here is a dense contraction (largest dense object: the 51x50 Hessenberg).
 #include "isph_internal.h"
+#include <cuda.h>                                                // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace isph {
 
@@ -108,19 +109,23 @@ __global__ void __launch_bounds__(VB) k_dot(const double *a, const double *b, in
 //   pass 1: skipped unless the DGKS test asks for a second pass; h2[k] = V_k . w1, h2[nv] = w1.w1
 template <int G> __global__ void __launch_bounds__(VB, G == 16 ? 2 : (G == 8 ? 3 : 5))
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
-           double *S, int pass, double *partials, unsigned *counters, P2PRed pr) {
+           double *S, int pass, int rev, double *partials, unsigned *counters, P2PRed pr) {
   __shared__ bool go;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fused update sweep that follows may start its prologue (it waits for this grid before it reads S / w)
   if (pass == 1) { if (threadIdx.x == 0) go = dgks_second(S, nv, nvec != nullptr); __syncthreads(); if (!go) return; }
   const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
   const bool with_n = (pass == 0 && nvec != nullptr && g == 0);
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
-  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+  const int r0 = (rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * chunk, r1 = min(n, r0 + chunk);
   const double *Vg = V + (size_t)k0 * ld;
   double acc[G + 2];
 #pragma unroll
   for (int k = 0; k < G + 2; ++k) acc[k] = 0.0;
-  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+  // rev: the chunks and the rows inside a chunk are walked backwards (the sweeps of an Arnoldi step alternate direction so that
+  // each starts on what the previous one left in L2, see k_update_dot_tma)
+  const int i_lo = r0 + 2 * (int)threadIdx.x, nit = i_lo < r1 ? (r1 - i_lo + 2 * VB - 1) / (2 * VB) : 0;
+  for (int t = 0; t < nit; ++t) {
+    const int i = i_lo + (rev ? nit - 1 - t : t) * 2 * VB;
     double2 wi, nn = make_double2(0.0, 0.0);
     if (i + 1 < r1) { wi = *reinterpret_cast<const double2 *>(w + i); if (with_n) nn = *reinterpret_cast<const double2 *>(nvec + i); }
     else { wi.x = w[i]; wi.y = 0.0; if (with_n) nn.x = nvec[i]; }
@@ -174,14 +179,16 @@ k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restric
 // first Gram-Schmidt update: w1 = y - (n.y) n - sum_k h_k V_k.  One contiguous row chunk per block, 128-bit accesses; no
 // reduction (||w1||^2 travels with the pass-1 message, see above).
 __global__ void __launch_bounds__(VB)
-k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, const double *S) {
+k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, const double *S, int rev) {
   __shared__ double sh[64];
   if (threadIdx.x < nv) sh[threadIdx.x] = S[S_H + threadIdx.x];
   __syncthreads();
   const double proj = nvec ? S[S_H + nv + 1] : 0.0;
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + 1) & ~1;
-  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
-  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+  const int r0 = (rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * chunk, r1 = min(n, r0 + chunk);
+  const int i_lo = r0 + 2 * (int)threadIdx.x, nit = i_lo < r1 ? (r1 - i_lo + 2 * VB - 1) / (2 * VB) : 0;
+  for (int t = 0; t < nit; ++t) {
+    const int i = i_lo + (rev ? nit - 1 - t : t) * 2 * VB;
     if (i + 1 < r1) {
       double2 wi = *reinterpret_cast<const double2 *>(w + i);
       if (nvec) { const double2 nn = *reinterpret_cast<const double2 *>(nvec + i); wi.x -= proj * nn.x; wi.y -= proj * nn.y; }
@@ -205,7 +212,7 @@ k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
 // (known from the pass-0 message) asks for a second pass.  Used for nv > 8; shorter bases keep the two streaming kernels.
 static const int KPW = 7;                                       // 8 warps x 7 vectors >= 51 basis vectors
 template <int HV> __global__ void __launch_bounds__(VB, HV == 1 ? 3 : 2)     // HV = 64-row halves per tile
-k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n,
+k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, int rev,
              double *S, double *partials, unsigned *counter, P2PRed pr) {
   constexpr int UT = 64 * HV;
   __shared__ __align__(16) double s_part[VB / 32][UT];
@@ -219,11 +226,12 @@ k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   const bool go = s_go;
   const double proj = nvec ? S[S_H + nv + 1] : 0.0;
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + UT - 1) / UT * UT;
-  const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk);
+  const int r0 = min(n, (rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * chunk), r1 = min(n, r0 + chunk), ntl = (r1 - r0 + UT - 1) / UT;
   double acc[KPW], nrm = 0.0;
 #pragma unroll
   for (int q = 0; q < KPW; ++q) acc[q] = 0.0;
-  for (int t0 = r0; t0 < r1; t0 += UT) {
+  for (int tl = 0; tl < ntl; ++tl) {
+    const int t0 = r0 + (rev ? ntl - 1 - tl : tl) * UT;
     // the tile's w (and n) values are requested together with the basis values: one memory latency per tile, not two
     double wv = 0.0, nn = 0.0;
     if (tid < UT && t0 + tid < r1) { wv = w[t0 + tid]; if (nvec) nn = nvec[t0 + tid]; }
@@ -301,96 +309,114 @@ k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
 // ---- the same fused sweep as a TMA pipeline (default for nv > 8) -----------------------------------------------------------
 // w1 = y - (n.y) n - sum_k h_k V_k ,  h2[k] = V_k . w1 ,  h2[nv] = w1.w1        (one read of the basis, as above)
 // k_update_dot stages every tile through registers and meets two block barriers per tile with nothing in flight behind them
-// (ncu: 24 % warp occupancy, barrier + long-scoreboard stalls: profiles/r01_prof_update_dot_c2_ncu.txt).  Here the tile's
-// nv basis segments (+ y and n) are brought into shared memory by the bulk-copy engine (cp.async.bulk, one copy per vector
-// segment of TT rows = 1 KB, completion counted by an mbarrier per stage), NS stages deep: while the 4 warps of the CTA work on
-// tile i (thread-per-row update, then warp-per-vector dots out of the SAME shared-memory tile) the copies of tiles i+1 .. i+NS-1
-// are in flight, so the barriers no longer drain the memory pipeline.  With programmatic dependent launch the kernel starts
-// while the pass-0 reduction kernel is still finishing its all-reduce and pre-issues the basis copies of its first stages
-// (they do not depend on that kernel) before it waits for the coefficients.
-static const int TT = 128;                                       // rows per tile = threads per CTA
+// (ncu: 24 % warp occupancy, barrier + long-scoreboard stalls: profiles/r01_prof_update_dot_c2_ncu.txt).  Here the Krylov basis is
+// described to the TMA unit as a 2-D tensor [basis vector][row] (cuTensorMapEncodeTiled, one map per basis size) and ONE
+// cp.async.bulk.tensor instruction brings a tile — TT rows of the nv basis vectors AND of y, which is row nv of the same array —
+// into shared memory, completion counted by an mbarrier per stage, NS stages deep.  Warp 0 is the producer (waits for a free stage,
+// arms the barrier, issues the copy); warps 1-4 are the consumers: thread-per-row update out of shared memory, a named barrier
+// among the 128 consumer threads, warp-per-vector dot products out of the SAME tile, then one arrive per warp frees the stage.
+// While a tile is being worked on, the copies of the next NS-1 tiles are in flight, so the barriers no longer drain the memory
+// pipeline.  (A first version issued nv+2 one-dimensional cp.async.bulk copies per tile from a compute thread: the ~50 serial
+// UBLKCP issues per tile made it 1.8x SLOWER than the register-tile kernel, gpurun_out/r2_ud_*_c2.err.)
+// Sweep direction: `rev` walks the row chunks and the tiles inside a chunk backwards.  The orthogonalisation kernels of a step
+// alternate direction, so each starts on the rows the previous one touched last — the part of the basis still in the 126 MB L2.
+static const int TT = 128;                                       // rows per tile = consumer threads per CTA
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__global__ void __launch_bounds__(TT)
-k_update_dot_tma(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, int ns,
+__device__ __forceinline__ void tma_tile_2d(void *dst, const CUtensorMap *tm, int c0, int c1, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(TT + 32)
+k_update_dot_tma(const __grid_constant__ CUtensorMap tm, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, int ns, int rev,
                  double *S, double *partials, unsigned *counter, P2PRed pr) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ __align__(8) unsigned long long full[4];
-  __shared__ __align__(16) double s_w1[TT];
+  __shared__ __align__(8) unsigned long long full[4], empty[4];
+  __shared__ __align__(16) double s_w1[2][TT];
   __shared__ double s_h[64], s_red[TT / 32];
   __shared__ bool s_go, s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nrow = nv + (nvec ? 2 : 1);                          // segments per stage: nv basis vectors, y, [n]
-  const size_t stage_doubles = (size_t)nrow * TT;
+  const size_t stage_doubles = (size_t)(nv + 1) * TT + (nvec ? TT : 0);           // [nv basis segments][y][n]
   double *stage0 = reinterpret_cast<double *>(dsm);
   int chunk = (n + gridDim.x - 1) / gridDim.x; chunk = (chunk + TT - 1) / TT * TT;
-  const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk), ntiles = (r1 - r0 + TT - 1) / TT;
-  if (tid == 0) { for (int q = 0; q < ns; ++q) mbar_init(&full[q], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  const int cb = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int r0 = min(n, cb * chunk), r1 = min(n, r0 + chunk), ntiles = (r1 - r0 + TT - 1) / TT;
+  if (tid == 0) { for (int q = 0; q < ns; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], TT / 32); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  // one thread feeds the copy engine: basis segments first (they are not written by the preceding kernels), then y (and n)
-  auto issue = [&](int tile, bool basis, bool rest) {
-    const int q = tile % ns, t0 = r0 + tile * TT, rows = min(TT, r1 - t0);
-    const unsigned bytes = (unsigned)(((rows + 1) & ~1) * 8);    // 16-byte granules; the row padding of ld (a multiple of 32) covers an odd tail
-    double *dst = stage0 + (size_t)q * stage_doubles;
-    if (basis) { mbar_expect_tx(&full[q], bytes * (unsigned)nrow);
-      for (int k = 0; k < nv; ++k) bulk_g2s(dst + (size_t)k * TT, V + (size_t)k * ld + t0, bytes, &full[q]); }
-    if (rest) { bulk_g2s(dst + (size_t)nv * TT, w + t0, bytes, &full[q]); if (nvec) bulk_g2s(dst + (size_t)(nv + 1) * TT, nvec + t0, bytes, &full[q]); }
-  };
-  const int pre = min(ns, ntiles);
-  if (tid == 0) for (int t = 0; t < pre; ++t) issue(t, true, false);
   asm volatile("griddepcontrol.wait;" ::: "memory");             // everything below reads what the pass-0 kernel produced (coefficients, y)
-  if (tid == 0) { for (int t = 0; t < pre; ++t) issue(t, false, true); s_go = dgks_second(S, nv, nvec != nullptr); }
+  if (tid == 0) s_go = dgks_second(S, nv, nvec != nullptr);
   if (tid < nv) s_h[tid] = S[S_H + tid];
   __syncthreads();
   const bool go = s_go;
-  const double proj = nvec ? S[S_H + nv + 1] : 0.0;
-  constexpr int KW = 13;                                         // 4 warps x 13 vectors >= 51 basis vectors
+  constexpr int KW = 13;                                         // 4 consumer warps x 13 vectors >= 51 basis vectors
   double acc[KW], nrm = 0.0;
 #pragma unroll
   for (int q = 0; q < KW; ++q) acc[q] = 0.0;
-  for (int it = 0; it < ntiles; ++it) {
-    const int q = it % ns, t0 = r0 + it * TT, rows = min(TT, r1 - t0);
-    const double *sv = stage0 + (size_t)q * stage_doubles;
-    mbar_wait(&full[q], (unsigned)((it / ns) & 1));
-    double w1 = 0.0;
-    if (tid < rows) {                                            // thread-per-row update out of shared memory (conflict-free: consecutive rows)
-      double s0 = 0.0, s1 = 0.0; int k = 0;
-      for (; k + 2 <= nv; k += 2) { s0 += s_h[k] * sv[(size_t)k * TT + tid]; s1 += s_h[k + 1] * sv[(size_t)(k + 1) * TT + tid]; }
-      if (k < nv) s0 += s_h[k] * sv[(size_t)k * TT + tid];
-      w1 = sv[(size_t)nv * TT + tid]; if (nvec) w1 -= proj * sv[(size_t)(nv + 1) * TT + tid];
-      w1 -= (s0 + s1); w[t0 + tid] = w1; nrm += w1 * w1;
-    }
-    if (go) {
-      s_w1[tid] = w1;
-      __syncthreads();
-      double ww[TT / 32];
-#pragma unroll
-      for (int i = 0; i < TT / 32; ++i) ww[i] = s_w1[lane + 32 * i];      // rows past the tile's end carry w1 = 0 ...
-#pragma unroll
-      for (int j = 0; j < KW; ++j) {
-        const int k = warp + (TT / 32) * j;
-        if (k < nv) {
-          const double *vk = sv + (size_t)k * TT;
-#pragma unroll
-          for (int i = 0; i < TT / 32; ++i) { const int r = lane + 32 * i; if (r < rows) acc[j] += vk[r] * ww[i]; }     // ... and their (stale) basis cells are never read
-        }
+  if (warp == 0) {                                               // ---- producer
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)(((size_t)(nv + 1) * TT + (nvec ? TT : 0)) * sizeof(double));
+      for (int it = 0; it < ntiles; ++it) {
+        const int q = it % ns, tile = rev ? ntiles - 1 - it : it, t0 = r0 + tile * TT;
+        if (it >= ns) mbar_wait(&empty[q], (unsigned)(((it / ns) - 1) & 1));
+        double *dst = stage0 + (size_t)q * stage_doubles;
+        mbar_expect_tx(&full[q], bytes);
+        tma_tile_2d(dst, &tm, t0, 0, &full[q]);
+        if (nvec) bulk_g2s(dst + (size_t)(nv + 1) * TT, nvec + t0, TT * sizeof(double), &full[q]);     // the null vector is allocated with ld >= t0 + TT entries
       }
     }
-    __syncthreads();                                             // every warp is done with stage q (and with s_w1)
-    if (tid == 0 && it + ns < ntiles) issue(it + ns, true, true);
+  } else {                                                       // ---- consumers: threads 32..159
+    const int ct = tid - 32, cw = warp - 1;
+    const double proj = nvec ? S[S_H + nv + 1] : 0.0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int q = it % ns, tile = rev ? ntiles - 1 - it : it, t0 = r0 + tile * TT, rows = min(TT, r1 - t0);
+      const double *sv = stage0 + (size_t)q * stage_doubles;
+      mbar_wait(&full[q], (unsigned)((it / ns) & 1));
+      double w1 = 0.0;
+      if (ct < rows) {                                           // thread-per-row update out of shared memory (conflict-free: consecutive rows)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; int k = 0;
+        for (; k + 4 <= nv; k += 4) { s0 += s_h[k] * sv[(size_t)k * TT + ct]; s1 += s_h[k + 1] * sv[(size_t)(k + 1) * TT + ct];
+                                      s2 += s_h[k + 2] * sv[(size_t)(k + 2) * TT + ct]; s3 += s_h[k + 3] * sv[(size_t)(k + 3) * TT + ct]; }
+        for (; k < nv; ++k) s0 += s_h[k] * sv[(size_t)k * TT + ct];
+        w1 = sv[(size_t)nv * TT + ct]; if (nvec) w1 -= proj * sv[(size_t)(nv + 1) * TT + ct];
+        w1 -= ((s0 + s1) + (s2 + s3)); w[t0 + ct] = w1; nrm += w1 * w1;
+      }
+      if (go) {
+        double *sw = s_w1[it & 1];
+        sw[ct] = w1;
+        asm volatile("bar.sync 1, %0;" ::"n"(TT) : "memory");    // the 128 consumer threads: w1 of the tile is complete
+        double ww[TT / 32];
+#pragma unroll
+        for (int i = 0; i < TT / 32; ++i) ww[i] = sw[lane + 32 * i];       // rows past the tile's end carry w1 = 0 ...
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+          const int k = cw + (TT / 32) * j;
+          if (k < nv) {
+            const double *vk = sv + (size_t)k * TT;
+#pragma unroll
+            for (int i = 0; i < TT / 32; ++i) { const int r = lane + 32 * i; if (r < rows) acc[j] += vk[r] * ww[i]; }   // ... and their basis cells are never read
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[q]);                     // this warp is done with stage q
+    }
   }
   if (!go) return;                                               // block-uniform: the DGKS decision is the same everywhere (and on every rank)
   double *mine = partials + (size_t)blockIdx.x * 64;
+  if (warp > 0) {
+    const int cw = warp - 1;
 #pragma unroll
-  for (int j = 0; j < KW; ++j) { const double s = warp_sum(acc[j]); const int k = warp + (TT / 32) * j; if (lane == 0 && k < nv) mine[k] = s; }
-  { const double s = warp_sum(nrm); if (lane == 0) s_red[warp] = s; }
+    for (int j = 0; j < KW; ++j) { const double s = warp_sum(acc[j]); const int k = cw + (TT / 32) * j; if (lane == 0 && k < nv) mine[k] = s; }
+    const double s = warp_sum(nrm); if (lane == 0) s_red[cw] = s;
+  }
   __syncthreads();
   if (tid == 0) { double t = 0.0; for (int q = 0; q < TT / 32; ++q) t += s_red[q]; mine[63] = t; }
   __threadfence(); __syncthreads();
@@ -398,7 +424,7 @@ k_update_dot_tma(const double *__restrict__ V, int ld, int nv, double *__restric
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int k = warp; k < 64; k += TT / 32) {
+    for (int k = warp; k < 64; k += (TT + 32) / 32) {
       if (!(k < nv || k == 63)) continue;
       double s = 0.0;
       for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 64 + k);
@@ -451,7 +477,7 @@ __device__ __forceinline__ void prepush_row(const PrePush &pp, int hslot, int b,
 }
 __global__ void __launch_bounds__(VB)
 k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, int n, double *S, int singular,
-         const double *__restrict__ invdiag, double damping, int post, double *__restrict__ z, double *host_res, int slot, PrePush pp) {
+         const double *__restrict__ invdiag, double damping, int post, double *__restrict__ z, double *host_res, int slot, int rev, PrePush pp) {
   if (blockIdx.x == 0) {      // block 0 is dedicated to the (sequential, ~10 us) Hessenberg/Givens step: hidden behind the sweep
     if (threadIdx.x < 32) givens_step(S, nv - 1, singular != 0, host_res, slot);
     return;
@@ -461,10 +487,12 @@ k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, i
   if (threadIdx.x < nv) sh[threadIdx.x] = S[S_H2 + threadIdx.x];
   __syncthreads();
   const double inv = s_inv; const int nk = s_second ? nv : 0;
-  const int nb = gridDim.x - 1, bx = blockIdx.x - 1, hslot = (int)(pp.seq % MB_SLOTS);
+  const int nb = gridDim.x - 1, bx = rev ? nb - (int)blockIdx.x : (int)blockIdx.x - 1, hslot = (int)(pp.seq % MB_SLOTS);
   int chunk = (n + nb - 1) / nb; chunk = (chunk + 1) & ~1;
   const int r0 = bx * chunk, r1 = min(n, r0 + chunk);
-  for (int i = r0 + 2 * threadIdx.x; i < r1; i += 2 * VB) {
+  const int i_lo = r0 + 2 * (int)threadIdx.x, nit = i_lo < r1 ? (r1 - i_lo + 2 * VB - 1) / (2 * VB) : 0;
+  for (int t = 0; t < nit; ++t) {
+    const int i = i_lo + (rev ? nit - 1 - t : t) * 2 * VB;
     if (i + 1 < r1) {
       double2 wi = *reinterpret_cast<const double2 *>(w + i);
 #pragma unroll 8
@@ -619,7 +647,7 @@ static DiagPrec diag_prec_of(Ctx *c, bool use_prec) {
   return d;
 }
 
-static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass) {
+static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, int pass, int rev) {
   const int n = c->A.n; double *S = c->hbuf.p; const double *nv_ = c->is_singular ? c->nullvec.p : nullptr; unsigned *cnt = (unsigned *)c->flag.p + 9;
   const int G = nv <= 4 ? 4 : (nv <= 8 ? 8 : 16);            // short bases: do not pay for 16 (aliased) loads per thread
   const int groups = (nv + G - 1) / G;
@@ -628,31 +656,54 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   const int mdcap = mdenv ? mdenv : (G == 16 ? 296 : (G == 8 ? 444 : 740));
   int gx = mdcap / groups; if (gx < 74) gx = 74; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
   P2PRed pr = halo_p2p_ticket(c);
-  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
-  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
-  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, c->red.p, cnt, pr);
+  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
+  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
+  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
   ++c->launches;
   // NCCL fallback (no peer access).  Pass 1 is conditional on the device: a rank-independent decision (it is taken from the
   // already reduced pass-0 message), so every rank either contributes fresh sums or the same stale, unused ones.
   if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + (pass == 0 ? S_H : S_H2), pass == 0 ? nv + (nv_ ? 2 : 1) : nv + 1);
 }
 
-// fused update + second-pass sweep, bulk-copy pipeline; launched with programmatic stream serialization so that its prologue
-// (barrier init, first basis copies) overlaps the tail (last-block reduction, peer all-reduce) of the pass-0 kernel before it
-static void launch_update_dot_tma(Ctx *c, const double *V, int ld, int nv, double *w, const double *nvp, int n, double *S, unsigned *counter, P2PRed pr) {
+// fused update + second-pass sweep, TMA pipeline; launched with programmatic stream serialization so that its launch and prologue
+// overlap the tail (last-block reduction, peer all-reduce) of the pass-0 kernel before it.  Tensor maps: the basis array
+// V[(m+1)][ld] as a rank-2 tensor {ld (contiguous), m + 1}, box {TT rows, nv + 1 vectors}; one map per basis size, re-encoded
+// only when the basis buffer or its leading dimension changes.
+struct TmaMaps { const double *V = nullptr; int ld = 0, rows = 0; CUtensorMap map[64]; bool ok[64] = {}; };
+static bool tma_map_for(Ctx *c, TmaMaps &T, const double *V, int ld, int rows_total, int nv, CUtensorMap *out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn enc = nullptr; static bool tried = false;
+  if (!tried) { tried = true; void *fn = nullptr; cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) enc = (EncodeFn)fn; else cudaGetLastError(); }
+  if (!enc) return false;
+  if (T.V != V || T.ld != ld || T.rows != rows_total) { T.V = V; T.ld = ld; T.rows = rows_total; memset(T.ok, 0, sizeof(T.ok)); }
+  if (!T.ok[nv]) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows_total}, gstr[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)TT, (cuuint32_t)(nv + 1)}, estr[2] = {1, 1};
+    if (enc(&T.map[nv], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    T.ok[nv] = true;
+  }
+  (void)c; *out = T.map[nv]; return true;
+}
+static bool launch_update_dot_tma(Ctx *c, const double *V, int ld, int rows_total, int nv, double *w, const double *nvp, int n, int rev, double *S, unsigned *counter, P2PRed pr) {
   static const int grid_env = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : 0, ns_env = getenv("ISPH_UD_STAGES") ? atoi(getenv("ISPH_UD_STAGES")) : 0;
   static const bool pdl = getenv("ISPH_NO_PDL") == nullptr;
-  static int sms = 0; static bool attr_set = false;
+  static int sms = 0; static bool attr_set = false; static TmaMaps maps;
+  if (w != V + (size_t)nv * ld) return false;                   // y must be row nv of the basis array (it is: v_{j+1} is formed in place)
+  CUtensorMap tm; if (!tma_map_for(c, maps, V, ld, rows_total, nv, &tm)) return false;
   if (!attr_set) { CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     CUDA_CHECK(cudaFuncSetAttribute(k_update_dot_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr_set = true; }
-  const size_t stage = (size_t)(nv + (nvp ? 2 : 1)) * TT * sizeof(double);
+  const size_t stage = ((size_t)(nv + 1) * TT + (nvp ? TT : 0)) * sizeof(double);
   int ns = ns_env ? ns_env : (int)((size_t)(106 * 1024) / stage); ns = std::max(2, std::min(4, ns));      // two CTAs of <= 106 KB per SM
   const int grid = std::max(1, std::min(grid_env ? grid_env : 2 * sms, ceil_div(n, TT)));
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = stage * ns; cfg.stream = c->stream;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TT + 32); cfg.dynamicSmemBytes = stage * ns; cfg.stream = c->stream;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_update_dot_tma, V, ld, nv, w, nvp, n, ns, S, c->red.p, counter, pr));
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_update_dot_tma, tm, nv, w, nvp, n, ns, rev, S, c->red.p, counter, pr));
+  return true;
 }
 
 static void dbg(Ctx *c, const char *what) {      // ISPH_DEBUG_SYNC=1: synchronise after every phase and name the one that faulted
@@ -670,6 +721,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   const int sing = c->is_singular ? 1 : 0;
   static const bool fuse_ud = getenv("ISPH_NO_FUSE_UD") == nullptr;
   static const bool ud_tma = !(getenv("ISPH_UD_TMA") && atoi(getenv("ISPH_UD_TMA")) == 0);      // TMA-pipelined sweep (default) vs the register-tile kernel
+  static const bool pingpong = getenv("ISPH_NO_PINGPONG") == nullptr;
+  int sweep_dir = 0; auto sweep = [&]() { if (!pingpong) return 0; sweep_dir ^= 1; return sweep_dir; };
   static const int ud_hv = getenv("ISPH_UD_HV") ? atoi(getenv("ISPH_UD_HV")) : 2;            // 64-row halves per tile of the fused sweep
   static const int udcap = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : (ud_hv == 1 ? 444 : 296);       // 148 SMs x resident CTAs
   const int gud = std::max(1, std::min(udcap, ceil_div(n, 64 * ud_hv)));
@@ -696,17 +749,20 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
       double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
       dbg(c, "prologue");
       { ProfScope ps(c, "op_apply"); spmv(c, zj, vn, 1, ld, ld); } dbg(c, "op_apply");          // y = A z_j ; the PoissonProjection tail rides on the Gram-Schmidt sweep
-      { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0); } dbg(c, "multidot0");
+      // the sweeps over the basis alternate direction (ISPH_NO_PINGPONG=1: all forward): each starts where the previous one ended, on the
+      // part of the basis that is still in L2
+      { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0, sweep()); } dbg(c, "multidot0");
       if (fuse_ud && j + 1 > 8) {                                // one sweep: first update + second-pass coefficients
-        ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c);
-        if (ud_tma) launch_update_dot_tma(c, V, ld, j + 1, vn, nvp, n, S, cnt + 6, pr);                                        // flag word 14
-        else if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);
-        else k_update_dot<2><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, c->red.p, cnt + 6, pr);
+        ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c); const int rv = sweep();
+        if (!(ud_tma && launch_update_dot_tma(c, V, ld, m + 1, j + 1, vn, nvp, n, rv, S, cnt + 6, pr))) {                     // flag word 14
+          if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
+          else k_update_dot<2><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
+        }
         ++c->launches;
         if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_H2, j + 2);
       } else {
-        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S); ++c->launches; }
-        { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1); }
+        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, sweep()); ++c->launches; }
+        { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1, sweep()); }
       }
       dbg(c, "update0/dot1");
       ++iters;
@@ -715,8 +771,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
         double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
         PrePush pp; pp.plan = nullptr; pp.sp = pp.sd = nullptr; pp.seq = 0;
         if (jacobi_fused) { halo_prepush_begin(c, zn, &pp);       // z_{j+1} is the next SpMV input: its halo rows leave from this kernel
-          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, dp.invdiag, dp.scale, dp.post, zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
-        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, 0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, pp); ++c->launches; }
+          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, dp.invdiag, dp.scale, dp.post, zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
+        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, 0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
       } else { k_givens<<<1, 32, 0, c->stream>>>(S, j, sing, c->h_scal.p + 8, iters); ++c->launches; }   // last column of the cycle: v_{m} is never used
       dbg(c, "finish");
       CUDA_CHECK(cudaEventRecord(ev[j], c->stream));
@@ -833,7 +889,7 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   load_from_host(c); c->b_dev_fresh = false;                     // borrowed b: the host View is uploaded unless a device functor wrote the load vector since the last solve
   double *S = c->hbuf.p;
   if (c->is_singular) {     // createNullVector (solver_lin.cpp:59-77) ; b -= (b.n) n (solver_lin_belos.h:138-144)
-    c->nullvec.ensure(ld);
+    c->nullvec.ensure((size_t)ld + 256);                        // + one tile: the TMA sweep copies whole tiles of it
     k_mask_to_vec<<<g, VB, 0, c->stream>>>(c->have_mask ? c->mask.p : nullptr, c->nullvec.p, n); ++c->launches;
     dot_dev(c, c->nullvec.p, nullptr, n, S + S_TMP);
     const double nrm = sqrt(read_scalar(c, S + S_TMP));

@@ -131,6 +131,22 @@ int isph_pb_jacobian(isph_ctx *ctx, int morris_holmes, int linearized, double ez
  * vstar -= dt/rho grad(dp), then forward_comm(Vstar)), correctPressure (functor_correct_pressure.h:29-43).  dp = the device
  * solution of the last solve, or dp_owned[nlocal] when given.  Results: fields ISPH_F_DP, ISPH_F_VSTAR, ISPH_F_PRESSURE. */
 int isph_ns_correct(isph_ctx *ctx, double dt, int anti, int incremental_pressure, const double *dp_owned);
+/* "fixed" particle types, pinfo[1][type] (pair_isph.cpp:165-167; XML `type:N = "solid:fixed"`), fixed_of_type[ntypes+1]; default none */
+int isph_pair_fixed(isph_ctx *ctx, const int *fixed_of_type);
+/* PairISPH_Corrected::advanceTime (pair_isph_corrected.cpp:1183-1194): FunctorOuterAdvanceTimeBegin
+ * (functor_advance_time_begin.h:52-81: dp_i = grad(p)_i . 0.5 dt (v^{n+1} + v^n) on fluid rows, matrix-free corrected gradient with
+ * FilterBinary(Fluid, Fluid); forward_comm(DeltaP)) and FunctorOuterAdvanceTimeEnd over owned + ghost atoms
+ * (functor_advance_time_end.h:48-66: fixed types v = v^{n+1}; others p += dp, x += 0.5 dt (v^{n+1} + v^n), v = v^{n+1}).
+ * Fields: ISPH_F_VELOCITY = v^n in / v^{n+1} out, ISPH_F_VSTAR = v^{n+1}, ISPH_F_PRESSURE, ISPH_F_DP; the device positions move
+ * (isph_atoms_get_x reads them back) and the graph is invalidated.  Needs the graph of the current positions. */
+int isph_advance_time(isph_ctx *ctx, double dt, int anti);
+int isph_atoms_get_x(isph_ctx *ctx, double *x /*[nall][3]*/);
+/* Row modifiers applied after the Helmholtz functor for ns.boundary = NavierSlip / Dirichlet (pair_isph_corrected.cpp:918-934):
+ * Corrected::FunctorOuterBoundaryNavierSlip (functor_boundary_navier_slip.h:54-174, iblock < 0, add_neumann_term; Robin rows summed
+ * into A; normals = ISPH_F_NORMAL, rho = ISPH_F_DENSITY) and Corrected::FunctorOuterBoundaryDirichlet (functor_boundary_dirichlet.h:
+ * 47-150; fluid rows with a solid within h REPLACED by the extrapolation stencil, their load-vector rows zeroed). */
+int isph_boundary_navier_slip(isph_ctx *ctx, double beta);
+int isph_boundary_dirichlet(isph_ctx *ctx);
 /* FunctorOuterAppliedElectricPotential (functor_applied_electric_potential.h:34-96; call site pair_isph_corrected.cpp:598-617,
  * pair_isph.cpp:628-663): A = Laplacian(alpha = -1, material = sigma, FilterMatchBinary(Fluid, Fluid)); A.diagonal = diag(A);
  * b = 0; Solid rows: diagonal 1; buffer rows: diagonal 1, b = phi; ReplaceDiagonalValues.  Fields ISPH_F_SIGMA, ISPH_F_PHI;

@@ -77,7 +77,7 @@ inline bool fyes2(int m0, int m1, int ik, int jk) { return fyes1(m0, ik) && (jk 
 struct orc_problem {
   int dim, dimL, nlocal, nghost, nall, ntypes, inum;
   std::vector<double> x, f[ORC_F_COUNT];
-  std::vector<int> type, tag, ilist, neigh, kind_of_type, owner_of_ghost;
+  std::vector<int> type, tag, ilist, neigh, kind_of_type, fixed_of_type, owner_of_ghost;
   std::vector<long long> noff;
   std::vector<double> cutsq, h;         // (ntypes+1)^2
   KernelFn kern; double morris_safe;
@@ -773,6 +773,110 @@ int orc_ns_correct(orc_problem *q, double dt, int anti, int incp, const double *
   for (int i = 0; i < q->nall; ++i) { if (incp) pr[i] += dp[i]; else pr[i] = dp[i]; }
   return 0;
 }
+int orc_set_fixed(orc_problem *q, const int *fixed_of_type) { q->fixed_of_type.assign(fixed_of_type, fixed_of_type + q->ntypes + 1); return 0; }
+int orc_get_x(orc_problem *q, double *x) { memcpy(x, q->x.data(), sizeof(double) * 3 * q->nall); return 0; }
+
+// PairISPH_Corrected::advanceTime, pair_isph_corrected.cpp:1183-1194
+int orc_advance_time(orc_problem *q, double dt, int anti) {
+  const int dim = q->dim; double *dp = q->f[ORC_F_DP].data(), *v = q->f[ORC_F_VELOCITY].data(), *pr = q->f[ORC_F_PRESSURE].data();
+  const double *vnp1 = q->f[ORC_F_VSTAR].data();
+  // FunctorOuterAdvanceTimeBegin, functor_advance_time_begin.h:52-81: dp_i = grad(p)_i . dx_i, dx = 0.5 dt (v^{n+1} + v^n); the gradient
+  // operator carries FilterBinary(Fluid, Fluid) and alpha = 1 (functor_gradient.h:80-169)
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii], ikind = q->kind(q->type[i]);
+    double dx[3] = {};
+    for (int k = 0; k < dim; ++k) dx[k] = 0.5 * dt * (vnp1[3 * (size_t)i + k] + v[3 * (size_t)i + k]);
+    double g[3] = {};
+    grad_like_loop(q, ii, anti != 0, false, ORC_FLUID, ORC_FLUID, [&](int j, int k2, double gitmp, double vjtmp) { const double ijtmp = gitmp * vjtmp; g[k2] += ijtmp * (sph_op(anti != 0, pr[i], pr[j])); });
+    for (int k = 0; k < dim; ++k) g[k] *= 1.0;
+    if (fyes1(ORC_FLUID, ikind)) { double s = 0.0; for (int k = 0; k < dim; ++k) s += g[k] * dx[k]; dp[i] = s; }      // util.dotVectors
+    else dp[i] = 0.0;
+  }
+  q->forward(ORC_F_DP);                                                                    // exitFor :74-78
+  // FunctorOuterAdvanceTimeEnd over owned + ghost atoms, functor_advance_time_end.h:48-66
+  for (int i = 0; i < q->nall; ++i) {
+    if (!q->fixed_of_type.empty() && q->fixed_of_type[q->type[i]]) { for (int k = 0; k < dim; ++k) v[3 * (size_t)i + k] = vnp1[3 * (size_t)i + k]; continue; }
+    pr[i] += dp[i];
+    for (int k = 0; k < dim; ++k) {
+      const double delta = 0.5 * dt * (vnp1[3 * (size_t)i + k] + v[3 * (size_t)i + k]);
+      q->x[3 * (size_t)i + k] += delta; v[3 * (size_t)i + k] = vnp1[3 * (size_t)i + k];
+    }
+  }
+  return 0;
+}
+
+// Corrected::FunctorOuterBoundaryNavierSlip, functor_boundary_navier_slip.h:54-174 (iblock < 0, add_neumann_term = true)
+int orc_boundary_navier_slip(orc_problem *q, double beta) {
+  if (!q->have_graph) return -1;
+  if (beta == 0.0) return 0;                                                               // pair_isph_corrected.cpp:922
+  const int dim = q->dim; const double *vfrac = q->f[ORC_F_VFRAC].data(), *rho = q->f[ORC_F_DENSITY].data(), *nrm = q->f[ORC_F_NORMAL].data();
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii], itype = q->type[i], ikind = q->kind(itype), row = q->row_of(i);
+    if (ikind == ORC_SOLID) continue;
+    if (!(ikind == ORC_FLUID || ikind == ORC_BUFFER_DIRICHLET || ikind == ORC_BUFFER_NEUMANN)) continue;   // (the reference raises an error for other kinds)
+    const double *G = &q->f[ORC_F_GC][(size_t)9 * i];
+    double robin_at_i = 0.0;
+    for (long long p = q->noff[ii]; p < q->noff[ii + 1]; ++p) {
+      const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j];
+      if (q->kind(jtype) != ORC_SOLID) continue;
+      double rsq = 0.0, rij[3] = {};
+      for (int k = 0; k < dim; ++k) { rij[k] = q->X(i)[k] - q->X(j)[k]; rsq += (rij[k] * rij[k]); }
+      if (rsq < q->cut2(itype, jtype)) {
+        const double r = sqrt(rsq) + EPS_R, dwdr = q->kern.dval(r, q->hh(itype, jtype));
+        double aij[3] = {};
+        for (int k2 = 0; k2 < dim; ++k2) for (int k1 = 0; k1 < dim; ++k1) aij[k2] += G[k2 * dim + k1] * rij[k1];     // VIEW2(G, dim, k1, k2)
+        double tmp = 0.0;
+        for (int k = 0; k < dim; ++k) tmp += (nrm[3 * (size_t)i + k] + nrm[3 * (size_t)j + k]) * aij[k];
+        const double robin_at_j = beta * dwdr / r * vfrac[j] / rho[i] * tmp;
+        const int pos = q->find(row, q->tag[j]); if (pos >= 0) q->val[pos] += robin_at_j;                            // SumIntoGlobalValues
+        robin_at_i -= robin_at_j;
+      }
+    }
+    const int pos = q->find(row, q->tag[i]); if (pos >= 0) q->val[pos] += robin_at_i;
+  }
+  return 0;
+}
+
+// Corrected::FunctorOuterBoundaryDirichlet, functor_boundary_dirichlet.h:47-150
+int orc_boundary_dirichlet(orc_problem *q, double *b, int lda) {
+  if (!q->have_graph) return -1;
+  const int dim = q->dim; const double *nrm = q->f[ORC_F_NORMAL].data();
+  for (int ii = 0; ii < q->inum; ++ii) {
+    const int i = q->ilist[ii], itype = q->type[i], ikind = q->kind(itype), row = q->row_of(i);
+    if (ikind == ORC_SOLID) continue;
+    if (ikind != ORC_FLUID) return -1;                                                     // "Particle types are not supported"
+    int n_solid = 0;
+    for (long long p = q->noff[ii]; p < q->noff[ii + 1]; ++p) {
+      const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j];
+      double rsq = 0.0; for (int k = 0; k < dim; ++k) { const double d = q->X(i)[k] - q->X(j)[k]; rsq += (d * d); }
+      if (rsq < pow(q->hh(itype, jtype), 2)) n_solid += int(q->kind(jtype) == ORC_SOLID);
+    }
+    if (n_solid <= 0) continue;
+    double xn_i = 0.0, xn_av = 0.0;
+    for (int k = 0; k < dim; ++k) xn_i += q->X(i)[k] * nrm[3 * (size_t)i + k];
+    std::vector<double> xn; std::vector<int> tg, idx; std::vector<double> val;
+    for (long long p = q->noff[ii]; p < q->noff[ii + 1]; ++p) {
+      const int j = q->neigh[p] & NEIGHMASK, jtype = q->type[j];
+      double rsq = 0.0; for (int k = 0; k < dim; ++k) { const double d = q->X(i)[k] - q->X(j)[k]; rsq += (d * d); }
+      if (rsq < pow(q->hh(itype, jtype), 2)) {                                              // the interface layer is h wide, not cut
+        double xn_j = 0.0; for (int k = 0; k < dim; ++k) xn_j += q->X(j)[k] * nrm[3 * (size_t)i + k];
+        xn_av += xn_j; tg.push_back(q->tag[j]); xn.push_back(xn_j);
+      } else if (rsq < q->cut2(itype, jtype)) { val.push_back(0.0); idx.push_back(q->tag[j]); }
+    }
+    const int natoms_cut = (int)xn.size();
+    xn_av /= natoms_cut;
+    double xterm = 0.0;
+    for (int j = 0; j < natoms_cut; ++j) xterm += xn[j] * (xn[j] - xn_av);
+    for (int j = 0; j < natoms_cut; ++j) { val.push_back(-(xn_i - xn_av) * (xn[j] - xn_av) / xterm - 1.0 / natoms_cut); idx.push_back(tg[j]); }
+    val.push_back(1.0); idx.push_back(q->tag[i]);
+    for (size_t k = 0; k < idx.size(); ++k) { const int pos = q->find(row, idx[k]); if (pos >= 0) q->val[pos] = val[k]; }      // ReplaceGlobalValues, in list order
+    for (int k = 0; k < dim; ++k) b[(size_t)k * lda + i] = 0;                               // VIEW2(_b, _lda, i, k)
+  }
+  return 0;
+}
+
 int orc_invalidate_matrix(orc_problem *q) { q->is_filled = 0; return 0; }
 int orc_matrix_get(orc_problem *q, double *val) { if (!q->have_graph) return -1; memcpy(val, q->val.data(), sizeof(double) * q->val.size()); return 0; }
 int orc_diag_get(orc_problem *q, double *d, double *s) {

@@ -75,6 +75,11 @@ def _load(kind):
     L.orc_solute_transport.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp]
     L.orc_pb_residual.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
     L.orc_matrix_get.argtypes = [C.c_void_p, _dp]
+    L.orc_set_fixed.argtypes = [C.c_void_p, _ip]
+    L.orc_get_x.argtypes = [C.c_void_p, _dp]
+    L.orc_advance_time.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    L.orc_boundary_navier_slip.argtypes = [C.c_void_p, C.c_double]
+    L.orc_boundary_dirichlet.argtypes = [C.c_void_p, _dp, C.c_int]
     L.orc_diag_get.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_spmv.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
     _libs[kind] = L
@@ -174,6 +179,22 @@ class Oracle:
     def ns_correct(self, dt, dp, anti=True, incremental_pressure=True):
         dp = np.ascontiguousarray(dp, dtype=np.float64); assert dp.size == self.nlocal
         self._ck(self.L.orc_ns_correct(self.p, dt, int(anti), int(incremental_pressure), _d(dp)), "ns_correct")
+
+    def set_fixed(self, fixed_of_type):
+        a = np.ascontiguousarray(fixed_of_type, dtype=np.int32); self._ck(self.L.orc_set_fixed(self.p, _i(a)), "set_fixed")
+
+    def get_x(self):
+        x = np.empty((self.nall, 3)); self._ck(self.L.orc_get_x(self.p, _d(x)), "get_x"); return x
+
+    def advance_time(self, dt, anti=True):
+        self._ck(self.L.orc_advance_time(self.p, dt, int(anti)), "advance_time")
+
+    def boundary_navier_slip(self, beta):
+        self._ck(self.L.orc_boundary_navier_slip(self.p, beta), "boundary_navier_slip")
+
+    def boundary_dirichlet(self, b):
+        b = np.asfortranarray(np.array(b, dtype=np.float64).reshape(self.nlocal, self.dim, order="F"))
+        self._ck(self.L.orc_boundary_dirichlet(self.p, _d(b), self.nlocal), "boundary_dirichlet"); return b
 
     def invalidate_matrix(self):
         self.L.orc_invalidate_matrix(self.p)

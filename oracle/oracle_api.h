@@ -75,6 +75,20 @@ int orc_pb_residual(orc_problem *p, int morris_holmes, int linearized, double ez
  * (:422-464, when incremental pressure is used), correctVelocity (functor_correct_velocity.h:52-78, pair_isph_corrected.cpp
  * :1019-1034) incl. forward_comm(Vstar), correctPressure (functor_correct_pressure.h:29-43).  dp_owned[nlocal] = the solution. */
 int orc_ns_correct(orc_problem *p, double dt, int anti, int incremental_pressure, const double *dp_owned);
+/* pinfo[1][type] ("fixed" particles, pair_isph.cpp:165-167), [ntypes+1]; default all 0 */
+int orc_set_fixed(orc_problem *p, const int *fixed_of_type);
+int orc_get_x(orc_problem *p, double *x);               /* positions [nall][3] (moved by orc_advance_time) */
+/* PairISPH_Corrected::advanceTime (pair_isph_corrected.cpp:1183-1194): FunctorOuterAdvanceTimeBegin (functor_advance_time_begin.h:52-81:
+ * dp_i = grad(p)_i . 0.5 dt (v^{n+1} + v^n) on fluid rows, gradient with FilterBinary(Fluid, Fluid), then forward_comm(DeltaP)) and
+ * FunctorOuterAdvanceTimeEnd over owned + ghost atoms (functor_advance_time_end.h:48-66: fixed: v = v^{n+1}; else p += dp,
+ * x += 0.5 dt (v^{n+1} + v^n), v = v^{n+1}).  Fields: VELOCITY (v^n in, v^{n+1} out), VSTAR (v^{n+1}), PRESSURE, DP; positions. */
+int orc_advance_time(orc_problem *p, double dt, int anti);
+/* Corrected::FunctorOuterBoundaryNavierSlip (functor_boundary_navier_slip.h:54-174, iblock < 0, add_neumann_term): Robin rows summed
+ * into A (call site pair_isph_corrected.cpp:921-926, after the Helmholtz functor); normals from the NORMAL field */
+int orc_boundary_navier_slip(orc_problem *p, double beta);
+/* Corrected::FunctorOuterBoundaryDirichlet (functor_boundary_dirichlet.h:47-150): rows of fluid particles with a solid within h are
+ * REPLACED by the least-squares extrapolation stencil, their b entries (dim columns, leading dimension lda) zeroed */
+int orc_boundary_dirichlet(orc_problem *p, double *b, int lda);
 int orc_invalidate_matrix(orc_problem *p);              /* A.is_filled = 0, pair_isph.cpp:982,1026 */
 
 int orc_matrix_get(orc_problem *p, double *val);        /* aligned with orc_graph_get order */

@@ -48,6 +48,10 @@ namespace LAMMPS_NS { Utils util; }
 #include "functor_solute_transport.h"
 #include "functor_correct_velocity.h"
 #include "functor_correct_pressure.h"
+#include "functor_advance_time_begin.h"
+#include "functor_advance_time_end.h"
+#include "functor_boundary_navier_slip.h"
+#include "functor_boundary_dirichlet.h"
 
 #include "oracle_api.h"
 
@@ -80,10 +84,11 @@ struct MockPair {
   struct { int singular_poisson; bool is_incremental_pressure_used; double g[3]; } ns;
   struct { bool is_linearized; double ezcb, psiref, gamma; } pb;
   CommType comm_variable; int comm_forward;
-  std::vector<int> kind_of_type;
+  std::vector<int> kind_of_type, fixed_of_type;   // pinfo[0] (kind), pinfo[1] (fixed), pair_isph.cpp:160-167
   std::vector<int> owner_of_ghost;   // ghost atom -> owned atom with the same tag (single-process periodic images)
 
   int getParticleKind(int itype) const { return kind_of_type[itype]; }
+  bool isParticleFixed(int itype) const { return fixed_of_type[itype] != 0; }
 
   // restated from pair_isph.cpp:493-520 (PairISPH::modifySingularMatrix)
   void modifySingularMatrix(const int row, double &diag, double &b) {
@@ -171,6 +176,7 @@ orc_problem *orc_create(int dim, int nlocal, int nghost, const double *x, const 
   q->domain.dimension = dim; q->comm.me = 0; q->comm.owner = &p;
   p.atom = &q->atom; p.list = &q->list; p.domain = &q->domain; p.error = &q->error; p.comm = &q->comm;
   p.kind_of_type.assign(kind_of_type, kind_of_type + ntypes + 1);
+  p.fixed_of_type.assign(ntypes + 1, 0);
 
   // restated from pair_isph_corrected.cpp:1289-1337 (PairISPH_Corrected::coeff): kernel choice, one cutoff for all
   // type pairs, h = h_one for equal kinds else h_min, MorrisSafeCoeff.
@@ -365,6 +371,30 @@ int orc_ns_correct(orc_problem *q, double dt, int anti, int incp, const double *
     if (anti) { FunctorOuterCorrectVelocity<P, FunctorOuterGradientAntiSymmetric> f(&p, dt, p.atom->density, p.dp, p.vstar); PairFor(f, f.getNumberOfWork()); }
     else { FunctorOuterCorrectVelocity<P, FunctorOuterGradientSymmetric> f(&p, dt, p.atom->density, p.dp, p.vstar); PairFor(f, f.getNumberOfWork()); }
     { FunctorOuterCorrectPressure<P> f(&p, p.atom->pressure, p.dp, p.atom->nghost); PairFor(f, f.getNumberOfWork()); }   // pair_isph_corrected.cpp:1039-1052
+  })
+}
+int orc_set_fixed(orc_problem *q, const int *fixed_of_type) { q->pair.fixed_of_type.assign(fixed_of_type, fixed_of_type + q->ntypes + 1); return 0; }
+int orc_get_x(orc_problem *q, double *x) { memcpy(x, q->x.d.data(), sizeof(double) * 3 * q->nall); return 0; }
+int orc_advance_time(orc_problem *q, double dt, int anti) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    // bindings pair_isph_corrected.cpp:185-187,226-228 ; call :1183-1194 (PairISPH_Corrected::advanceTime, ns enabled, no ALE)
+    if (anti) { FunctorOuterAdvanceTimeBegin<P, FunctorOuterGradientAntiSymmetric> f(&p, dt, p.atom->v, p.atom->pressure); PairFor(f, f.getNumberOfWork()); }
+    else { FunctorOuterAdvanceTimeBegin<P, FunctorOuterGradientSymmetric> f(&p, dt, p.atom->v, p.atom->pressure); PairFor(f, f.getNumberOfWork()); }
+    { FunctorOuterAdvanceTimeEnd<P> f(&p, dt, p.atom->v, p.atom->pressure, p.atom->nghost); PairFor(f, f.getNumberOfWork()); }
+  })
+}
+int orc_boundary_navier_slip(orc_problem *q, double beta) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    // call pair_isph_corrected.cpp:921-926 (after the Helmholtz functor; SumInto A.crs)
+    if (beta != 0.0) { FunctorOuterBoundaryNavierSlip<P> f(&p, beta, p.normal, p.atom->density); PairFor(f, f.getNumberOfWork()); }
+  })
+}
+int orc_boundary_dirichlet(orc_problem *q, double *b, int lda) {
+  ORC_TRY({
+    MockPair &p = q->pair; using namespace Corrected;
+    FunctorOuterBoundaryDirichlet<P> f(&p, p.normal, b, lda); PairFor(f, f.getNumberOfWork());       // call pair_isph_corrected.cpp:928-932
   })
 }
 int orc_invalidate_matrix(orc_problem *q) { q->pair.A.is_filled = 0; return 0; }

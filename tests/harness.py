@@ -34,8 +34,19 @@ def run_oracle(P, F, kind="port", anti=True, singular=O.NULLSPACE, mh=False):
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = o.spmv(x)
     dp = np.sin(2 * P["xw"][:nl, 0]) * np.cos(P["xw"][:nl, 1]) + 0.3          # stand-in Poisson solution for the post-solve block
     o.ns_correct(cs["dt"], dp, anti=anti); out["corr_vstar"] = o.get_field(O.F_VSTAR); out["corr_p"] = o.get_field(O.F_PRESSURE); out["corr_dp"] = o.get_field(O.F_DP)
+    if cs["has_solid"]:          # boundary-condition row modifiers applied after the Helmholtz functor (pair_isph_corrected.cpp:918-934)
+        o.invalidate_matrix(); o.ns_helmholtz(cs["dt"], cs["theta"], b0, anti=anti, morris_holmes=mh); o.boundary_navier_slip(0.7); out["A_slip"] = o.matrix()
+        o.invalidate_matrix(); bh = o.ns_helmholtz(cs["dt"], cs["theta"], b0, anti=anti, morris_holmes=mh); out["b_dirichlet"] = o.boundary_dirichlet(bh); out["A_dirichlet"] = o.matrix()
+    # advanceTime (v^{n+1} = the corrected vstar left by ns_correct; type 2 is "fixed" where it exists)
+    o.set_fixed(FIXED(cs)); o.set_field(O.F_PRESSURE, F["pressure"]); o.set_field(O.F_VELOCITY, F["velocity"])
+    o.advance_time(cs["dt"], anti=anti)
+    out["adv_dp"] = o.get_field(O.F_DP); out["adv_p"] = o.get_field(O.F_PRESSURE); out["adv_v"] = o.get_field(O.F_VELOCITY); out["adv_x"] = o.get_x()
     o.close()
     return out
+
+
+def FIXED(cs):
+    return [0, 0, 1][:len(cs["kinds"])] if len(cs["kinds"]) >= 3 else [0] * len(cs["kinds"])
 
 
 def cuda_context(P, F, device=0):
@@ -75,6 +86,14 @@ def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
     x = np.random.default_rng(3).standard_normal((nl, 2)); out["spmv_x"] = x; out["spmv_y"] = c.matrix_multiply(x)
     dp = np.sin(2 * P["xw"][:nl, 0]) * np.cos(P["xw"][:nl, 1]) + 0.3
     c.ns_correct(cs["dt"], anti=anti, dp=dp); out["corr_vstar"] = c.field_get(isph.F_VSTAR); out["corr_p"] = c.field_get(isph.F_PRESSURE); out["corr_dp"] = c.field_get(isph.F_DP)
+    if cs["has_solid"]:
+        b0 = np.asfortranarray(F["velocity"][:nl, :dim])
+        c.matrix_invalidate(); c.create_load(None, dim); c.load_set(b0); c.ns_helmholtz(cs["dt"], cs["theta"], anti=anti, morris_holmes=mh); c.boundary_navier_slip(0.7); out["A_slip"] = c.matrix_get()
+        c.matrix_invalidate(); c.create_load(None, dim); c.load_set(b0); c.ns_helmholtz(cs["dt"], cs["theta"], anti=anti, morris_holmes=mh); c.boundary_dirichlet()
+        out["b_dirichlet"] = c.load_get(dim); out["A_dirichlet"] = c.matrix_get()
+    c.pair_fixed(FIXED(cs)); c.field_set(isph.F_PRESSURE, F["pressure"]); c.field_set(isph.F_VELOCITY, F["velocity"])
+    c.advance_time(cs["dt"], anti=anti)
+    out["adv_dp"] = c.field_get(isph.F_DP); out["adv_p"] = c.field_get(isph.F_PRESSURE); out["adv_v"] = c.field_get(isph.F_VELOCITY); out["adv_x"] = c.atoms_get_x()
     out["launches"] = c.launches
     c.close()
     return out
