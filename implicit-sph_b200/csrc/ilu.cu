@@ -28,6 +28,9 @@ struct IluData {
   int n = 0; long long nnz = 0; int nlev_l = 0, nlev_u = 0, maxw_l = 0, maxw_u = 0;
   DevBuf<int> rp, ci, dpos, order_l, order_u, lptr_l, lptr_u, cnt, lev, hist, rp0, ci0; DevBuf<double> fv, fv0, dinv, y; DevBuf<char> tmp;
   int grid_f = 1, grid_s = 1, maxlen = 0, tb_f = ILU_TB; bool sync_free = true; size_t smem_f = 0; DevBuf<int> fault;
+  // level-ordered split copy of the factors for the apply: position idx of the forward (backward) sweep owns the contiguous
+  // entries Lrp[idx]..Lrp[idx+1] (Urp..) of row order_l[idx] (order_u[idx]) — no row-pointer / diagonal-position indirection
+  DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1;
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
@@ -187,6 +190,72 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_factor_sf(const int *rp, const i
   }
 }
 
+
+// Same factorisation, with the pivot metadata hoisted out of the sequential pivot loop.  In k_ilu_factor_sf every pivot of a row
+// costs three dependent global round trips (dinv[j] -> dpos[j], rp[j+1] -> ci[u], fv[u]) and a row has ~60 pivots.  The pivot
+// list of a row is its own L pattern, so the lanes fetch the extents of ALL pivot rows (and a first look at their dinv) in
+// parallel when the row is staged, and the U part of the NEXT pivot row is requested while the current pivot is being applied
+// (values are re-read after the wait if that row was not finished yet).  Arithmetic and its order are unchanged.
+// shared memory per warp: values, columns, pivot extents (begin, end) and the first look at dinv: 28 B per row entry.
+__global__ void __launch_bounds__(ILU_TB) k_ilu_factor_pf(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
+                                                          const int *order, int n, int maxlen, int *fault) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  double *s_val = reinterpret_cast<double *>(smem_raw) + (size_t)wib * maxlen;
+  double *s_dj = reinterpret_cast<double *>(smem_raw) + (size_t)nwb * maxlen + (size_t)wib * maxlen;
+  int *ibase = reinterpret_cast<int *>(smem_raw + (size_t)nwb * maxlen * 2 * sizeof(double));
+  int *s_col = ibase + (size_t)wib * maxlen, *s_ub = ibase + (size_t)nwb * maxlen + (size_t)wib * maxlen, *s_ue = ibase + (size_t)2 * nwb * maxlen + (size_t)wib * maxlen;
+  for (int idx = gw; idx < n; idx += nw) {
+    const int i = order[idx], b = rp[i], len = rp[i + 1] - b, dp = dpos[i] - b;
+    for (int t = lane; t < len; t += 32) {
+      const int cc = ci[b + t]; s_col[t] = cc; s_val[t] = fv[b + t];
+      if (t < dp) { s_ub[t] = __ldg(dpos + cc) + 1; s_ue[t] = __ldg(rp + cc + 1); s_dj[t] = __ldcg(dinv + cc); }      // pivot metadata, all pivots at once
+    }
+    __syncwarp();
+    __threadfence();                                        // the values requested below are ordered after the dinv looks above
+    // U part of the first pivot row (two entries per lane cover 64; longer rows loop below)
+    int pc0 = -1, pc1 = -1; double pf0 = 0.0, pf1 = 0.0;
+    if (dp > 0) { const int ub = s_ub[0], ue = s_ue[0];
+      if (ub + lane < ue) { pc0 = __ldcg(ci + ub + lane); pf0 = __ldcg(fv + ub + lane); }
+      if (ub + lane + 32 < ue) { pc1 = __ldcg(ci + ub + lane + 32); pf1 = __ldcg(fv + ub + lane + 32); } }
+    for (int q = 0; q < dp; ++q) {                          // strictly-lower entries, ascending column
+      const int j = s_col[q], ub = s_ub[q], ue = s_ue[q];
+      double dj = s_dj[q]; bool late = false;
+      if (dj != dj) {                                       // row j was not finished when this row was staged: wait, then re-read its values
+        if (lane == 0) dj = wait_value(dinv + j, fault);
+        dj = __shfl_sync(0xffffffffu, dj, 0); late = true;
+      }
+      __threadfence();
+      int c0 = pc0, c1 = pc1; double f0 = pf0, f1 = pf1;
+      if (late) { if (ub + lane < ue) f0 = __ldcg(fv + ub + lane); if (ub + lane + 32 < ue) f1 = __ldcg(fv + ub + lane + 32); }
+      // request the next pivot row before applying this one
+      pc0 = pc1 = -1;
+      if (q + 1 < dp) { const int nb = s_ub[q + 1], ne = s_ue[q + 1];
+        if (nb + lane < ne) { pc0 = __ldcg(ci + nb + lane); pf0 = __ldcg(fv + nb + lane); }
+        if (nb + lane + 32 < ne) { pc1 = __ldcg(ci + nb + lane + 32); pf1 = __ldcg(fv + nb + lane + 32); } }
+      const double multiplier = s_val[q];
+      if (ub + lane < ue) { int lo = q + 1, hi = len; while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < c0) lo = mid + 1; else hi = mid; }
+        if (lo < len && s_col[lo] == c0) s_val[lo] -= multiplier * f0; }
+      if (ub + lane + 32 < ue) { int lo = q + 1, hi = len; while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < c1) lo = mid + 1; else hi = mid; }
+        if (lo < len && s_col[lo] == c1) s_val[lo] -= multiplier * f1; }
+      for (int u = ub + lane + 64; u < ue; u += 32) {
+        const int k = __ldcg(ci + u); int lo = q + 1, hi = len;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < k) lo = mid + 1; else hi = mid; }
+        if (lo < len && s_col[lo] == k) s_val[lo] -= multiplier * __ldcg(fv + u);
+      }
+      __syncwarp();
+      if (lane == 0) s_val[q] = multiplier * dj;
+      __syncwarp();
+    }
+    const double d = 1.0 / s_val[dp];
+    __syncwarp();
+    for (int t = lane; t < len; t += 32) fv[b + t] = t > dp ? s_val[t] * d : s_val[t];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile double *>(dinv + i) = publishable(d, fault);
+  }
+}
+
 __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sf(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
                                                          const int *order_l, const int *order_u, int n, const double *r, double *y, double *z, int *fault) {
   const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -204,6 +273,71 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sf(const int *rp, const in
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { const double yi = wait_value(y + i, fault); *reinterpret_cast<volatile double *>(z + i) = publishable(yi * dinv[i] - s, fault); }
   }
+}
+
+// ---- level-ordered apply (default) ---------------------------------------------------------------------------------
+// The sync-free solve above spends ~4 dependent global loads per row (order -> rp/dpos -> ci/fv -> y[ci]) with one row in
+// flight per warp: ~6 us per row and warp, 15 % of the HBM roofline on the 8M-row problem (BENCH r2: ilu_roofline).  Here the
+// factors are copied once per factorisation into two arrays in SWEEP order (L parts in forward-level order, U parts + D^-1 in
+// backward-level order), so position idx of a sweep finds its entries without the row-pointer / diagonal indirection, and the
+// sweep is software-pipelined: while a warp waits for the dependencies of row idx it already holds the entries of row idx + nw
+// and the extents of row idx + 2 nw in registers.  Same data-is-the-flag protocol (NaN = not solved yet), same arithmetic order
+// within a row (lanes over entries, shuffle tree), so the result is bit-identical to k_ilu_solve_sf.
+__global__ void k_ilu_perm_len(const int *rp, const int *dpos, const int *order, int n, int upper, int *len) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= n) return;
+  const int i = order[idx]; len[idx] = upper ? rp[i + 1] - dpos[i] - 1 : dpos[i] - rp[i];
+  if (idx == 0) len[n] = 0;
+}
+__global__ void __launch_bounds__(256) k_ilu_perm_fill(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv, const int *order, int n, int upper,
+                                                       const int *prp, int *pci, double *pfv, double *pdinv) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31; if (idx >= n) return;
+  const int i = order[idx], src = upper ? dpos[i] + 1 : rp[i], dst = prp[idx], len = prp[idx + 1] - dst;
+  for (int t = lane; t < len; t += 32) { pci[dst + t] = ci[src + t]; pfv[dst + t] = fv[src + t]; }
+  if (upper && lane == 0) pdinv[idx] = dinv[i];
+}
+// one sweep: out[row] = (UPPER ? in[row] * dinv : in[row]) - sum_k pfv[k] * out[pci[k]] ; rows in level order
+template <bool UPPER> __device__ __forceinline__ void ilu_sweep_lv(const int *__restrict__ prp, const int *__restrict__ pci, const double *__restrict__ pfv, const int *__restrict__ order,
+                                                                  const double *__restrict__ pdinv, int n, const double *in, double *out, int *fault, int gw, int nw, int lane) {
+  int idx = gw;
+  // pipeline registers: row A = current (entries loaded), row B = next (extents loaded)
+  int iA = 0, bA = 0, eA = 0, iB = 0, bB = 0, eB = 0; int cA0 = 0, cA1 = 0; double fA0 = 0.0, fA1 = 0.0, rhsA = 0.0, dA = 1.0;
+  if (idx < n) { iA = __ldg(order + idx); bA = __ldg(prp + idx); eA = __ldg(prp + idx + 1); }
+  if (idx + nw < n) { iB = __ldg(order + idx + nw); bB = __ldg(prp + idx + nw); eB = __ldg(prp + idx + nw + 1); }
+  if (idx < n) {
+    if (bA + lane < eA) { cA0 = __ldcs(pci + bA + lane); fA0 = __ldcs(pfv + bA + lane); }
+    if (bA + lane + 32 < eA) { cA1 = __ldcs(pci + bA + lane + 32); fA1 = __ldcs(pfv + bA + lane + 32); }
+    if (lane == 0) { rhsA = UPPER ? wait_value(in + iA, fault) : in[iA]; if (UPPER) dA = __ldg(pdinv + idx); }
+  }
+  while (idx < n) {
+    // (1) extents of row idx + 2 nw, (2) entries of row idx + nw: both in flight while row idx waits for its dependencies
+    int iC = 0, bC = 0, eC = 0; const int idxC = idx + 2 * nw;
+    if (idxC < n) { iC = __ldg(order + idxC); bC = __ldg(prp + idxC); eC = __ldg(prp + idxC + 1); }
+    int cB0 = 0, cB1 = 0; double fB0 = 0.0, fB1 = 0.0, rhsB = 0.0, dB = 1.0;
+    if (idx + nw < n) {
+      if (bB + lane < eB) { cB0 = __ldcs(pci + bB + lane); fB0 = __ldcs(pfv + bB + lane); }
+      if (bB + lane + 32 < eB) { cB1 = __ldcs(pci + bB + lane + 32); fB1 = __ldcs(pfv + bB + lane + 32); }
+      if (lane == 0 && !UPPER) rhsB = in[iB];
+      if (lane == 0 && UPPER) dB = __ldg(pdinv + idx + nw);
+    }
+    // row idx: same per-lane accumulation order as k_ilu_solve_sf (q = b + lane, b + lane + 32, ...)
+    double s = 0.0;
+    if (bA + lane < eA) s += fA0 * wait_value(out + cA0, fault);
+    if (bA + lane + 32 < eA) s += fA1 * wait_value(out + cA1, fault);
+    for (int q = bA + lane + 64; q < eA; q += 32) s += pfv[q] * wait_value(out + pci[q], fault);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) *reinterpret_cast<volatile double *>(out + iA) = publishable(UPPER ? rhsA * dA - s : rhsA - s, fault);
+    // rotate
+    if (UPPER && lane == 0 && idx + nw < n) rhsB = wait_value(in + iB, fault);           // y of the next row (forward sweep of this launch: published by some warp)
+    iA = iB; bA = bB; eA = eB; cA0 = cB0; cA1 = cB1; fA0 = fB0; fA1 = fB1; rhsA = rhsB; dA = dB;
+    iB = iC; bB = bC; eB = eC;
+    idx += nw;
+  }
+}
+__global__ void __launch_bounds__(ILU_TB) k_ilu_solve_lv(const int *Lrp, const int *Lci, const double *Lfv, const int *order_l, const int *Urp, const int *Uci, const double *Ufv,
+                                                         const int *order_u, const double *Udinv, int n, const double *r, double *y, double *z, int *fault) {
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  ilu_sweep_lv<false>(Lrp, Lci, Lfv, order_l, nullptr, n, r, y, fault, gw, nw, lane);
+  ilu_sweep_lv<true>(Urp, Uci, Ufv, order_u, Udinv, n, y, z, fault, gw, nw, lane);
 }
 
 // ---- dependency levels on the device -----------------------------------------------------------------------------
@@ -315,9 +449,16 @@ void ilu_create(Ctx *c) {
   size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, I.cnt.p, I.rp.p, n + 1, c->stream);
   I.tmp.ensure(tb);
   cub::DeviceScan::ExclusiveSum(I.tmp.p, tb, I.cnt.p, I.rp.p, n + 1, c->stream); ++c->launches;
-  std::vector<int> rp(n + 1);
-  CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  I.nnz = rp[n]; I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
+  // level 0 (the all-device path): only two integers come back — the number of stored entries and the longest row
+  std::vector<int> rp;
+  { int *d_max = c->flag.p + 6; size_t tbm = 0; cub::DeviceReduce::Max(nullptr, tbm, I.cnt.p, d_max, n, c->stream); I.tmp.ensure(tbm);
+    tbm = I.tmp.cap; cub::DeviceReduce::Max(I.tmp.p, tbm, I.cnt.p, d_max, n, c->stream); ++c->launches;
+    int h2[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(&h2[0], I.rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaMemcpyAsync(&h2[1], d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    I.nnz = h2[0]; I.maxlen = std::max(1, h2[1]); }
+  if (c->pp.fill > 0) { rp.resize(n + 1); CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+  I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
   I.sync_free = !getenv("ISPH_ILU_BARRIER"); I.fault.ensure(4); CUDA_CHECK(cudaMemsetAsync(I.fault.p, 0, 4 * sizeof(int), c->stream));
   k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
   if (c->pp.fill > 0) {                                          // level-of-fill pattern (host), values expanded on the device
@@ -331,8 +472,8 @@ void ilu_create(Ctx *c) {
     k_ilu_expand<<<ceil_div(n, 128), 128, 0, c->stream>>>(I.rp0.p, I.ci0.p, I.fv0.p, I.rp.p, I.ci.p, n, I.fv.p, I.dpos.p); ++c->launches;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));               // frp / fci are host temporaries
     rp = frp;
+    I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
   }
-  I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
   // dependency levels + level sets, on the device (no download of the pattern)
   I.order_l.ensure(n); I.order_u.ensure(n); I.lev.ensure(n); I.hist.ensure(n + 2); I.lptr_l.ensure(n + 2); I.lptr_u.ensure(n + 2);
   bool device_ok = !getenv("ISPH_ILU_HOST_LEVELS");
@@ -359,6 +500,7 @@ void ilu_create(Ctx *c) {
   }
   if (!device_ok) {   // host pass over the pattern (fallback)
     std::vector<int> ci(I.nnz), dpos(n);
+    if (rp.empty()) { rp.resize(n + 1); CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); }
     CUDA_CHECK(cudaMemcpyAsync(ci.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(dpos.data(), I.dpos.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) ISPH_REQUIRE(dpos[i] >= 0, "ILU: a row has no diagonal entry");
@@ -374,18 +516,36 @@ void ilu_create(Ctx *c) {
   if (I.sync_free) {
     int sms = 0, per_sm = 0; CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     { const char *e = getenv("ISPH_ILU_BACKOFF"); const int bo = (e && *e) ? atoi(e) : 0; CUDA_CHECK(cudaMemcpyToSymbolAsync(g_ilu_backoff, &bo, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream)); }
-    // factorisation: per-warp staging of the row in shared memory (12 B per entry); shrink the CTA until it fits
-    I.tb_f = ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * 12 > 200 * 1024) I.tb_f >>= 1;
-    I.smem_f = (size_t)(I.tb_f / 32) * I.maxlen * 12; ISPH_REQUIRE(I.smem_f <= 200 * 1024, "ILU: a row is too long for the factorisation kernel");
-    CUDA_CHECK(cudaFuncSetAttribute(k_ilu_factor_sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_f));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_factor_sf, I.tb_f, I.smem_f)); ISPH_REQUIRE(per_sm >= 1, "ILU: factorisation kernel does not fit an SM");
+    // factorisation: per-warp staging of the row in shared memory (28 B per entry with the hoisted pivot metadata, 12 B for the
+    // plain kernel); shrink the CTA until it fits
+    const bool pf = getenv("ISPH_ILU_FACTOR_OLD") == nullptr; const size_t per_entry = pf ? 28 : 12; const void *fk = pf ? (const void *)k_ilu_factor_pf : (const void *)k_ilu_factor_sf;
+    I.tb_f = pf ? 512 : ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * per_entry > 100 * 1024) I.tb_f >>= 1;
+    I.smem_f = (size_t)(I.tb_f / 32) * I.maxlen * per_entry; ISPH_REQUIRE(I.smem_f <= 200 * 1024, "ILU: a row is too long for the factorisation kernel");
+    CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_f));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, I.tb_f, I.smem_f)); ISPH_REQUIRE(per_sm >= 1, "ILU: factorisation kernel does not fit an SM");
     I.grid_f = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, I.tb_f)));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_solve_sf, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: solve kernel does not fit an SM");
     I.grid_s = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, ILU_TB)));
     CUDA_CHECK(cudaMemsetAsync(I.dinv.p, 0xff, sizeof(double) * n, c->stream));           // NaN = "row not factored yet"
     const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nn = n, ml = I.maxlen; int *flt = I.fault.p;
     void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ord, &nn, &ml, &flt};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_factor_sf, dim3(I.grid_f), dim3(I.tb_f), args, I.smem_f, c->stream)); ++c->launches;
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fk, dim3(I.grid_f), dim3(I.tb_f), args, I.smem_f, c->stream)); ++c->launches;
+    // level-ordered split copy for the apply (stream order: after the factorisation)
+    I.lv = getenv("ISPH_ILU_APPLY_OLD") == nullptr;
+    if (I.lv) {
+      I.plen.ensure(n + 1); I.Lrp.ensure(n + 1); I.Urp.ensure(n + 1); I.Lci.ensure(I.nnz); I.Uci.ensure(I.nnz); I.Lfv.ensure(I.nnz); I.Ufv.ensure(I.nnz); I.Udinv.ensure(n);
+      for (int upper = 0; upper < 2; ++upper) {
+        const int *ord = upper ? I.order_u.p : I.order_l.p; int *prp = upper ? I.Urp.p : I.Lrp.p;
+        k_ilu_perm_len<<<ceil_div(n, 256), 256, 0, c->stream>>>(I.rp.p, I.dpos.p, ord, n, upper, I.plen.p);
+        size_t tb3 = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb3, I.plen.p, prp, n + 1, c->stream); I.tmp.ensure(tb3);
+        tb3 = I.tmp.cap; cub::DeviceScan::ExclusiveSum(I.tmp.p, tb3, I.plen.p, prp, n + 1, c->stream);
+        k_ilu_perm_fill<<<ceil_div((long long)n * 32, 256), 256, 0, c->stream>>>(I.rp.p, I.ci.p, I.dpos.p, I.fv.p, I.dinv.p, ord, n, upper, prp, upper ? I.Uci.p : I.Lci.p,
+                                                                                upper ? I.Ufv.p : I.Lfv.p, I.Udinv.p);
+        c->launches += 3;
+      }
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_solve_lv, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: level-ordered solve kernel does not fit an SM");
+      I.grid_lv = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, ILU_TB)));
+    }
     return;
   }
   I.grid_f = coop_grid(c, (const void *)k_ilu_factor, I.maxw_l);
@@ -417,6 +577,13 @@ void ilu_apply(Ctx *c, const double *r, double *z) {
 }
 static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
   IluData &I = *c->ilu;
+  if (I.sync_free && I.lv) {
+    CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"
+    const int *a0 = I.Lrp.p, *a1 = I.Lci.p, *a3 = I.order_l.p, *a4 = I.Urp.p, *a5 = I.Uci.p, *a7 = I.order_u.p; const double *a2 = I.Lfv.p, *a6 = I.Ufv.p, *a8 = I.Udinv.p; double *y = I.y.p; int nn = I.n; int *flt = I.fault.p;
+    void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &nn, &r, &y, &z, &flt};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve_lv, dim3(I.grid_lv), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
+    return;
+  }
   if (I.sync_free) {
     CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"
     const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ol = I.order_l.p, *ou = I.order_u.p; const double *fv = I.fv.p, *dinv = I.dinv.p; double *y = I.y.p; int nn = I.n; int *flt = I.fault.p;
@@ -433,6 +600,7 @@ static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
+  I.Lrp.release(); I.Lci.release(); I.Urp.release(); I.Uci.release(); I.plen.release(); I.Lfv.release(); I.Ufv.release(); I.Udinv.release();
   I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.rp0.release(); I.ci0.release(); I.fv0.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
 }
 

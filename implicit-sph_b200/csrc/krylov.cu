@@ -720,8 +720,13 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
   const DiagPrec dp = diag_prec_of(c, use_prec); const bool jacobi_fused = dp.on;
   const int sing = c->is_singular ? 1 : 0;
   static const bool fuse_ud = getenv("ISPH_NO_FUSE_UD") == nullptr;
-  static const bool ud_tma = !(getenv("ISPH_UD_TMA") && atoi(getenv("ISPH_UD_TMA")) == 0);      // TMA-pipelined sweep (default) vs the register-tile kernel
-  static const bool pingpong = getenv("ISPH_NO_PINGPONG") == nullptr;
+  // TMA-pipelined sweep vs the register-tile kernel: measured (gpurun_out/r2_v2_*: 8M rows 365 vs 381 us per sweep, 1M rows 65 vs 62 us,
+  // where the fixed costs of a launch dominate both) => TMA from 3M rows per GPU up; ISPH_UD_TMA=0 / 1 forces one of them
+  static const int ud_tma_env = getenv("ISPH_UD_TMA") ? atoi(getenv("ISPH_UD_TMA")) : -1;
+  const bool ud_tma = ud_tma_env >= 0 ? ud_tma_env != 0 : n >= 3000000;
+  // alternating sweep direction (each sweep starts on the rows the previous one touched last): measured neutral on B200 — the L2 does not
+  // keep the tail of a 200+ MB stream in a usable way (gpurun_out/r2_v2_oldpp_* vs r2_v2_old_*) — so it is off unless ISPH_PINGPONG=1
+  static const bool pingpong = getenv("ISPH_PINGPONG") != nullptr;
   int sweep_dir = 0; auto sweep = [&]() { if (!pingpong) return 0; sweep_dir ^= 1; return sweep_dir; };
   static const int ud_hv = getenv("ISPH_UD_HV") ? atoi(getenv("ISPH_UD_HV")) : 2;            // 64-row halves per tile of the fused sweep
   static const int udcap = getenv("ISPH_UDGRID") ? atoi(getenv("ISPH_UDGRID")) : (ud_hv == 1 ? 444 : 296);       // 148 SMs x resident CTAs
@@ -749,8 +754,7 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
       double *zj = flex ? Z + (size_t)j * ld : Z, *vn = V + (size_t)(j + 1) * ld;
       dbg(c, "prologue");
       { ProfScope ps(c, "op_apply"); spmv(c, zj, vn, 1, ld, ld); } dbg(c, "op_apply");          // y = A z_j ; the PoissonProjection tail rides on the Gram-Schmidt sweep
-      // the sweeps over the basis alternate direction (ISPH_NO_PINGPONG=1: all forward): each starts where the previous one ended, on the
-      // part of the basis that is still in L2
+      // ISPH_PINGPONG=1: the sweeps over the basis alternate direction
       { ProfScope ps(c, "multidot0"); launch_multidot(c, V, j + 1, vn, 0, sweep()); } dbg(c, "multidot0");
       if (fuse_ud && j + 1 > 8) {                                // one sweep: first update + second-pass coefficients
         ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c); const int rv = sweep();
