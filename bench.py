@@ -141,6 +141,22 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
+def nvlink_counters(gpu):
+    """Cumulative NVLink data counters of one GPU in bytes (nvidia-smi nvlink -gt d: per-link 'Data Tx/Rx: N KiB'), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = rx = 0; seen = False
+    for line in out.splitlines():
+        t = line.replace(":", " ").split()
+        if "Tx" in t and "KiB" in t:
+            tx += int(t[t.index("KiB") - 1]) * 1024; seen = True
+        elif "Rx" in t and "KiB" in t:
+            rx += int(t[t.index("KiB") - 1]) * 1024; seen = True
+    return dict(tx=tx, rx=rx) if seen else None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -358,6 +374,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         sampler.start()
     c.timer_reset(); c.profile_spmv(True); c.profile_spmv_get()
     launches0 = c.launches
+    nvl0 = nvlink_counters(local_rank) if (world > 1 and rank == 0) else None
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -367,11 +384,14 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1) / steps
+    nvl1 = nvlink_counters(local_rank) if nvl0 is not None else None
     spmv_ms, spmv_cnt = c.profile_spmv_get(); prec_ms, prec_cnt = c.profile_precond_get(); c.profile_spmv(False)
     ilu = c.precond_info() if w["prec"] == "ILU" else None
     launches = (c.launches - launches0) // steps
     timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "precondCreate", "solve" + solve_label) +
               (("computeFPoissonBoltzmann", "computeJacobianPoissonBoltzmann") if pbs else ("compute" + solve_label,))}
+    if w["prec"] == "ILU":
+        timers.update({k: c.timer_ms(k) / steps for k in ("iluPattern", "iluLevels", "iluFactor", "iluPermute")})
     c.timer_reset()
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the C ABI with host buffers (H2D of the step's inputs, D2H of the solution)
@@ -392,6 +412,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     else:
         solve_ms = timers["solve" + solve_label]
     nnz = c.nnz
+    fp64_peak = c.measure_fp64_peak() if rank == 0 else None
     halo = None
     if world > 1:
         try:
@@ -431,6 +452,16 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                               share_of_step=spmv_ms / steps / ms_dev,
                               note="per-launch time from CUDA events on the launching stream; at n_gpus > 1 it includes the NVLink import of the halo"),
                 breakdown_ms=timers, ms_per_iter=solve_ms / max(st["iters"], 1))
+    if fp64_peak:                                            # assembly against both rooflines (~160 flop per in-cut pair, ~1530 B per row in 3-D)
+        key = "compute" + solve_label; t_asm = timers.get(key, 0.0)
+        if t_asm > 0 and not pbs:
+            fl = 160.0 * nnz if dim == 3 else 90.0 * nnz; by = 4.0 * float(P["noff"][-1]) + (44.0 + (0.0 if anti else 120.0)) * nl + 12.0 * nnz
+            line["assembly_roofline"] = dict(kernel="k_laplacian_rows + system rows (" + key + ")", ms=t_asm, flops_per_launch=fl, bytes_per_launch=by,
+                                             achieved_tflops=fl / (t_asm * 1e-3) / 1e12, fp64_peak_tflops=fp64_peak, frac_fp64=fl / (t_asm * 1e-3) / 1e12 / fp64_peak,
+                                             achieved_gbs=by / (t_asm * 1e-3) / 1e9, frac_hbm=by / (t_asm * 1e-3) / 1e9 / peak,
+                                             note="flop and byte counts are SURVEY.md §8(d)'s per-pair / per-row figures x this launch's pairs / rows (divisions and square roots "
+                                                  "counted as one flop each: the FP64-pipe time they take is several times that); fp64 peak = FMA loop measured in this run (isph_measure_fp64_peak)")
+        line["fp64_peak_tflops"] = fp64_peak
     if ilu is not None and prec_cnt:                         # triangular solves of the block-Jacobi ILU apply (12 nnz_factor + 32 n, and the level count)
         pav = prec_ms / prec_cnt; pb = 12.0 * ilu["factor_nnz"] + 32.0 * nl
         line["ilu_roofline"] = dict(bound="hbm", kernel="k_ilu_solve", achieved=pb / (pav * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=pb / (pav * 1e-3) / 1e9 / peak,
@@ -445,6 +476,12 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                               bytes_sent_per_spmv=8 * halo["nsend"], bytes_sent_per_second=8.0 * halo["nsend"] * spmv_per_s,
                               peak_gbs_per_direction=900.0, frac_of_nvlink_peak=8.0 * halo["nsend"] * spmv_per_s / 900e9,
                               note="0.1 % of the local SpMV traffic: the exchange is latency-, not bandwidth-bound (DESIGN.md §6)")
+        if nvl0 is not None and nvl1 is not None:            # MEASURED: this GPU's NVLink data counters around the timed region (nvidia-smi nvlink -gt d)
+            dtx = nvl1["tx"] - nvl0["tx"]; drx = nvl1["rx"] - nvl0["rx"]
+            line["nvlink"]["measured"] = dict(tx_bytes_per_step=dtx / steps, rx_bytes_per_step=drx / steps, tx_bytes_per_spmv=dtx / max(spmv_cnt, 1), rx_bytes_per_spmv=drx / max(spmv_cnt, 1),
+                                              tx_gbs=dtx / max(steps * ms_dev * 1e-3, 1e-12) / 1e9, frac_of_nvlink_peak=dtx / max(steps * ms_dev * 1e-3, 1e-12) / 900e9,
+                                              how="difference of the per-link Data Tx/Rx counters of rank 0's GPU (nvidia-smi nvlink -gt d) around the timed region: halo values, "
+                                                  "peer all-reduce messages, sentinel re-arming is local; includes the per-step field forwards over NCCL")
     if w["prec"] == "point relaxation" and w["solver"] == "Block GMRES" and not pbs:
         kb = krylov_bytes_per_solve(nl, nnz, st["iters"], st.get("second_passes", st["iters"]))
         sg = kb / (solve_ms * 1e-3) / 1e9

@@ -337,6 +337,9 @@ class Context:
     def launches(self):
         return int(self.L.isph_kernel_launches(self.h))
 
+    def measure_fp64_peak(self):
+        t = C.c_double(); self.call("isph_measure_fp64_peak", C.byref(t)); return t.value
+
     def bench_spmv(self, reps=20):
         ms = C.c_double(); self.call("isph_bench_spmv", reps, C.byref(ms)); return ms.value
 

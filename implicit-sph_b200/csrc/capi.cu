@@ -107,7 +107,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
   Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
   c->xs.release(); c->bs.release(); c->nullvec.release(); c->mask.release(); c->V.release(); c->Z.release(); c->wk.release(); c->red.release(); c->hbuf.release(); c->flag.release(); c->h_scal.release();
-  c->spmv_ticket.release(); c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
+  c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
   for (auto e : c->pprof_ev) if (e) cudaEventDestroy(e);

@@ -30,7 +30,7 @@ struct IluData {
   int grid_f = 1, grid_s = 1, maxlen = 0, tb_f = ILU_TB; bool sync_free = true; size_t smem_f = 0; DevBuf<int> fault;
   // level-ordered split copy of the factors for the apply: position idx of the forward (backward) sweep owns the contiguous
   // entries Lrp[idx]..Lrp[idx+1] (Urp..) of row order_l[idx] (order_u[idx]) — no row-pointer / diagonal-position indirection
-  DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1;
+  DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1, lpr = 32;
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
@@ -340,6 +340,35 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_lv(const int *Lrp, const i
   ilu_sweep_lv<true>(Urp, Uci, Ufv, order_u, Udinv, n, y, z, fault, gw, nw, lane);
 }
 
+// Sub-warp variant for wide levels.  With one warp per row the 64 warps of an SM hold 9472 rows in flight; an 8M-row problem in
+// 64 blocks has ~12500 rows per level, so every level takes two rounds of a ~3-4 us dependency round trip (measured: 8 us per level,
+// BENCH r2 configs3_c4).  Here LPR = 16 or 8 lanes share a row (the L / U halves hold ~60 entries), 2 or 4 rows per warp, so that a
+// whole level is in flight at once.  The groups of a warp are independent: shuffles use the group's own lane mask, so a group
+// that waits for a row of an earlier level never holds up the group that produces it (independent thread scheduling).
+template <int LPR, bool UPPER> __device__ __forceinline__ void ilu_sweep_sub(const int *__restrict__ prp, const int *__restrict__ pci, const double *__restrict__ pfv,
+                                                                             const int *__restrict__ order, const double *__restrict__ pdinv, int n, const double *in, double *out,
+                                                                             int *fault, int gw, int nw, int lane) {
+  constexpr int G = 32 / LPR;
+  const int sub = lane / LPR, sl = lane % LPR; const unsigned gmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u) << (sub * LPR));
+  for (long long idx = (long long)gw * G + sub; idx < n; idx += (long long)nw * G) {
+    const int i = __ldg(order + idx), b = __ldg(prp + idx), e = __ldg(prp + idx + 1);
+    double s = 0.0;
+    for (int q = b + sl; q < e; q += LPR) s += __ldcs(pfv + q) * wait_value(out + __ldcs(pci + q), fault);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
+    if (sl == 0) {
+      const double rhs = UPPER ? wait_value(in + i, fault) * __ldg(pdinv + idx) : in[i];
+      *reinterpret_cast<volatile double *>(out + i) = publishable(rhs - s, fault);
+    }
+  }
+}
+template <int LPR> __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sub(const int *Lrp, const int *Lci, const double *Lfv, const int *order_l, const int *Urp, const int *Uci,
+                                                                            const double *Ufv, const int *order_u, const double *Udinv, int n, const double *r, double *y, double *z, int *fault) {
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  ilu_sweep_sub<LPR, false>(Lrp, Lci, Lfv, order_l, nullptr, n, r, y, fault, gw, nw, lane);
+  ilu_sweep_sub<LPR, true>(Urp, Uci, Ufv, order_u, Udinv, n, y, z, fault, gw, nw, lane);
+}
+
 // ---- dependency levels on the device -----------------------------------------------------------------------------
 // level[i] = 1 + max(level[j] : j in L(i)) (0 without dependencies).  One warp per row in dependency order (ascending
 // rows for L, descending for U): lanes read the levels of the row's dependencies and spin until they are published.
@@ -444,6 +473,7 @@ void ilu_create(Ctx *c) {
   IluData &I = *c->ilu; I.n = n;
   const int *blk = c->have_blocks ? c->block_of_row.p : nullptr;
   I.cnt.ensure(n + 1); I.rp.ensure(n + 1); I.dpos.ensure(n); I.dinv.ensure(n); I.y.ensure(c->ld);
+  c->tic("iluPattern");
   k_ilu_count<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, blk, n, I.cnt.p); ++c->launches;
   CUDA_CHECK(cudaMemsetAsync(I.cnt.p + n, 0, sizeof(int), c->stream));
   size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, I.cnt.p, I.rp.p, n + 1, c->stream);
@@ -474,6 +504,7 @@ void ilu_create(Ctx *c) {
     rp = frp;
     I.maxlen = 1; for (int i = 0; i < n; ++i) I.maxlen = std::max(I.maxlen, rp[i + 1] - rp[i]);
   }
+  c->toc("iluPattern"); c->tic("iluLevels");
   // dependency levels + level sets, on the device (no download of the pattern)
   I.order_l.ensure(n); I.order_u.ensure(n); I.lev.ensure(n); I.hist.ensure(n + 2); I.lptr_l.ensure(n + 2); I.lptr_u.ensure(n + 2);
   bool device_ok = !getenv("ISPH_ILU_HOST_LEVELS");
@@ -513,6 +544,7 @@ void ilu_create(Ctx *c) {
     CUDA_CHECK(cudaMemcpyAsync(I.lptr_u.p, pu.data(), sizeof(int) * pu.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
+  c->toc("iluLevels");
   if (I.sync_free) {
     int sms = 0, per_sm = 0; CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     { const char *e = getenv("ISPH_ILU_BACKOFF"); const int bo = (e && *e) ? atoi(e) : 0; CUDA_CHECK(cudaMemcpyToSymbolAsync(g_ilu_backoff, &bo, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream)); }
@@ -529,7 +561,9 @@ void ilu_create(Ctx *c) {
     CUDA_CHECK(cudaMemsetAsync(I.dinv.p, 0xff, sizeof(double) * n, c->stream));           // NaN = "row not factored yet"
     const int *rpp = I.rp.p, *cip = I.ci.p, *dpp = I.dpos.p, *ord = I.order_l.p; double *fv = I.fv.p, *dinv = I.dinv.p; int nn = n, ml = I.maxlen; int *flt = I.fault.p;
     void *args[] = {&rpp, &cip, &dpp, &fv, &dinv, &ord, &nn, &ml, &flt};
+    c->tic("iluFactor");
     CUDA_CHECK(cudaLaunchCooperativeKernel(fk, dim3(I.grid_f), dim3(I.tb_f), args, I.smem_f, c->stream)); ++c->launches;
+    c->toc("iluFactor"); c->tic("iluPermute");
     // level-ordered split copy for the apply (stream order: after the factorisation)
     I.lv = getenv("ISPH_ILU_APPLY_OLD") == nullptr;
     if (I.lv) {
@@ -543,9 +577,15 @@ void ilu_create(Ctx *c) {
                                                                                 upper ? I.Ufv.p : I.Lfv.p, I.Udinv.p);
         c->launches += 3;
       }
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_solve_lv, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: level-ordered solve kernel does not fit an SM");
-      I.grid_lv = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, ILU_TB)));
+      // lanes per row: a whole level should be in flight (rows per level vs resident warps); ISPH_ILU_LPR = 32 | 16 | 8 overrides
+      const double rows_per_level = (double)n / std::max(1, std::max(I.nlev_l, I.nlev_u)); const int resident_warps = 2 * sms * (ILU_TB / 32);
+      I.lpr = rows_per_level > 2.0 * resident_warps ? 8 : (rows_per_level > 0.75 * resident_warps ? 16 : 32);
+      if (getenv("ISPH_ILU_LPR")) { const int v = atoi(getenv("ISPH_ILU_LPR")); if (v == 8 || v == 16 || v == 32) I.lpr = v; }
+      const void *sk = I.lpr == 32 ? (const void *)k_ilu_solve_lv : (I.lpr == 16 ? (const void *)k_ilu_solve_sub<16> : (const void *)k_ilu_solve_sub<8>);
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: level-ordered solve kernel does not fit an SM");
+      I.grid_lv = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * I.lpr, ILU_TB)));
     }
+    c->toc("iluPermute");
     return;
   }
   I.grid_f = coop_grid(c, (const void *)k_ilu_factor, I.maxw_l);
@@ -581,7 +621,8 @@ static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
     CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"
     const int *a0 = I.Lrp.p, *a1 = I.Lci.p, *a3 = I.order_l.p, *a4 = I.Urp.p, *a5 = I.Uci.p, *a7 = I.order_u.p; const double *a2 = I.Lfv.p, *a6 = I.Ufv.p, *a8 = I.Udinv.p; double *y = I.y.p; int nn = I.n; int *flt = I.fault.p;
     void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &nn, &r, &y, &z, &flt};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve_lv, dim3(I.grid_lv), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
+    const void *sk = I.lpr == 32 ? (const void *)k_ilu_solve_lv : (I.lpr == 16 ? (const void *)k_ilu_solve_sub<16> : (const void *)k_ilu_solve_sub<8>);
+    CUDA_CHECK(cudaLaunchCooperativeKernel(sk, dim3(I.grid_lv), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
     return;
   }
   if (I.sync_free) {

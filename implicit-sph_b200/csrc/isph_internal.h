@@ -94,7 +94,7 @@ struct Ctx {
   DevBuf<int> ilist, neigh; DevBuf<long long> noff; std::vector<long long> h_noff;
   PinBuf<int> pin_neigh;
   // matrix
-  Matrix A; DevBuf<unsigned> spmv_ticket; unsigned spmv_ticket_base = 0;     // ticket counter of the dynamically scheduled SpMV (spmv.cu)
+  Matrix A;
   // solver state (SolverLin members, solver_lin.h:70-97)
   SolverParams sp; PrecondParams pp;
   double *x_host = nullptr, *b_host = nullptr; int x_lda = 0, b_lda = 0, x_nvec = 0, b_nvec = 0; bool x_owned = true, b_owned = true;

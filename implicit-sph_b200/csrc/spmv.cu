@@ -74,51 +74,9 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
 }
 
 
-// Dynamic variant for bricks of ~1M rows.  With one warp per slice and 8 slices per CTA the hardware scheduler balances the load
-// at CTA granularity: a 100^3 brick is 3907 CTAs = 3.3 waves of the 1184 resident ones, and the SMs that run out of CTAs idle for
-// up to one CTA duration (~65 us of a 222 us launch; BENCH r1: 88 % of the HBM peak at 1M rows against 95 % at 8M).  Here one wave
-// of persistent CTAs is launched and every WARP draws its next slice from a global ticket counter, so the tail is one slice, not
-// eight.  The counter is never reset: a launch consumes exactly nslices + (number of warps) tickets (every warp draws one ticket
-// past the end), so the host knows the first ticket of the next launch (`base`).
-template <int NV, bool DOT> __global__ void __launch_bounds__(256, 8)
-k_spmv_sell_dyn(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col,
-                const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy,
-                const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr, unsigned *ticket, unsigned base) {
-  const int lane = threadIdx.x & 31;
-  double dsum = 0.0;
-  while (true) {
-    unsigned t = 0; if (lane == 0) t = atomicAdd(ticket, 1u) - base;
-    const int s = (int)__shfl_sync(0xffffffffu, t, 0);
-    if (s >= nslices) break;
-    const int row = s * 32 + lane;
-    const long long sb = slice_off[s] + lane; const int slen = slice_len[s];
-    const int *cp = col + sb; const double *vp = val + sb;
-    double acc[NV];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) acc[q] = 0.0;
-    int k = 0;
-    for (; k + 4 <= slen; k += 4) {
-      const int c0 = __ldcs(cp + 32 * (k + 0)), c1 = __ldcs(cp + 32 * (k + 1)), c2 = __ldcs(cp + 32 * (k + 2)), c3 = __ldcs(cp + 32 * (k + 3));
-      const double v0 = __ldcs(vp + 32 * (k + 0)), v1 = __ldcs(vp + 32 * (k + 1)), v2 = __ldcs(vp + 32 * (k + 2)), v3 = __ldcs(vp + 32 * (k + 3));
-#pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        const double *xq = x + (size_t)q * ldx;
-        acc[q] += v0 * __ldg(xq + c0); acc[q] += v1 * __ldg(xq + c1); acc[q] += v2 * __ldg(xq + c2); acc[q] += v3 * __ldg(xq + c3);
-      }
-    }
-    for (; k < slen; ++k) {
-      const int c0 = __ldcs(cp + 32 * k); const double v0 = __ldcs(vp + 32 * k);
-#pragma unroll
-      for (int q = 0; q < NV; ++q) acc[q] += v0 * __ldg(x + (size_t)q * ldx + c0);
-    }
-    if (row < n) {
-#pragma unroll
-      for (int q = 0; q < NV; ++q) y[(size_t)q * ldy + row] = acc[q];
-      if (DOT) dsum += acc[0] * dvec[row];
-    }
-  }
-  if (DOT) spmv_dot_finish(dsum, partials, counter, out, pr);
-}
+// (A persistent variant in which every warp draws its next slice from a global ticket counter was measured on the 1M-row brick:
+// 233 us per launch against 226 us for this kernel — the hardware CTA scheduler already balances at the granularity that matters,
+// and consecutive slices on one SM share the x gather in L1.  gpurun_out/r2_dyn*_c2.json; not kept.)
 
 // With several ranks the off-rank x entries (Epetra_Import) land behind the owned rows of x before the multiply starts —
 // pushed by the kernel that produced x (krylov.cu: k_finish) or by halo_exchange — so the multiply itself is the same
@@ -136,29 +94,10 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const 
   else if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);
   P2PRed none; none.tab = nullptr; none.seq = 0; none.nranks = 1;
 #define SPMV_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr
-  // dynamic (ticket) scheduling where the static grid is only a few waves deep: ISPH_SPMV_DYN=0 / 1 forces it off / on
-  static const int dyn_env = getenv("ISPH_SPMV_DYN") ? atoi(getenv("ISPH_SPMV_DYN")) : -1; static int sms = 0;
-  if (!sms) CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-  const int dgrid = 8 * sms; const bool dyn = dyn_env >= 0 ? dyn_env != 0 : (grid > dgrid && grid < 12 * dgrid);
-  if (dyn && !c->spmv_ticket.p) { c->spmv_ticket.ensure(4); CUDA_CHECK(cudaMemsetAsync(c->spmv_ticket.p, 0, 4 * sizeof(unsigned), c->stream)); c->spmv_ticket_base = 0; }
-#define DYN_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr, c->spmv_ticket.p, c->spmv_ticket_base
   int done = 0;
   while (done < nvec) {
     const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
     const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy;
-    if (dyn) {
-      if (nv == 3) k_spmv_sell_dyn<3, false><<<dgrid, 256, 0, c->stream>>>(DYN_ARGS(xx, yy, nullptr, none));
-      else if (nv == 2) k_spmv_sell_dyn<2, false><<<dgrid, 256, 0, c->stream>>>(DYN_ARGS(xx, yy, nullptr, none));
-      else if (dot_vec && nvec == 1) {
-        ISPH_REQUIRE(c->red.cap >= (size_t)dgrid, "spmv: reduction workspace too small");
-        P2PRed pr = halo_p2p_ticket(c);
-        k_spmv_sell_dyn<1, true><<<dgrid, 256, 0, c->stream>>>(DYN_ARGS(xx, yy, dot_vec, pr));
-        if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, dot_out, 1);
-      }
-      else k_spmv_sell_dyn<1, false><<<dgrid, 256, 0, c->stream>>>(DYN_ARGS(xx, yy, nullptr, none));
-      c->spmv_ticket_base += (unsigned)A.nslices + (unsigned)dgrid * 8u;      // tickets drawn by this launch: one per slice + one failing draw per warp
-      ++c->launches; done += nv; continue;
-    }
     if (nv == 3) k_spmv_sell<3, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     else if (nv == 2) k_spmv_sell<2, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     else if (dot_vec && nvec == 1) {
@@ -171,7 +110,6 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const 
     ++c->launches; done += nv;
   }
 #undef SPMV_ARGS
-#undef DYN_ARGS
   if (e1) CUDA_CHECK(cudaEventRecord(e1, c->stream));
 }
 

@@ -230,6 +230,9 @@ int isph_profile_precond_get(isph_ctx *ctx, double *total_ms, long long *launche
 /* the ILU factors of the last isph_precond_create / solve: stored entries of L + D + U (all blocks), dependency levels of the
  * forward and backward sweeps (the critical path of the level-scheduled solves), longest factor row */
 int isph_precond_info(isph_ctx *ctx, long long *factor_nnz, int *levels_lower, int *levels_upper, int *max_row);
+/* FP64 FMA-loop peak of this GPU in TFLOP/s (16 independent DFMA chains per thread, no memory traffic): the denominator the
+ * assembly kernels' flop rates are quoted against ("not in MEASURED_PEAKS.json; measure") */
+int isph_measure_fp64_peak(isph_ctx *ctx, double *tflops);
 /* last SpMV-only micro benchmark: runs `reps` SpMVs on the current matrix, returns average ms (device events) */
 int isph_bench_spmv(isph_ctx *ctx, int reps, double *avg_ms);
 
