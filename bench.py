@@ -297,9 +297,12 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
         bx = (li % ng[0]) * nb // ng[0]; by = ((li // ng[0]) % ng[1]) * nb // ng[1]; bz = (li // (ng[0] * ng[1])) * nb // ng[2]
         blk = (bx + nb * (by + nb * bz)).astype(np.int32)
 
-    def upload():
+    def upload(device_list=False):
         c.atoms_set(nl, P["nghost"], hx[1], htype[1], htag[1])
-        c.neighbors_set_packed(hil[1], hnoff[1], hneigh[1])
+        if device_list:
+            c.neighbors_build()                              # the list is built on the device from the atoms: nothing but atoms and fields cross PCIe
+        else:
+            c.neighbors_set_packed(hil[1], hnoff[1], hneigh[1])
         c.field_set(isph.F_VSTAR, hv[1]); c.field_set(isph.F_DENSITY, hrho[1])
         if helm:
             c.field_set(isph.F_VELOCITY, hv[1]); c.field_set(isph.F_VISCOSITY, hnu[1])
@@ -407,8 +410,20 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     wall_e2e = (time.perf_counter() - t0) * 1e3 / steps
     e2e_timers = {k: c.timer_ms(k) / steps for k in ("h2dAtoms", "h2dNeighbors", "haloSetup")}
     ms_e2e = max(ms_e2e, wall_e2e)          # host-side packing/validation inside the ABI calls is part of the end-to-end cost
+    # ---- timed region 3: end to end with the neighbor list built on the device (isph_neighbors_build) instead of uploaded
+    c.timer_reset(); barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            upload(device_list=True); st_dl = device_step()
+        e1.record(stream)
+    barrier()
+    ms_e2e_dl = max(e0.elapsed_time(e1) / steps, (time.perf_counter() - t0) * 1e3 / steps)
+    dl_build_ms = c.timer_ms("buildNeighbors") / steps
+    dl_same = (st_dl["iters"] == st["iters"])
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, timers["solve" + solve_label]], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms = t.tolist()
+        t = torch.tensor([ms_dev, ms_e2e, timers["solve" + solve_label], ms_e2e_dl], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_dev, ms_e2e, solve_ms, ms_e2e_dl = t.tolist()
     else:
         solve_ms = timers["solve" + solve_label]
     nnz = c.nnz
@@ -444,6 +459,10 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                 config=workload_config(wname, w, world, lat), result=result,
                 e2e=dict(value=rows_g / (ms_e2e * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes),
                          upload_ms=e2e_timers),
+                e2e_device_neighbors=dict(value=rows_g / (ms_e2e_dl * 1e-3) / 1e6, unit="Mrow/s", ms_per_step=ms_e2e_dl, build_neighbors_ms=dl_build_ms,
+                                          h2d_bytes_per_step=int(h2d_bytes - hneigh[1].nbytes - hnoff[1].nbytes - hil[1].nbytes), d2h_bytes_per_step=int(d2h_bytes), same_iterations=bool(dl_same),
+                                          note="same step with the full neighbor list built on the device from the uploaded atoms (isph_neighbors_build, SURVEY.md §8f.4) instead of "
+                                               "uploaded from the host; `e2e` above is the reference-shaped hand-over (LAMMPS builds the list on the host)"),
                 gpu_launches=int(launches), clocks=clocks,
                 roofline=dict(bound="hbm", kernel="k_spmv_sell<1>", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                               traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload "

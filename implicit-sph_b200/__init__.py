@@ -49,6 +49,7 @@ def lib():
         L.isph_last_error.restype = C.c_char_p
         L.isph_version.restype = C.c_char_p
         L.isph_graph_nnz.restype = C.c_longlong
+        L.isph_neighbors_count.restype = C.c_longlong
         L.isph_kernel_launches.restype = C.c_longlong
         L.isph_solver_second_passes.restype = C.c_longlong
         L.isph_timer_ms.restype = C.c_double
@@ -128,6 +129,14 @@ class Context:
         ilist = np.ascontiguousarray(ilist, dtype=np.int32); numneigh = np.ascontiguousarray(numneigh, dtype=np.int32)
         ptrs = (_ip * len(firstneigh_rows))(*[r.ctypes.data_as(_ip) for r in firstneigh_rows])
         self.call("isph_neighbors_set", len(ilist), _i(ilist), _i(numneigh), ptrs)
+
+    def neighbors_build(self, cutneigh=0.0):
+        """full neighbor list built on the device from the atoms already set (cutneigh <= 0: the pair cutoff)"""
+        self.call("isph_neighbors_build", C.c_double(cutneigh))
+
+    def neighbors_get(self):
+        n = int(self.L.isph_neighbors_count(self.h)); noff = np.empty(self.nlocal + 1, dtype=np.int64); neigh = np.empty(max(n, 1), dtype=np.int32)
+        self.call("isph_neighbors_get", noff.ctypes.data_as(_lp), _i(neigh)); return noff, neigh[:n]
 
     def set_particles(self, P, kinds=(0, KIND_FLUID), h_over_dx=1.5, h=None, h_min=None, cut_over_h=2.0, kernel=WENDLAND, morris_safe=0.43301):
         """Convenience: everything `lattice.make_brick` produced, in the call order LAMMPS would use."""

@@ -101,11 +101,11 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   if (!ctx) return ISPH_FAILURE; Ctx *c = reinterpret_cast<Ctx *>(ctx);
   cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
   if (c->prec_ready) { try { precond_free(c); } catch (...) {} }
-  halo_destroy(c); ilu_destroy(c);
+  halo_destroy(c); ilu_destroy(c); neighbors_destroy(c);
   c->d_tab.release(); c->x.release(); c->type.release(); c->tag.release(); c->kind.release(); c->col_of_atom.release(); c->tag2own.release();
   for (auto &f : c->field) f.release();
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
-  Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
+  Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.col16.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
   c->xs.release(); c->bs.release(); c->nullvec.release(); c->mask.release(); c->V.release(); c->Z.release(); c->wk.release(); c->red.release(); c->hbuf.release(); c->flag.release(); c->h_scal.release();
   c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -168,7 +168,7 @@ static void finish_neighbors(Ctx *c, int inum, const int *ilist) {
   CUDA_CHECK(cudaMemcpyAsync(c->ilist.p, ilist, sizeof(int) * inum, cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->noff.p, c->h_noff.data(), sizeof(long long) * (inum + 1), cudaMemcpyHostToDevice, c->stream));
   long long mj = 0; for (int ii = 0; ii < inum; ++ii) mj = std::max(mj, c->h_noff[ii + 1] - c->h_noff[ii]);
-  c->max_jnum = (int)mj; c->nneigh = c->h_noff[inum]; c->have_neigh = true; c->A.built = false;
+  c->max_jnum = (int)mj; c->nneigh = c->h_noff[inum]; c->have_neigh = true; c->neigh_on_device = false; c->A.built = false;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
@@ -199,6 +199,13 @@ int isph_neighbors_set_packed(isph_ctx *ctx, int inum, const int *ilist, const l
   API_END
 }
 
+int isph_neighbors_build(isph_ctx *ctx, double cutneigh) { API_BEGIN(ctx) neighbors_build(c, cutneigh); API_END }
+long long isph_neighbors_count(isph_ctx *ctx) { if (!ctx) return -1; Ctx *c = reinterpret_cast<Ctx *>(ctx); return c->have_neigh ? c->nneigh : -1; }
+int isph_neighbors_get(isph_ctx *ctx, long long *noff, int *neigh) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->have_neigh && noff && neigh, "no neighbor list");
+  CUDA_CHECK(cudaMemcpyAsync(noff, c->noff.p, sizeof(long long) * (c->inum + 1), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(neigh, c->neigh.p, sizeof(int) * c->nneigh, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+}
 int isph_field_set(isph_ctx *ctx, int f, const double *data) {
   API_BEGIN(ctx) ISPH_REQUIRE(f >= 0 && f < ISPH_F_COUNT && data && c->have_atoms, "bad field / atoms not set");
   CUDA_CHECK(cudaMemcpyAsync(c->field[f].p, data, sizeof(double) * c->nall * FIELD_NC[f], cudaMemcpyHostToDevice, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END

@@ -156,16 +156,22 @@ void graph_build(Ctx *c) {
   Matrix &A = c->A; const int n = c->nlocal;
   A.n = n; A.nslices = (n + 31) / 32; A.external = false;
   // slice capacities from the neighbor-list upper bound jnum+1 (the reference's static profile, functor_graph.h:46-52)
-  A.h_slice_off.assign(A.nslices + 1, 0);
-  for (int s = 0; s < A.nslices; ++s) {
-    long long cap = 0; const int r1 = std::min(n, (s + 1) * 32);
-    for (int r = s * 32; r < r1; ++r) cap = std::max(cap, c->h_noff[r + 1] - c->h_noff[r] + 1);
-    A.h_slice_off[s + 1] = A.h_slice_off[s] + 32 * cap;
+  A.slice_off.ensure(A.nslices + 1);
+  if (c->neigh_on_device) {                                       // list built on the device: offsets never visit the host
+    A.h_slice_off.clear();
+    A.total = slice_offsets_device(c, n, A.nslices, A.slice_off.p);
+  } else {
+    A.h_slice_off.assign(A.nslices + 1, 0);
+    for (int s = 0; s < A.nslices; ++s) {
+      long long cap = 0; const int r1 = std::min(n, (s + 1) * 32);
+      for (int r = s * 32; r < r1; ++r) cap = std::max(cap, c->h_noff[r + 1] - c->h_noff[r] + 1);
+      A.h_slice_off[s + 1] = A.h_slice_off[s] + 32 * cap;
+    }
+    A.total = A.h_slice_off[A.nslices];
+    CUDA_CHECK(cudaMemcpyAsync(A.slice_off.p, A.h_slice_off.data(), sizeof(long long) * (A.nslices + 1), cudaMemcpyHostToDevice, c->stream));
   }
-  A.total = A.h_slice_off[A.nslices];
-  A.slice_off.ensure(A.nslices + 1); A.slice_len.ensure(A.nslices); A.row_len.ensure(n); A.diag_k.ensure(n);
+  A.slice_len.ensure(A.nslices); A.row_len.ensure(n); A.diag_k.ensure(n);
   A.col.ensure(A.total); A.atom.ensure(A.total); A.val.ensure(A.total); A.diagonal.ensure(n); A.sld.ensure(n);
-  CUDA_CHECK(cudaMemcpyAsync(A.slice_off.p, A.h_slice_off.data(), sizeof(long long) * (A.nslices + 1), cudaMemcpyHostToDevice, c->stream));
   c->flag.ensure(16);
   CUDA_CHECK(cudaMemsetAsync(c->flag.p, 0, 16 * sizeof(int), c->stream));
   CUDA_CHECK(cudaMemsetAsync(A.diag_k.p, 0xff, sizeof(int) * n, c->stream));
@@ -195,6 +201,7 @@ void graph_build(Ctx *c) {
   A.ndup = h[0]; unsigned long long nnz; memcpy(&nnz, &h[2], 8); A.nnz = (long long)nnz;
   A.ncols = c->nranks > 1 ? halo_ncols(c) : n;
   A.max_row = -1; A.is_filled = 0; A.built = true;
+  spmv_compress_columns(c);
   solver_prepare_vectors(c);
 }
 
@@ -205,6 +212,7 @@ void graph_export(Ctx *c, int *rowptr, int *col_tags, double *val) {
   Matrix &A = c->A; ISPH_REQUIRE(A.built, "matrix not built");
   std::vector<int> col(A.total), rlen(A.n); std::vector<double> v; if (val) v.resize(A.total);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (A.h_slice_off.empty()) { A.h_slice_off.resize(A.nslices + 1); CUDA_CHECK(cudaMemcpy(A.h_slice_off.data(), A.slice_off.p, sizeof(long long) * (A.nslices + 1), cudaMemcpyDeviceToHost)); }
   CUDA_CHECK(cudaMemcpy(col.data(), A.col.p, sizeof(int) * A.total, cudaMemcpyDeviceToHost));
   CUDA_CHECK(cudaMemcpy(rlen.data(), A.row_len.p, sizeof(int) * A.n, cudaMemcpyDeviceToHost));
   if (val) CUDA_CHECK(cudaMemcpy(v.data(), A.val.p, sizeof(double) * A.total, cudaMemcpyDeviceToHost));
@@ -262,6 +270,7 @@ void matrix_from_csr(Ctx *c, int n, const int *rowptr, const int *col, const dou
   CUDA_CHECK(cudaMemcpy(A.val.p, hv.data(), sizeof(double) * A.total, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemset(A.diagonal.p, 0, sizeof(double) * n)); CUDA_CHECK(cudaMemset(A.sld.p, 0, sizeof(double) * n));
   c->nlocal = n; A.is_filled = 1; A.built = true; A.max_row = *std::max_element(rlen.begin(), rlen.end());
+  spmv_compress_columns(c);
   solver_prepare_vectors(c);
 }
 

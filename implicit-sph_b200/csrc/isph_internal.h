@@ -58,6 +58,7 @@ struct PairTab {
 struct Matrix {
   int n = 0, ncols = 0, nslices = 0; long long total = 0, nnz = 0; int max_row = 0, ndup = 0;
   DevBuf<long long> slice_off; DevBuf<int> slice_len, row_len, diag_k, col, atom; DevBuf<double> val;
+  DevBuf<unsigned short> col16; bool have_col16 = false;   // SpMV column stream: 16-bit deltas along a row, 0xFFFF = "read the 32-bit column" (spmv.cu)
   DevBuf<double> diagonal, sld;          // A.diagonal, A.scaled_laplace_diagonal (pair_isph.h:385-392)
   std::vector<long long> h_slice_off;
   int is_filled = 0; bool built = false; bool external = false;
@@ -76,6 +77,7 @@ struct PrecondParams {             // names of precond_ifpack.h:28-48 + Ifpack's
 };
 
 struct Halo;      // halo.cu
+struct NeighWork; // neighbor.cu
 struct IluData;   // precond.cu
 
 struct Ctx {
@@ -92,7 +94,7 @@ struct Ctx {
   // neighbors
   int inum = 0, max_jnum = 0; long long nneigh = 0; bool have_neigh = false;
   DevBuf<int> ilist, neigh; DevBuf<long long> noff; std::vector<long long> h_noff;
-  PinBuf<int> pin_neigh;
+  PinBuf<int> pin_neigh; bool neigh_on_device = false; NeighWork *nwork = nullptr;    // list built by isph_neighbors_build: no host copy of the offsets
   // matrix
   Matrix A;
   // solver state (SolverLin members, solver_lin.h:70-97)
@@ -169,6 +171,7 @@ void boundary_dirichlet(Ctx *c);
 void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f);
 void forward_comm(Ctx *c, int field);
 
+void spmv_compress_columns(Ctx *c);                           // spmv.cu: builds Matrix::col16 from Matrix::col (after every pattern change)
 void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, const double *dot_vec = nullptr, double *dot_out = nullptr);   // spmv.cu (does the halo exchange when nranks > 1)
 
 void precond_create(Ctx *c);                                 // precond.cu
@@ -197,6 +200,9 @@ struct HaloDev {
 // complete) when the SpMV is launched.  sp/sd = per-row send list (CSR over owned rows; entry = peer << 28 | offset).
 struct PrePush { const HaloDev *plan; const int *sp, *sd; unsigned long long seq; };
 
+void neighbors_build(Ctx *c, double cutneigh);                // neighbor.cu
+void neighbors_destroy(Ctx *c);
+long long slice_offsets_device(Ctx *c, int n, int nslices, long long *d_slice_off);
 void halo_setup(Ctx *c);                                     // halo.cu
 bool halo_prepush_begin(Ctx *c, const double *x_next, PrePush *pp);   // reserves the exchange of the SpMV that will read x_next
 void halo_wait_unstage(Ctx *c, double *d_x, unsigned long long seq);  // completes a pre-pushed exchange: halo lands behind x's owned rows

@@ -78,6 +78,14 @@ int isph_atoms_set(isph_ctx *ctx, int nlocal, int nghost, const double *x /*[nal
 int isph_neighbors_set(isph_ctx *ctx, int inum, const int *ilist, const int *numneigh, int *const *firstneigh);
 /* packed layout: row ii owns neigh[noff[ii] .. noff[ii+1]) */
 int isph_neighbors_set_packed(isph_ctx *ctx, int inum, const int *ilist, const long long *noff, const int *neigh);
+/* The full neighbor list built ON THE DEVICE from the atoms already set (replaces the host-built LAMMPS list the
+ * pair style requests in init_style, pair_isph.cpp:1887-1894): every owned atom's row holds all atoms j != i (owned or ghost) with
+ * |x_i - x_j|^2 <= cutneigh^2, cutneigh <= 0 meaning the pair cutoff (skin 0, as the reference's scripts run).  Cell binning; row
+ * order = cell stencil order, then atom index.  The list is a superset for the functors' own rsq < cutsq test, so the graph does not
+ * depend on it; removes the per-step upload of the list (the bulk of the host-to-device traffic of a step). */
+int isph_neighbors_build(isph_ctx *ctx, double cutneigh);
+long long isph_neighbors_count(isph_ctx *ctx);                     /* entries of the current list */
+int isph_neighbors_get(isph_ctx *ctx, long long *noff /*[inum+1]*/, int *neigh /*[count]*/);   /* copy the current list out (packed layout) */
 int isph_field_set(isph_ctx *ctx, int field, const double *data);
 int isph_field_get(isph_ctx *ctx, int field, double *data);
 /* owner -> ghost copy of a field: comm->forward_comm_pair(this), pair_isph.cpp:1924-2074 */

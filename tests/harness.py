@@ -49,10 +49,12 @@ def FIXED(cs):
     return [0, 0, 1][:len(cs["kinds"])] if len(cs["kinds"]) >= 3 else [0] * len(cs["kinds"])
 
 
-def cuda_context(P, F, device=0):
+def cuda_context(P, F, device=0, device_neighbors=False):
     cs = P["case"]
     c = isph.Context(device)
     c.set_particles(P, kinds=cs["kinds"], kernel=cs["kernel"], h_min=cs["h_min"])
+    if device_neighbors:          # the list LAMMPS would hand over is replaced by the one built on the device from the atoms (isph_neighbors_build)
+        c.neighbors_build()
     c.field_set(isph.F_DENSITY, F["density"]); c.field_set(isph.F_VISCOSITY, F["viscosity"]); c.field_set(isph.F_PRESSURE, F["pressure"])
     c.field_set(isph.F_VSTAR, F["velocity"]); c.field_set(isph.F_VELOCITY, F["velocity"]); c.field_set(isph.F_FORCE, F["force"])
     c.field_set(isph.F_EPS, F["eps"]); c.field_set(isph.F_PSI, F["psi"]); c.field_set(isph.F_PSI0, F["psi0"])
@@ -60,9 +62,11 @@ def cuda_context(P, F, device=0):
     return c
 
 
-def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
+def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0, device_neighbors=False):
     cs = P["case"]
-    c = cuda_context(P, F, device)
+    c = cuda_context(P, F, device, device_neighbors)
+    if device_neighbors:
+        noff, neigh = c.neighbors_get()
     c.compute_pre(normals=cs["has_solid"])
     out = dict(vfrac=c.field_get(isph.F_VFRAC), gc=c.field_get(isph.F_GC), lc=c.field_get(isph.F_LC))
     if cs["has_solid"]:
@@ -95,5 +99,7 @@ def run_cuda(P, F, anti=True, singular=isph.NULLSPACE, mh=False, device=0):
     c.advance_time(cs["dt"], anti=anti)
     out["adv_dp"] = c.field_get(isph.F_DP); out["adv_p"] = c.field_get(isph.F_PRESSURE); out["adv_v"] = c.field_get(isph.F_VELOCITY); out["adv_x"] = c.atoms_get_x()
     out["launches"] = c.launches
+    if device_neighbors:
+        out["neigh_noff"], out["neigh"] = noff, neigh
     c.close()
     return out

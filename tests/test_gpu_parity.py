@@ -133,3 +133,28 @@ def test_device_halo_planner_matches_host_planner(isph):
         for a, b in zip(out["host"], out["device"]):
             assert np.array_equal(a, b)
     c.close()
+
+
+@pytest.mark.parametrize("name,anti", [("jitter3d", True), ("solid2d", False), ("cloud3d", False), ("cloud3d_50k", True)])
+def test_device_built_neighbor_list(name, anti):
+    """SURVEY.md §8f.4 (first half): the full neighbor list built on the device from the atoms alone (cell binning).  (1) every row
+    holds exactly the atoms within the cutoff (brute force on the small cases); (2) the whole path run on that list — the list never
+    leaves the device on the product side — against the oracle given the SAME list: graph bit-exact, values within the bars."""
+    import harness
+    P, F = make_case(name); nl = P["nlocal"]; mh = P["case"]["has_solid"]
+    got = harness.run_cuda(P, F, anti=anti, mh=mh, device_neighbors=True)
+    noff, neigh = got.pop("neigh_noff"), got.pop("neigh")
+    assert len(noff) == nl + 1 and noff[0] == 0 and noff[-1] == len(neigh) and neigh.min() >= 0 and neigh.max() < nl + P["nghost"]
+    cut2 = (2.0 * 1.5 * P["dx"]) ** 2
+    if nl <= 5000:
+        x = P["x"]
+        for i in range(nl):
+            d = x - x[i]; r2 = (d * d).sum(axis=1); want = np.nonzero(r2 <= cut2)[0]; want = want[want != i]
+            assert np.array_equal(np.sort(neigh[noff[i]:noff[i + 1]]), want), i
+    else:
+        rows = np.repeat(np.arange(nl), np.diff(noff)); d = P["x"][rows] - P["x"][neigh]
+        assert ((d * d).sum(axis=1) <= cut2).all() and (neigh != rows).all()
+        host_cnt = np.diff(P["noff"]); assert (np.diff(noff) <= host_cnt).all()               # the host list reaches 5 % further
+    Q = dict(P); Q["noff"] = noff.astype(np.int64); Q["neigh"] = neigh.astype(np.int32)
+    ref = harness.run_oracle(Q, F, "port", anti=anti, mh=mh)
+    _compare(got, ref, mh, f"{name}/anti{int(anti)}/device-list", mixed=name.startswith("cloud"))
