@@ -105,7 +105,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   c->d_tab.release(); c->x.release(); c->type.release(); c->tag.release(); c->kind.release(); c->col_of_atom.release(); c->tag2own.release();
   for (auto &f : c->field) f.release();
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
-  Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.col16.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
+  Matrix &A = c->A; A.slice_off.release(); A.slice_len.release(); A.row_len.release(); A.diag_k.release(); A.col.release(); A.atom.release(); A.val.release(); A.diagonal.release(); A.sld.release();
   c->xs.release(); c->bs.release(); c->nullvec.release(); c->mask.release(); c->V.release(); c->Z.release(); c->wk.release(); c->red.release(); c->hbuf.release(); c->flag.release(); c->h_scal.release();
   c->invdiag.release(); c->cw.release(); c->cv.release(); c->block_of_row.release(); c->pb_extra.release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }

@@ -201,7 +201,6 @@ void graph_build(Ctx *c) {
   A.ndup = h[0]; unsigned long long nnz; memcpy(&nnz, &h[2], 8); A.nnz = (long long)nnz;
   A.ncols = c->nranks > 1 ? halo_ncols(c) : n;
   A.max_row = -1; A.is_filled = 0; A.built = true;
-  spmv_compress_columns(c);
   solver_prepare_vectors(c);
 }
 
@@ -270,7 +269,6 @@ void matrix_from_csr(Ctx *c, int n, const int *rowptr, const int *col, const dou
   CUDA_CHECK(cudaMemcpy(A.val.p, hv.data(), sizeof(double) * A.total, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemset(A.diagonal.p, 0, sizeof(double) * n)); CUDA_CHECK(cudaMemset(A.sld.p, 0, sizeof(double) * n));
   c->nlocal = n; A.is_filled = 1; A.built = true; A.max_row = *std::max_element(rlen.begin(), rlen.end());
-  spmv_compress_columns(c);
   solver_prepare_vectors(c);
 }
 

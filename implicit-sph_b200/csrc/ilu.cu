@@ -30,7 +30,7 @@ struct IluData {
   int grid_f = 1, grid_s = 1, maxlen = 0, tb_f = ILU_TB; bool sync_free = true; size_t smem_f = 0; DevBuf<int> fault;
   // level-ordered split copy of the factors for the apply: position idx of the forward (backward) sweep owns the contiguous
   // entries Lrp[idx]..Lrp[idx+1] (Urp..) of row order_l[idx] (order_u[idx]) — no row-pointer / diagonal-position indirection
-  DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1, lpr = 32;
+  DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1;
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
@@ -191,70 +191,10 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_factor_sf(const int *rp, const i
 }
 
 
-// Same factorisation, with the pivot metadata hoisted out of the sequential pivot loop.  In k_ilu_factor_sf every pivot of a row
-// costs three dependent global round trips (dinv[j] -> dpos[j], rp[j+1] -> ci[u], fv[u]) and a row has ~60 pivots.  The pivot
-// list of a row is its own L pattern, so the lanes fetch the extents of ALL pivot rows (and a first look at their dinv) in
-// parallel when the row is staged, and the U part of the NEXT pivot row is requested while the current pivot is being applied
-// (values are re-read after the wait if that row was not finished yet).  Arithmetic and its order are unchanged.
-// shared memory per warp: values, columns, pivot extents (begin, end) and the first look at dinv: 28 B per row entry.
-__global__ void __launch_bounds__(ILU_TB) k_ilu_factor_pf(const int *rp, const int *ci, const int *dpos, double *fv, double *dinv,
-                                                          const int *order, int n, int maxlen, int *fault) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  double *s_val = reinterpret_cast<double *>(smem_raw) + (size_t)wib * maxlen;
-  double *s_dj = reinterpret_cast<double *>(smem_raw) + (size_t)nwb * maxlen + (size_t)wib * maxlen;
-  int *ibase = reinterpret_cast<int *>(smem_raw + (size_t)nwb * maxlen * 2 * sizeof(double));
-  int *s_col = ibase + (size_t)wib * maxlen, *s_ub = ibase + (size_t)nwb * maxlen + (size_t)wib * maxlen, *s_ue = ibase + (size_t)2 * nwb * maxlen + (size_t)wib * maxlen;
-  for (int idx = gw; idx < n; idx += nw) {
-    const int i = order[idx], b = rp[i], len = rp[i + 1] - b, dp = dpos[i] - b;
-    for (int t = lane; t < len; t += 32) {
-      const int cc = ci[b + t]; s_col[t] = cc; s_val[t] = fv[b + t];
-      if (t < dp) { s_ub[t] = __ldg(dpos + cc) + 1; s_ue[t] = __ldg(rp + cc + 1); s_dj[t] = __ldcg(dinv + cc); }      // pivot metadata, all pivots at once
-    }
-    __syncwarp();
-    __threadfence();                                        // the values requested below are ordered after the dinv looks above
-    // U part of the first pivot row (two entries per lane cover 64; longer rows loop below)
-    int pc0 = -1, pc1 = -1; double pf0 = 0.0, pf1 = 0.0;
-    if (dp > 0) { const int ub = s_ub[0], ue = s_ue[0];
-      if (ub + lane < ue) { pc0 = __ldcg(ci + ub + lane); pf0 = __ldcg(fv + ub + lane); }
-      if (ub + lane + 32 < ue) { pc1 = __ldcg(ci + ub + lane + 32); pf1 = __ldcg(fv + ub + lane + 32); } }
-    for (int q = 0; q < dp; ++q) {                          // strictly-lower entries, ascending column
-      const int j = s_col[q], ub = s_ub[q], ue = s_ue[q];
-      double dj = s_dj[q]; bool late = false;
-      if (dj != dj) {                                       // row j was not finished when this row was staged: wait, then re-read its values
-        if (lane == 0) dj = wait_value(dinv + j, fault);
-        dj = __shfl_sync(0xffffffffu, dj, 0); late = true;
-      }
-      __threadfence();
-      int c0 = pc0, c1 = pc1; double f0 = pf0, f1 = pf1;
-      if (late) { if (ub + lane < ue) f0 = __ldcg(fv + ub + lane); if (ub + lane + 32 < ue) f1 = __ldcg(fv + ub + lane + 32); }
-      // request the next pivot row before applying this one
-      pc0 = pc1 = -1;
-      if (q + 1 < dp) { const int nb = s_ub[q + 1], ne = s_ue[q + 1];
-        if (nb + lane < ne) { pc0 = __ldcg(ci + nb + lane); pf0 = __ldcg(fv + nb + lane); }
-        if (nb + lane + 32 < ne) { pc1 = __ldcg(ci + nb + lane + 32); pf1 = __ldcg(fv + nb + lane + 32); } }
-      const double multiplier = s_val[q];
-      if (ub + lane < ue) { int lo = q + 1, hi = len; while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < c0) lo = mid + 1; else hi = mid; }
-        if (lo < len && s_col[lo] == c0) s_val[lo] -= multiplier * f0; }
-      if (ub + lane + 32 < ue) { int lo = q + 1, hi = len; while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < c1) lo = mid + 1; else hi = mid; }
-        if (lo < len && s_col[lo] == c1) s_val[lo] -= multiplier * f1; }
-      for (int u = ub + lane + 64; u < ue; u += 32) {
-        const int k = __ldcg(ci + u); int lo = q + 1, hi = len;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[mid] < k) lo = mid + 1; else hi = mid; }
-        if (lo < len && s_col[lo] == k) s_val[lo] -= multiplier * __ldcg(fv + u);
-      }
-      __syncwarp();
-      if (lane == 0) s_val[q] = multiplier * dj;
-      __syncwarp();
-    }
-    const double d = 1.0 / s_val[dp];
-    __syncwarp();
-    for (int t = lane; t < len; t += 32) fv[b + t] = t > dp ? s_val[t] * d : s_val[t];
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) *reinterpret_cast<volatile double *>(dinv + i) = publishable(d, fault);
-  }
-}
+// (Round 2 also measured a factorisation kernel with the pivot metadata (dpos[j], rp[j+1], a first look at dinv[j]) fetched for all
+// pivots of a row at once and the next pivot row requested while the current one is applied: 171 ms against 171 ms on the 8M-row /
+// 64-block problem, 54 against 51 ms on 1M rows / 8 blocks — the row-to-row dependency wait, not the per-pivot round trips, is what
+// the factorisation spends its time in.  Not kept.)
 
 __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sf(const int *rp, const int *ci, const int *dpos, const double *fv, const double *dinv,
                                                          const int *order_l, const int *order_u, int n, const double *r, double *y, double *z, int *fault) {
@@ -340,34 +280,9 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_lv(const int *Lrp, const i
   ilu_sweep_lv<true>(Urp, Uci, Ufv, order_u, Udinv, n, y, z, fault, gw, nw, lane);
 }
 
-// Sub-warp variant for wide levels.  With one warp per row the 64 warps of an SM hold 9472 rows in flight; an 8M-row problem in
-// 64 blocks has ~12500 rows per level, so every level takes two rounds of a ~3-4 us dependency round trip (measured: 8 us per level,
-// BENCH r2 configs3_c4).  Here LPR = 16 or 8 lanes share a row (the L / U halves hold ~60 entries), 2 or 4 rows per warp, so that a
-// whole level is in flight at once.  The groups of a warp are independent: shuffles use the group's own lane mask, so a group
-// that waits for a row of an earlier level never holds up the group that produces it (independent thread scheduling).
-template <int LPR, bool UPPER> __device__ __forceinline__ void ilu_sweep_sub(const int *__restrict__ prp, const int *__restrict__ pci, const double *__restrict__ pfv,
-                                                                             const int *__restrict__ order, const double *__restrict__ pdinv, int n, const double *in, double *out,
-                                                                             int *fault, int gw, int nw, int lane) {
-  constexpr int G = 32 / LPR;
-  const int sub = lane / LPR, sl = lane % LPR; const unsigned gmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u) << (sub * LPR));
-  for (long long idx = (long long)gw * G + sub; idx < n; idx += (long long)nw * G) {
-    const int i = __ldg(order + idx), b = __ldg(prp + idx), e = __ldg(prp + idx + 1);
-    double s = 0.0;
-    for (int q = b + sl; q < e; q += LPR) s += __ldcs(pfv + q) * wait_value(out + __ldcs(pci + q), fault);
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
-    if (sl == 0) {
-      const double rhs = UPPER ? wait_value(in + i, fault) * __ldg(pdinv + idx) : in[i];
-      *reinterpret_cast<volatile double *>(out + i) = publishable(rhs - s, fault);
-    }
-  }
-}
-template <int LPR> __global__ void __launch_bounds__(ILU_TB) k_ilu_solve_sub(const int *Lrp, const int *Lci, const double *Lfv, const int *order_l, const int *Urp, const int *Uci,
-                                                                            const double *Ufv, const int *order_u, const double *Udinv, int n, const double *r, double *y, double *z, int *fault) {
-  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  ilu_sweep_sub<LPR, false>(Lrp, Lci, Lfv, order_l, nullptr, n, r, y, fault, gw, nw, lane);
-  ilu_sweep_sub<LPR, true>(Urp, Uci, Ufv, order_u, Udinv, n, y, z, fault, gw, nw, lane);
-}
+// (Sub-warp rows — 16 or 8 lanes per row, 2 or 4 rows per warp, to hold a whole wide level in flight — were measured on the 8M-row /
+// 64-block problem: 13.9 ms and 21.1 ms per apply against 12.1 ms for the kernel above and 10.3 ms for k_ilu_solve_sf; the spinning
+// groups of a warp serialise each other.  Not kept.  Which kernel runs is decided by the width of the levels, see ilu_create.)
 
 // ---- dependency levels on the device -----------------------------------------------------------------------------
 // level[i] = 1 + max(level[j] : j in L(i)) (0 without dependencies).  One warp per row in dependency order (ascending
@@ -548,10 +463,9 @@ void ilu_create(Ctx *c) {
   if (I.sync_free) {
     int sms = 0, per_sm = 0; CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     { const char *e = getenv("ISPH_ILU_BACKOFF"); const int bo = (e && *e) ? atoi(e) : 0; CUDA_CHECK(cudaMemcpyToSymbolAsync(g_ilu_backoff, &bo, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream)); }
-    // factorisation: per-warp staging of the row in shared memory (28 B per entry with the hoisted pivot metadata, 12 B for the
-    // plain kernel); shrink the CTA until it fits
-    const bool pf = getenv("ISPH_ILU_FACTOR_OLD") == nullptr; const size_t per_entry = pf ? 28 : 12; const void *fk = pf ? (const void *)k_ilu_factor_pf : (const void *)k_ilu_factor_sf;
-    I.tb_f = pf ? 512 : ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * per_entry > 100 * 1024) I.tb_f >>= 1;
+    // factorisation: per-warp staging of the row in shared memory (12 B per entry); shrink the CTA until it fits
+    const size_t per_entry = 12; const void *fk = (const void *)k_ilu_factor_sf;
+    I.tb_f = ILU_TB; while (I.tb_f > 32 && (size_t)(I.tb_f / 32) * I.maxlen * per_entry > 200 * 1024) I.tb_f >>= 1;
     I.smem_f = (size_t)(I.tb_f / 32) * I.maxlen * per_entry; ISPH_REQUIRE(I.smem_f <= 200 * 1024, "ILU: a row is too long for the factorisation kernel");
     CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_f));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, I.tb_f, I.smem_f)); ISPH_REQUIRE(per_sm >= 1, "ILU: factorisation kernel does not fit an SM");
@@ -565,7 +479,13 @@ void ilu_create(Ctx *c) {
     CUDA_CHECK(cudaLaunchCooperativeKernel(fk, dim3(I.grid_f), dim3(I.tb_f), args, I.smem_f, c->stream)); ++c->launches;
     c->toc("iluFactor"); c->tic("iluPermute");
     // level-ordered split copy for the apply (stream order: after the factorisation)
-    I.lv = getenv("ISPH_ILU_APPLY_OLD") == nullptr;
+    // narrow levels (fewer rows per level than resident warps: the 1M-row / 8-block case, 1600 rows per level) are latency-bound per
+    // row and gain from the level-ordered pipelined kernel (3.2 ms against 5.2 ms per apply); wide levels (8M rows / 64 blocks, 12500
+    // rows per level) are bound by the level-to-level hand-over and run faster on the plain kernel (10.3 against 12.1 ms).
+    // ISPH_ILU_APPLY = sf | lv forces one of them.
+    { const double rows_per_level = (double)n / std::max(1, std::max(I.nlev_l, I.nlev_u)); const int resident_warps = 2 * sms * (ILU_TB / 32);
+      I.lv = rows_per_level < 0.5 * resident_warps;
+      const char *e = getenv("ISPH_ILU_APPLY"); if (e && !strcmp(e, "sf")) I.lv = false; else if (e && !strcmp(e, "lv")) I.lv = true; }
     if (I.lv) {
       I.plen.ensure(n + 1); I.Lrp.ensure(n + 1); I.Urp.ensure(n + 1); I.Lci.ensure(I.nnz); I.Uci.ensure(I.nnz); I.Lfv.ensure(I.nnz); I.Ufv.ensure(I.nnz); I.Udinv.ensure(n);
       for (int upper = 0; upper < 2; ++upper) {
@@ -577,13 +497,8 @@ void ilu_create(Ctx *c) {
                                                                                 upper ? I.Ufv.p : I.Lfv.p, I.Udinv.p);
         c->launches += 3;
       }
-      // lanes per row: a whole level should be in flight (rows per level vs resident warps); ISPH_ILU_LPR = 32 | 16 | 8 overrides
-      const double rows_per_level = (double)n / std::max(1, std::max(I.nlev_l, I.nlev_u)); const int resident_warps = 2 * sms * (ILU_TB / 32);
-      I.lpr = rows_per_level > 2.0 * resident_warps ? 8 : (rows_per_level > 0.75 * resident_warps ? 16 : 32);
-      if (getenv("ISPH_ILU_LPR")) { const int v = atoi(getenv("ISPH_ILU_LPR")); if (v == 8 || v == 16 || v == 32) I.lpr = v; }
-      const void *sk = I.lpr == 32 ? (const void *)k_ilu_solve_lv : (I.lpr == 16 ? (const void *)k_ilu_solve_sub<16> : (const void *)k_ilu_solve_sub<8>);
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: level-ordered solve kernel does not fit an SM");
-      I.grid_lv = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * I.lpr, ILU_TB)));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_solve_lv, ILU_TB, 0)); ISPH_REQUIRE(per_sm >= 1, "ILU: level-ordered solve kernel does not fit an SM");
+      I.grid_lv = std::max(1, std::min(per_sm * sms, ceil_div((long long)n * 32, ILU_TB)));
     }
     c->toc("iluPermute");
     return;
@@ -621,8 +536,7 @@ static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
     CUDA_CHECK(cudaMemsetAsync(I.y.p, 0xff, sizeof(double) * I.n, c->stream)); CUDA_CHECK(cudaMemsetAsync(z, 0xff, sizeof(double) * I.n, c->stream));   // NaN = "not solved yet"
     const int *a0 = I.Lrp.p, *a1 = I.Lci.p, *a3 = I.order_l.p, *a4 = I.Urp.p, *a5 = I.Uci.p, *a7 = I.order_u.p; const double *a2 = I.Lfv.p, *a6 = I.Ufv.p, *a8 = I.Udinv.p; double *y = I.y.p; int nn = I.n; int *flt = I.fault.p;
     void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &nn, &r, &y, &z, &flt};
-    const void *sk = I.lpr == 32 ? (const void *)k_ilu_solve_lv : (I.lpr == 16 ? (const void *)k_ilu_solve_sub<16> : (const void *)k_ilu_solve_sub<8>);
-    CUDA_CHECK(cudaLaunchCooperativeKernel(sk, dim3(I.grid_lv), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_ilu_solve_lv, dim3(I.grid_lv), dim3(ILU_TB), args, 0, c->stream)); ++c->launches;
     return;
   }
   if (I.sync_free) {

@@ -58,7 +58,6 @@ struct PairTab {
 struct Matrix {
   int n = 0, ncols = 0, nslices = 0; long long total = 0, nnz = 0; int max_row = 0, ndup = 0;
   DevBuf<long long> slice_off; DevBuf<int> slice_len, row_len, diag_k, col, atom; DevBuf<double> val;
-  DevBuf<unsigned short> col16; bool have_col16 = false;   // SpMV column stream: 16-bit deltas along a row, 0xFFFF = "read the 32-bit column" (spmv.cu)
   DevBuf<double> diagonal, sld;          // A.diagonal, A.scaled_laplace_diagonal (pair_isph.h:385-392)
   std::vector<long long> h_slice_off;
   int is_filled = 0; bool built = false; bool external = false;
@@ -171,7 +170,6 @@ void boundary_dirichlet(Ctx *c);
 void pb_residual(Ctx *c, bool mh, bool linearized, double ezcb, double psiref, double gamma, const double *d_extra, double *d_f);
 void forward_comm(Ctx *c, int field);
 
-void spmv_compress_columns(Ctx *c);                           // spmv.cu: builds Matrix::col16 from Matrix::col (after every pattern change)
 void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, const double *dot_vec = nullptr, double *dot_out = nullptr);   // spmv.cu (does the halo exchange when nranks > 1)
 
 void precond_create(Ctx *c);                                 // precond.cu

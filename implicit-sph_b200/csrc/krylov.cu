@@ -16,6 +16,20 @@
 namespace isph {
 
 static const int VB = 256;              // threads per block of the vector kernels
+
+// Programmatic dependent launch: the kernel may be scheduled while the previous kernel of the stream is still draining (its CTAs
+// become resident as SMs free up and wait at `griddepcontrol.wait`, which every kernel launched this way executes before it reads
+// anything the previous kernel wrote).  Hides the launch latency and the ramp of the four kernels of an Arnoldi step behind the
+// tails (last-block reduction, peer all-reduce) of their predecessors.  ISPH_NO_PDL=1: plain launches.
+template <class... KA, class... A> static void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  static const bool pdl = getenv("ISPH_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg)); cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...));
+}
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 static const double DEP_TOL = 0.70710678118654752440;   // DGKSOrthoManager dep_tol = 1/sqrt(2)
 
 // layout of the small device scalar block `hbuf`
@@ -111,7 +125,7 @@ template <int G> __global__ void __launch_bounds__(VB, G == 16 ? 2 : (G == 8 ? 3
 k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restrict__ w, const double *__restrict__ nvec, int n,
            double *S, int pass, int rev, double *partials, unsigned *counters, P2PRed pr) {
   __shared__ bool go;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fused update sweep that follows may start its prologue (it waits for this grid before it reads S / w)
+  PDL_WAIT(); PDL_TRIGGER();                                 // launched dependent on the SpMV (pass 0); the sweep that follows may start its prologue
   if (pass == 1) { if (threadIdx.x == 0) go = dgks_second(S, nv, nvec != nullptr); __syncthreads(); if (!go) return; }
   const int g = blockIdx.y, k0 = g * G, cnt = min(G, nv - k0);
   const bool with_n = (pass == 0 && nvec != nullptr && g == 0);
@@ -181,6 +195,7 @@ k_multidot(const double *__restrict__ V, int ld, int nv, const double *__restric
 __global__ void __launch_bounds__(VB)
 k_cgs_update(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, const double *__restrict__ nvec, int n, const double *S, int rev) {
   __shared__ double sh[64];
+  PDL_WAIT(); PDL_TRIGGER();
   if (threadIdx.x < nv) sh[threadIdx.x] = S[S_H + threadIdx.x];
   __syncthreads();
   const double proj = nvec ? S[S_H + nv + 1] : 0.0;
@@ -220,6 +235,7 @@ k_update_dot(const double *__restrict__ V, int ld, int nv, double *__restrict__ 
   __shared__ double s_h[64], s_red[UT / 32];
   __shared__ bool s_go, s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PDL_WAIT(); PDL_TRIGGER();
   if (tid == 0) s_go = dgks_second(S, nv, nvec != nullptr);
   if (tid < nv) s_h[tid] = S[S_H + tid];
   __syncthreads();
@@ -351,7 +367,7 @@ k_update_dot_tma(const __grid_constant__ CUtensorMap tm, int nv, double *__restr
   const int r0 = min(n, cb * chunk), r1 = min(n, r0 + chunk), ntiles = (r1 - r0 + TT - 1) / TT;
   if (tid == 0) { for (int q = 0; q < ns; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], TT / 32); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  asm volatile("griddepcontrol.wait;" ::: "memory");             // everything below reads what the pass-0 kernel produced (coefficients, y)
+  PDL_WAIT(); PDL_TRIGGER();                                     // everything below reads what the pass-0 kernel produced (coefficients, y)
   if (tid == 0) s_go = dgks_second(S, nv, nvec != nullptr);
   if (tid < nv) s_h[tid] = S[S_H + tid];
   __syncthreads();
@@ -478,6 +494,7 @@ __device__ __forceinline__ void prepush_row(const PrePush &pp, int hslot, int b,
 __global__ void __launch_bounds__(VB)
 k_finish(const double *__restrict__ V, int ld, int nv, double *__restrict__ w, int n, double *S, int singular,
          const double *__restrict__ invdiag, double damping, int post, double *__restrict__ z, double *host_res, int slot, int rev, PrePush pp) {
+  PDL_WAIT(); PDL_TRIGGER();
   if (blockIdx.x == 0) {      // block 0 is dedicated to the (sequential, ~10 us) Hessenberg/Givens step: hidden behind the sweep
     if (threadIdx.x < 32) givens_step(S, nv - 1, singular != 0, host_res, slot);
     return;
@@ -656,9 +673,9 @@ static void launch_multidot(Ctx *c, const double *V, int nv, const double *w, in
   const int mdcap = mdenv ? mdenv : (G == 16 ? 296 : (G == 8 ? 444 : 740));
   int gx = mdcap / groups; if (gx < 74) gx = 74; { const int mx = ceil_div(n, 2 * VB); if (gx > mx) gx = mx < 1 ? 1 : mx; }
   P2PRed pr = halo_p2p_ticket(c);
-  if (G == 4) k_multidot<4><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
-  else if (G == 8) k_multidot<8><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
-  else k_multidot<16><<<dim3(gx, groups), VB, 0, c->stream>>>(V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
+  if (G == 4) launch_pdl(k_multidot<4>, dim3(gx, groups), dim3(VB), 0, c->stream, V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
+  else if (G == 8) launch_pdl(k_multidot<8>, dim3(gx, groups), dim3(VB), 0, c->stream, V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
+  else launch_pdl(k_multidot<16>, dim3(gx, groups), dim3(VB), 0, c->stream, V, c->ld, nv, w, nv_, n, S, pass, rev, c->red.p, cnt, pr);
   ++c->launches;
   // NCCL fallback (no peer access).  Pass 1 is conditional on the device: a rank-independent decision (it is taken from the
   // already reduced pass-0 message), so every rank either contributes fresh sums or the same stale, unused ones.
@@ -759,13 +776,13 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
       if (fuse_ud && j + 1 > 8) {                                // one sweep: first update + second-pass coefficients
         ProfScope ps(c, "update0+dot1"); P2PRed pr = halo_p2p_ticket(c); const int rv = sweep();
         if (!(ud_tma && launch_update_dot_tma(c, V, ld, m + 1, j + 1, vn, nvp, n, rv, S, cnt + 6, pr))) {                     // flag word 14
-          if (ud_hv == 1) k_update_dot<1><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
-          else k_update_dot<2><<<gud, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
+          if (ud_hv == 1) launch_pdl(k_update_dot<1>, dim3(gud), dim3(VB), 0, c->stream, V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
+          else launch_pdl(k_update_dot<2>, dim3(gud), dim3(VB), 0, c->stream, V, ld, j + 1, vn, nvp, n, rv, S, c->red.p, cnt + 6, pr);
         }
         ++c->launches;
         if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, S + S_H2, j + 2);
       } else {
-        { ProfScope ps(c, "update0"); k_cgs_update<<<g, VB, 0, c->stream>>>(V, ld, j + 1, vn, nvp, n, S, sweep()); ++c->launches; }
+        { ProfScope ps(c, "update0"); launch_pdl(k_cgs_update, dim3(g), dim3(VB), 0, c->stream, V, ld, j + 1, vn, nvp, n, S, sweep()); ++c->launches; }
         { ProfScope ps(c, "multidot1"); launch_multidot(c, V, j + 1, vn, 1, sweep()); }
       }
       dbg(c, "update0/dot1");
@@ -775,8 +792,8 @@ static int gmres_solve(Ctx *c, bool use_prec, double *x, double *b, int *iters_o
         double *zn = flex ? Z + (size_t)(j + 1) * ld : Z;
         PrePush pp; pp.plan = nullptr; pp.sp = pp.sd = nullptr; pp.seq = 0;
         if (jacobi_fused) { halo_prepush_begin(c, zn, &pp);       // z_{j+1} is the next SpMV input: its halo rows leave from this kernel
-          k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, dp.invdiag, dp.scale, dp.post, zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
-        else { k_finish<<<g + 1, VB, 0, c->stream>>>(V, ld, j + 1, vn, n, S, sing, nullptr, 1.0, 0, use_prec ? nullptr : zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
+          launch_pdl(k_finish, dim3(g + 1), dim3(VB), 0, c->stream, V, ld, j + 1, vn, n, S, sing, dp.invdiag, dp.scale, dp.post, zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
+        else { launch_pdl(k_finish, dim3(g + 1), dim3(VB), 0, c->stream, V, ld, j + 1, vn, n, S, sing, (const double *)nullptr, 1.0, 0, use_prec ? (double *)nullptr : zn, c->h_scal.p + 8, iters, sweep(), pp); ++c->launches; }
       } else { k_givens<<<1, 32, 0, c->stream>>>(S, j, sing, c->h_scal.p + 8, iters); ++c->launches; }   // last column of the cycle: v_{m} is never used
       dbg(c, "finish");
       CUDA_CHECK(cudaEventRecord(ev[j], c->stream));

@@ -41,6 +41,7 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
             const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy,
             const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the reduction kernel that follows may be scheduled into the tail of this grid (it waits for it)
   if (!DOT && s >= nslices) return;
   // DOT: warps past the last slice do no row work (slen = 0) but fall through to the ONE spmv_dot_finish call site below, so
   // every thread of the block meets the same barrier instructions
@@ -74,74 +75,11 @@ k_spmv_sell(const long long *__restrict__ slice_off, const int *__restrict__ sli
 }
 
 
-// ---- 16-bit column deltas -------------------------------------------------------------------------------------------------
-// The matrix stream is 12 B per stored entry (8 B value + 4 B column) and the kernel above moves it at 95-97 % of the HBM peak, so
-// the only way to make the multiply faster is to move fewer bytes.  Columns ascend along a row and, with rows in particle
-// order, consecutive columns of a row are close (<= one lattice plane apart: 40 000 for a 200^3 brick), so the column of entry k
-// is stored as a 16-bit difference to entry k-1 in the same [k][32 rows] layout (a warp reads 64 contiguous bytes per k).  The
-// code 0xFFFF means "take the column from the 32-bit array" — first entry of a row, periodic wrap-around, the jump from the
-// owned columns to the halo columns, the first padding entry — which stays in memory anyway because the assembly kernels and the
-// ILU set-up use it.  Stream: 10 B per stored entry instead of 12 (+ 4 B for the escaped ones, < 2 %).
-__global__ void k_compress_columns(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col, int nslices, unsigned short *__restrict__ col16) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5; if (s >= nslices) return;
-  const long long base = slice_off[s] + (row & 31); const int slen = slice_len[s];
-  int prev = 0;
-  for (int k = 0; k < slen; ++k) {
-    const int cc = col[base + 32ll * k]; const long long d = (long long)cc - prev;
-    col16[base + 32ll * k] = (k == 0 || d < 0 || d >= 0xFFFF) ? (unsigned short)0xFFFF : (unsigned short)d;
-    prev = cc;
-  }
-}
-void spmv_compress_columns(Ctx *c) {
-  Matrix &A = c->A; static const bool off = getenv("ISPH_SPMV_COL32") != nullptr;
-  A.have_col16 = false; if (off || A.total <= 0) return;
-  A.col16.ensure(A.total);
-  k_compress_columns<<<ceil_div((long long)A.nslices * 32, 256), 256, 0, c->stream>>>(A.slice_off.p, A.slice_len.p, A.col.p, A.nslices, A.col16.p); ++c->launches;
-  A.have_col16 = true;
-}
-
-template <int NV, bool DOT> __global__ void __launch_bounds__(256, 8)
-k_spmv_sell16(const long long *__restrict__ slice_off, const int *__restrict__ slice_len, const int *__restrict__ col, const unsigned short *__restrict__ col16,
-              const double *__restrict__ val, int n, int nslices, const double *__restrict__ x, int ldx, double *__restrict__ y, int ldy,
-              const double *__restrict__ dvec, double *partials, unsigned *counter, double *out, P2PRed pr) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5;
-  if (!DOT && s >= nslices) return;
-  const bool active = s < nslices;
-  const long long base = active ? slice_off[s] + (row & 31) : 0;
-  const int slen = active ? slice_len[s] : 0;
-  const int *cp = col + base; const unsigned short *dp = col16 + base; const double *vp = val + base;
-  double acc[NV];
-#pragma unroll
-  for (int q = 0; q < NV; ++q) acc[q] = 0.0;
-  int k = 0, cc = 0;
-  for (; k + 4 <= slen; k += 4) {
-    const unsigned d0 = __ldcs(dp + 32 * (k + 0)), d1 = __ldcs(dp + 32 * (k + 1)), d2 = __ldcs(dp + 32 * (k + 2)), d3 = __ldcs(dp + 32 * (k + 3));
-    const double v0 = __ldcs(vp + 32 * (k + 0)), v1 = __ldcs(vp + 32 * (k + 1)), v2 = __ldcs(vp + 32 * (k + 2)), v3 = __ldcs(vp + 32 * (k + 3));
-    const int c0 = d0 == 0xFFFFu ? __ldcs(cp + 32 * (k + 0)) : cc + (int)d0;
-    const int c1 = d1 == 0xFFFFu ? __ldcs(cp + 32 * (k + 1)) : c0 + (int)d1;
-    const int c2 = d2 == 0xFFFFu ? __ldcs(cp + 32 * (k + 2)) : c1 + (int)d2;
-    const int c3 = d3 == 0xFFFFu ? __ldcs(cp + 32 * (k + 3)) : c2 + (int)d3;
-    cc = c3;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      const double *xq = x + (size_t)q * ldx;
-      acc[q] += v0 * __ldg(xq + c0); acc[q] += v1 * __ldg(xq + c1); acc[q] += v2 * __ldg(xq + c2); acc[q] += v3 * __ldg(xq + c3);
-    }
-  }
-  for (; k < slen; ++k) {
-    const unsigned d0 = __ldcs(dp + 32 * k); const double v0 = __ldcs(vp + 32 * k);
-    cc = d0 == 0xFFFFu ? __ldcs(cp + 32 * k) : cc + (int)d0;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) acc[q] += v0 * __ldg(x + (size_t)q * ldx + cc);
-  }
-  if (row < n) {
-#pragma unroll
-    for (int q = 0; q < NV; ++q) y[(size_t)q * ldy + row] = acc[q];
-  }
-  if (DOT) spmv_dot_finish(row < n ? acc[0] * dvec[row] : 0.0, partials, counter, out, pr);
-}
-
-// (A persistent variant in which every warp draws its next slice from a global ticket counter was measured on the 1M-row brick:
+// (Two variants were built and measured in round 2 and are not kept.  (1) The column stream as 16-bit deltas along a row with
+// 32-bit escapes — 10 B per stored entry instead of 12: SLOWER, 250 us against 226 us per launch on the 1M-row brick and 1.77 ms
+// against 1.71 ms on 8M rows (gpurun_out/r2_c16_*.json vs r2_c32_*.json): the kernel issues the same number of memory requests
+// for fewer bytes and gains a serial add chain per row, i.e. at 95 % of the HBM peak it is also at the limit of its request rate.
+// (2) A persistent variant in which every warp draws its next slice from a global ticket counter, measured on the 1M-row brick:
 // 233 us per launch against 226 us for this kernel — the hardware CTA scheduler already balances at the granularity that matters,
 // and consecutive slices on one SM share the x gather in L1.  gpurun_out/r2_dyn*_c2.json; not kept.)
 
@@ -161,23 +99,10 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const 
   else if (c->nranks > 1) halo_exchange(c, const_cast<double *>(x), nvec, ldx);
   P2PRed none; none.tab = nullptr; none.seq = 0; none.nranks = 1;
 #define SPMV_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr
-#define SPMV16_ARGS(xx, yy, dv, pr) A.slice_off.p, A.slice_len.p, A.col.p, A.col16.p, A.val.p, A.n, A.nslices, xx, ldx, yy, ldy, dv, c->red.p, (unsigned *)c->flag.p + 13, dot_out, pr
   int done = 0;
   while (done < nvec) {
     const int nv = nvec - done >= 3 ? 3 : (nvec - done >= 2 ? 2 : 1);
     const double *xx = x + (size_t)done * ldx; double *yy = y + (size_t)done * ldy;
-    if (A.have_col16) {
-      if (nv == 3) k_spmv_sell16<3, false><<<grid, 256, 0, c->stream>>>(SPMV16_ARGS(xx, yy, nullptr, none));
-      else if (nv == 2) k_spmv_sell16<2, false><<<grid, 256, 0, c->stream>>>(SPMV16_ARGS(xx, yy, nullptr, none));
-      else if (dot_vec && nvec == 1) {
-        ISPH_REQUIRE(c->red.cap >= (size_t)grid, "spmv: reduction workspace too small");
-        P2PRed pr = halo_p2p_ticket(c);
-        k_spmv_sell16<1, true><<<grid, 256, 0, c->stream>>>(SPMV16_ARGS(xx, yy, dot_vec, pr));
-        if (c->nranks > 1 && pr.nranks <= 1) halo_allreduce(c, dot_out, 1);
-      }
-      else k_spmv_sell16<1, false><<<grid, 256, 0, c->stream>>>(SPMV16_ARGS(xx, yy, nullptr, none));
-      ++c->launches; done += nv; continue;
-    }
     if (nv == 3) k_spmv_sell<3, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     else if (nv == 2) k_spmv_sell<2, false><<<grid, 256, 0, c->stream>>>(SPMV_ARGS(xx, yy, nullptr, none));
     else if (dot_vec && nvec == 1) {
@@ -190,7 +115,6 @@ void spmv(Ctx *c, const double *x, double *y, int nvec, int ldx, int ldy, const 
     ++c->launches; done += nv;
   }
 #undef SPMV_ARGS
-#undef SPMV16_ARGS
   if (e1) CUDA_CHECK(cudaEventRecord(e1, c->stream));
 }
 
