@@ -396,6 +396,92 @@ void halo_allreduce(Ctx *c, double *buf, int count) {
   NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, c->stream));
 }
 
+// ---- "Overlap Level" 1 (Ifpack_OverlappingRowMatrix / Ifpack_AdditiveSchwarz, precond_ifpack.h:35-43) ------------------------------
+// The extended local problem of a rank = its owned rows + the rows of its halo columns (one level of overlap), restricted to that set.
+// Owned rows need nothing from outside (every column of an owned row is an owned or a halo column).  The rows of the halo particles live
+// on their owners: each owner packs, for every row on its send list, (global tag, value) of the stored entries; lengths, tags and values
+// travel with grouped ncclSend/ncclRecv along the halo plan; the receiver maps tags to its own column ids (entries outside the extended
+// set are dropped: Ifpack_LocalFilter) and sorts every row by column (cub segmented sort).  Once per preconditioner creation.
+__global__ void k_coltag(const int *tag, const int *col_of_atom, int nall, int *coltag, int *tag2col) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x; if (a >= nall) return;
+  const int c = col_of_atom[a]; if (c < 0) return;
+  coltag[c] = tag[a]; tag2col[tag[a]] = c;                        // all copies of a particle carry the same tag and column
+}
+__global__ void k_rows_len(const int *row_len, const int *send_idx, int nsend, int *len) { const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < nsend) len[k] = row_len[send_idx[k]]; }
+__global__ void k_rows_pack(const long long *slice_off, const int *col, const double *val, const int *send_idx, const long long *off, const int *len, int nsend, const int *coltag, int *tags, double *vals) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31; if (k >= nsend) return;
+  const int r = send_idx[k]; const long long base = slice_off[r >> 5] + (r & 31), o = off[k];
+  for (int e = lane; e < len[k]; e += 32) { tags[o + e] = coltag[col[base + 32ll * e]]; vals[o + e] = val[base + 32ll * e]; }
+}
+__global__ void k_rows_map(const int *tags, long long ntot, const int *tag2col, int max_tag, int *cols) {
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (j >= ntot) return;
+  const int t = tags[j]; const int c = (t >= 0 && t <= max_tag) ? tag2col[t] : -1;
+  cols[j] = c < 0 ? 0x7fffffff : c;
+}
+__global__ void k_add_rows_from(double *z, const int *send_idx, const double *buf, int k0, int k1) { const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; if (k < k1) z[send_idx[k]] += buf[k]; }
+
+void halo_import_rows(Ctx *c, OverlapRows *out) {
+  Halo *h = get(c); Matrix &A = c->A; const int R = c->nranks, nl = c->nlocal, nh = h->nhalo, ns = h->nsend;
+  out->nhalo = nh;
+  out->coltag.ensure(A.ncols + 1); out->tag2col.ensure((size_t)c->max_tag + 2);
+  CUDA_CHECK(cudaMemsetAsync(out->tag2col.p, 0xff, sizeof(int) * ((size_t)c->max_tag + 2), c->stream));
+  k_coltag<<<ceil_div(c->nall, 256), 256, 0, c->stream>>>(c->tag.p, c->col_of_atom.p, c->nall, out->coltag.p, out->tag2col.p); ++c->launches;
+  out->len_s.ensure(ns + 1); out->len_r.ensure(nh + 1);
+  if (ns) { k_rows_len<<<ceil_div(ns, 256), 256, 0, c->stream>>>(A.row_len.p, h->send_idx.p, ns, out->len_s.p); ++c->launches; }
+  NCCL_CHECK(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    if (h->send_count[p]) NCCL_CHECK(g_nccl.Send(out->len_s.p + h->send_off[p], h->send_count[p], ncclInt, p, h->comm, c->stream));
+    if (h->recv_count[p]) NCCL_CHECK(g_nccl.Recv(out->len_r.p + h->recv_off[p], h->recv_count[p], ncclInt, p, h->comm, c->stream));
+  }
+  NCCL_CHECK(g_nccl.GroupEnd());
+  std::vector<int> ls(ns), lr(nh);
+  if (ns) CUDA_CHECK(cudaMemcpyAsync(ls.data(), out->len_s.p, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+  if (nh) CUDA_CHECK(cudaMemcpyAsync(lr.data(), out->len_r.p, sizeof(int) * nh, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  std::vector<long long> os(ns + 1, 0), orr(nh + 1, 0);
+  for (int k = 0; k < ns; ++k) os[k + 1] = os[k] + ls[k];
+  for (int k = 0; k < nh; ++k) orr[k + 1] = orr[k] + lr[k];
+  const long long tot_s = os[ns], tot_r = orr[nh];
+  out->off_s.ensure(ns + 1); out->off_r.ensure(nh + 1);
+  CUDA_CHECK(cudaMemcpyAsync(out->off_s.p, os.data(), sizeof(long long) * (ns + 1), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(out->off_r.p, orr.data(), sizeof(long long) * (nh + 1), cudaMemcpyHostToDevice, c->stream));
+  out->tag_s.ensure(tot_s + 1); out->val_s.ensure(tot_s + 1); out->tag_r.ensure(tot_r + 1); out->val_r.ensure(tot_r + 1); out->col_r.ensure(tot_r + 1); out->col_r2.ensure(tot_r + 1); out->val_r2.ensure(tot_r + 1);
+  if (ns) { k_rows_pack<<<ceil_div((long long)ns * 32, 256), 256, 0, c->stream>>>(A.slice_off.p, A.col.p, A.val.p, h->send_idx.p, out->off_s.p, out->len_s.p, ns, out->coltag.p, out->tag_s.p, out->val_s.p); ++c->launches; }
+  NCCL_CHECK(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    const long long s0 = os[h->send_off[p]], s1 = os[h->send_off[p + 1]], r0 = orr[h->recv_off[p]], r1 = orr[h->recv_off[p + 1]];
+    if (s1 > s0) { NCCL_CHECK(g_nccl.Send(out->tag_s.p + s0, (size_t)(s1 - s0), ncclInt, p, h->comm, c->stream)); NCCL_CHECK(g_nccl.Send(out->val_s.p + s0, (size_t)(s1 - s0), ncclDouble, p, h->comm, c->stream)); }
+    if (r1 > r0) { NCCL_CHECK(g_nccl.Recv(out->tag_r.p + r0, (size_t)(r1 - r0), ncclInt, p, h->comm, c->stream)); NCCL_CHECK(g_nccl.Recv(out->val_r.p + r0, (size_t)(r1 - r0), ncclDouble, p, h->comm, c->stream)); }
+  }
+  NCCL_CHECK(g_nccl.GroupEnd());
+  out->total = tot_r;
+  if (tot_r > 0) {
+    k_rows_map<<<ceil_div(tot_r, 256), 256, 0, c->stream>>>(out->tag_r.p, tot_r, out->tag2col.p, c->max_tag, out->col_r.p); ++c->launches;
+    size_t tb = 0;
+    cub::DeviceSegmentedSort::SortPairs(nullptr, tb, out->col_r.p, out->col_r2.p, out->val_r.p, out->val_r2.p, tot_r, nh, out->off_r.p, out->off_r.p + 1, c->stream);
+    h->cubtmp.ensure(tb); tb = h->cubtmp.cap;
+    cub::DeviceSegmentedSort::SortPairs(h->cubtmp.p, tb, out->col_r.p, out->col_r2.p, out->val_r.p, out->val_r2.p, tot_r, nh, out->off_r.p, out->off_r.p + 1, c->stream); ++c->launches;
+  }
+  (void)nl;
+}
+
+// additive Schwarz, combine mode Add: the extended solution at the halo rows goes back to the owners and is added to their rows
+// (peer after peer, in rank order: a row requested by several peers is summed in a fixed order)
+void halo_export_add(Ctx *c, const double *zext_halo, double *z) {
+  Halo *h = get(c); const int R = c->nranks;
+  if (h->nhalo == 0 && h->nsend == 0) return;
+  h->sendbuf.ensure((size_t)h->nsend * 9 + 8);
+  NCCL_CHECK(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    if (h->recv_count[p]) NCCL_CHECK(g_nccl.Send(zext_halo + h->recv_off[p], h->recv_count[p], ncclDouble, p, h->comm, c->stream));
+    if (h->send_count[p]) NCCL_CHECK(g_nccl.Recv(h->sendbuf.p + h->send_off[p], h->send_count[p], ncclDouble, p, h->comm, c->stream));
+  }
+  NCCL_CHECK(g_nccl.GroupEnd());
+  for (int p = 0; p < R; ++p) if (h->send_count[p]) {
+    k_add_rows_from<<<ceil_div(h->send_count[p], 256), 256, 0, c->stream>>>(z, h->send_idx.p, h->sendbuf.p, h->send_off[p], h->send_off[p + 1]); ++c->launches;
+  }
+}
+
 bool halo_fault(Ctx *c) {
   if (!c->halo || !c->halo->fault) return false;
   int f = 0; cudaMemcpy(&f, c->halo->fault, sizeof(int), cudaMemcpyDeviceToHost); return f != 0;

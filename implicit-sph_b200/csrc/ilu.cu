@@ -31,24 +31,44 @@ struct IluData {
   // level-ordered split copy of the factors for the apply: position idx of the forward (backward) sweep owns the contiguous
   // entries Lrp[idx]..Lrp[idx+1] (Urp..) of row order_l[idx] (order_u[idx]) — no row-pointer / diagonal-position indirection
   DevBuf<int> Lrp, Lci, Urp, Uci, plen; DevBuf<double> Lfv, Ufv, Udinv; bool lv = false; int grid_lv = 1;
+  // "Overlap Level" 1 across ranks: the factored problem has n = n_own + nhalo rows (owned rows, then the imported rows of the halo
+  // particles in halo-slot order); r / z of an apply are extended with the imported / exported halo part
+  bool ext = false; int n_own = 0; OverlapRows ov; DevBuf<double> rext, zext;
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
-__global__ void k_ilu_count(const long long *slice_off, const int *row_len, const int *col, const int *blk, int n, int *cnt) {
+__global__ void k_ilu_count(const long long *slice_off, const int *row_len, const int *col, const int *blk, int n, int climit, int *cnt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
   const long long base = slice_off[row >> 5] + (row & 31); const int rlen = row_len[row]; const int mb = blk ? blk[row] : 0;
   int c = 0, prev = -1;
-  for (int k = 0; k < rlen; ++k) { const int cc = col[base + 32ll * k]; if (cc < n && cc != prev && (!blk || blk[cc] == mb)) ++c; prev = cc; }
+  for (int k = 0; k < rlen; ++k) { const int cc = col[base + 32ll * k]; if (cc < climit && cc != prev && (!blk || blk[cc] == mb)) ++c; prev = cc; }
   cnt[row] = c;
 }
+// rows of the halo particles (overlap 1): sorted (column, value) segments from halo_import_rows; duplicate columns are summed
+__global__ void k_ilu_ext_count(const long long *off, const int *cols, int nh, int *cnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= nh) return;
+  int c = 0, prev = -1;
+  for (long long j = off[s]; j < off[s + 1]; ++j) { const int cc = cols[j]; if (cc == 0x7fffffff) break; if (cc != prev) ++c; prev = cc; }
+  cnt[s] = c;
+}
+__global__ void k_ilu_ext_fill(const long long *off, const int *cols, const double *vals, int nh, int n_own, const int *rp, int *ci, double *fv, int *dpos) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= nh) return;
+  const int row = n_own + s; int o = rp[row], prev = -1, dp = -1;
+  for (long long j = off[s]; j < off[s + 1]; ++j) {
+    const int cc = cols[j]; if (cc == 0x7fffffff) break;
+    if (cc != prev) { ci[o] = cc; fv[o] = vals[j]; if (cc == row) dp = o; ++o; } else fv[o - 1] += vals[j];
+    prev = cc;
+  }
+  dpos[row] = dp;
+}
 __global__ void k_ilu_fill(const long long *slice_off, const int *row_len, const int *col, const double *val, const int *blk, int n,
-                           const int *rp, int *ci, double *fv, int *dpos) {
+                           int climit, const int *rp, int *ci, double *fv, int *dpos) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
   const long long base = slice_off[row >> 5] + (row & 31); const int rlen = row_len[row]; const int mb = blk ? blk[row] : 0;
   int o = rp[row], prev = -1, dp = -1;
   for (int k = 0; k < rlen; ++k) {
     const int cc = col[base + 32ll * k];
-    if (cc < n && cc != prev && (!blk || blk[cc] == mb)) { ci[o] = cc; fv[o] = val[base + 32ll * k]; if (cc == row) dp = o; ++o; }
+    if (cc < climit && cc != prev && (!blk || blk[cc] == mb)) { ci[o] = cc; fv[o] = val[base + 32ll * k]; if (cc == row) dp = o; ++o; }
     prev = cc;
   }
   dpos[row] = dp;
@@ -382,14 +402,20 @@ static int coop_grid(Ctx *c, const void *fn, int max_width) {
 }
 
 void ilu_create(Ctx *c) {
-  Matrix &A = c->A; const int n = A.n;
+  Matrix &A = c->A; const int n_own = A.n;
   matrix_merge_duplicates(c);
   if (!c->ilu) c->ilu = new IluData();
-  IluData &I = *c->ilu; I.n = n;
-  const int *blk = c->have_blocks ? c->block_of_row.p : nullptr;
-  I.cnt.ensure(n + 1); I.rp.ensure(n + 1); I.dpos.ensure(n); I.dinv.ensure(n); I.y.ensure(c->ld);
+  IluData &I = *c->ilu;
+  // "Overlap Level" 1 across ranks (validated in precond_create: ILU, no sub-blocks): the rows of the halo particles join the local problem
+  const bool ext = c->nranks > 1 && c->pp.overlap >= 1;
+  if (ext) { c->tic("iluImportRows"); halo_import_rows(c, &I.ov); c->toc("iluImportRows"); }
+  const int n = n_own + (ext ? I.ov.nhalo : 0), climit = ext ? n : n_own;
+  I.n = n; I.n_own = n_own; I.ext = ext;
+  const int *blk = (c->have_blocks && !ext) ? c->block_of_row.p : nullptr;
+  I.cnt.ensure(n + 1); I.rp.ensure(n + 1); I.dpos.ensure(n); I.dinv.ensure(n); I.y.ensure(std::max(c->ld, n));
   c->tic("iluPattern");
-  k_ilu_count<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, blk, n, I.cnt.p); ++c->launches;
+  k_ilu_count<<<ceil_div(n_own, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, blk, n_own, climit, I.cnt.p); ++c->launches;
+  if (ext && I.ov.nhalo) { k_ilu_ext_count<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.ov.nhalo, I.cnt.p + n_own); ++c->launches; }
   CUDA_CHECK(cudaMemsetAsync(I.cnt.p + n, 0, sizeof(int), c->stream));
   size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, I.cnt.p, I.rp.p, n + 1, c->stream);
   I.tmp.ensure(tb);
@@ -405,7 +431,8 @@ void ilu_create(Ctx *c) {
   if (c->pp.fill > 0) { rp.resize(n + 1); CUDA_CHECK(cudaMemcpyAsync(rp.data(), I.rp.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
   I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
   I.sync_free = !getenv("ISPH_ILU_BARRIER"); I.fault.ensure(4); CUDA_CHECK(cudaMemsetAsync(I.fault.p, 0, 4 * sizeof(int), c->stream));
-  k_ilu_fill<<<ceil_div(n, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
+  k_ilu_fill<<<ceil_div(n_own, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n_own, climit, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
+  if (ext && I.ov.nhalo) { k_ilu_ext_fill<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.ov.val_r2.p, I.ov.nhalo, n_own, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches; }
   if (c->pp.fill > 0) {                                          // level-of-fill pattern (host), values expanded on the device
     std::vector<int> ci0(I.nnz), frp, fci;
     CUDA_CHECK(cudaMemcpyAsync(ci0.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -523,7 +550,20 @@ void ilu_info(Ctx *c, long long *nnz, int *nlev_l, int *nlev_u, int *maxlen) {
 }
 
 static void ilu_apply_launch(Ctx *c, const double *r, double *z);
+static void ilu_apply_core(Ctx *c, const double *r, double *z);
 void ilu_apply(Ctx *c, const double *r, double *z) {
+  IluData &I = *c->ilu;
+  if (!I.ext) { ilu_apply_core(c, r, z); return; }
+  // additive Schwarz with one level of overlap, combine mode Add (Ifpack_AdditiveSchwarz::ApplyInverse): import r at the halo rows,
+  // solve the extended local problem, keep the owned part and add the halo part of the solution into the owners' rows
+  I.rext.ensure(I.n + 32); I.zext.ensure(I.n + 32);
+  CUDA_CHECK(cudaMemcpyAsync(I.rext.p, r, sizeof(double) * I.n_own, cudaMemcpyDeviceToDevice, c->stream));
+  halo_exchange(c, I.rext.p, 1, I.n);
+  ilu_apply_core(c, I.rext.p, I.zext.p);
+  CUDA_CHECK(cudaMemcpyAsync(z, I.zext.p, sizeof(double) * I.n_own, cudaMemcpyDeviceToDevice, c->stream));
+  halo_export_add(c, I.zext.p + I.n_own, z);
+}
+static void ilu_apply_core(Ctx *c, const double *r, double *z) {
   if (!c->prof_spmv) { ilu_apply_launch(c, r, z); return; }
   // per-launch device timing on the launching stream (bench.py: achieved GB/s of the triangular solves)
   if (c->pprof_used + 2 > c->pprof_ev.size()) { const size_t o = c->pprof_ev.size(); c->pprof_ev.resize(o + 512, nullptr); for (size_t q = o; q < c->pprof_ev.size(); ++q) CUDA_CHECK(cudaEventCreate(&c->pprof_ev[q])); }
@@ -555,6 +595,7 @@ static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
+  I.ov.release(); I.rext.release(); I.zext.release();
   I.Lrp.release(); I.Lci.release(); I.Urp.release(); I.Uci.release(); I.plen.release(); I.Lfv.release(); I.Ufv.release(); I.Udinv.release();
   I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.rp0.release(); I.ci0.release(); I.fv0.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
 }

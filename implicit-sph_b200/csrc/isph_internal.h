@@ -201,6 +201,15 @@ struct PrePush { const HaloDev *plan; const int *sp, *sd; unsigned long long seq
 void neighbors_build(Ctx *c, double cutneigh);                // neighbor.cu
 void neighbors_destroy(Ctx *c);
 long long slice_offsets_device(Ctx *c, int n, int nslices, long long *d_slice_off);
+// matrix rows of the halo particles, imported from their owners for "Overlap Level" 1 (halo.cu): row of halo slot s = entries
+// off_r[s] .. off_r[s+1] of (col_r2, val_r2), sorted by local column id, columns outside the extended set = 0x7fffffff at the end
+struct OverlapRows {
+  int nhalo = 0; long long total = 0;
+  DevBuf<int> coltag, tag2col, len_s, len_r, tag_s, tag_r, col_r, col_r2; DevBuf<long long> off_s, off_r; DevBuf<double> val_s, val_r, val_r2;
+  void release() { coltag.release(); tag2col.release(); len_s.release(); len_r.release(); tag_s.release(); tag_r.release(); col_r.release(); col_r2.release(); off_s.release(); off_r.release(); val_s.release(); val_r.release(); val_r2.release(); }
+};
+void halo_import_rows(Ctx *c, OverlapRows *out);
+void halo_export_add(Ctx *c, const double *zext_halo, double *z);
 void halo_setup(Ctx *c);                                     // halo.cu
 bool halo_prepush_begin(Ctx *c, const double *x_next, PrePush *pp);   // reserves the exchange of the SpMV that will read x_next
 void halo_wait_unstage(Ctx *c, double *d_x, unsigned long long seq);  // completes a pre-pushed exchange: halo lands behind x's owned rows

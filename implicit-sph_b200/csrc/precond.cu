@@ -69,7 +69,11 @@ void precond_create(Ctx *c) {
   const int n = A.n, ld = c->ld; const std::string &t = c->pp.type;
   c->tic("precondCreate");
   // with one rank and one block there is nothing to overlap with: Ifpack's "Overlap Level" (default 1, precond_ifpack.h:37) is a no-op
-  ISPH_REQUIRE(c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks), "Overlap Level > 0 across ranks / blocks is not implemented (block-Jacobi, overlap 0)");
+  // across ranks "Overlap Level" 1 (the reference's own default, precond_ifpack.h:37) is the additive-Schwarz ILU of ilu.cu (rows of the
+  // halo particles imported from their owners, combine mode Add); not provided: more than one level, overlap between sub-blocks of a
+  // rank, overlap for the relaxation / Chebyshev types
+  ISPH_REQUIRE(c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks) || (c->pp.overlap == 1 && !c->have_blocks && t == "ILU"),
+               "Overlap Level: 0, or 1 with Precond Type ILU and one block per rank (more levels, overlapping sub-blocks and overlapping relaxation are not implemented)");
   if (t == "none") c->prec_kind = 0;
   else if (t == "point relaxation" || t == "point relaxation stand-alone" || t == "Jacobi") { ISPH_REQUIRE(c->pp.relax_type == "Jacobi", "relaxation: type must be Jacobi"); c->prec_kind = 1; }
   else if (t == "Chebyshev") c->prec_kind = 2;

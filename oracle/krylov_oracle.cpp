@@ -62,9 +62,44 @@ struct Precond {
   // ILU(0): factors stored on A's pattern restricted to the row's block
   std::vector<double> fv, dinv; std::vector<int> diagpos, frp, fci; const int *blk;
   std::vector<double> V, W;
+  // "Overlap Level" 1: one extended local problem per block (Ifpack_OverlappingRowMatrix + Ifpack_AdditiveSchwarz, combine mode Add)
+  struct Sub { std::vector<int> idx, rp, ci; std::vector<double> v, r, z; Csr A; orc_krylov_params prm; Precond *M; };
+  std::vector<Sub> subs;
+  ~Precond() { for (auto &s : subs) delete s.M; }
+
+  void setup_overlap(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
+    const int n = A_.n; int nb = 0; for (int i = 0; i < n; ++i) nb = std::max(nb, block_of_row[i] + 1);
+    subs.resize(nb);
+    std::vector<int> pos(n, -1);
+    for (int b = 0; b < nb; ++b) {
+      Sub &S = subs[b];
+      for (int i = 0; i < n; ++i) if (block_of_row[i] == b) S.idx.push_back(i);                     // own rows, local order
+      std::vector<int> ghost; std::vector<char> seen(n, 0);
+      for (int i : S.idx) for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) { const int c = A_.ci[q]; if (c >= 0 && block_of_row[c] != b && !seen[c]) { seen[c] = 1; ghost.push_back(c); } }
+      std::sort(ghost.begin(), ghost.end(), [&](int a, int c) {                                       // behind the own rows, by (owner block, global id)
+        if (block_of_row[a] != block_of_row[c]) return block_of_row[a] < block_of_row[c];
+        const int ga = p->row_gid ? p->row_gid[a] : a, gc = p->row_gid ? p->row_gid[c] : c; return ga < gc; });
+      S.idx.insert(S.idx.end(), ghost.begin(), ghost.end());
+      for (size_t k = 0; k < S.idx.size(); ++k) pos[S.idx[k]] = (int)k;
+      S.rp.assign(1, 0);
+      for (int i : S.idx) {                                                                           // rows restricted to the extended set (Ifpack_LocalFilter)
+        std::vector<std::pair<int, double>> row;
+        for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) { const int c = A_.ci[q]; if (c >= 0 && pos[c] >= 0) row.emplace_back(pos[c], A_.v[q]); }
+        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &c) { return a.first < c.first; });
+        for (auto &e : row) { S.ci.push_back(e.first); S.v.push_back(e.second); }
+        S.rp.push_back((int)S.ci.size());
+      }
+      for (int i : S.idx) pos[i] = -1;
+      S.A = Csr{(int)S.idx.size(), S.rp.data(), S.ci.data(), S.v.data()};
+      S.prm = *p; S.prm.overlap = 0; S.prm.row_gid = nullptr;
+      S.M = new Precond(); S.M->setup(S.A, &S.prm, nullptr);
+      S.r.assign(S.idx.size(), 0.0); S.z.assign(S.idx.size(), 0.0);
+    }
+  }
 
   void setup(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
     A = &A_; prm = p; type = p->precond; blk = block_of_row; const int n = A_.n;
+    if (type == ORC_PREC_ILU0 && p->overlap >= 1 && block_of_row) { setup_overlap(A_, p, block_of_row); return; }
     if (type == ORC_PREC_JACOBI || type == ORC_PREC_CHEBYSHEV) {
       invdiag.assign(n, 0.0);
       for (int i = 0; i < n; ++i) { double d = 0.0; for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] == i) d += A_.v[q];
@@ -153,6 +188,15 @@ struct Precond {
       }
       break; }
     case ORC_PREC_ILU0: {                                   // Ifpack_ILU::ApplyInverse: L (unit) solve, D^-1 scale, U (unit) solve
+      if (!subs.empty()) {                                   // additive Schwarz, combine mode Add: every block's extended solution is added
+        for (int i = 0; i < n; ++i) z[i] = 0.0;
+        for (auto &S : subs) {
+          for (size_t k = 0; k < S.idx.size(); ++k) S.r[k] = r[S.idx[k]];
+          S.M->apply(S.r.data(), S.z.data());
+          for (size_t k = 0; k < S.idx.size(); ++k) z[S.idx[k]] += S.z[k];
+        }
+        break;
+      }
       for (int i = 0; i < n; ++i) { double s = r[i]; for (int q = frp[i]; q < frp[i + 1]; ++q) { const int j = fci[q]; if (j < i) s -= fv[q] * z[j]; } z[i] = s; }
       for (int i = 0; i < n; ++i) z[i] *= dinv[i];
       for (int i = n - 1; i >= 0; --i) { double s = z[i]; for (int q = frp[i]; q < frp[i + 1]; ++q) { const int j = fci[q]; if (j > i) s -= fv[q] * z[j]; } z[i] = s; }
@@ -186,7 +230,7 @@ int orc_set_num_threads(int n) {
 void orc_krylov_default_params(orc_krylov_params *p) {
   memset(p, 0, sizeof(*p));
   p->solver = ORC_SOLVER_GMRES; p->flexible = 1; p->num_blocks = 50; p->max_iters = 500; p->max_restarts = 15; p->tol = 1.0e-8;   // solver_lin_belos.h:231-240
-  p->precond = ORC_PREC_NONE; p->jacobi_sweeps = 1; p->jacobi_damping = 1.0; p->min_diag = 0.0;
+  p->overlap = 0; p->precond = ORC_PREC_NONE; p->jacobi_sweeps = 1; p->jacobi_damping = 1.0; p->min_diag = 0.0;
   p->cheb_degree = 1; p->cheb_ratio = 30.0; p->cheb_lambda_max = -1.0; p->cheb_eig_iters = 10; p->row_gid = 0; p->ilu_fill = 0;
 }
 

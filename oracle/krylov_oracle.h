@@ -24,6 +24,9 @@ typedef struct {
   int cheb_eig_iters;    /* "chebyshev: eigenvalue max iterations" */
   const int *row_gid;    /* global id per row for the power-method start vector (NULL: row+1) */
   int ilu_fill;          /* "fact: level-of-fill" (Ifpack_IlukGraph level rule) */
+  int overlap;           /* "Overlap Level" 0 | 1 with block_of_row = the rank of every row (Ifpack_AdditiveSchwarz over an
+                            Ifpack_OverlappingRowMatrix, "schwarz: combine mode" = Add: precond_ifpack.h:35-43).  Every block is extended
+                            by the rows of its off-block columns (one level), ordered behind its own rows by (block, row_gid) */
 } orc_krylov_params;
 
 int orc_set_num_threads(int n);   /* OpenMP threads of the port's row loops; returns the count in effect */

@@ -221,7 +221,7 @@ class KrylovParams(C.Structure):
     _fields_ = [("solver", C.c_int), ("flexible", C.c_int), ("num_blocks", C.c_int), ("max_iters", C.c_int), ("max_restarts", C.c_int),
                 ("tol", C.c_double), ("precond", C.c_int), ("jacobi_sweeps", C.c_int), ("jacobi_damping", C.c_double), ("min_diag", C.c_double),
                 ("cheb_degree", C.c_int), ("cheb_ratio", C.c_double), ("cheb_lambda_max", C.c_double), ("cheb_eig_iters", C.c_int),
-                ("row_gid", _ip), ("ilu_fill", C.c_int)]
+                ("row_gid", _ip), ("ilu_fill", C.c_int), ("overlap", C.c_int)]
 
 
 SOLVER_GMRES, SOLVER_CG = 0, 1

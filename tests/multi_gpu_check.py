@@ -7,6 +7,7 @@ all-reduces over NVLink peer memory, or NCCL with ISPH_NO_P2P=1) and are compare
 GLOBAL problem: graph bit-exact, values <= 1e-12, iteration counts +-2, solutions <= 1e-6 (kappa ~ 1e3).
   1. pressure Poisson, NullSpace, flexible GMRES(50) + Jacobi                       (BASELINE configs[1])
   2. the same system with block-Jacobi ILU(0), one open block per rank (= Ifpack overlap 0 on an MPI run)   (configs[3])
+  2b. ILU(0) with Overlap Level 1 and combine mode Add — Ifpack's defaults as the reference sets them (precond_ifpack.h:35-43)
   3. velocity Helmholtz, 3 right-hand sides one after another, CG + Chebyshev(2)     (configs[2]; SpMM with a 3-vector import)
   4. Poisson-Boltzmann Newton iteration (computeF / computeJacobian / GMRES + Jacobi Jacobian solves)      (configs[4])
 tests/test_gpu_multi.py wraps this for pytest when >= 2 GPUs are visible.
@@ -65,6 +66,11 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
     x2 = np.zeros(nl); c.create_solution(x2, 1); c.set_initial_solution(isph.INIT_ZERO)
     c.precond_param("Precond Type", "ILU"); c.precond_param("Overlap Level", 0); c.precond_param("fact: level-of-fill", 0)
     st2 = c.solve(True, "PoissonILU")
+    # 2b. the reference's own Ifpack default across ranks: ILU with Overlap Level 1, combine mode Add (precond_ifpack.h:35-43)
+    x2b = np.zeros(nl); c.create_solution(x2b, 1); c.set_initial_solution(isph.INIT_ZERO)
+    c.precond_param("Overlap Level", 1)
+    st2b = c.solve(True, "PoissonILUoverlap1")
+    c.precond_param("Overlap Level", 0)
     # 3. Helmholtz, dim right-hand sides, CG + Chebyshev(2)
     theta = 0.5
     c.matrix_invalidate(); c.create_load(None, dim); c.load_set(np.asfortranarray(v[:nl, :dim])); c.ns_helmholtz(dt, theta)
@@ -78,7 +84,7 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
     c.create_solution(None, 1); c.create_load(None, 1); c.set_matrix_is_singular(False)
     c.solver_param("Solver Type", "Block GMRES"); c.precond_param("Precond Type", "point relaxation")
     st4 = c.pb_newton(extra_f=ex); psi4 = c.field_get(isph.F_PSI)[:nl].copy()
-    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
+    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, x2b=x2b, st2b=st2b, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
     allr = [None] * world
     dist.gather_object(mine, allr if rank == 0 else None, 0)
     ok = True; rep = {}
@@ -116,6 +122,14 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
         its2 = allr[0]["st2"]["iters"]; x2err = np.linalg.norm(x2d - x2o) / np.linalg.norm(x2o)
         say(f"  block-Jacobi ILU(0): iters gpu {its2} vs oracle {info2['iters']}; x rel diff {x2err:.2e}; converged {allr[0]['st2']['converged']}")
         ok = ok and abs(its2 - info2["iters"]) <= 2 and x2err <= 1e-6 and allr[0]["st2"]["converged"]
+        # 2b. Overlap Level 1: every rank's block extended by the rows of its halo columns, additive Schwarz with combine mode Add
+        x2bd = np.zeros(n)
+        for d in allr:
+            x2bd[row_of_tag[d["tag"]]] = d["x2b"]
+        x2bo, info2b = O.krylov_solve(grp, colL, gA, gb.copy(), params=O.krylov_params(precond=O.PREC_ILU0, overlap=1, row_gid=G["tag"][:n]), null_mask=np.ones(n, dtype=np.int32), use_null=True, blocks=blocks)
+        its2b = allr[0]["st2b"]["iters"]; x2berr = np.linalg.norm(x2bd - x2bo) / np.linalg.norm(x2bo)
+        say(f"  ILU(0), Overlap Level 1 (Add): iters gpu {its2b} vs oracle {info2b['iters']}; x rel diff {x2berr:.2e}; converged {allr[0]['st2b']['converged']}")
+        ok = ok and abs(its2b - info2b["iters"]) <= 2 and x2berr <= 1e-6 and allr[0]["st2b"]["converged"]
         # 3. Helmholtz, CG + Chebyshev(2), dim right-hand sides
         o.invalidate_matrix(); gbh = o.ns_helmholtz(dt, 0.5, np.asfortranarray(vg[:n, :dim])); gAh = o.matrix()
         x3d = np.zeros((n, dim)); worst3 = 0.0
@@ -152,6 +166,7 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
         say("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
         rep = dict(rows=int(n), graph="bit-exact", values_max_rel_err=float(worst), gmres_jacobi=dict(iters=int(its), oracle_iters=int(info["iters"]), x_rel_diff=float(xerr)),
                    gmres_block_ilu0=dict(iters=int(its2), oracle_iters=int(info2["iters"]), x_rel_diff=float(x2err)),
+                   gmres_ilu0_overlap1=dict(iters=int(its2b), oracle_iters=int(info2b["iters"]), x_rel_diff=float(x2berr)),
                    helmholtz_cg_chebyshev=dict(iters=int(its3), oracle_iters=int(its3o), x_rel_diff=float(x3err), values_max_rel_err=float(worst3)),
                    pb_newton=dict(newton_iters=int(s4["newton_iters"]), oracle_newton_iters=int(kn), linear_iters=int(s4["linear_iters"]), oracle_linear_iters=int(lin), psi_rel_diff=float(p4err)))
     c.close()
