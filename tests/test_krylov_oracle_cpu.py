@@ -141,3 +141,50 @@ def test_iluk_factors_match_a_dense_level_of_fill_factorisation(fill, blocked):
     # more fill => a better preconditioner on this matrix
     its = [O.krylov_solve(rp, ci, v, r, params=O.krylov_params(precond=O.PREC_ILU0, ilu_fill=f))[1]["iters"] for f in (0, fill)]
     assert its[1] <= its[0]
+
+
+def _dense_ilu0_solve(S, r):
+    """ILU(0) of the dense matrix S on its own pattern (IKJ, Ifpack's scaled-U form) applied to r."""
+    n = S.shape[0]; pat = S != 0; F = S.astype(float).copy(); dinv = np.zeros(n)
+    for i in range(n):
+        for j in range(i):
+            if pat[i, j]:
+                m = F[i, j]; F[i, j] = m * dinv[j]
+                upd = pat[i, j + 1:] & pat[j, j + 1:]
+                F[i, j + 1:] -= np.where(upd, m * F[j, j + 1:], 0.0)
+        dinv[i] = 1.0 / F[i, i]; F[i, i + 1:] *= dinv[i]
+    z = r.astype(float).copy()
+    for i in range(n):
+        z[i] -= F[i, :i] @ z[:i]
+    z *= dinv
+    for i in range(n - 1, -1, -1):
+        z[i] -= F[i, i + 1:] @ z[i + 1:]
+    return z
+
+
+def test_ilu_overlap_one_is_additive_schwarz_with_add(oracle_mod):
+    """"Overlap Level" 1 in the oracle (Ifpack_OverlappingRowMatrix + Ifpack_AdditiveSchwarz, combine mode Add — the values the reference
+    sets, precond_ifpack.h:35-43): the apply must equal sum_B R_B^T ILU0(R_B A R_B^T)^-1 R_B r with every block extended by the rows of
+    its off-block columns, appended BEHIND the own rows in (owner block, id) order (the ordering matters: ILU(0) of the extended
+    tridiagonal block is exact only where the ghost row happens to stay adjacent), formed densely here."""
+    O = oracle_mod; n = 24
+    A = np.zeros((n, n)); i = np.arange(n); A[i, i] = 2.1; A[i[:-1], i[:-1] + 1] = -1.0; A[i[1:], i[1:] - 1] = -1.3
+    rp = [0]; ci = []; va = []
+    for r in range(n):
+        for c in np.nonzero(A[r])[0]:
+            ci.append(c); va.append(A[r, c])
+        rp.append(len(ci))
+    blocks = (i // 8).astype(np.int32); r = np.random.default_rng(4).standard_normal(n)
+    z, _ = O.precond_apply(rp, ci, va, r, O.krylov_params(precond=O.PREC_ILU0, overlap=1), blocks=blocks)
+    want = np.zeros(n)
+    for b in range(3):
+        own = np.nonzero(blocks == b)[0]; ghost = sorted({c for rr in own for c in np.nonzero(A[rr])[0] if blocks[c] != b}, key=lambda c: (blocks[c], c))
+        E = np.concatenate([own, np.array(ghost, dtype=int)])
+        want[E] += _dense_ilu0_solve(A[np.ix_(E, E)], r[E])
+    assert np.abs(z - want).max() <= 1e-13 * np.abs(want).max()
+    E0 = np.arange(9)                                                            # block 0 + ghost row 8 stays tridiagonal: its ILU(0) is the exact LU
+    assert np.abs(_dense_ilu0_solve(A[np.ix_(E0, E0)], r[E0]) - np.linalg.solve(A[np.ix_(E0, E0)], r[E0])).max() <= 1e-13
+    z0, _ = O.precond_apply(rp, ci, va, r, O.krylov_params(precond=O.PREC_ILU0, overlap=0), blocks=blocks)
+    assert np.abs(z0 - want).max() > 1e-3                                       # ... and differs from block Jacobi without overlap
+    z1, _ = O.precond_apply(rp, ci, va, r, O.krylov_params(precond=O.PREC_ILU0, overlap=1), blocks=np.zeros(n, dtype=np.int32))
+    assert np.abs(z1 - np.linalg.solve(A, r)).max() <= 1e-13                    # one block: nothing to overlap with
