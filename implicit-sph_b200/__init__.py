@@ -252,6 +252,16 @@ class Context:
         z = C.c_longlong(); a = C.c_int(); b = C.c_int(); m = C.c_int(); self.call("isph_precond_info", C.byref(z), C.byref(a), C.byref(b), C.byref(m))
         return dict(factor_nnz=z.value, levels_lower=a.value, levels_upper=b.value, max_row=m.value)
 
+    def precond_ml_info(self):
+        nl = C.c_int(); rows = (C.c_int * 16)(); nnz = (C.c_longlong * 16)(); lm = (C.c_double * 16)()
+        self.call("isph_precond_ml_info", C.byref(nl), rows, nnz, lm, 16)
+        L = lib(); L.isph_precond_ml_setup_ms.restype = C.c_double
+        return dict(levels=nl.value, rows=list(rows[:nl.value]), nnz=list(nnz[:nl.value]), lambda_max=list(lm[:nl.value]),
+                    setup_ms={k: L.isph_precond_ml_setup_ms(self.h, k.encode()) for k in ("aggregate", "galerkin", "eigen")})
+
+    def precond_ml_aggregates(self):
+        a = np.zeros(self.nlocal, dtype=np.int32); self.call("isph_precond_ml_aggregates", _i(a)); return a
+
     # ---- SolverLin mirror
     def create_solution(self, x=None, nvec=1):
         """x: Fortran-ordered (nlocal, nvec) float64 array that receives the solution (a View, like the reference), or None."""

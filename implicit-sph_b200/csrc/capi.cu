@@ -101,7 +101,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   if (!ctx) return ISPH_FAILURE; Ctx *c = reinterpret_cast<Ctx *>(ctx);
   cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
   if (c->prec_ready) { try { precond_free(c); } catch (...) {} }
-  halo_destroy(c); ilu_destroy(c); neighbors_destroy(c);
+  halo_destroy(c); ilu_destroy(c); amg_destroy(c); neighbors_destroy(c);
   c->d_tab.release(); c->x.release(); c->type.release(); c->tag.release(); c->kind.release(); c->col_of_atom.release(); c->tag2own.release();
   for (auto &f : c->field) f.release();
   c->ilist.release(); c->neigh.release(); c->noff.release(); c->pin_neigh.release();
@@ -394,6 +394,12 @@ int isph_precond_set_param_int(isph_ctx *ctx, const char *name, int v) {
   API_BEGIN(ctx) const std::string k(name ? name : "");
   if (k == "Overlap Level") c->pp.overlap = v; else if (k == "fact: level-of-fill") c->pp.fill = v; else if (k == "relaxation: sweeps") c->pp.sweeps = v;
   else if (k == "chebyshev: degree") c->pp.cheb_degree = v; else if (k == "chebyshev: eigenvalue max iterations") c->pp.cheb_eig_iters = v;
+  // ML's parameter list (precond_ml.h:44-58 and the keys PrecondWrapper_ML::setNullVector adds, :108-120)
+  else if (k == "max levels") c->pp.ml_max_levels = v; else if (k == "smoother: sweeps") { ISPH_REQUIRE(v >= 0, "smoother: sweeps >= 0"); c->pp.ml_pre = c->pp.ml_post = v; }
+  else if (k == "smoother: pre sweeps") c->pp.ml_pre = v; else if (k == "smoother: post sweeps") c->pp.ml_post = v; else if (k == "smoother: sweeps (coarse levels)") c->pp.ml_level_sweeps = v;
+  else if (k == "coarse: sweeps") c->pp.ml_coarse_sweeps = v; else if (k == "coarse: max size") c->pp.ml_max_coarse = v; else if (k == "eigen-analysis: iterations") c->pp.ml_eig_iters = v;
+  else if (k == "ML output" || k == "repartition: enable") { /* verbosity / Zoltan repartitioning: nothing to do on one GPU per rank */ }
+  else if (k == "null space: dimension") ISPH_REQUIRE(v == 1, "null space: dimension must be 1");
   else ISPH_REQUIRE(false, "unknown integer preconditioner parameter: " + k);
   API_END
 }
@@ -406,12 +412,23 @@ int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v) {
     const double dflt = (k == "fact: relative threshold") ? 1.0 : 0.0;
     ISPH_REQUIRE(v == dflt, "preconditioner parameter '" + k + "' is only supported at its Ifpack default value");
   }
+  else if (k == "aggregation: threshold") { ISPH_REQUIRE(v >= 0.0, "aggregation: threshold >= 0"); c->pp.ml_threshold = v; }
+  else if (k == "aggregation: damping factor") c->pp.ml_agg_damping = v;          // only 0 (non-smoothed aggregation) is provided: checked at create
+  else if (k == "smoother: Chebyshev alpha") c->pp.ml_alpha = v; else if (k == "coarse: Chebyshev alpha") c->pp.ml_coarse_alpha = v;
+  else if (k == "smoother: damping factor") c->pp.ml_damping = v; else if (k == "coarse correction scale") c->pp.ml_scale = v;
   else ISPH_REQUIRE(false, "unknown double preconditioner parameter: " + k);
   API_END
 }
 int isph_precond_set_param_str(isph_ctx *ctx, const char *name, const char *v) {
   API_BEGIN(ctx) const std::string k(name ? name : ""), s(v ? v : "");
   if (k == "Precond Type") c->pp.type = s; else if (k == "relaxation: type") c->pp.relax_type = s; else if (k == "schwarz: combine mode") { /* overlap 0: no combine */ }
+  // pair_isph.cpp:325-329: "Precond Package" picks the wrapper class; ML = the multilevel stand-in (amg.cu), Ifpack = "Precond Type" as set
+  else if (k == "Precond Package") { ISPH_REQUIRE(s == "ML" || s == "Ifpack", "Preconditioner is not in supported list: Ifpack, ML"); if (s == "ML") c->pp.type = "ML"; else if (c->pp.type == "ML") c->pp.type = "ILU"; }
+  else if (k == "aggregation: type") { ISPH_REQUIRE(s == "Uncoupled" || s == "MIS" || s == "Uncoupled-MIS", "aggregation: type: Uncoupled | MIS | Uncoupled-MIS (aggregates are always formed inside a rank by a distance-2 independent set)"); c->pp.ml_agg_type = s; }
+  else if (k == "smoother: type") c->pp.ml_smoother = s;                             // checked at create: Chebyshev | Jacobi
+  else if (k == "coarse: type") c->pp.ml_coarse = s;
+  else if (k == "smoother: pre or post") { ISPH_REQUIRE(s == "both" || s == "pre" || s == "post", "smoother: pre or post: both | pre | post"); if (s == "pre") c->pp.ml_post = 0; if (s == "post") c->pp.ml_pre = 0; }
+  else if (k == "increasing or decreasing" || k == "null space: type" || k == "eigen-analysis: type") { /* level numbering / pre-computed null space / power method: the only behaviour here */ }
   else ISPH_REQUIRE(false, "unknown string preconditioner parameter: " + k);
   API_END
 }
@@ -461,6 +478,11 @@ int isph_profile_precond_get(isph_ctx *ctx, double *total_ms, long long *launche
   c->pprof_ms = 0.0; c->pprof_cnt = 0;
   API_END
 }
+int isph_precond_ml_info(isph_ctx *ctx, int *levels, int *rows, long long *nnz, double *lambda_max, int cap) {
+  API_BEGIN(ctx) const int nl = amg_info(c, rows, nnz, lambda_max, cap); if (levels) *levels = nl; API_END
+}
+int isph_precond_ml_aggregates(isph_ctx *ctx, int *agg) { API_BEGIN(ctx) amg_aggregates(c, agg); API_END }
+double isph_precond_ml_setup_ms(isph_ctx *ctx, const char *phase) { if (!ctx) return 0.0; return amg_setup_ms((Ctx *)ctx, phase); }
 int isph_precond_info(isph_ctx *ctx, long long *factor_nnz, int *levels_lower, int *levels_upper, int *max_row) {
   API_BEGIN(ctx) long long z = 0; int a = 0, b = 0, m = 0; ilu_info(c, &z, &a, &b, &m);
   if (factor_nnz) *factor_nnz = z; if (levels_lower) *levels_lower = a; if (levels_upper) *levels_upper = b; if (max_row) *max_row = m; API_END

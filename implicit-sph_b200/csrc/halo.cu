@@ -396,6 +396,13 @@ void halo_allreduce(Ctx *c, double *buf, int count) {
   NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, c->stream));
 }
 
+// equal-size all-gather of raw bytes (setup of the replicated coarse levels, amg.cu); one rank: a copy
+void halo_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes) {
+  if (c->nranks <= 1) { CUDA_CHECK(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c->stream)); return; }
+  Halo *h = get(c);
+  NCCL_CHECK(g_nccl.AllGather(send, recv, bytes, ncclChar, h->comm, c->stream));
+}
+
 // ---- "Overlap Level" 1 (Ifpack_OverlappingRowMatrix / Ifpack_AdditiveSchwarz, precond_ifpack.h:35-43) ------------------------------
 // The extended local problem of a rank = its owned rows + the rows of its halo columns (one level of overlap), restricted to that set.
 // Owned rows need nothing from outside (every column of an owned row is an owned or a halo column).  The rows of the halo particles live

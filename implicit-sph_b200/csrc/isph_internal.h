@@ -73,11 +73,17 @@ struct PrecondParams {             // names of precond_ifpack.h:28-48 + Ifpack's
   std::string type = "ILU", relax_type = "Jacobi";
   int overlap = 0, fill = 0, sweeps = 1, cheb_degree = 1, cheb_eig_iters = 10;
   double damping = 1.0, min_diag = 0.0, cheb_ratio = 30.0, cheb_lmax = -1.0;
+  // "Precond Package" = ML: the multilevel stand-in of amg.cu; names = ML's parameter list (precond_ml.h:44-58), defaults chosen for the GPU
+  // (Chebyshev instead of the sequential symmetric Gauss-Seidel, non-smoothed MIS aggregation)
+  std::string ml_smoother = "Chebyshev", ml_coarse = "Chebyshev", ml_agg_type = "MIS";
+  int ml_max_levels = 5, ml_pre = 1, ml_post = 2, ml_level_sweeps = 3, ml_coarse_sweeps = 8, ml_eig_iters = 10, ml_max_coarse = 128;
+  double ml_threshold = 0.02, ml_agg_damping = 0.0, ml_alpha = 10.0, ml_coarse_alpha = 30.0, ml_scale = 2.0, ml_damping = 0.67;
 };
 
 struct Halo;      // halo.cu
 struct NeighWork; // neighbor.cu
 struct IluData;   // precond.cu
+struct AmgData;   // amg.cu
 
 struct Ctx {
   int device = 0, nranks = 1, rank = 0;
@@ -109,7 +115,7 @@ struct Ctx {
   long long last_second_passes = 0; int last_iters = 0, last_converged = 0; double last_relres = 0.0, last_lmax = 0.0;
   // preconditioner
   bool prec_ready = false; int prec_kind = 0; DevBuf<double> invdiag, cw, cv; DevBuf<int> block_of_row; bool have_blocks = false;
-  IluData *ilu = nullptr;
+  IluData *ilu = nullptr; AmgData *amg = nullptr;
   DevBuf<double> pb_extra;         // Poisson-Boltzmann extra source term staged for the Newton loop
   // multi-GPU
   Halo *halo = nullptr;
@@ -175,6 +181,13 @@ void spmv(Ctx *c, const double *d_x, double *d_y, int nvec, int ldx, int ldy, co
 void precond_create(Ctx *c);                                 // precond.cu
 void precond_free(Ctx *c);
 void precond_apply(Ctx *c, const double *d_r, double *d_z);  // z = M^-1 r
+void amg_create(Ctx *c);                                     // amg.cu: the multilevel stand-in for PrecondWrapper_ML
+void amg_free(Ctx *c);
+void amg_destroy(Ctx *c);
+void amg_apply(Ctx *c, const double *d_r, double *d_z);
+int amg_info(Ctx *c, int *rows, long long *nnz, double *lmax, int cap);
+void amg_aggregates(Ctx *c, int *agg_host);
+double amg_setup_ms(Ctx *c, const char *phase);
 void ilu_destroy(Ctx *c);                                    // ilu.cu
 bool ilu_fault(Ctx *c);
 void ilu_info(Ctx *c, long long *nnz, int *nlev_l, int *nlev_u, int *maxlen);

@@ -72,12 +72,13 @@ void precond_create(Ctx *c) {
   // across ranks "Overlap Level" 1 (the reference's own default, precond_ifpack.h:37) is the additive-Schwarz ILU of ilu.cu (rows of the
   // halo particles imported from their owners, combine mode Add); not provided: more than one level, overlap between sub-blocks of a
   // rank, overlap for the relaxation / Chebyshev types
-  ISPH_REQUIRE(c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks) || (c->pp.overlap == 1 && !c->have_blocks && t == "ILU"),
+  ISPH_REQUIRE(t == "ML" || c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks) || (c->pp.overlap == 1 && !c->have_blocks && t == "ILU"),
                "Overlap Level: 0, or 1 with Precond Type ILU and one block per rank (more levels, overlapping sub-blocks and overlapping relaxation are not implemented)");
   if (t == "none") c->prec_kind = 0;
   else if (t == "point relaxation" || t == "point relaxation stand-alone" || t == "Jacobi") { ISPH_REQUIRE(c->pp.relax_type == "Jacobi", "relaxation: type must be Jacobi"); c->prec_kind = 1; }
   else if (t == "Chebyshev") c->prec_kind = 2;
   else if (t == "ILU") { ISPH_REQUIRE(c->pp.fill >= 0 && c->pp.fill <= 255, "fact: level-of-fill must be in 0..255"); c->prec_kind = 3; }
+  else if (t == "ML") c->prec_kind = 4;                                           // Precond Package = ML (pair_isph.cpp:325-329): amg.cu
   else ISPH_REQUIRE(false, "Precond Type not supported: " + t);
   if (c->prec_kind == 1 || c->prec_kind == 2) {
     c->invdiag.ensure(ld); c->cv.ensure(ld); c->cw.ensure(ld);
@@ -103,11 +104,12 @@ void precond_create(Ctx *c) {
     c->last_lmax = lmax;
   }
   if (c->prec_kind == 3) ilu_create(c);
+  if (c->prec_kind == 4) { amg_create(c); c->last_lmax = 0.0; }
   c->prec_ready = true;
   c->toc("precondCreate");
 }
 
-void precond_free(Ctx *c) { if (c->prec_kind == 3) ilu_free(c); c->prec_ready = false; }
+void precond_free(Ctx *c) { if (c->prec_kind == 3) ilu_free(c); if (c->prec_kind == 4) amg_free(c); c->prec_ready = false; }
 
 // z = M^-1 r  (Ifpack_Preconditioner::ApplyInverse as wrapped by Belos::EpetraPrecOp, solver_lin_belos.h:155)
 void precond_apply(Ctx *c, const double *r, double *z) {
@@ -130,6 +132,7 @@ void precond_apply(Ctx *c, const double *r, double *z) {
     }
     break; }
   case 3: ilu_apply(c, r, z); break;
+  case 4: amg_apply(c, r, z); break;
   }
 }
 

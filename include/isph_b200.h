@@ -206,6 +206,17 @@ int isph_solver_set_default_params(isph_ctx *ctx);                        /* set
  * "relaxation: sweeps", "relaxation: damping factor", "chebyshev: degree", "chebyshev: ratio eigenvalue",
  * "chebyshev: max eigenvalue", "chebyshev: eigenvalue max iterations".  "b200: ilu blocks" = {bx,by,bz} split of the
  * local rows into Ifpack-rank-equivalent bricks is set with isph_precond_set_blocks(). */
+/* PrecondWrapper_ML (precond_ml.h:17-172; "Precond Package" = "ML" is the reference's default, pair_isph.cpp:325-329,359-361): a multilevel
+ * preconditioner built on the device stands in for ML — PARITY UNPINNED (ML is un-vendored, un-pinned third-party code) and not ML's default
+ * algorithm but the data-parallel member of its option space: distance-2 independent-set aggregation inside each rank, non-smoothed
+ * aggregation ("aggregation: damping factor" 0), Chebyshev or Jacobi smoothers on every level incl. the coarsest, V-cycle.  ML's names are
+ * kept: "Precond Package" ("ML" | "Ifpack"), "max levels" (5), "aggregation: type" ("Uncoupled" | "MIS" | "Uncoupled-MIS"),
+ * "aggregation: threshold" (0.02; ML's criterion a_ij^2 > eps^2 |a_ii a_jj|), "aggregation: damping factor" (must be 0), "smoother: type"
+ * ("Chebyshev" | "Jacobi"; "symmetric Gauss-Seidel", the value precond_ml.h:53 sets, is sequential within a rank and is refused),
+ * "smoother: sweeps" (Chebyshev degree / Jacobi sweeps before and after the coarse correction), "smoother: pre or post", "smoother: Chebyshev
+ * alpha" (10), "smoother: damping factor" (Jacobi, 0.67), "coarse: type" (= smoother: type; direct solvers are refused), "coarse: sweeps" (8),
+ * "coarse: Chebyshev alpha" (30), "coarse: max size" (128), "eigen-analysis: iterations" (10).  Extensions (not ML keys): "smoother: pre
+ * sweeps" (1), "smoother: post sweeps" (2), "smoother: sweeps (coarse levels)" (3), "coarse correction scale" (2.0). */
 int isph_precond_set_param_int(isph_ctx *ctx, const char *name, int v);
 int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v);
 int isph_precond_set_param_str(isph_ctx *ctx, const char *name, const char *v);
@@ -237,6 +248,12 @@ int isph_profile_spmv_get(isph_ctx *ctx, double *total_ms, long long *launches);
 int isph_profile_precond_get(isph_ctx *ctx, double *total_ms, long long *launches);
 /* the ILU factors of the last isph_precond_create / solve: stored entries of L + D + U (all blocks), dependency levels of the
  * forward and backward sweeps (the critical path of the level-scheduled solves), longest factor row */
+/* hierarchy of the last multilevel preconditioner: number of levels, rows / stored entries / lambda_max(D^-1 A) per level (cap entries);
+ * the aggregate (coarse index) of every local row of the finest level (-1: row without strong connections); device time of a setup
+ * phase ("aggregate" | "galerkin" | "eigen") in ms */
+int isph_precond_ml_info(isph_ctx *ctx, int *levels, int *rows, long long *nnz, double *lambda_max, int cap);
+int isph_precond_ml_aggregates(isph_ctx *ctx, int *agg /*[nlocal]*/);
+double isph_precond_ml_setup_ms(isph_ctx *ctx, const char *phase);
 int isph_precond_info(isph_ctx *ctx, long long *factor_nnz, int *levels_lower, int *levels_upper, int *max_row);
 /* FP64 FMA-loop peak of this GPU in TFLOP/s (16 independent DFMA chains per thread, no memory traffic): the denominator the
  * assembly kernels' flop rates are quoted against ("not in MEASURED_PEAKS.json; measure") */

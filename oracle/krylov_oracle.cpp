@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <map>
 #include "krylov_oracle.h"
+#include "amg_oracle.h"
 
 namespace {
 
@@ -65,7 +66,8 @@ struct Precond {
   // "Overlap Level" 1: one extended local problem per block (Ifpack_OverlappingRowMatrix + Ifpack_AdditiveSchwarz, combine mode Add)
   struct Sub { std::vector<int> idx, rp, ci; std::vector<double> v, r, z; Csr A; orc_krylov_params prm; Precond *M; };
   std::vector<Sub> subs;
-  ~Precond() { for (auto &s : subs) delete s.M; }
+  amg_oracle::Hierarchy *amg = nullptr;
+  ~Precond() { for (auto &s : subs) delete s.M; delete amg; }
 
   void setup_overlap(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
     const int n = A_.n; int nb = 0; for (int i = 0; i < n; ++i) nb = std::max(nb, block_of_row[i] + 1);
@@ -100,6 +102,12 @@ struct Precond {
   void setup(const Csr &A_, const orc_krylov_params *p, const int *block_of_row) {
     A = &A_; prm = p; type = p->precond; blk = block_of_row; const int n = A_.n;
     if (type == ORC_PREC_ILU0 && p->overlap >= 1 && block_of_row) { setup_overlap(A_, p, block_of_row); return; }
+    if (type == ORC_PREC_AMG) {                             // PrecondWrapper_ML::create, precond_ml.h:128-135 (stand-in: amg_oracle.h)
+      amg_oracle::Params q; q.max_levels = p->amg_max_levels; q.theta = p->amg_threshold; q.smoother = p->amg_smoother; q.pre = p->amg_pre; q.post = p->amg_post;
+      q.level_sweeps = p->amg_level_sweeps; q.coarse_sweeps = p->amg_coarse_sweeps; q.alpha = p->amg_alpha; q.coarse_alpha = p->amg_coarse_alpha;
+      q.eig_iters = p->amg_eig_iters; q.max_coarse = p->amg_max_coarse; q.oc = p->amg_scale; q.damping = p->amg_damping;
+      amg = new amg_oracle::Hierarchy(); amg->setup(n, A_.rp, A_.ci, A_.v, p->row_gid, block_of_row, q); lmax = amg->L[0].lmax; return;
+    }
     if (type == ORC_PREC_JACOBI || type == ORC_PREC_CHEBYSHEV) {
       invdiag.assign(n, 0.0);
       for (int i = 0; i < n; ++i) { double d = 0.0; for (int q = A_.rp[i]; q < A_.rp[i + 1]; ++q) if (A_.ci[q] == i) d += A_.v[q];
@@ -169,6 +177,7 @@ struct Precond {
     const int n = A->n;
     switch (type) {
     case ORC_PREC_NONE: memcpy(z, r, sizeof(double) * n); break;
+    case ORC_PREC_AMG: amg->apply(r, z); break;
     case ORC_PREC_JACOBI:                                   // Ifpack_PointRelaxation, Jacobi, zero starting solution
       for (int i = 0; i < n; ++i) z[i] = 0.0;
       for (int s = 0; s < prm->jacobi_sweeps; ++s) {
@@ -232,6 +241,10 @@ void orc_krylov_default_params(orc_krylov_params *p) {
   p->solver = ORC_SOLVER_GMRES; p->flexible = 1; p->num_blocks = 50; p->max_iters = 500; p->max_restarts = 15; p->tol = 1.0e-8;   // solver_lin_belos.h:231-240
   p->overlap = 0; p->precond = ORC_PREC_NONE; p->jacobi_sweeps = 1; p->jacobi_damping = 1.0; p->min_diag = 0.0;
   p->cheb_degree = 1; p->cheb_ratio = 30.0; p->cheb_lambda_max = -1.0; p->cheb_eig_iters = 10; p->row_gid = 0; p->ilu_fill = 0;
+  amg_oracle::Params q;                                    // defaults of the multilevel stand-in (implicit-sph_b200/csrc/amg.cu)
+  p->amg_max_levels = q.max_levels; p->amg_threshold = q.theta; p->amg_smoother = q.smoother; p->amg_pre = q.pre; p->amg_post = q.post; p->amg_level_sweeps = q.level_sweeps;
+  p->amg_coarse_sweeps = q.coarse_sweeps; p->amg_alpha = q.alpha; p->amg_coarse_alpha = q.coarse_alpha; p->amg_eig_iters = q.eig_iters; p->amg_max_coarse = q.max_coarse;
+  p->amg_scale = q.oc; p->amg_damping = q.damping;
 }
 
 int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
@@ -334,6 +347,18 @@ int orc_precond_apply(int n, const int *rowptr, const int *col, const double *va
   Csr A{n, rowptr, col, val}; Precond M; M.setup(A, prm, block_of_row); M.apply(r, z);
   if (lambda_max_out) *lambda_max_out = M.lmax;
   return 0;
+}
+
+int orc_amg_hierarchy(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm, const int *block_of_row,
+                      int *rows, long long *nnz, double *lmax, int *agg0, int cap_rows, long long cap_nnz, int *c_rowptr, int *c_col, double *c_val) {
+  Csr A{n, rowptr, col, val}; orc_krylov_params p = *prm; p.precond = ORC_PREC_AMG; Precond M; M.setup(A, &p, block_of_row);
+  const auto &L = M.amg->L;
+  for (size_t l = 0; l < L.size(); ++l) { rows[l] = L[l].A.n; nnz[l] = (long long)L[l].A.ci.size(); lmax[l] = L[l].lmax; }
+  if (agg0) for (int i = 0; i < n; ++i) agg0[i] = L[0].agg.empty() ? -1 : L[0].agg[i];
+  if (L.size() > 1 && c_rowptr && L[1].A.n <= cap_rows && (long long)L[1].A.ci.size() <= cap_nnz) {
+    std::copy(L[1].A.rp.begin(), L[1].A.rp.end(), c_rowptr); std::copy(L[1].A.ci.begin(), L[1].A.ci.end(), c_col); std::copy(L[1].A.v.begin(), L[1].A.v.end(), c_val);
+  }
+  return (int)L.size();
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@
 extern "C" {
 #endif
 enum { ORC_SOLVER_GMRES = 0, ORC_SOLVER_CG = 1 };
-enum { ORC_PREC_NONE = 0, ORC_PREC_JACOBI = 1, ORC_PREC_CHEBYSHEV = 2, ORC_PREC_ILU0 = 3 };
+enum { ORC_PREC_NONE = 0, ORC_PREC_JACOBI = 1, ORC_PREC_CHEBYSHEV = 2, ORC_PREC_ILU0 = 3, ORC_PREC_AMG = 4 };
 typedef struct {
   int solver;            /* "Solver Type": Block GMRES | Block CG   (solver_lin_belos.h:173-182) */
   int flexible;          /* "Flexible Gmres" */
@@ -27,6 +27,19 @@ typedef struct {
   int overlap;           /* "Overlap Level" 0 | 1 with block_of_row = the rank of every row (Ifpack_AdditiveSchwarz over an
                             Ifpack_OverlappingRowMatrix, "schwarz: combine mode" = Add: precond_ifpack.h:35-43).  Every block is extended
                             by the rows of its off-block columns (one level), ordered behind its own rows by (block, row_gid) */
+  /* ORC_PREC_AMG: the multilevel stand-in for ML (amg_oracle.h; names = ML's parameter list, precond_ml.h:44-58) */
+  int amg_max_levels;        /* "max levels" */
+  double amg_threshold;      /* "aggregation: threshold" */
+  int amg_smoother;          /* "smoother: type": 0 Chebyshev | 1 Jacobi */
+  int amg_pre, amg_post;     /* degree / sweeps before and after the coarse correction on the finest level ("smoother: sweeps", "smoother: pre or post") */
+  int amg_level_sweeps;      /* the same on the intermediate levels */
+  int amg_coarse_sweeps;     /* "coarse: sweeps" */
+  double amg_alpha;          /* "smoother: Chebyshev alpha" (eigenvalue ratio) */
+  double amg_coarse_alpha;   /* the same on the coarsest level */
+  int amg_eig_iters;         /* "eigen-analysis: iterations" (power method) */
+  int amg_max_coarse;        /* "coarse: max size" */
+  double amg_scale;          /* scaling of the coarse-grid correction */
+  double amg_damping;        /* "smoother: damping factor" (Jacobi) */
 } orc_krylov_params;
 
 int orc_set_num_threads(int n);   /* OpenMP threads of the port's row loops; returns the count in effect */
@@ -38,6 +51,10 @@ int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val
                      int *iters_out, double *relres_out, double *history, int history_cap);
 int orc_precond_apply(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
                       const int *block_of_row, const double *r, double *z, double *lambda_max_out);
+/* hierarchy of ORC_PREC_AMG for the tests: returns the number of levels; rows[l], nnz[l], lmax[l] per level; agg0[n] = aggregate of every
+ * finest-level row (-1: none); the level-1 operator in CSR when it fits the given capacities (c_rowptr: cap_rows + 1, c_col/c_val: cap_nnz) */
+int orc_amg_hierarchy(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm, const int *block_of_row,
+                      int *rows, long long *nnz, double *lmax, int *agg0, int cap_rows, long long cap_nnz, int *c_rowptr, int *c_col, double *c_val);
 #ifdef __cplusplus
 }
 #endif

@@ -221,11 +221,14 @@ class KrylovParams(C.Structure):
     _fields_ = [("solver", C.c_int), ("flexible", C.c_int), ("num_blocks", C.c_int), ("max_iters", C.c_int), ("max_restarts", C.c_int),
                 ("tol", C.c_double), ("precond", C.c_int), ("jacobi_sweeps", C.c_int), ("jacobi_damping", C.c_double), ("min_diag", C.c_double),
                 ("cheb_degree", C.c_int), ("cheb_ratio", C.c_double), ("cheb_lambda_max", C.c_double), ("cheb_eig_iters", C.c_int),
-                ("row_gid", _ip), ("ilu_fill", C.c_int), ("overlap", C.c_int)]
+                ("row_gid", _ip), ("ilu_fill", C.c_int), ("overlap", C.c_int),
+                ("amg_max_levels", C.c_int), ("amg_threshold", C.c_double), ("amg_smoother", C.c_int), ("amg_pre", C.c_int), ("amg_post", C.c_int),
+                ("amg_level_sweeps", C.c_int), ("amg_coarse_sweeps", C.c_int), ("amg_alpha", C.c_double), ("amg_coarse_alpha", C.c_double),
+                ("amg_eig_iters", C.c_int), ("amg_max_coarse", C.c_int), ("amg_scale", C.c_double), ("amg_damping", C.c_double)]
 
 
 SOLVER_GMRES, SOLVER_CG = 0, 1
-PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV, PREC_ILU0 = 0, 1, 2, 3
+PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV, PREC_ILU0, PREC_AMG = 0, 1, 2, 3, 4
 
 
 def krylov_params(**kw):
@@ -264,6 +267,23 @@ def precond_apply(rowptr, col, val, r, params, blocks=None):
     bl = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.int32)
     L.orc_precond_apply(n, _i(rowptr), _i(col), _d(val), C.byref(params), None if bl is None else _i(bl), _d(r), _d(z), C.byref(lm))
     return z, lm.value
+
+
+def amg_hierarchy(rowptr, col, val, params, blocks=None, cap_rows=0, cap_nnz=0):
+    """Hierarchy of the multilevel stand-in for ML (amg_oracle.h): sizes per level, the aggregates of the finest level and (when it fits
+    the capacities) the level-1 Galerkin operator."""
+    L = _load("port")
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(rowptr) - 1; rows = np.zeros(16, dtype=np.int32); nnz = np.zeros(16, dtype=np.int64); lmax = np.zeros(16); agg = np.zeros(n, dtype=np.int32)
+    bl = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.int32)
+    crp = np.zeros(cap_rows + 1, dtype=np.int32); cci = np.zeros(max(cap_nnz, 1), dtype=np.int32); cva = np.zeros(max(cap_nnz, 1))
+    L.orc_amg_hierarchy.restype = C.c_int
+    nl = L.orc_amg_hierarchy(n, _i(rowptr), _i(col), _d(val), C.byref(params), None if bl is None else _i(bl), _i(rows), nnz.ctypes.data_as(C.POINTER(C.c_longlong)), _d(lmax), _i(agg),
+                             int(cap_rows), C.c_longlong(int(cap_nnz)), _i(crp) if cap_rows else None, _i(cci) if cap_rows else None, _d(cva) if cap_rows else None)
+    out = dict(levels=nl, rows=rows[:nl].copy(), nnz=nnz[:nl].copy(), lmax=lmax[:nl].copy(), agg=agg)
+    if cap_rows and nl > 1 and rows[1] <= cap_rows and nnz[1] <= cap_nnz:
+        out["coarse"] = (crp[:rows[1] + 1].copy(), cci[:nnz[1]].copy(), cva[:nnz[1]].copy())
+    return out
 
 
 def set_num_threads(n):

@@ -188,3 +188,63 @@ def test_ilu_overlap_one_is_additive_schwarz_with_add(oracle_mod):
     assert np.abs(z0 - want).max() > 1e-3                                       # ... and differs from block Jacobi without overlap
     z1, _ = O.precond_apply(rp, ci, va, r, O.krylov_params(precond=O.PREC_ILU0, overlap=1), blocks=np.zeros(n, dtype=np.int32))
     assert np.abs(z1 - np.linalg.solve(A, r)).max() <= 1e-13                    # one block: nothing to overlap with
+
+
+# ---- multilevel stand-in for ML (oracle/amg_oracle.h; precond_ml.h:17-172) -----------------------------------------------------------
+def _amg_case(n1=36, shift=0.002):
+    A = lap2d(n1, shift, 0.2); rp, ci, v = csr(A)
+    return A, rp, ci, v
+
+
+def test_ml_standin_hierarchy_is_a_galerkin_hierarchy_of_disjoint_aggregates(oracle_mod):
+    """aggregates = a partition of the rows with strong connections; roots form a distance-2 independent set of the strength graph (no two
+    aggregates were founded by rows closer than three hops); level 1 = P^T A P with P the 0/1 aggregation matrix (scipy, independent)."""
+    O = oracle_mod; A, rp, ci, v = _amg_case()
+    n = A.shape[0]; prm = O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_coarse=10)
+    h = O.amg_hierarchy(rp, ci, v, prm, cap_rows=n, cap_nnz=A.nnz)
+    agg = h["agg"]; nc = h["rows"][1]
+    assert h["levels"] >= 3 and np.all(np.diff(h["rows"]) < 0)
+    assert agg.min() >= 0 and np.array_equal(np.unique(agg), np.arange(nc))          # every row aggregated (no Dirichlet rows here), ids dense
+    sizes = np.bincount(agg); assert sizes.max() <= 16 and sizes.mean() >= 4          # 5-point stencil: root + its distance <= 2 neighbourhood at most
+    P = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, nc))
+    Ac = sp.csr_matrix(P.T @ A @ P); Ac.sort_indices(); crp, cci, cva = h["coarse"]
+    C = sp.csr_matrix((cva, cci, crp), shape=(nc, nc))
+    assert abs(C - Ac).max() <= 1e-13 * abs(Ac).max() and np.array_equal(crp, Ac.indptr) and np.array_equal(cci, Ac.indices)
+    # every aggregate is connected through strong connections to its founder within two hops: aggregate diameter <= 4 in the 5-point graph
+    g = A.copy(); g.data[:] = 1.0; g2 = sp.csr_matrix(g @ g @ g @ g)
+    for a in range(0, nc, 7):
+        rows = np.nonzero(agg == a)[0]
+        assert g2[rows][:, rows].nnz == len(rows) ** 2
+
+
+def test_ml_standin_vcycle_is_linear_and_cuts_the_iteration_count(oracle_mod):
+    O = oracle_mod; A, rp, ci, v = _amg_case(48, 0.0005); n = A.shape[0]; rng = np.random.default_rng(3)
+    prm = O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_coarse=30)
+    r1, r2 = rng.standard_normal(n), rng.standard_normal(n)
+    z1, _ = O.precond_apply(rp, ci, v, r1, prm); z2, _ = O.precond_apply(rp, ci, v, r2, prm); z3, _ = O.precond_apply(rp, ci, v, 2.0 * r1 - 0.5 * r2, prm)
+    assert np.abs(z3 - (2.0 * z1 - 0.5 * z2)).max() <= 1e-12 * np.abs(z3).max()      # a fixed polynomial V-cycle is a linear operator (no inner Krylov, no adaptivity)
+    b = rng.standard_normal(n)
+    its = {}
+    for name, p in (("jacobi", O.krylov_params(precond=O.PREC_JACOBI)), ("ml", prm), ("ml_jacobi_smoother", O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_coarse=30, amg_smoother=1, amg_pre=2, amg_post=2))):
+        x, info = O.krylov_solve(rp, ci, v, b, params=p); assert info["converged"]; its[name] = info["iters"]
+        assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) <= 2e-8
+    assert its["ml"] * 4 <= its["jacobi"] and its["ml_jacobi_smoother"] * 3 <= its["jacobi"], its
+
+
+def test_ml_standin_uncoupled_aggregates_and_rows_without_strong_connections(oracle_mod):
+    """aggregates never cross a block (ML 'Uncoupled': one block per MPI rank); identity rows (solid particles: diag 1, nothing else) have no
+    strong connection, stay out of every aggregate and get no coarse correction."""
+    O = oracle_mod; A, rp, ci, v = _amg_case(24, 0.01); n = A.shape[0]
+    blocks = (np.arange(n) % 24 >= 12).astype(np.int32)
+    h = O.amg_hierarchy(rp, ci, v, O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_coarse=10), blocks=blocks)
+    for a in np.unique(h["agg"]):
+        assert len(np.unique(blocks[h["agg"] == a])) == 1
+    B = sp.lil_matrix(A); dead = np.arange(0, n, 11)
+    for r in dead:
+        B.rows[r] = [r]; B.data[r] = [1.0]
+    B = sp.csr_matrix(B); B.sort_indices(); rp2, ci2, v2 = csr(B)
+    prm = O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_coarse=10)
+    h2 = O.amg_hierarchy(rp2, ci2, v2, prm)
+    assert np.all(h2["agg"][dead] == -1) and np.all(np.delete(h2["agg"], dead) >= 0)
+    b = np.random.default_rng(5).standard_normal(n); x, info = O.krylov_solve(rp2, ci2, v2, b, params=prm)
+    assert info["converged"] and np.linalg.norm(b - B @ x) / np.linalg.norm(b) <= 2e-8
