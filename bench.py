@@ -7,7 +7,7 @@ One *step* = what `PairISPH::compute` does per time step for the pressure Poisso
 reference does.  Metric: rows assembled-and-solved per second (whole job), with `ms_per_step` = the absolute Poisson
 step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM bandwidth inside the solve.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|c2|c1|c3|c4|c4s|c5|c2j] [--n LATTICE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|p8m_ml|c2|c2_ml|c1|c3|c4|c4s|c5|c2j] [--n LATTICE]
 
 Default workload = the configuration BASELINE.json's metric and target are quoted on: the 3-D 8M-particle (200^3) pressure
 Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  The line
@@ -55,6 +55,11 @@ WORKLOADS = {
     # BASELINE configs[4]: Poisson-Boltzmann Newton-Krylov (full-step Newton, NormF 1e-8 AND NormUpdate 1e-5), manufactured source
     "c5": dict(dim=3, n=160, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True, system="pb",
                desc="BASELINE configs[4]: 3-D Poisson-Boltzmann electrostatics, 4M particles (160^3), Newton iteration with device-resident computeF / computeJacobian and GMRES(50)+Jacobi Jacobian solves, manufactured source of poisson-boltzmann-harmonic.xml, psi0 = 0, fixed global size (strong scaling)"),
+    # the headline problems with the reference's DEFAULT preconditioner package (ML, pair_isph.cpp:325-329): the multilevel stand-in of csrc/amg.cu
+    "p8m_ml": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="ML", solver="Block GMRES", strong=True,
+                   desc="north_star problem (3-D 8M-particle pressure Poisson) with the reference's default preconditioner package: flexible GMRES(50) + the multilevel stand-in for ML (MIS aggregation, Chebyshev smoothers, V-cycle), fixed global size (strong scaling)"),
+    "c2_ml": dict(dim=3, n=100, jitter=0.0, rs2=9, prec="ML", solver="Block GMRES",
+                  desc="BASELINE configs[1] problem (1M particles) with flexible GMRES(50) + the multilevel stand-in for ML"),
     # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
     "p8m": dict(dim=3, n=200, jitter=0.0, rs2=9, prec="point relaxation", solver="Block GMRES", strong=True,
                 desc="north_star target: 3-D 8M-particle (200^3) pressure Poisson, flexible GMRES(50)+Jacobi, fixed global size (strong scaling)"),
@@ -390,6 +395,7 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
     nvl1 = nvlink_counters(local_rank) if nvl0 is not None else None
     spmv_ms, spmv_cnt = c.profile_spmv_get(); prec_ms, prec_cnt = c.profile_precond_get(); c.profile_spmv(False)
     ilu = c.precond_info() if w["prec"] == "ILU" else None
+    ml = c.precond_ml_info() if w["prec"] == "ML" else None
     launches = (c.launches - launches0) // steps
     timers = {k: c.timer_ms(k) / steps for k in ("computeVolumes", "computeGradientCorrection", "computeLaplacianCorrection", "computeGraph", "precondCreate", "solve" + solve_label) +
               (("computeFPoissonBoltzmann", "computeJacobianPoissonBoltzmann") if pbs else ("compute" + solve_label,))}
@@ -489,6 +495,10 @@ def measure(args, wname, steps, isph, lat, torch, dist, rank, world, local_rank,
                                     factor_nnz=ilu["factor_nnz"], levels_lower=ilu["levels_lower"], levels_upper=ilu["levels_upper"],
                                     us_per_level=1e3 * pav / max(ilu["levels_lower"] + ilu["levels_upper"], 1),
                                     note="latency-bound by the dependency levels of the forward + backward sweeps, not by bytes (DESIGN.md §3)")
+    if ml is not None:                                       # hierarchy of the multilevel preconditioner (rebuilt every solve, like every preconditioner of the reference)
+        line["ml_hierarchy"] = dict(levels=ml["levels"], rows=ml["rows"], nnz=ml["nnz"], lambda_max=ml["lambda_max"], setup_ms_last_solve=ml["setup_ms"],
+                                    spmv_per_iteration=spmv_cnt / max(steps, 1) / max(st["iters"], 1),
+                                    note="finest level = this rank's SELL matrix; coarser levels replicated on every GPU; 'parity unpinned' against ML by construction (DESIGN.md)")
     if halo is not None:                                     # NVLink side of the roofline (rank 0's brick): bytes that leave this GPU per operator apply
         spmv_per_s = spmv_cnt / max(steps, 1) / max(ms_dev * 1e-3, 1e-12)
         line["nvlink"] = dict(what="halo import of one SpMV on rank 0 (NVLink peer stores, 8 B per value) and the two all-reduces of an Arnoldi step (<= 53 doubles to each peer)",
@@ -580,12 +590,12 @@ def main():
     # the other BASELINE configs beside the headline line: same code path, measured in the same run, at this GPU count
     if args.workload == "p8m" and not args.n and not args.no_secondary:
         sec_steps = max(1, min(args.steps, 3))
-        todo = ([("configs1_c2", "c2")] if world == 1 else []) + [("configs2_c3", "c3"), ("configs3_c4", "c4s"), ("configs4_c5", "c5")]
+        todo = ([("configs1_c2", "c2"), ("configs1_c2_ml", "c2_ml")] if world == 1 else []) + [("p8m_ml", "p8m_ml"), ("configs2_c3", "c3"), ("configs3_c4", "c4s"), ("configs4_c5", "c5")]
         for key, wn in todo:
             sec = measure(args, wn, min(args.steps, 5) if wn == "c2" else sec_steps, isph, lat, torch, dist, rank, world, local_rank, fresh_id(), with_cpu=False, warmup=3)
             if rank != 0:
                 continue
-            blk = {k: sec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "breakdown_ms", "ms_per_iter", "result", "ilu_roofline", "nvlink") if k in sec}
+            blk = {k: sec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "breakdown_ms", "ms_per_iter", "result", "ilu_roofline", "nvlink", "ml_hierarchy") if k in sec}
             blk.update(workload=sec["config"]["description"], rows=sec["config"]["rows"], iters=sec["result"]["iters"], converged=sec["result"]["converged"],
                        spmv_roofline_frac=sec["roofline"]["frac"], spmv_gbs=sec["roofline"]["achieved"], spmv_bytes_per_launch=sec["roofline"]["algorithmic_bytes_per_launch"],
                        solve_roofline_frac=sec.get("solve_roofline", {}).get("frac"))

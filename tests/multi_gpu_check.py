@@ -8,6 +8,7 @@ GLOBAL problem: graph bit-exact, values <= 1e-12, iteration counts +-2, solution
   1. pressure Poisson, NullSpace, flexible GMRES(50) + Jacobi                       (BASELINE configs[1])
   2. the same system with block-Jacobi ILU(0), one open block per rank (= Ifpack overlap 0 on an MPI run)   (configs[3])
   2b. ILU(0) with Overlap Level 1 and combine mode Add — Ifpack's defaults as the reference sets them (precond_ifpack.h:35-43)
+  2c. the multilevel stand-in for ML, the reference's default package (aggregates inside each rank, coarse levels replicated)
   3. velocity Helmholtz, 3 right-hand sides one after another, CG + Chebyshev(2)     (configs[2]; SpMM with a 3-vector import)
   4. Poisson-Boltzmann Newton iteration (computeF / computeJacobian / GMRES + Jacobi Jacobian solves)      (configs[4])
 tests/test_gpu_multi.py wraps this for pytest when >= 2 GPUs are visible.
@@ -71,6 +72,11 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
     c.precond_param("Overlap Level", 1)
     st2b = c.solve(True, "PoissonILUoverlap1")
     c.precond_param("Overlap Level", 0)
+    # 2c. the reference's DEFAULT preconditioner package (ML, pair_isph.cpp:325-329): the multilevel stand-in, aggregates inside each rank
+    x2c = np.zeros(nl); c.create_solution(x2c, 1); c.set_initial_solution(isph.INIT_ZERO)
+    c.precond_param("Precond Package", "ML"); c.precond_param("coarse: max size", 20)
+    st2c = c.solve(True, "PoissonML"); agg2c = c.precond_ml_aggregates(); ml2c = c.precond_ml_info()
+    c.precond_param("Precond Package", "Ifpack")
     # 3. Helmholtz, dim right-hand sides, CG + Chebyshev(2)
     theta = 0.5
     c.matrix_invalidate(); c.create_load(None, dim); c.load_set(np.asfortranarray(v[:nl, :dim])); c.ns_helmholtz(dt, theta)
@@ -84,7 +90,7 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
     c.create_solution(None, 1); c.create_load(None, 1); c.set_matrix_is_singular(False)
     c.solver_param("Solver Type", "Block GMRES"); c.precond_param("Precond Type", "point relaxation")
     st4 = c.pb_newton(extra_f=ex); psi4 = c.field_get(isph.F_PSI)[:nl].copy()
-    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, x2b=x2b, st2b=st2b, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
+    mine = dict(tag=P["tag"][:nl].copy(), rp=rp, col=col, A=A, b=b, x=x, vf=vf, st=st, x2=x2, st2=st2, x2b=x2b, st2b=st2b, x2c=x2c, st2c=st2c, agg2c=agg2c, ml2c=ml2c, Ah=Ah, bh=bh, x3=x3, st3=st3, st4=st4, psi4=psi4)
     allr = [None] * world
     dist.gather_object(mine, allr if rank == 0 else None, 0)
     ok = True; rep = {}
@@ -130,6 +136,19 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
         its2b = allr[0]["st2b"]["iters"]; x2berr = np.linalg.norm(x2bd - x2bo) / np.linalg.norm(x2bo)
         say(f"  ILU(0), Overlap Level 1 (Add): iters gpu {its2b} vs oracle {info2b['iters']}; x rel diff {x2berr:.2e}; converged {allr[0]['st2b']['converged']}")
         ok = ok and abs(its2b - info2b["iters"]) <= 2 and x2berr <= 1e-6 and allr[0]["st2b"]["converged"]
+        # 2c. multilevel stand-in for ML: the same aggregates as the restatement on the global problem (as a partition: the coarse numbering is
+        # rank-major on the GPUs, row-major in the oracle), the same level sizes, the same iteration count
+        x2cd = np.zeros(n); aggd = -np.ones(n, dtype=np.int64)
+        for d in allr:
+            gi = row_of_tag[d["tag"]]; x2cd[gi] = d["x2c"]; aggd[gi] = d["agg2c"]
+        prm2c = O.krylov_params(precond=O.PREC_AMG, amg_max_coarse=20, row_gid=G["tag"][:n])
+        x2co, info2c = O.krylov_solve(grp, colL, gA, gb.copy(), params=prm2c, null_mask=np.ones(n, dtype=np.int32), use_null=True, blocks=blocks)
+        hier = O.amg_hierarchy(grp, colL, gA, prm2c, blocks=blocks)
+        same_part = len(set(zip(aggd.tolist(), hier["agg"].tolist()))) == len(set(aggd.tolist())) == len(set(hier["agg"].tolist()))
+        same_lev = all(list(d["ml2c"]["rows"][1:]) == list(hier["rows"][1:]) for d in allr) and sum(d["ml2c"]["rows"][0] for d in allr) == n
+        its2c = allr[0]["st2c"]["iters"]; x2cerr = np.linalg.norm(x2cd - x2co) / np.linalg.norm(x2co)
+        say(f"  ML stand-in (levels {hier['levels']}, rows {list(hier['rows'])}): same aggregates {same_part}, same level sizes {same_lev}; iters gpu {its2c} vs oracle {info2c['iters']}; x rel diff {x2cerr:.2e}; converged {allr[0]['st2c']['converged']}")
+        ok = ok and same_part and same_lev and hier["levels"] >= 2 and abs(its2c - info2c["iters"]) <= 2 and x2cerr <= 1e-6 and allr[0]["st2c"]["converged"]
         # 3. Helmholtz, CG + Chebyshev(2), dim right-hand sides
         o.invalidate_matrix(); gbh = o.ns_helmholtz(dt, 0.5, np.asfortranarray(vg[:n, :dim])); gAh = o.matrix()
         x3d = np.zeros((n, dim)); worst3 = 0.0
@@ -167,6 +186,7 @@ def run_check(isph, lat, torch, dist, rank, world, lr, nccl_id, quiet=False):
         rep = dict(rows=int(n), graph="bit-exact", values_max_rel_err=float(worst), gmres_jacobi=dict(iters=int(its), oracle_iters=int(info["iters"]), x_rel_diff=float(xerr)),
                    gmres_block_ilu0=dict(iters=int(its2), oracle_iters=int(info2["iters"]), x_rel_diff=float(x2err)),
                    gmres_ilu0_overlap1=dict(iters=int(its2b), oracle_iters=int(info2b["iters"]), x_rel_diff=float(x2berr)),
+                   gmres_ml_standin=dict(iters=int(its2c), oracle_iters=int(info2c["iters"]), x_rel_diff=float(x2cerr), same_aggregates=bool(same_part), levels=int(hier["levels"]), rows=[int(v) for v in hier["rows"]]),
                    helmholtz_cg_chebyshev=dict(iters=int(its3), oracle_iters=int(its3o), x_rel_diff=float(x3err), values_max_rel_err=float(worst3)),
                    pb_newton=dict(newton_iters=int(s4["newton_iters"]), oracle_newton_iters=int(kn), linear_iters=int(s4["linear_iters"]), oracle_linear_iters=int(lin), psi_rel_diff=float(p4err)))
     c.close()
