@@ -51,6 +51,29 @@ class PrecondWrapper_B200 {
   isph_ctx *_ctx;
 };
 
+// PrecondWrapper_ML (precond_ml.h:17-172) — the reference's default package (pair_isph.cpp:325-329,359-361).  The multilevel
+// preconditioner of csrc/amg.cu stands in for ML ("parity unpinned": ML is un-vendored third-party code; see isph_b200.h for what is
+// and is not ML's algorithm).  Same method set as the reference's class; ML's parameter names are kept.
+class PrecondWrapper_ML_B200 : public PrecondWrapper_B200 {
+ public:
+  explicit PrecondWrapper_ML_B200(isph_ctx *ctx) : PrecondWrapper_B200(ctx) {}
+  // setParameters(NULL), precond_ml.h:44-58: "max levels" 5, "aggregation: type" Uncoupled, smoother 1 sweep pre and post, coarse solve.
+  // Deviations, each forced by the device: "smoother: type" Chebyshev instead of symmetric Gauss-Seidel (sequential within a
+  // rank), "coarse: type" = the smoother instead of Amesos-KLU (the choice PrecondWrapper_ML::setNullVector makes itself, :118-120).
+  virtual void setParameters() {
+    set("Precond Package", "ML"); set("max levels", 5); set("increasing or decreasing", "increasing"); set("aggregation: type", "Uncoupled");
+    set("smoother: type", "Chebyshev"); set("smoother: pre or post", "both"); set("coarse: type", "Chebyshev");
+  }
+  // for zoltan re-partition (precond_ml.h:65-99): one GPU per rank, the coarse levels are replicated — nothing to repartition
+  void setCoordinates(const int, double *, double *, double *) {}
+  // precond_ml.h:101-126: ML is told the null vector and switches the coarse solver to the smoother.  Here the coarse solver already is
+  // the smoother and the tentative prolongator is piecewise constant (the null vector of every singular system of the reference is the
+  // normalised 0/1 mask of solver_lin.cpp:59-77, which piecewise constants span inside the masked rows)
+  virtual void setNullVector(double *) {}
+  virtual void create(const int /*dim*/) { create(); }          // block variant: one hierarchy, applied to every diagonal block (precond_ml.h:137-154)
+  virtual void create() { set("Precond Package", "ML"); PrecondWrapper_B200::create(); }
+};
+
 // SolverLin / SolverLin_Belos (solver_lin.h:23-98, solver_lin_belos.h:35-49)
 class SolverLin_B200 {
  public:

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <string>
 #include "solver_lin_b200.h"
 
 using namespace isph_b200;
@@ -35,7 +36,13 @@ int main(int argc, char **argv) {
   CK(isph_compute_volumes(ctx)); CK(isph_compute_gradient_correction(ctx)); CK(isph_compute_laplacian_correction(ctx));   // computePre()
   CK(isph_graph_build(ctx));                                                                         // nodal map + computeGraph + new CrsMatrix
 
-  PrecondWrapper_B200 prec(ctx); prec.set("Precond Type", "point relaxation"); prec.set("Overlap Level", 0);
+  // pair_isph.cpp:325-329: the wrapper class follows "Precond Package" (default "ML")
+  const std::string prec_package = argc > 3 ? argv[3] : "Ifpack";
+  PrecondWrapper_B200 *precp = NULL;
+  if (prec_package == "Ifpack") { precp = new PrecondWrapper_B200(ctx); precp->set("Precond Type", "point relaxation"); precp->set("Overlap Level", 0); }
+  else if (prec_package == "ML") { precp = new PrecondWrapper_ML_B200(ctx); precp->setParameters(); precp->setNullVector(NULL); }
+  else { fprintf(stderr, "Preconditioner is not in supported list: Ifpack, ML\n"); return 4; }
+  PrecondWrapper_B200 &prec = *precp;
   SolverLin_B200 li_solver(ctx); li_solver.setParameters();
   li_solver.setNodalMap(ctx); li_solver.setMatrix(ctx); prec.setMatrix(ctx);                         // pair_isph.cpp:924-926
   std::vector<double> dp(nlocal, 0.0);
@@ -51,6 +58,7 @@ int main(int argc, char **argv) {
   CK(isph_matrix_invalidate(ctx));                                                                   // A.is_filled = 0, :1026
   printf("iterations %d\n", li_solver.iterations());
   FILE *o = fopen(argv[2], "wb"); fwrite(dp.data(), sizeof(double), nlocal, o); fclose(o);
+  delete precp;
   isph_ctx_destroy(ctx);
   return 0;
 }

@@ -26,7 +26,8 @@ def test_adapter_compiles_against_the_abi(tmp_path):
 
 
 @pytest.mark.gpu
-def test_adapter_poisson_matches_oracle(tmp_path):
+@pytest.mark.parametrize("package", ["Ifpack", "ML"])
+def test_adapter_poisson_matches_oracle(tmp_path, package):
     import oracle as O
     P, F = make_case("jitter3d"); cs = P["case"]; nl, nall = P["nlocal"], P["nlocal"] + P["nghost"]
     rho = np.ones(nall); v = F["velocity"]
@@ -40,10 +41,10 @@ def test_adapter_poisson_matches_oracle(tmp_path):
         for a in (P["type"], P["tag"], np.diff(P["noff"]).astype(np.int32), P["neigh"]):
             f.write(np.ascontiguousarray(a, dtype=np.int32).tobytes())
     exe = _build(str(tmp_path))
-    r = subprocess.run([exe, fn, out], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, fn, out, package], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     its = int([l for l in r.stdout.splitlines() if l.startswith("iterations")][0].split()[1])
     x = np.fromfile(out, dtype=np.float64)
     o = O.Oracle(P, kind="port"); o.set_field(O.F_VSTAR, v); o.set_field(O.F_DENSITY, rho); o.compute_pre(); rp, col = o.graph(); b = o.ns_poisson(cs["dt"]); A = o.matrix()
-    xo, info = O.krylov_solve(rp, O.tags_to_local(col, P["tag"][:nl]), A, b, params=O.krylov_params(precond=O.PREC_JACOBI), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
+    xo, info = O.krylov_solve(rp, O.tags_to_local(col, P["tag"][:nl]), A, b, params=O.krylov_params(precond=O.PREC_JACOBI if package == "Ifpack" else O.PREC_AMG, row_gid=P["tag"][:nl]), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
     assert abs(its - info["iters"]) <= 2 and np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-6
