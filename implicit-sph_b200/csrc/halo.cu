@@ -420,14 +420,15 @@ __global__ void k_rows_pack(const long long *slice_off, const int *col, const do
   const int r = send_idx[k]; const long long base = slice_off[r >> 5] + (r & 31), o = off[k];
   for (int e = lane; e < len[k]; e += 32) { tags[o + e] = coltag[col[base + 32ll * e]]; vals[o + e] = val[base + 32ll * e]; }
 }
-__global__ void k_rows_map(const int *tags, long long ntot, const int *tag2col, int max_tag, int *cols) {
+__global__ void k_rows_map(const int *tags, long long ntot, const int *tag2col, int max_tag, int n_own, const int *slot_ref, int *cols) {
   const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (j >= ntot) return;
-  const int t = tags[j]; const int c = (t >= 0 && t <= max_tag) ? tag2col[t] : -1;
+  const int t = tags[j]; int c = (t >= 0 && t <= max_tag) ? tag2col[t] : -1;
+  if (c >= n_own && slot_ref && !slot_ref[c - n_own]) c = -1;      // a halo slot no owned row reaches is outside the extended set
   cols[j] = c < 0 ? 0x7fffffff : c;
 }
 __global__ void k_add_rows_from(double *z, const int *send_idx, const double *buf, int k0, int k1) { const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; if (k < k1) z[send_idx[k]] += buf[k]; }
 
-void halo_import_rows(Ctx *c, OverlapRows *out) {
+void halo_import_rows(Ctx *c, OverlapRows *out, const int *slot_ref) {
   Halo *h = get(c); Matrix &A = c->A; const int R = c->nranks, nl = c->nlocal, nh = h->nhalo, ns = h->nsend;
   out->nhalo = nh;
   out->coltag.ensure(A.ncols + 1); out->tag2col.ensure((size_t)c->max_tag + 2);
@@ -463,7 +464,7 @@ void halo_import_rows(Ctx *c, OverlapRows *out) {
   NCCL_CHECK(g_nccl.GroupEnd());
   out->total = tot_r;
   if (tot_r > 0) {
-    k_rows_map<<<ceil_div(tot_r, 256), 256, 0, c->stream>>>(out->tag_r.p, tot_r, out->tag2col.p, c->max_tag, out->col_r.p); ++c->launches;
+    k_rows_map<<<ceil_div(tot_r, 256), 256, 0, c->stream>>>(out->tag_r.p, tot_r, out->tag2col.p, c->max_tag, nl, slot_ref, out->col_r.p); ++c->launches;
     size_t tb = 0;
     cub::DeviceSegmentedSort::SortPairs(nullptr, tb, out->col_r.p, out->col_r2.p, out->val_r.p, out->val_r2.p, tot_r, nh, out->off_r.p, out->off_r.p + 1, c->stream);
     h->cubtmp.ensure(tb); tb = h->cubtmp.cap;

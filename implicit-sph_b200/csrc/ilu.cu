@@ -34,6 +34,8 @@ struct IluData {
   // "Overlap Level" 1 across ranks: the factored problem has n = n_own + nhalo rows (owned rows, then the imported rows of the halo
   // particles in halo-slot order); r / z of an apply are extended with the imported / exported halo part
   bool ext = false; int n_own = 0; OverlapRows ov; DevBuf<double> rext, zext;
+  DevBuf<int> slot_ref;   // halo slot referenced by an owned row?  Ifpack_OverlappingRowMatrix extends a rank by the off-rank columns of ITS rows (the column map of A); LAMMPS ghosts that no owned
+                          // row reaches (corners of the ghost shell) have a halo slot here but are not part of the overlap: their rows are replaced by identity rows that nothing couples to
 };
 
 // ---- block-restricted row-major copy of A --------------------------------------------------------------------------
@@ -45,15 +47,23 @@ __global__ void k_ilu_count(const long long *slice_off, const int *row_len, cons
   cnt[row] = c;
 }
 // rows of the halo particles (overlap 1): sorted (column, value) segments from halo_import_rows; duplicate columns are summed
-__global__ void k_ilu_ext_count(const long long *off, const int *cols, int nh, int *cnt) {
+__global__ void k_ilu_mark_ref(const long long *slice_off, const int *row_len, const int *col, int n_own, int *slot_ref) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n_own) return;
+  const long long base = slice_off[row >> 5] + (row & 31); const int rlen = row_len[row];
+  for (int k = 0; k < rlen; ++k) { const int cc = col[base + 32ll * k]; if (cc >= n_own) slot_ref[cc - n_own] = 1; }
+}
+__global__ void k_ilu_zero_unref(double *rext_halo, const int *slot_ref, int nh) { const int s = blockIdx.x * blockDim.x + threadIdx.x; if (s < nh && !slot_ref[s]) rext_halo[s] = 0.0; }
+__global__ void k_ilu_ext_count(const long long *off, const int *cols, const int *slot_ref, int nh, int *cnt) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= nh) return;
+  if (!slot_ref[s]) { cnt[s] = 1; return; }
   int c = 0, prev = -1;
   for (long long j = off[s]; j < off[s + 1]; ++j) { const int cc = cols[j]; if (cc == 0x7fffffff) break; if (cc != prev) ++c; prev = cc; }
   cnt[s] = c;
 }
-__global__ void k_ilu_ext_fill(const long long *off, const int *cols, const double *vals, int nh, int n_own, const int *rp, int *ci, double *fv, int *dpos) {
+__global__ void k_ilu_ext_fill(const long long *off, const int *cols, const double *vals, const int *slot_ref, int nh, int n_own, const int *rp, int *ci, double *fv, int *dpos) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= nh) return;
   const int row = n_own + s; int o = rp[row], prev = -1, dp = -1;
+  if (!slot_ref[s]) { ci[o] = row; fv[o] = 1.0; dpos[row] = o; return; }
   for (long long j = off[s]; j < off[s + 1]; ++j) {
     const int cc = cols[j]; if (cc == 0x7fffffff) break;
     if (cc != prev) { ci[o] = cc; fv[o] = vals[j]; if (cc == row) dp = o; ++o; } else fv[o - 1] += vals[j];
@@ -408,14 +418,20 @@ void ilu_create(Ctx *c) {
   IluData &I = *c->ilu;
   // "Overlap Level" 1 across ranks (validated in precond_create: ILU, no sub-blocks): the rows of the halo particles join the local problem
   const bool ext = c->nranks > 1 && c->pp.overlap >= 1;
-  if (ext) { c->tic("iluImportRows"); halo_import_rows(c, &I.ov); c->toc("iluImportRows"); }
+  if (ext) {
+    c->tic("iluImportRows");
+    const int nh = halo_ncols(c) - n_own; I.slot_ref.ensure(nh + 1); CUDA_CHECK(cudaMemsetAsync(I.slot_ref.p, 0, sizeof(int) * (nh + 1), c->stream));
+    k_ilu_mark_ref<<<ceil_div(n_own, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, n_own, I.slot_ref.p); ++c->launches;
+    halo_import_rows(c, &I.ov, I.slot_ref.p);
+    c->toc("iluImportRows");
+  }
   const int n = n_own + (ext ? I.ov.nhalo : 0), climit = ext ? n : n_own;
   I.n = n; I.n_own = n_own; I.ext = ext;
   const int *blk = (c->have_blocks && !ext) ? c->block_of_row.p : nullptr;
   I.cnt.ensure(n + 1); I.rp.ensure(n + 1); I.dpos.ensure(n); I.dinv.ensure(n); I.y.ensure(std::max(c->ld, n));
   c->tic("iluPattern");
   k_ilu_count<<<ceil_div(n_own, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, blk, n_own, climit, I.cnt.p); ++c->launches;
-  if (ext && I.ov.nhalo) { k_ilu_ext_count<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.ov.nhalo, I.cnt.p + n_own); ++c->launches; }
+  if (ext && I.ov.nhalo) { k_ilu_ext_count<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.slot_ref.p, I.ov.nhalo, I.cnt.p + n_own); ++c->launches; }
   CUDA_CHECK(cudaMemsetAsync(I.cnt.p + n, 0, sizeof(int), c->stream));
   size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, I.cnt.p, I.rp.p, n + 1, c->stream);
   I.tmp.ensure(tb);
@@ -432,7 +448,7 @@ void ilu_create(Ctx *c) {
   I.ci.ensure(I.nnz); I.fv.ensure(I.nnz);
   I.sync_free = !getenv("ISPH_ILU_BARRIER"); I.fault.ensure(4); CUDA_CHECK(cudaMemsetAsync(I.fault.p, 0, 4 * sizeof(int), c->stream));
   k_ilu_fill<<<ceil_div(n_own, 128), 128, 0, c->stream>>>(A.slice_off.p, A.row_len.p, A.col.p, A.val.p, blk, n_own, climit, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches;
-  if (ext && I.ov.nhalo) { k_ilu_ext_fill<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.ov.val_r2.p, I.ov.nhalo, n_own, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches; }
+  if (ext && I.ov.nhalo) { k_ilu_ext_fill<<<ceil_div(I.ov.nhalo, 128), 128, 0, c->stream>>>(I.ov.off_r.p, I.ov.col_r2.p, I.ov.val_r2.p, I.slot_ref.p, I.ov.nhalo, n_own, I.rp.p, I.ci.p, I.fv.p, I.dpos.p); ++c->launches; }
   if (c->pp.fill > 0) {                                          // level-of-fill pattern (host), values expanded on the device
     std::vector<int> ci0(I.nnz), frp, fci;
     CUDA_CHECK(cudaMemcpyAsync(ci0.data(), I.ci.p, sizeof(int) * I.nnz, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -559,6 +575,7 @@ void ilu_apply(Ctx *c, const double *r, double *z) {
   I.rext.ensure(I.n + 32); I.zext.ensure(I.n + 32);
   CUDA_CHECK(cudaMemcpyAsync(I.rext.p, r, sizeof(double) * I.n_own, cudaMemcpyDeviceToDevice, c->stream));
   halo_exchange(c, I.rext.p, 1, I.n);
+  if (I.ov.nhalo) { k_ilu_zero_unref<<<ceil_div(I.ov.nhalo, 256), 256, 0, c->stream>>>(I.rext.p + I.n_own, I.slot_ref.p, I.ov.nhalo); ++c->launches; }   // not part of the overlap: solves to 0, exports 0
   ilu_apply_core(c, I.rext.p, I.zext.p);
   CUDA_CHECK(cudaMemcpyAsync(z, I.zext.p, sizeof(double) * I.n_own, cudaMemcpyDeviceToDevice, c->stream));
   halo_export_add(c, I.zext.p + I.n_own, z);

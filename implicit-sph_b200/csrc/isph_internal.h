@@ -221,7 +221,7 @@ struct OverlapRows {
   DevBuf<int> coltag, tag2col, len_s, len_r, tag_s, tag_r, col_r, col_r2; DevBuf<long long> off_s, off_r; DevBuf<double> val_s, val_r, val_r2;
   void release() { coltag.release(); tag2col.release(); len_s.release(); len_r.release(); tag_s.release(); tag_r.release(); col_r.release(); col_r2.release(); off_s.release(); off_r.release(); val_s.release(); val_r.release(); val_r2.release(); }
 };
-void halo_import_rows(Ctx *c, OverlapRows *out);
+void halo_import_rows(Ctx *c, OverlapRows *out, const int *slot_ref /* per halo slot: part of the extended set? (device) */);
 void halo_export_add(Ctx *c, const double *zext_halo, double *z);
 void halo_setup(Ctx *c);                                     // halo.cu
 bool halo_prepush_begin(Ctx *c, const double *x_next, PrePush *pp);   // reserves the exchange of the SpMV that will read x_next
