@@ -335,6 +335,20 @@ class Context:
     def precond_apply(self, r):
         r = np.ascontiguousarray(r, dtype=np.float64); z = np.empty_like(r); self.call("isph_precond_apply", _d(r), _d(z)); return z
 
+    def block_matrix(self, dim, blocks, name="Block"):
+        """blocks: {(i, j): scipy CSR} over the nodal map (createBlockMatrix / setBlock / setBlockEnd, solver_lin.cpp:78-138)"""
+        self.call("isph_solver_create_block_matrix", int(dim), name.encode())
+        for (i, j), A in blocks.items():
+            rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32); va = np.ascontiguousarray(A.data, dtype=np.float64)
+            self.call("isph_solver_set_block_csr", int(i), int(j), A.shape[0], _i(rp), _i(ci), _d(va))
+        self.call("isph_solver_set_block_end")
+
+    def solve_block(self, use_prec=True, label="Block"):
+        self.call("isph_solver_solve_block", int(use_prec), label.encode())
+        it = C.c_int(); rr = C.c_double(); cv = C.c_int(); lm = C.c_double()
+        self.call("isph_solver_stats", C.byref(it), C.byref(rr), C.byref(cv), C.byref(lm))
+        return dict(iters=it.value, relres=rr.value, converged=bool(cv.value))
+
     def solve(self, use_prec=True, label="Poisson"):
         self.call("isph_solver_solve", int(use_prec), label.encode())
         it = C.c_int(); rr = C.c_double(); cv = C.c_int(); lm = C.c_double()

@@ -74,6 +74,8 @@ using namespace isph;
 #define API_BEGIN(ctx) if (!(ctx)) return ISPH_FAILURE; Ctx *c = reinterpret_cast<Ctx *>(ctx); try { CUDA_CHECK(cudaSetDevice(c->device));
 #define API_END } catch (const std::exception &e) { c->err = e.what(); cudaGetLastError(); return ISPH_FAILURE; } return ISPH_SUCCESS;
 
+namespace isph { struct BlockSys { int dim = 0, n = 0; std::string name; std::vector<std::vector<int>> rp, ci; std::vector<std::vector<double>> va; isph_ctx *child = nullptr; bool filled = false; }; }
+
 extern "C" {
 
 const char *isph_version(void) { return "isph_b200 0.1 (sm_100a)"; }
@@ -101,6 +103,7 @@ int isph_ctx_destroy(isph_ctx *ctx) {
   if (!ctx) return ISPH_FAILURE; Ctx *c = reinterpret_cast<Ctx *>(ctx);
   cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
   if (c->prec_ready) { try { precond_free(c); } catch (...) {} }
+  if (c->blk) { if (c->blk->child) isph_ctx_destroy(c->blk->child); delete c->blk; c->blk = nullptr; }
   halo_destroy(c); ilu_destroy(c); amg_destroy(c); neighbors_destroy(c);
   c->d_tab.release(); c->x.release(); c->type.release(); c->tag.release(); c->kind.release(); c->col_of_atom.release(); c->tag2own.release();
   for (auto &f : c->field) f.release();
@@ -444,6 +447,69 @@ int isph_precond_apply(isph_ctx *ctx, const double *r, double *z) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->prec_ready && r && z, "preconditioner not created"); const int n = c->A.n, ld = c->ld; c->V.ensure((size_t)2 * ld);
   CUDA_CHECK(cudaMemcpyAsync(c->V.p, r, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream)); precond_apply(c, c->V.p, c->V.p + ld);
   CUDA_CHECK(cudaMemcpyAsync(z, c->V.p + ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); API_END
+}
+// ---- SolverLin block interface (solver_lin.h:43-56, solver_lin.cpp:78-138) and SolverLin_Belos::solveBlockProblem (solver_lin_belos.h:53-128) ----
+// The dim x dim block operator (Thyra::PhysicallyBlockedLinearOp of Epetra matrices that share the nodal map) becomes ONE stacked SELL matrix
+// with dim * n rows held by a child context; x and b (n x dim multivectors, one column per block row: createBlockVector, solver_lin.cpp:93-107)
+// are the stacked vectors.  The preconditioner is the reference's: ONE operator built from the scalar matrix the wrapper holds, applied to
+// every diagonal block (getBlockPrecondOperator).  One rank only (the reference's own block path is experimental, pair_isph.cpp:1750).
+int isph_solver_create_block_matrix(isph_ctx *ctx, int dim, const char *name) {
+  API_BEGIN(ctx) ISPH_REQUIRE(dim >= 1 && dim <= 3, "createBlockMatrix: dim must be 1..3"); ISPH_REQUIRE(c->nranks == 1, "createBlockMatrix: the block system is provided on one rank only");
+  if (!c->blk) c->blk = new BlockSys();
+  BlockSys &B = *c->blk; B.dim = dim; B.n = 0; B.name = name ? name : ""; B.filled = false;
+  B.rp.assign((size_t)dim * dim, {}); B.ci.assign((size_t)dim * dim, {}); B.va.assign((size_t)dim * dim, {});
+  API_END
+}
+int isph_solver_free_block_matrix(isph_ctx *ctx) {
+  API_BEGIN(ctx) if (c->blk) { if (c->blk->child) isph_ctx_destroy(c->blk->child); delete c->blk; c->blk = nullptr; } API_END
+}
+int isph_solver_set_block_csr(isph_ctx *ctx, int i, int j, int n, const int *rowptr, const int *col, const double *val) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->blk && c->blk->dim > 0, "setBlock: createBlockMatrix first");
+  BlockSys &B = *c->blk;
+  if (!rowptr || i < 0 || j < 0 || i >= B.dim || j >= B.dim) return ISPH_SUCCESS;          // solver_lin.cpp:133: silently ignored, like the reference
+  ISPH_REQUIRE(n > 0 && (B.n == 0 || B.n == n), "setBlock: all blocks share the nodal map (same number of rows)");
+  B.n = n; const size_t q = (size_t)i * B.dim + j;
+  B.rp[q].assign(rowptr, rowptr + n + 1); B.ci[q].assign(col, col + rowptr[n]); B.va[q].assign(val, val + rowptr[n]); B.filled = false;
+  API_END
+}
+int isph_solver_set_block_end(isph_ctx *ctx) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->blk && c->blk->n > 0, "setBlockEnd: no block was set");
+  BlockSys &B = *c->blk; const int n = B.n, d = B.dim; const long long N = (long long)n * d; ISPH_REQUIRE(N < (1ll << 31) - 64, "block system too large");
+  std::vector<int> rp(N + 1, 0), ci; std::vector<double> va;
+  for (int ib = 0; ib < d; ++ib) for (int r = 0; r < n; ++r) {
+    for (int jb = 0; jb < d; ++jb) { const size_t q = (size_t)ib * d + jb; if (B.rp[q].empty()) continue;
+      for (int e = B.rp[q][r]; e < B.rp[q][r + 1]; ++e) { ISPH_REQUIRE(B.ci[q][e] >= 0 && B.ci[q][e] < n, "setBlock: column outside the nodal map"); ci.push_back(jb * n + B.ci[q][e]); va.push_back(B.va[q][e]); } }
+    rp[(size_t)ib * n + r + 1] = (int)ci.size();
+  }
+  if (!B.child) { ISPH_REQUIRE(isph_ctx_create(&B.child, c->device, 1, 0, nullptr) == ISPH_SUCCESS, "block system: no child context"); }
+  Ctx *k = reinterpret_cast<Ctx *>(B.child);
+  CUDA_CHECK(cudaStreamSynchronize(k->stream)); if (k->own_stream) { cudaStreamDestroy(k->stream); k->own_stream = false; } k->stream = c->stream;
+  matrix_from_csr(k, (int)N, rp.data(), ci.data(), va.data()); B.filled = true;
+  API_END
+}
+int isph_solver_solve_block(isph_ctx *ctx, int use_prec, const char *label) {
+  API_BEGIN(ctx) ISPH_REQUIRE(c->blk && c->blk->filled, "solveBlockProblem: createBlockMatrix / setBlock / setBlockEnd first");
+  BlockSys &B = *c->blk; Ctx *k = reinterpret_cast<Ctx *>(B.child); const int n = B.n, d = B.dim;
+  ISPH_REQUIRE(c->b_nvec == d && c->x_nvec == d && c->xs.p && c->bs.p, ">> SolverLin_Belos::solveBlockProblem, dimension of rhs does not match to the block matrix");   // solver_lin_belos.h:58-59
+  ISPH_REQUIRE(!c->is_singular, ">> SolverLin_Belos::solveBlockProblem does not support singular problems");                                                    // :60-61
+  ISPH_REQUIRE(!use_prec || (c->A.built && c->A.n == n), "solveBlockProblem: the preconditioner is built from the scalar matrix (prec->setMatrix): it must have the blocks' row map");
+  const int ld = c->ld; const size_t xl = (size_t)ld * d;
+  // initial solution and load vector exactly as solveProblem prepares them, then stacked
+  if (c->init_type == ISPH_INIT_ZERO) CUDA_CHECK(cudaMemsetAsync(c->xs.p, 0, sizeof(double) * xl, c->stream));
+  else if (c->init_type == ISPH_INIT_VALUE) { std::vector<double> f(xl, c->init_val); CUDA_CHECK(cudaMemcpyAsync(c->xs.p, f.data(), sizeof(double) * xl, cudaMemcpyHostToDevice, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+  else if (c->init_type == ISPH_INIT_RANDOM) ISPH_REQUIRE(false, "solveBlockProblem: setInitialSolution(Random) is not provided for the block system");
+  else if (c->x_host) for (int q = 0; q < d; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * ld, c->x_host + (size_t)q * c->x_lda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  load_from_host(c); c->b_dev_fresh = false;
+  k->sp = c->sp; k->xs.ensure(k->ld); k->bs.ensure(k->ld); k->x_nvec = k->b_nvec = 1; k->x_host = k->b_host = nullptr; k->x_owned = k->b_owned = true; k->init_type = -1; k->is_singular = false;
+  for (int q = 0; q < d; ++q) { CUDA_CHECK(cudaMemcpyAsync(k->xs.p + (size_t)q * n, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+                                CUDA_CHECK(cudaMemcpyAsync(k->bs.p + (size_t)q * n, c->bs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); }
+  k->prec_parent = use_prec ? c : nullptr; k->prec_dim = d; k->launches = 0;
+  solver_solve(k, use_prec != 0, label);                          // Belos on the product space: the same GMRES / CG on the stacked vectors
+  for (int q = 0; q < d; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * ld, k->xs.p + (size_t)q * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->x_host) for (int q = 0; q < d; ++q) CUDA_CHECK(cudaMemcpyAsync(c->x_host + (size_t)q * c->x_lda, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->last_iters = k->last_iters; c->last_converged = k->last_converged; c->last_relres = k->last_relres; c->launches += k->launches; c->init_type = -1;
+  API_END
 }
 int isph_solver_solve(isph_ctx *ctx, int use_prec, const char *label) { API_BEGIN(ctx) solver_solve(c, use_prec != 0, label); API_END }
 int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged, double *lmax) {

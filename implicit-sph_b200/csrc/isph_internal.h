@@ -84,6 +84,7 @@ struct Halo;      // halo.cu
 struct NeighWork; // neighbor.cu
 struct IluData;   // precond.cu
 struct AmgData;   // amg.cu
+struct BlockSys;  // capi.cu: the dim x dim block operator of solveBlockProblem
 
 struct Ctx {
   int device = 0, nranks = 1, rank = 0;
@@ -116,6 +117,8 @@ struct Ctx {
   // preconditioner
   bool prec_ready = false; int prec_kind = 0; DevBuf<double> invdiag, cw, cv; DevBuf<int> block_of_row; bool have_blocks = false;
   IluData *ilu = nullptr; AmgData *amg = nullptr;
+  BlockSys *blk = nullptr;          // createBlockMatrix / setBlock (solver_lin.cpp:78-138)
+  Ctx *prec_parent = nullptr; int prec_dim = 0;   // block-diagonal preconditioner of a block solve: the parent's preconditioner applied to every diagonal block (precond_ifpack.h:77-81, precond_ml.h:137-154)
   DevBuf<double> pb_extra;         // Poisson-Boltzmann extra source term staged for the Newton loop
   // multi-GPU
   Halo *halo = nullptr;

@@ -74,6 +74,9 @@ void precond_create(Ctx *c) {
   // rank, overlap for the relaxation / Chebyshev types
   ISPH_REQUIRE(t == "ML" || c->pp.overlap == 0 || (c->nranks == 1 && !c->have_blocks) || (c->pp.overlap == 1 && !c->have_blocks && t == "ILU"),
                "Overlap Level: 0, or 1 with Precond Type ILU and one block per rank (more levels, overlapping sub-blocks and overlapping relaxation are not implemented)");
+  if (c->prec_parent) {                                                          // block solve: prec->create(dim) builds ONE preconditioner from the scalar matrix the wrapper was given (prec->setMatrix(A.crs))
+    c->prec_kind = 5; precond_create(c->prec_parent); c->prec_ready = true; c->toc("precondCreate"); return;
+  }
   if (t == "none") c->prec_kind = 0;
   else if (t == "point relaxation" || t == "point relaxation stand-alone" || t == "Jacobi") { ISPH_REQUIRE(c->pp.relax_type == "Jacobi", "relaxation: type must be Jacobi"); c->prec_kind = 1; }
   else if (t == "Chebyshev") c->prec_kind = 2;
@@ -109,7 +112,7 @@ void precond_create(Ctx *c) {
   c->toc("precondCreate");
 }
 
-void precond_free(Ctx *c) { if (c->prec_kind == 3) ilu_free(c); if (c->prec_kind == 4) amg_free(c); c->prec_ready = false; }
+void precond_free(Ctx *c) { if (c->prec_kind == 5 && c->prec_parent) precond_free(c->prec_parent); if (c->prec_kind == 3) ilu_free(c); if (c->prec_kind == 4) amg_free(c); c->prec_ready = false; }
 
 // z = M^-1 r  (Ifpack_Preconditioner::ApplyInverse as wrapped by Belos::EpetraPrecOp, solver_lin_belos.h:155)
 void precond_apply(Ctx *c, const double *r, double *z) {
@@ -133,6 +136,7 @@ void precond_apply(Ctx *c, const double *r, double *z) {
     break; }
   case 3: ilu_apply(c, r, z); break;
   case 4: amg_apply(c, r, z); break;
+  case 5: { const int nb = c->prec_parent->A.n; for (int k = 0; k < c->prec_dim; ++k) precond_apply(c->prec_parent, r + (size_t)k * nb, z + (size_t)k * nb); break; }   // the same operator on every diagonal block
   }
 }
 

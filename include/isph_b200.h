@@ -228,6 +228,16 @@ int isph_precond_create(isph_ctx *ctx);     /* PrecondWrapper::create(), precond
 int isph_iluk_symbolic_host(int n, const int *rowptr, const int *col, int fill, int *rowptr_out, int *col_out, long long cap, long long *nnz_out);
 int isph_precond_free(isph_ctx *ctx);       /* PrecondWrapper::free() */
 int isph_precond_apply(isph_ctx *ctx, const double *r, double *z);        /* ApplyInverse, host vectors (tests) */
+/* SolverLin block interface (solver_lin.h:43-56, solver_lin.cpp:78-138) and SolverLin_Belos::solveBlockProblem (solver_lin_belos.h:53-128): a
+ * dim x dim block operator whose blocks are CSR matrices over the nodal map (col = local row index; a NULL block is ignored like a NULL
+ * Epetra_CrsMatrix*, solver_lin.cpp:133).  x and b are the n x dim multivectors of createSolution/LoadMultiVector, one column per block row.
+ * The preconditioner is ONE operator built from the scalar matrix of the context (prec->setMatrix(A.crs), pair_isph.cpp:925) and applied to
+ * every diagonal block (getBlockPrecondOperator).  Errors as the reference: rhs columns != dim, singular problems.  One rank only. */
+int isph_solver_create_block_matrix(isph_ctx *ctx, int dim, const char *name);      /* createBlockMatrix + setBlockBegin */
+int isph_solver_set_block_csr(isph_ctx *ctx, int i, int j, int n, const int *rowptr, const int *col, const double *val);   /* setBlock(i, j, A) */
+int isph_solver_set_block_end(isph_ctx *ctx);                                       /* setBlockEnd */
+int isph_solver_free_block_matrix(isph_ctx *ctx);                                   /* freeBlockMatrix */
+int isph_solver_solve_block(isph_ctx *ctx, int use_prec, const char *label);        /* solveBlockProblem(prec, name) */
 /* SolverLin_Belos::solveProblem(prec, name): use_prec != 0 creates and frees the preconditioner around the solve */
 int isph_solver_solve(isph_ctx *ctx, int use_prec, const char *label);
 int isph_solver_stats(isph_ctx *ctx, int *iters, double *relres, int *converged, double *lambda_max);

@@ -115,6 +115,23 @@ class SolverLin_B200 {
   }
   int iterations() const { int it = 0; isph_solver_stats(_ctx, &it, NULL, NULL, NULL); return it; }
 
+  // block interface, solver_lin.h:43-56 / solver_lin.cpp:78-138; a block = CSR over the nodal map instead of an Epetra_CrsMatrix*
+  int createBlockMatrix(const int dim, const char *name) { return rc(isph_solver_create_block_matrix(_ctx, dim, name)); }
+  int freeBlockMatrix() { return rc(isph_solver_free_block_matrix(_ctx)); }
+  void setMatrixIsBlocked(const bool) {}
+  void setBlockBegin() {}
+  void setBlock(const int i, const int j, int n, const int *rowptr, const int *col, const double *val) { isph_solver_set_block_csr(_ctx, i, j, n, rowptr, col, val); }
+  void setBlockEnd() { isph_solver_set_block_end(_ctx); }
+  // SolverLin_Belos::solveBlockProblem(prec, name), solver_lin_belos.h:53-128
+  virtual int solveBlockProblem(PrecondWrapper_B200 *prec = NULL, const char *name = NULL) {
+    if (name != NULL) std::printf(">> isph_b200(Block)::Label - %s\n", name);
+    const int r = isph_solver_solve_block(_ctx, prec != NULL ? 1 : 0, name);
+    if (r != ISPH_SUCCESS) { std::fprintf(stderr, ">> isph_b200 error: %s\n", isph_last_error(_ctx)); return LAMMPS_FAILURE; }
+    int iters = 0, conv = 0; double relres = 0.0; isph_solver_stats(_ctx, &iters, &relres, &conv, NULL);
+    if (conv) std::printf(">> isph_b200::Status - Passed! %s (%d iterations, %.3e)\n", name ? name : " ", iters, relres);
+    return LAMMPS_SUCCESS;
+  }
+
  protected:
   static int rc(int r) { return r == ISPH_SUCCESS ? LAMMPS_SUCCESS : LAMMPS_FAILURE; }
   isph_ctx *_ctx;

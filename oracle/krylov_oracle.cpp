@@ -247,10 +247,14 @@ void orc_krylov_default_params(orc_krylov_params *p) {
   p->amg_scale = q.oc; p->amg_damping = q.damping;
 }
 
-int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
-                     const int *block_of_row, const int *null_mask, int use_null, double *b, double *x,
-                     int *iters_out, double *relres_out, double *history, int history_cap) {
-  Csr A{n, rowptr, col, val};
+}  // extern "C"
+namespace {
+// the preconditioner of SolverLin_Belos::solveBlockProblem: ONE operator built from the scalar matrix, applied to every diagonal block
+// (PrecondWrapper_Ifpack::getBlockPrecondOperator, precond_ifpack.h:77-81; PrecondWrapper_ML::create(dim), precond_ml.h:137-154)
+struct BlockDiagPrecond { Precond *P; int dim, nb; double lmax = 0.0; void apply(const double *r, double *z) { for (int k = 0; k < dim; ++k) P->apply(r + (size_t)k * nb, z + (size_t)k * nb); } };
+template <class MT> int krylov_impl(const Csr &A, const orc_krylov_params *prm, MT &M, const int *null_mask, int use_null, double *b, double *x,
+                                    int *iters_out, double *relres_out, double *history, int history_cap) {
+  const int n = A.n;
   std::vector<double> nvec;
   if (use_null) {                                           // solver_lin.cpp:59-77 ; solver_lin_belos.h:138-144
     nvec.assign(n, 1.0);
@@ -260,7 +264,6 @@ int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val
     const double bn = dot(n, b, nvec.data()); axpy(n, -bn, nvec.data(), b);
   }
   Op op{&A, use_null ? nvec.data() : nullptr};
-  Precond M; M.setup(A, prm, block_of_row);                 // prec->create(), solver_lin_belos.h:153
   int iters = 0, nhist = 0; bool converged = false; double scale = 0.0, res = 0.0;
   std::vector<double> r(n), w(n);
 
@@ -340,6 +343,25 @@ int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val
   if (iters_out) *iters_out = iters;
   if (relres_out) *relres_out = scale > 0.0 ? res / scale : 0.0;
   return converged ? 0 : 1;
+}
+}  // namespace
+extern "C" {
+int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
+                     const int *block_of_row, const int *null_mask, int use_null, double *b, double *x,
+                     int *iters_out, double *relres_out, double *history, int history_cap) {
+  Csr A{n, rowptr, col, val};
+  Precond M; M.setup(A, prm, block_of_row);                 // prec->create(), solver_lin_belos.h:153
+  return krylov_impl(A, prm, M, null_mask, use_null, b, x, iters_out, relres_out, history, history_cap);
+}
+// SolverLin_Belos::solveBlockProblem (solver_lin_belos.h:53-128): the dim x dim block operator as ONE stacked CSR matrix of dim * nb rows
+// (block row ib = rows ib*nb .. ib*nb+nb-1, block column jb = columns jb*nb ..), the preconditioner built from the scalar nb x nb matrix
+// (prec_*) and applied to every diagonal block; no null space (the reference refuses singular block problems, :60-61)
+int orc_krylov_solve_block(int nb, int dim, const int *rowptr, const int *col, const double *val, const int *prec_rowptr, const int *prec_col, const double *prec_val,
+                           const orc_krylov_params *prm, double *b, double *x, int *iters_out, double *relres_out) {
+  Csr A{nb * dim, rowptr, col, val}, Ap{nb, prec_rowptr, prec_col, prec_val};
+  Precond P; P.setup(Ap, prm, nullptr);
+  BlockDiagPrecond M{&P, dim, nb};
+  return krylov_impl(A, prm, M, nullptr, 0, b, x, iters_out, relres_out, nullptr, 0);
 }
 
 int orc_precond_apply(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,

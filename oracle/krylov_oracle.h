@@ -49,6 +49,8 @@ void orc_krylov_default_params(orc_krylov_params *p);
 int orc_krylov_solve(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
                      const int *block_of_row, const int *null_mask, int use_null, double *b, double *x,
                      int *iters_out, double *relres_out, double *history, int history_cap);
+int orc_krylov_solve_block(int nb, int dim, const int *rowptr, const int *col, const double *val, const int *prec_rowptr, const int *prec_col, const double *prec_val,
+                           const orc_krylov_params *prm, double *b, double *x, int *iters_out, double *relres_out);
 int orc_precond_apply(int n, const int *rowptr, const int *col, const double *val, const orc_krylov_params *prm,
                       const int *block_of_row, const double *r, double *z, double *lambda_max_out);
 /* hierarchy of ORC_PREC_AMG for the tests: returns the number of levels; rows[l], nnz[l], lmax[l] per level; agg0[n] = aggregate of every

@@ -260,6 +260,18 @@ def krylov_solve(rowptr, col, val, b, x0=None, params=None, blocks=None, null_ma
     return x, dict(iters=it.value, relres=rr.value, converged=(rc == 0), history=None if hist is None else hist[:it.value + 1], b=b)
 
 
+def krylov_solve_block(dim, stacked, prec, b, x0=None, params=None):
+    """solveBlockProblem: `stacked` = scipy CSR of the dim x dim block operator (dim * nb rows), `prec` = scipy CSR of the scalar nb x nb matrix
+    the block-diagonal preconditioner is built from; b, x = stacked vectors."""
+    L = _load("port"); nb = prec.shape[0]
+    rp = np.ascontiguousarray(stacked.indptr, dtype=np.int32); ci = np.ascontiguousarray(stacked.indices, dtype=np.int32); va = np.ascontiguousarray(stacked.data, dtype=np.float64)
+    prp = np.ascontiguousarray(prec.indptr, dtype=np.int32); pci = np.ascontiguousarray(prec.indices, dtype=np.int32); pva = np.ascontiguousarray(prec.data, dtype=np.float64)
+    b = np.array(b, dtype=np.float64); x = np.zeros(nb * dim) if x0 is None else np.array(x0, dtype=np.float64)
+    p = params if params is not None else krylov_params(); it = C.c_int(); rr = C.c_double()
+    rc = L.orc_krylov_solve_block(nb, int(dim), _i(rp), _i(ci), _d(va), _i(prp), _i(pci), _d(pva), C.byref(p), _d(b), _d(x), C.byref(it), C.byref(rr))
+    return x, dict(iters=it.value, relres=rr.value, converged=(rc == 0))
+
+
 def precond_apply(rowptr, col, val, r, params, blocks=None):
     L = _load("port")
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)

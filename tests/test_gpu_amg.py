@@ -129,3 +129,36 @@ def test_ml_parameter_list_is_checked():
     with pytest.raises(isph.IsphError):
         c.precond_param("Precond Package", "Hypre")
     c.close()
+
+
+# ---- solveBlockProblem (solver_lin_belos.h:53-128) through the ABI ----------------------------------------------------------------------
+@pytest.mark.parametrize("prec,name", [(O.PREC_JACOBI, "point relaxation"), (O.PREC_ILU0, "ILU"), (O.PREC_AMG, "ML"), (None, None)])
+def test_solve_block_problem_matches_the_stacked_oracle(prec, name):
+    """The 3 x 3 block operator of SolverLin::setBlock (Thyra blocked operator over one nodal map) as one stacked matrix, x / b as n x 3
+    multivectors, ONE preconditioner built from the scalar matrix and applied to every diagonal block — against the oracle's stacked solve."""
+    from test_krylov_oracle_cpu import block_system
+    dim = 3; blocks, S, A0 = block_system(); n = A0.shape[0]; rng = np.random.default_rng(0)
+    b = np.asfortranarray(rng.standard_normal((n, dim)))
+    prm = O.krylov_params(precond=prec if prec is not None else O.PREC_NONE, amg_threshold=0.1, amg_max_coarse=20)
+    xo, info = O.krylov_solve_block(dim, S, A0, b.reshape(-1, order="F"), params=prm)
+    c = isph.Context(); c.matrix_set_csr(A0.indptr, A0.indices, A0.data)               # li_solver->setMatrix(A.crs); prec->setMatrix(A.crs)
+    x = np.asfortranarray(np.zeros((n, dim))); c.create_solution(x, dim); c.create_load(None, dim); c.load_set(b)
+    c.solver_param("Solver Type", "Block GMRES"); c.solver_param("Flexible Gmres", True)
+    if prec is not None:
+        if name == "ML":
+            ml_configure(c, **{"aggregation: threshold": 0.1, "coarse: max size": 20})
+        else:
+            c.precond_param("Precond Package", "Ifpack"); c.precond_param("Precond Type", name); c.precond_param("Overlap Level", 0); c.precond_param("fact: level-of-fill", 0)
+    c.block_matrix(dim, blocks, "Block 3x3"); c.set_matrix_is_singular(False); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve_block(prec is not None, "Block 3x3 Helmholtz")
+    assert st["converged"] and info["converged"] and abs(st["iters"] - info["iters"]) <= 2, (st, info)
+    assert np.linalg.norm(x.reshape(-1, order="F") - xo) / np.linalg.norm(xo) <= 1e-7
+    assert np.linalg.norm(b.reshape(-1, order="F") - S @ x.reshape(-1, order="F")) / np.linalg.norm(b) <= 2e-8
+    # error behaviour of the reference (solver_lin_belos.h:58-61): rhs columns != dim, singular problems
+    c.set_matrix_is_singular(True)
+    with pytest.raises(isph.IsphError, match="singular"):
+        c.solve_block(False, "x")
+    c.set_matrix_is_singular(False); c.create_load(None, 1); c.create_solution(None, 1)
+    with pytest.raises(isph.IsphError, match="dimension of rhs"):
+        c.solve_block(False, "x")
+    c.close()

@@ -248,3 +248,33 @@ def test_ml_standin_uncoupled_aggregates_and_rows_without_strong_connections(ora
     assert np.all(h2["agg"][dead] == -1) and np.all(np.delete(h2["agg"], dead) >= 0)
     b = np.random.default_rng(5).standard_normal(n); x, info = O.krylov_solve(rp2, ci2, v2, b, params=prm)
     assert info["converged"] and np.linalg.norm(b - B @ x) / np.linalg.norm(b) <= 2e-8
+
+
+# ---- solveBlockProblem (solver_lin_belos.h:53-128) -------------------------------------------------------------------------------------
+def block_system(n1=14, dim=3, seed=2):
+    """a Helmholtz-like dim x dim block operator over one nodal map: diagonal blocks I + theta*L (different per component), sparse
+    off-diagonal couplings on a subset of rows (the block-Helmholtz functor couples components only near boundaries)"""
+    rng = np.random.default_rng(seed); L = lap2d(n1, 0.0, 0.1); n = L.shape[0]
+    blocks = {}
+    for i in range(dim):
+        blocks[(i, i)] = sp.csr_matrix(sp.eye(n) + (0.3 + 0.1 * i) * L)
+        for j in range(dim):
+            if i != j:
+                rows = np.arange(0, n, 3 + i + j); C = sp.csr_matrix((0.05 * rng.standard_normal(len(rows)), (rows, (rows + 1 + j) % n)), shape=(n, n)); blocks[(i, j)] = C
+    stacked = sp.bmat([[blocks[(i, j)] for j in range(dim)] for i in range(dim)], format="csr"); stacked.sort_indices()
+    scalar = sp.csr_matrix(sp.eye(n) + 0.35 * L); scalar.sort_indices()            # what prec->setMatrix(A.crs) holds: NOT one of the blocks
+    return blocks, stacked, scalar
+
+
+@pytest.mark.parametrize("prec", ["PREC_JACOBI", "PREC_ILU0", "PREC_AMG"])
+def test_block_problem_is_the_stacked_system_with_one_preconditioner_on_every_diagonal_block(oracle_mod, prec):
+    O = oracle_mod; dim = 3; blocks, S, A0 = block_system(); n = A0.shape[0]; b = np.random.default_rng(0).standard_normal(dim * n)
+    prm = O.krylov_params(precond=getattr(O, prec), amg_threshold=0.1, amg_max_coarse=20)
+    x, info = O.krylov_solve_block(dim, S, A0, b, params=prm)
+    assert info["converged"] and np.linalg.norm(b - S @ x) / np.linalg.norm(b) <= 2e-8
+    # the preconditioner really is M(A0) on every segment: one application through the scalar API, segment by segment, reproduces an
+    # independent right-preconditioned first Krylov vector  A M^-1 r0
+    z = np.concatenate([O.precond_apply(A0.indptr, A0.indices, A0.data, b[k * n:(k + 1) * n], prm)[0] for k in range(dim)])
+    x1, info1 = O.krylov_solve_block(dim, S, A0, b, params=O.krylov_params(precond=getattr(O, prec), amg_threshold=0.1, amg_max_coarse=20, max_iters=1))
+    w = S @ z; alpha = (w @ b) / (w @ w)                                       # GMRES(1): x1 = alpha z minimises ||b - alpha A z||
+    assert np.linalg.norm(x1 - alpha * z) <= 1e-12 * np.linalg.norm(x1)
