@@ -160,7 +160,9 @@ template <int N> __device__ void gesv_small(double *A, double *b) {
   for (int k = N - 1; k >= 0; --k) { b[k] /= A[k + k * N]; for (int r = 0; r < k; ++r) b[r] -= A[r + k * N] * b[k]; }
 }
 
-template <int DIM, int OCC> __global__ void __launch_bounds__(128, OCC) k_laplacian_correction(Dev d, double *Lc_out) {  // functor_laplacian_correction.h:25-153
+// register budget: 4 resident blocks per SM (128 registers, 176 B spilled in 3-D) measured against 2 / 3 (no spills) / 5 on the 1M-row brick: 4.78 ms vs 6.55 / 4.85 / 6.13 ms
+// (gpurun_out/r2_lc_occ*.json) — the spills cost less than the occupancy they buy
+template <int DIM> __global__ void __launch_bounds__(128, 4) k_laplacian_correction(Dev d, double *Lc_out) {  // functor_laplacian_correction.h:25-153
   constexpr int DIMSQ = DIM * DIM, DIML = DIM * (DIM + 1) / 2;
   LIST_SETUP(d)
   double A[DIM * DIMSQ], L[DIML * DIML];
@@ -810,12 +812,7 @@ void compute_gradient_correction(Ctx *c) {
 }
 void compute_laplacian_correction(Ctx *c) {
   Dev d = make_dev(c, false); c->tic("computeLaplacianCorrection");
-  static const int occ = getenv("ISPH_LC_OCC") ? atoi(getenv("ISPH_LC_OCC")) : 4;      // resident blocks per SM the register budget is set for (A/B switch)
-  if (d.dim == 2) k_laplacian_correction<2, 4><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
-  else if (occ == 2) k_laplacian_correction<3, 2><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
-  else if (occ == 3) k_laplacian_correction<3, 3><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
-  else if (occ == 5) k_laplacian_correction<3, 5><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
-  else k_laplacian_correction<3, 4><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
+  if (d.dim == 2) k_laplacian_correction<2><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p); else k_laplacian_correction<3><<<LGRID(c)>>>(d, c->field[ISPH_F_LC].p);
   ++c->launches; c->toc("computeLaplacianCorrection");
 }
 void compute_normals(Ctx *c) {
