@@ -365,10 +365,16 @@ void member_lists(Ctx *c, AmgData *D, AmgLevel *L) {
 
 // Galerkin operator of level `lev` -> local rows (nc_mine) with global coarse column ids, in D->rlen / Cn->ci / Cn->va (CSR by Cn->rp)
 template <class M> bool galerkin(Ctx *c, AmgData *D, AmgLevel *L, AmgLevel *Cn, M A, const int *aggc) {
-  const int n = L->n, nc = L->nc_mine; const int KQ = 48;
+  const int n = L->n, nc = L->nc_mine; const int KQ = 48, KQ2 = 160;
   D->qcnt.ensure(n); D->qj.ensure((size_t)n * KQ); D->qv.ensure((size_t)n * KQ); D->ctr.ensure(8);
   CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
   k_amg_compress<M, KQ><<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, aggc, L->agg.p, D->qcnt.p, D->qj.p, D->qv.p, D->ctr.p + 1); LAUNCH(c);
+  if (d2h(c, D->ctr.p + 1)) {                                             // a row reaches more than 48 aggregates (small aggregates under a wide stencil): the wide variant
+    D->qj.ensure((size_t)n * KQ2); D->qv.ensure((size_t)n * KQ2);
+    CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
+    k_amg_compress<M, KQ2><<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, aggc, L->agg.p, D->qcnt.p, D->qj.p, D->qv.p, D->ctr.p + 1); LAUNCH(c);
+    if (d2h(c, D->ctr.p + 1)) return false;
+  }
   D->rlen.ensure(nc + 2); Cn->rp.ensure(nc + 2);
   CUDA_CHECK(cudaMemsetAsync(D->rlen.p, 0, sizeof(int) * (nc + 2), c->stream));
   k_amg_merge<512, false><<<tgrid(nc, 4), 128, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, D->rlen.p, nullptr, nullptr, nullptr, D->ctr.p + 1); LAUNCH(c);

@@ -162,3 +162,24 @@ def test_solve_block_problem_matches_the_stacked_oracle(prec, name):
     with pytest.raises(isph.IsphError, match="dimension of rhs"):
         c.solve_block(False, "x")
     c.close()
+
+
+def test_ml_standin_rows_that_reach_many_aggregates():
+    """small aggregates under a wide stencil: only the two ring neighbours of a row are strong (aggregates of 3-5 rows) while every row has
+    ~80 weak entries spread over the whole matrix, so a row reaches > 48 aggregates — the wide variant of the row compression takes over;
+    hierarchy and iteration count still equal the restatement's"""
+    n = 600; rng = np.random.default_rng(7)
+    r = np.repeat(np.arange(n), 40); cidx = rng.integers(0, n, size=len(r)); keep = r != cidx
+    W = sp.coo_matrix((-np.ones(keep.sum()), (r[keep], cidx[keep])), shape=(n, n)).tocsr(); W.data[:] = -1.0; W = W + W.T; W.data[:] = -1.0
+    i = np.arange(n); R = sp.coo_matrix((-5.0 * np.ones(2 * n), (np.r_[i, i], np.r_[(i + 1) % n, (i - 1) % n])), shape=(n, n)).tocsr()
+    off = sp.csr_matrix(W + R); A = sp.csr_matrix(off + sp.diags(-np.asarray(off.sum(1)).ravel() + 0.5)); A.sum_duplicates(); A.sort_indices()
+    ml = {"aggregation: threshold": 0.03, "coarse: max size": 40}; okw = oracle_params(**ml)
+    h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw))
+    reach = max(len(set(h["agg"][A.indices[A.indptr[q]:A.indptr[q + 1]]])) for q in range(n)); assert reach > 48, reach
+    b = rng.standard_normal(n); xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    ml_configure(c, **ml); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "wide"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates(); c.close()
+    assert hi["levels"] == h["levels"] >= 2 and list(hi["rows"]) == list(h["rows"]) and np.array_equal(agg, h["agg"]), (hi, h)
+    check(st, info, x, xo, sol_tol=1e-6)
