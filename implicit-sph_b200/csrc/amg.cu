@@ -64,25 +64,26 @@ template <class M> __global__ void __launch_bounds__(128) k_amg_strength(M A, in
 }
 
 // ---- distance-2 maximal independent set, synchronous rounds.  state: 0 undecided, 1 root, -1 out, -2 no strong connection ----------
-__global__ void __launch_bounds__(VB) k_amg_mis_init(int n, const int *gid, const int *cnt, unsigned long long *key, int *state) {
+// tok = what a row shows its neighbours: all ones once it is a root, its priority while undecided, 0 when out / without strong connection
+// (one 8-byte gather per neighbour per sweep instead of state + priority)
+__global__ void __launch_bounds__(VB) k_amg_mis_init(int n, const int *gid, const int *cnt, unsigned long long *key, int *state, unsigned long long *tok) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
   const unsigned g = (unsigned)gid[r];
-  key[r] = ((mix64((unsigned long long)g, 3) >> 32) << 32) | g;
-  state[r] = cnt[r] == 0 ? -2 : 0;
+  const unsigned long long k = ((mix64((unsigned long long)g, 3) >> 32) << 32) | g;
+  key[r] = k; state[r] = cnt[r] == 0 ? -2 : 0; tok[r] = cnt[r] == 0 ? 0ULL : k;
 }
-__device__ __forceinline__ unsigned long long mis_token(int s, unsigned long long k) { return s == 1 ? ~0ULL : (s == 0 ? k : 0ULL); }
-__global__ void __launch_bounds__(VB) k_amg_mis_m1(int n, const int *sg, const int *cnt, const unsigned long long *key, const int *state, unsigned long long *m1) {
+__global__ void __launch_bounds__(VB) k_amg_mis_m1(int n, const int *sg, const int *cnt, const unsigned long long *tok, unsigned long long *m1) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
-  unsigned long long m = mis_token(state[r], key[r]);
-  for (int k = 0; k < cnt[r]; ++k) { const int j = sg[(size_t)k * n + r]; const unsigned long long t = mis_token(state[j], key[j]); m = t > m ? t : m; }
+  unsigned long long m = tok[r];
+  for (int k = 0; k < cnt[r]; ++k) { const unsigned long long t = tok[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
   m1[r] = m;
 }
-__global__ void __launch_bounds__(VB) k_amg_mis_m2(int n, const int *sg, const int *cnt, const unsigned long long *key, int *state, const unsigned long long *m1, int *undecided) {
+__global__ void __launch_bounds__(VB) k_amg_mis_m2(int n, const int *sg, const int *cnt, const unsigned long long *key, int *state, unsigned long long *tok, const unsigned long long *m1, int *undecided) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
-  if (state[r] != 0) return;                                        // only a row's own thread writes its state; neighbours are read through m1 (snapshot)
+  if (state[r] != 0) return;                                        // only a row's own thread writes its state / token; neighbours are read through m1 (snapshot)
   unsigned long long m = m1[r];
   for (int k = 0; k < cnt[r]; ++k) { const unsigned long long t = m1[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
-  if (m == ~0ULL) state[r] = -1; else if (m == key[r]) state[r] = 1; else atomicAdd(undecided, 1);
+  if (m == ~0ULL) { state[r] = -1; tok[r] = 0ULL; } else if (m == key[r]) { state[r] = 1; tok[r] = ~0ULL; } else atomicAdd(undecided, 1);
 }
 __global__ void __launch_bounds__(VB) k_amg_flag(int n, const int *state, const int *agg, int what, int *flag) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r > n) return;
@@ -152,13 +153,14 @@ template <int HS, bool FILL> __global__ void __launch_bounds__(128) k_amg_merge(
   for (int mi = m0; mi < m1; ++mi) {
     const int row = mem[mi], qc = qcnt[row];
     for (int k = lane; k < qc; k += 32) {
-      const int J = qj[(size_t)k * n + row]; unsigned h = ((unsigned)J * 2654435761u) & (HS - 1);
-      for (int probe = 0; probe < HS; ++probe) {
+      const int J = qj[(size_t)k * n + row]; unsigned h = ((unsigned)J * 2654435761u) & (HS - 1); bool placed = false;
+      for (int probe = 0; probe < HS && !placed; ++probe) {
         const int old = atomicCAS(&H[h], -1, J);
-        if (old == -1) { atomicAdd(&cnts[w], 1); break; }
-        if (old == J) break;
-        h = (h + 1) & (HS - 1);
+        if (old == -1) { atomicAdd(&cnts[w], 1); placed = true; }
+        else if (old == J) placed = true;
+        else h = (h + 1) & (HS - 1);
       }
+      if (!placed) atomicExch(&cnts[w], HS);                        // table full: reported as overflow below (never a silently dropped column)
     }
     __syncwarp();
     if (cnts[w] > HS * 3 / 4) { if (lane == 0) { *overflow = 1; if (!FILL) ccnt[I] = 0; } return; }
@@ -253,7 +255,7 @@ struct AmgLevel {
 struct AmgData {
   std::vector<AmgLevel *> L; int nlev = 0; bool ready = false;
   // setup scratch (grow-only, shared by all levels)
-  DevBuf<int> sg, cnt, state, flag, scan, agg2, skey, skey2, sval, ccnt, qcnt, qj, aggc, rlen, gbuf_i; DevBuf<float> sw; DevBuf<unsigned long long> key, m1; DevBuf<double> d, qv, aggd, gbuf_d, red;
+  DevBuf<int> sg, cnt, state, flag, scan, agg2, skey, skey2, sval, ccnt, qcnt, qj, aggc, rlen, gbuf_i; DevBuf<float> sw; DevBuf<unsigned long long> key, m1, tok; DevBuf<double> d, qv, aggd, gbuf_d, red;
   DevBuf<char> tmp; DevBuf<int> ctr; DevBuf<long long> cnt2;
   DevBuf<double> t0, w0;                           // finest-level work vectors (length ld: the product needs the halo tail)
   std::map<std::string, double> setup_ms;
@@ -330,14 +332,14 @@ struct PhaseTimer {                       // host wall-clock of a setup phase (t
 // aggregates of level `lev` (L->agg, L->root_of, L->nc_mine); M = its matrix view.  nown = rows/columns owned here.
 template <class M> void aggregate(Ctx *c, AmgData *D, AmgLevel *L, int lev, M A, int maxrow, const double *diag, const int *blk) {
   const int n = L->n; const double th = c->pp.ml_threshold;
-  D->sg.ensure((size_t)n * maxrow); D->sw.ensure((size_t)n * maxrow); D->cnt.ensure(n); D->state.ensure(n); D->key.ensure(n); D->m1.ensure(n);
+  D->sg.ensure((size_t)n * maxrow); D->sw.ensure((size_t)n * maxrow); D->cnt.ensure(n); D->state.ensure(n); D->key.ensure(n); D->m1.ensure(n); D->tok.ensure(n);
   D->flag.ensure(n + 1); D->scan.ensure(n + 1); D->agg2.ensure(n); D->ctr.ensure(8); L->agg.ensure(n); L->root_of.ensure(n);
   k_amg_strength<<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, n, diag, blk, th * th, D->sg.p, D->sw.p, D->cnt.p); LAUNCH(c);
-  k_amg_mis_init<<<tgrid(n), VB, 0, c->stream>>>(n, L->gid.p, D->cnt.p, D->key.p, D->state.p); LAUNCH(c);
+  k_amg_mis_init<<<tgrid(n), VB, 0, c->stream>>>(n, L->gid.p, D->cnt.p, D->key.p, D->state.p, D->tok.p); LAUNCH(c);
   for (int round = 0; round < 64; ++round) {
     CUDA_CHECK(cudaMemsetAsync(D->ctr.p, 0, sizeof(int), c->stream));
-    k_amg_mis_m1<<<tgrid(n), VB, 0, c->stream>>>(n, D->sg.p, D->cnt.p, D->key.p, D->state.p, D->m1.p); LAUNCH(c);
-    k_amg_mis_m2<<<tgrid(n), VB, 0, c->stream>>>(n, D->sg.p, D->cnt.p, D->key.p, D->state.p, D->m1.p, D->ctr.p); LAUNCH(c);
+    k_amg_mis_m1<<<tgrid(n), VB, 0, c->stream>>>(n, D->sg.p, D->cnt.p, D->tok.p, D->m1.p); LAUNCH(c);
+    k_amg_mis_m2<<<tgrid(n), VB, 0, c->stream>>>(n, D->sg.p, D->cnt.p, D->key.p, D->state.p, D->tok.p, D->m1.p, D->ctr.p); LAUNCH(c);
     if (d2h(c, D->ctr.p) == 0) break;
     ISPH_REQUIRE(round < 63, "ML stand-in: the independent-set rounds did not terminate");
   }
@@ -460,6 +462,11 @@ void amg_create(Ctx *c) {
         k_amg_double_to_agg<<<tgrid(ncols), VB, 0, c->stream>>>(ncols, D->aggd.p, D->aggc.p); LAUNCH(c);
       } else CUDA_CHECK(cudaMemcpyAsync(D->aggc.p, L->agg.p, sizeof(int) * nl, cudaMemcpyDeviceToDevice, c->stream));
       ok = lev == 0 ? galerkin(c, D, L, Cn, view(A), D->aggc.p) : galerkin(c, D, L, Cn, view(L), D->aggc.p);
+      if (lev == 0 && c->nranks > 1) {                                      // the decision to stop coarsening must be the same on every rank (collectives follow)
+        double bad = ok ? 0.0 : 1.0; double *dv = D->red.p + 592 * 3 + 4; CUDA_CHECK(cudaMemcpyAsync(dv, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        halo_allreduce(c, dv, 1); ok = d2h(c, dv) == 0.0;
+      }
+      if (!ok && c->rank == 0) fprintf(stderr, ">> isph_b200 ML stand-in: level %d is not coarsened further (a coarse row would hold more than %d columns); it becomes the coarsest level\n", lev, 384);
       if (ok) {
         Cn->gid.ensure(nc_all + 1);
         if (lev == 0 && c->nranks > 1) {

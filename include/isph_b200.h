@@ -202,7 +202,8 @@ int isph_solver_set_param_double(isph_ctx *ctx, const char *name, double v);
 int isph_solver_set_param_str(isph_ctx *ctx, const char *name, const char *v);
 int isph_solver_set_default_params(isph_ctx *ctx);                        /* setParameters(NULL), solver_lin_belos.h:224-264 */
 /* PrecondWrapper_Ifpack parameter names are kept (precond_ifpack.h:28-48): "Precond Type" ("point relaxation" |
- * "Chebyshev" | "ILU" | "none"), "Overlap Level" (0), "fact: level-of-fill" (0), "relaxation: type" ("Jacobi"),
+ * "Chebyshev" | "ILU" | "none"), "Overlap Level" (0; 1 = the reference's default, precond_ifpack.h:37: across ranks for "ILU" with one block per rank — halo rows imported,
+ * additive Schwarz with "schwarz: combine mode" Add; a no-op on one rank), "fact: level-of-fill" (0; k > 0 supported), "relaxation: type" ("Jacobi"),
  * "relaxation: sweeps", "relaxation: damping factor", "chebyshev: degree", "chebyshev: ratio eigenvalue",
  * "chebyshev: max eigenvalue", "chebyshev: eigenvalue max iterations".  "b200: ilu blocks" = {bx,by,bz} split of the
  * local rows into Ifpack-rank-equivalent bricks is set with isph_precond_set_blocks(). */

@@ -34,8 +34,8 @@ class PrecondWrapper_B200 {
   // setMatrix(Epetra_CrsMatrix*) : the matrix is the context's device matrix; kept for call-site compatibility
   virtual void setMatrix(isph_ctx *ctx) { if (ctx) _ctx = ctx; }
   // setParameters(NULL) loads the wrapper defaults of precond_ifpack.h:30-44 restricted to what BASELINE names (fill 0, overlap 0).
-  // The reference's own values (level-of-fill 1, overlap 1) can be set explicitly: level-of-fill k > 0 is supported, overlap > 0
-  // only where it is a no-op (one rank, one block).
+  // The reference's own values (level-of-fill 1, overlap 1) can be set explicitly: level-of-fill k > 0 is supported, overlap 1 across
+  // ranks too (ILU, one block per rank: additive Schwarz with combine mode Add); see isph_b200.h.
   virtual void setParameters() { set("Precond Type", "ILU"); set("Overlap Level", 0); set("fact: level-of-fill", 0); }
   int set(const char *name, int v) { return isph_precond_set_param_int(_ctx, name, v); }
   int set(const char *name, double v) { return isph_precond_set_param_double(_ctx, name, v); }

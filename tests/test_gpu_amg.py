@@ -183,3 +183,22 @@ def test_ml_standin_rows_that_reach_many_aggregates():
     st = c.solve(True, "wide"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates(); c.close()
     assert hi["levels"] == h["levels"] >= 2 and list(hi["rows"]) == list(h["rows"]) and np.array_equal(agg, h["agg"]), (hi, h)
     check(st, info, x, xo, sol_tol=1e-6)
+
+
+@pytest.mark.parametrize("N", [32, 64])
+def test_known_answer_poisson_boltzmann_table_with_the_ml_standin(N):
+    """The reference's recorded err.psi.norm2 (sph-script/conv-poisson-boltzmann-harmonic-2d-rev390.txt) was produced by a run with the
+    reference's default preconditioner package — ML — under GMRES.  The same table row from the CUDA path with the multilevel stand-in in the
+    Jacobian solves: a different preconditioner must not move the converged answer (and the Newton iteration count stays what it is with ILU)."""
+    from test_oracle_cpu import PB_TABLE, pb_harmonic_problem
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    P, s, ex = pb_harmonic_problem(lat, N); nl = P["nlocal"]
+    c = isph.Context(); c.set_particles(P)
+    c.field_set(isph.F_EPS, np.ones(len(s))); c.field_set(isph.F_PSI0, np.zeros(len(s))); c.field_set(isph.F_PSI, np.zeros(len(s)))
+    c.compute_pre(); c.graph_build(); c.create_solution(None, 1); c.create_load(None, 1)
+    ml_configure(c, **{"coarse: max size": 40}); c.solver_param("Convergence Tolerance", 1e-12); c.solver_param("Maximum Iterations", 2000)
+    st = c.pb_newton(extra_f=ex, tol_f=1e-12, tol_update=1e-6); h = c.precond_ml_info()
+    psi = c.field_get(isph.F_PSI)[:nl]; c.close()
+    err = np.sqrt(np.mean((psi - s[:nl]) ** 2))
+    assert st["converged"] and st["newton_iters"] < 10 and h["levels"] >= 2, (st, h)
+    assert abs(err - PB_TABLE[N]) <= 1e-10 * PB_TABLE[N], (err, PB_TABLE[N])
