@@ -123,17 +123,14 @@ template <class M, int KQ> __global__ void __launch_bounds__(128) k_amg_compress
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
   if (aggr[r] < 0) { qcnt[r] = 0; return; }
   long long base; int len, st; row_span(A, r, base, len, st);
-  // columns ascend within a row and aggregates are spatially compact: consecutive entries often share their aggregate, so a run is summed in
-  // registers and only its total goes through the (local-memory) list
-  int J[KQ]; double S[KQ]; int m = 0, runJ = -1; double run = 0.0;
-  for (int e = 0; e <= len; ++e) {
-    int jc = -2; double a = 0.0;
-    if (e < len) { jc = aggc[A.col[base + (long long)e * st]]; if (jc < 0) continue; a = A.val[base + (long long)e * st]; if (jc == runJ) { run += a; continue; } }
-    if (runJ >= 0) {
-      int k = 0; for (; k < m; ++k) if (J[k] == runJ) break;
-      if (k < m) S[k] += run; else if (m < KQ) { J[m] = runJ; S[m] = run; ++m; } else *overflow = 1;
-    }
-    runJ = jc; run = a;
+  // (summing runs of consecutive entries with the same aggregate in registers before touching the list was measured: 14.4 ms against 12.3 ms
+  // for this loop on 8M rows — the extra divergence costs more than the saved local-memory traffic; not kept)
+  int J[KQ]; double S[KQ]; int m = 0;
+  for (int e = 0; e < len; ++e) {
+    const int jc = aggc[A.col[base + (long long)e * st]]; if (jc < 0) continue;
+    const double a = A.val[base + (long long)e * st];
+    int k = 0; for (; k < m; ++k) if (J[k] == jc) break;
+    if (k < m) S[k] += a; else if (m < KQ) { J[m] = jc; S[m] = a; ++m; } else *overflow = 1;
   }
   qcnt[r] = m;
   for (int k = 0; k < m; ++k) { qj[(size_t)k * n + r] = J[k]; qv[(size_t)k * n + r] = S[k]; }

@@ -116,12 +116,10 @@ inline void galerkin(const Level &L, Level &C) {
     std::vector<int> cols; std::vector<double> sums;
     for (int i : L.members[I]) {
       // per fine row first (the device compresses every row to its aggregate columns before the rows of an aggregate are merged)
-      std::vector<int> rj; std::vector<double> rs; int runJ = -1; double run = 0.0;          // runs of consecutive entries with the same aggregate are summed first (as on the device)
-      auto flush = [&]() { if (runJ < 0) return; size_t k = 0; for (; k < rj.size(); ++k) if (rj[k] == runJ) break;
-                           if (k == rj.size()) { rj.push_back(runJ); rs.push_back(run); } else rs[k] += run; };
+      std::vector<int> rj; std::vector<double> rs;
       for (int q = A.rp[i]; q < A.rp[i + 1]; ++q) { const int c = A.ci[q]; if (c < 0) continue; const int J = L.agg[c]; if (J < 0) continue;
-        if (J == runJ) { run += A.v[q]; continue; }
-        flush(); runJ = J; run = A.v[q]; }
+        size_t k = 0; for (; k < rj.size(); ++k) if (rj[k] == J) break;
+        if (k == rj.size()) { rj.push_back(J); rs.push_back(A.v[q]); } else rs[k] += A.v[q]; } runJ = J; run = A.v[q]; }
       flush();
       for (size_t k = 0; k < rj.size(); ++k) { if (pos[rj[k]] < 0) { pos[rj[k]] = (int)cols.size(); cols.push_back(rj[k]); sums.push_back(rs[k]); } else sums[pos[rj[k]]] += rs[k]; }
     }
