@@ -119,8 +119,7 @@ inline void galerkin(const Level &L, Level &C) {
       std::vector<int> rj; std::vector<double> rs;
       for (int q = A.rp[i]; q < A.rp[i + 1]; ++q) { const int c = A.ci[q]; if (c < 0) continue; const int J = L.agg[c]; if (J < 0) continue;
         size_t k = 0; for (; k < rj.size(); ++k) if (rj[k] == J) break;
-        if (k == rj.size()) { rj.push_back(J); rs.push_back(A.v[q]); } else rs[k] += A.v[q]; } runJ = J; run = A.v[q]; }
-      flush();
+        if (k == rj.size()) { rj.push_back(J); rs.push_back(A.v[q]); } else rs[k] += A.v[q]; }
       for (size_t k = 0; k < rj.size(); ++k) { if (pos[rj[k]] < 0) { pos[rj[k]] = (int)cols.size(); cols.push_back(rj[k]); sums.push_back(rs[k]); } else sums[pos[rj[k]]] += rs[k]; }
     }
     std::vector<int> ord(cols.size()); for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int)k;
