@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(ILU_TB) k_ilu_solve(const int *rp, const int *
 // (#levels x one L2 round trip) instead of (#levels x one grid barrier).  Waits are bounded; a timeout or a computed NaN
 // is published as 0 with the fault word raised, so that nobody downstream spins on it.
 __device__ int g_ilu_backoff = 0;      // ns to sleep after a failed poll (0: spin); rows far ahead of the wavefront then stop hammering L2
+// (ld/st.relaxed.gpu instead of the volatile accesses — LDG/STG .STRONG.GPU instead of .STRONG.SYS in SASS — was measured on the 1M-row / 8-brick
+// case: 4.58 ms against 4.47 ms per apply with both behind a run-time switch, i.e. no gain from the narrower scope; the switch itself cost 1.3 ms
+// per apply (3.19 ms without it).  ncu source view of this loop: ~21 polls per row on the first dependency of the forward sweep.  Not kept.)
 __device__ __forceinline__ double wait_value(const double *p, int *fault) {
   const volatile double *vp = p; double v = *vp; int spins = 0;
   while (v != v) {
