@@ -241,6 +241,13 @@ __global__ void __launch_bounds__(VB) k_amg_restrict(int nc_total, int first, in
 __global__ void __launch_bounds__(VB) k_amg_prolong(int n, const int *agg, int offset, const double *ec, double scale, double *x) {
   for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) { const int a = agg[i]; if (a >= 0) x[i] += scale * ec[a + offset]; }
 }
+// coarsest level, "coarse: type" = Amesos-KLU: x = Ainv b with the explicit inverse (n <= 1024), one warp per row, fixed shuffle tree
+__global__ void __launch_bounds__(VB) k_amg_dense_apply(int n, const double *Ainv, const double *b, double *x) {
+  const int row = (blockIdx.x * VB + threadIdx.x) >> 5, lane = threadIdx.x & 31; if (row >= n) return;
+  double s = 0.0; for (int k = lane; k < n; k += 32) s += Ainv[(size_t)row * n + k] * b[k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) x[row] = s;
+}
 __global__ void __launch_bounds__(VB) k_amg_rowlen(int n, const int *rp, int *len) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) len[i] = rp[i + 1] - rp[i]; }
 
 }  // namespace
@@ -250,7 +257,7 @@ struct AmgLevel {
   DevBuf<int> rp, ci, gid, agg, root_of, moff, mem; DevBuf<double> va, invdiag, xa, xb, b, w;
 };
 struct AmgData {
-  std::vector<AmgLevel *> L; int nlev = 0; bool ready = false;
+  std::vector<AmgLevel *> L; int nlev = 0; bool ready = false, direct = false; DevBuf<double> coarse_inv;
   // setup scratch (grow-only, shared by all levels)
   DevBuf<int> sg, cnt, state, flag, scan, agg2, skey, skey2, sval, ccnt, qcnt, qj, aggc, rlen, gbuf_i; DevBuf<float> sw; DevBuf<unsigned long long> key, m1, tok; DevBuf<double> d, qv, aggd, gbuf_d, red;
   DevBuf<char> tmp; DevBuf<int> ctr; DevBuf<long long> cnt2;
@@ -393,6 +400,22 @@ template <class M> bool galerkin(Ctx *c, AmgData *D, AmgLevel *L, AmgLevel *Cn, 
 
 }  // namespace
 
+// dense inverse by Gauss-Jordan elimination with partial pivoting — the same routine as oracle/amg_oracle.h::dense_inverse (row-major n x n)
+static bool dense_inverse(int n, std::vector<double> &a, std::vector<double> &inv) {
+  inv.assign((size_t)n * n, 0.0); for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+  for (int col = 0; col < n; ++col) {
+    int piv = col; double best = std::fabs(a[(size_t)col * n + col]);
+    for (int r = col + 1; r < n; ++r) { const double v = std::fabs(a[(size_t)r * n + col]); if (v > best) { best = v; piv = r; } }
+    if (best == 0.0) return false;
+    if (piv != col) for (int k = 0; k < n; ++k) { std::swap(a[(size_t)col * n + k], a[(size_t)piv * n + k]); std::swap(inv[(size_t)col * n + k], inv[(size_t)piv * n + k]); }
+    const double d = 1.0 / a[(size_t)col * n + col];
+    for (int k = 0; k < n; ++k) { a[(size_t)col * n + k] *= d; inv[(size_t)col * n + k] *= d; }
+    for (int r = 0; r < n; ++r) if (r != col) { const double f = a[(size_t)r * n + col]; if (f == 0.0) continue;
+      for (int k = 0; k < n; ++k) { a[(size_t)r * n + k] -= f * a[(size_t)col * n + k]; inv[(size_t)r * n + k] -= f * inv[(size_t)col * n + k]; } }
+  }
+  return true;
+}
+
 void amg_free(Ctx *c) { if (c->amg) c->amg->ready = false; }
 void amg_destroy(Ctx *c) { delete c->amg; c->amg = nullptr; }
 
@@ -400,9 +423,11 @@ void amg_create(Ctx *c) {
   const PrecondParams &pp = c->pp;
   ISPH_REQUIRE(pp.ml_smoother == "Chebyshev" || pp.ml_smoother == "Jacobi",
                "ML stand-in: smoother: type must be Chebyshev or Jacobi (" + pp.ml_smoother + " is sequential within a rank and is not provided)");
-  ISPH_REQUIRE(pp.ml_coarse == "Chebyshev" || pp.ml_coarse == "Jacobi", "ML stand-in: coarse: type must be Chebyshev or Jacobi (direct coarse solves are not provided; the reference itself "
-               "switches the coarse solver to the smoother for singular problems, precond_ml.h:118-120)");
-  ISPH_REQUIRE(pp.ml_coarse == pp.ml_smoother, "ML stand-in: coarse: type must equal smoother: type");
+  // "coarse: type": Amesos-* = a direct solve of the coarsest operator (explicit inverse, the reference's default Amesos-KLU, precond_ml.h:55);
+  // for a singular problem the reference itself replaces it by the smoother (PrecondWrapper_ML::setNullVector, precond_ml.h:118-120, called
+  // from solveProblem, solver_lin_belos.h:150-151) — mirrored here.  Otherwise the coarse solver is the smoother.
+  const bool coarse_direct = pp.ml_coarse.rfind("Amesos", 0) == 0;
+  ISPH_REQUIRE(coarse_direct || pp.ml_coarse == pp.ml_smoother, "ML stand-in: coarse: type must be Amesos-KLU (direct) or equal smoother: type (" + pp.ml_coarse + " is not provided)");
   ISPH_REQUIRE(pp.ml_agg_damping == 0.0, "ML stand-in: aggregation: damping factor must be 0 (non-smoothed aggregation)");
   ISPH_REQUIRE(pp.ml_max_levels >= 1 && pp.ml_max_levels <= 16, "ML stand-in: max levels must be in 1..16");
   if (!c->amg) c->amg = new AmgData();
@@ -504,7 +529,19 @@ void amg_create(Ctx *c) {
     if (!ok) { L->nc = L->nc_mine = 0; break; }
     ++nlev;
   }
-  D->nlev = nlev; D->ready = true;
+  D->nlev = nlev; D->direct = false;
+  if (coarse_direct && !c->is_singular && nlev > 1) {
+    AmgLevel *L = D->L[nlev - 1]; const int nc = L->n;
+    ISPH_REQUIRE(nc <= 1024, "ML stand-in: the coarsest level has " + std::to_string(nc) + " rows — too many for the direct coarse solve (raise max levels or use coarse: type = the smoother)");
+    std::vector<int> rp(nc + 1), ci(L->nnz); std::vector<double> va(L->nnz), a((size_t)nc * nc, 0.0), inv;
+    CUDA_CHECK(cudaMemcpyAsync(rp.data(), L->rp.p, sizeof(int) * (nc + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaMemcpyAsync(ci.data(), L->ci.p, sizeof(int) * L->nnz, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(va.data(), L->va.p, sizeof(double) * L->nnz, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nc; ++i) for (int q = rp[i]; q < rp[i + 1]; ++q) a[(size_t)i * nc + ci[q]] += va[q];
+    ISPH_REQUIRE(dense_inverse(nc, a, inv), "ML stand-in: the coarsest operator is singular — a direct coarse solve (coarse: type = Amesos-KLU) needs a non-singular problem");
+    D->coarse_inv.ensure((size_t)nc * nc); CUDA_CHECK(cudaMemcpyAsync(D->coarse_inv.p, inv.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    D->direct = true;
+  }
+  D->ready = true;
 }
 
 namespace {
@@ -538,7 +575,10 @@ double *smooth_csr(Ctx *c, AmgLevel *L, const double *b, double *x, double *othe
 // V-cycle on the replicated coarse levels: right-hand side in L->b, returns the buffer with the correction
 double *vcycle_csr(Ctx *c, AmgData *D, int lev) {
   const PrecondParams &pp = c->pp; AmgLevel *L = D->L[lev]; const int n = L->n; const bool jac = pp.ml_smoother == "Jacobi";
-  if (lev + 1 == D->nlev) return smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_coarse_sweeps, pp.ml_coarse_alpha, pp.ml_coarse == "Jacobi", pp.ml_damping);
+  if (lev + 1 == D->nlev) {
+    if (D->direct) { k_amg_dense_apply<<<tgrid((long long)n * 32), VB, 0, c->stream>>>(n, D->coarse_inv.p, L->b.p, L->xa.p); LAUNCH(c); return L->xa.p; }
+    return smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_coarse_sweeps, pp.ml_coarse_alpha, jac, pp.ml_damping);
+  }
   AmgLevel *Cn = D->L[lev + 1];
   double *x = smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_level_sweeps, pp.ml_alpha, jac, pp.ml_damping);
   double *other = x == L->xa.p ? L->xb.p : L->xa.p;

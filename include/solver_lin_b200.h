@@ -58,11 +58,13 @@ class PrecondWrapper_ML_B200 : public PrecondWrapper_B200 {
  public:
   explicit PrecondWrapper_ML_B200(isph_ctx *ctx) : PrecondWrapper_B200(ctx) {}
   // setParameters(NULL), precond_ml.h:44-58: "max levels" 5, "aggregation: type" Uncoupled, smoother 1 sweep pre and post, coarse solve.
-  // Deviations, each forced by the device: "smoother: type" Chebyshev instead of symmetric Gauss-Seidel (sequential within a
-  // rank), "coarse: type" = the smoother instead of Amesos-KLU (the choice PrecondWrapper_ML::setNullVector makes itself, :118-120).
+  // One deviation, forced by the device: "smoother: type" Chebyshev — the alternative the reference's own benchmark file keeps
+  // commented next to its Gauss-Seidel line (bench-script/hopper/tgv/4096/ml.xml:15-18) — instead of symmetric Gauss-Seidel (sequential
+  // within a rank).  "coarse: type" Amesos-KLU = a direct solve of the coarsest operator; for singular problems it is replaced by the
+  // smoother, as PrecondWrapper_ML::setNullVector does (:118-120).
   virtual void setParameters() {
     set("Precond Package", "ML"); set("max levels", 5); set("increasing or decreasing", "increasing"); set("aggregation: type", "Uncoupled");
-    set("smoother: type", "Chebyshev"); set("smoother: pre or post", "both"); set("coarse: type", "Chebyshev");
+    set("smoother: type", "Chebyshev"); set("smoother: pre or post", "both"); set("coarse: type", "Amesos-KLU");
   }
   // for zoltan re-partition (precond_ml.h:65-99): one GPU per rank, the coarse levels are replicated — nothing to repartition
   void setCoordinates(const int, double *, double *, double *) {}

@@ -23,6 +23,7 @@ namespace amg_oracle {
 struct Params {
   int max_levels = 5, pre = 1, post = 2, level_sweeps = 3, coarse_sweeps = 8, eig_iters = 10, max_coarse = 128, smoother = 0;
   double theta = 0.02, alpha = 10.0, coarse_alpha = 30.0, oc = 2.0, damping = 0.67;
+  int coarse_direct = 0;      // "coarse: type" = Amesos-KLU: dense inverse of the coarsest operator (non-singular problems only)
 };
 
 struct CsrM { int n = 0; std::vector<int> rp, ci; std::vector<double> v; };
@@ -130,8 +131,25 @@ inline void galerkin(const Level &L, Level &C) {
   }
 }
 
+// dense inverse by Gauss-Jordan elimination with partial pivoting (row-major n x n); the SAME routine runs on the host side of csrc/amg.cu.
+// returns false on a zero pivot (singular coarsest operator)
+inline bool dense_inverse(int n, std::vector<double> &a, std::vector<double> &inv) {
+  inv.assign((size_t)n * n, 0.0); for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c; double best = std::fabs(a[(size_t)c * n + c]);
+    for (int r = c + 1; r < n; ++r) { const double v = std::fabs(a[(size_t)r * n + c]); if (v > best) { best = v; piv = r; } }
+    if (best == 0.0) return false;
+    if (piv != c) for (int k = 0; k < n; ++k) { std::swap(a[(size_t)c * n + k], a[(size_t)piv * n + k]); std::swap(inv[(size_t)c * n + k], inv[(size_t)piv * n + k]); }
+    const double d = 1.0 / a[(size_t)c * n + c];
+    for (int k = 0; k < n; ++k) { a[(size_t)c * n + k] *= d; inv[(size_t)c * n + k] *= d; }
+    for (int r = 0; r < n; ++r) if (r != c) { const double f = a[(size_t)r * n + c]; if (f == 0.0) continue;
+      for (int k = 0; k < n; ++k) { a[(size_t)r * n + k] -= f * a[(size_t)c * n + k]; inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k]; } }
+  }
+  return true;
+}
+
 struct Hierarchy {
-  Params P; std::vector<Level> L;
+  Params P; std::vector<Level> L; std::vector<double> coarse_inv; bool direct_ok = false;
 
   void smoother_setup(Level &Lv) {
     const CsrM &A = Lv.A; const int n = A.n;
@@ -154,6 +172,11 @@ struct Hierarchy {
       if (nc == 0 || nc >= (long long)nl * 9 / 10) { L.back().agg.clear(); L.back().nc = 0; break; }       // no coarsening left: this level is the coarsest
       Level C; galerkin(L.back(), C);
       L.push_back(std::move(C));
+    }
+    if (P.coarse_direct) {                                                        // Amesos-KLU stand-in: explicit inverse of the (small) coarsest operator
+      const CsrM &A = L.back().A; const int nc = A.n; std::vector<double> a((size_t)nc * nc, 0.0);
+      for (int i = 0; i < nc; ++i) for (int q = A.rp[i]; q < A.rp[i + 1]; ++q) if (A.ci[q] >= 0) a[(size_t)i * nc + A.ci[q]] += A.v[q];
+      direct_ok = dense_inverse(nc, a, coarse_inv);
     }
   }
 
@@ -181,7 +204,10 @@ struct Hierarchy {
 
   void vcycle(size_t l, const double *r, double *x) {
     Level &Lv = L[l]; const int n = Lv.A.n;
-    if (l + 1 == L.size()) { cheb(Lv, r, x, true, P.coarse_sweeps, P.coarse_alpha); return; }
+    if (l + 1 == L.size()) {
+      if (P.coarse_direct && direct_ok) { for (int i = 0; i < n; ++i) { double s = 0.0; for (int k = 0; k < n; ++k) s += coarse_inv[(size_t)i * n + k] * r[k]; x[i] = s; } return; }
+      cheb(Lv, r, x, true, P.coarse_sweeps, P.coarse_alpha); return;
+    }
     const int pre = l == 0 ? P.pre : P.level_sweeps, post = l == 0 ? P.post : P.level_sweeps;
     Level &C = L[l + 1];
     cheb(Lv, r, x, true, pre, P.alpha);

@@ -40,6 +40,7 @@ typedef struct {
   int amg_max_coarse;        /* "coarse: max size" */
   double amg_scale;          /* scaling of the coarse-grid correction */
   double amg_damping;        /* "smoother: damping factor" (Jacobi) */
+  int amg_coarse_direct;     /* "coarse: type" = Amesos-KLU: dense inverse of the coarsest operator (used for non-singular problems; the caller clears it for singular ones as PrecondWrapper_ML::setNullVector does, precond_ml.h:118-120) */
 } orc_krylov_params;
 
 int orc_set_num_threads(int n);   /* OpenMP threads of the port's row loops; returns the count in effect */

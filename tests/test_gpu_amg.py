@@ -24,29 +24,31 @@ ML = {"max levels": "amg_max_levels", "aggregation: threshold": "amg_threshold",
 
 def ml_configure(c, flexible=True, smoother="Chebyshev", **ml):
     c.solver_param("Solver Type", "Block GMRES"); c.solver_param("Flexible Gmres", bool(flexible))
-    c.precond_param("Precond Package", "ML"); c.precond_param("smoother: type", smoother); c.precond_param("coarse: type", smoother)
+    c.precond_param("Precond Package", "ML"); c.precond_param("smoother: type", smoother); c.precond_param("coarse: type", ml.pop("coarse: type", smoother))
     for k, v in ml.items():
         c.precond_param(k, v)
 
 
 def oracle_params(smoother="Chebyshev", **ml):
+    direct = ml.pop("coarse: type", "").startswith("Amesos")
     kw = {ML[k]: v for k, v in ml.items()}
-    return dict(precond=O.PREC_AMG, amg_smoother=1 if smoother == "Jacobi" else 0, **kw)
+    return dict(precond=O.PREC_AMG, amg_smoother=1 if smoother == "Jacobi" else 0, amg_coarse_direct=int(direct), **kw)
 
 
 @pytest.mark.parametrize("smoother,ml", [("Chebyshev", {}), ("Jacobi", {"smoother: pre sweeps": 2, "smoother: post sweeps": 2}),
-                                          ("Chebyshev", {"aggregation: threshold": 0.2, "coarse: max size": 20, "max levels": 4})])
+                                          ("Chebyshev", {"aggregation: threshold": 0.2, "coarse: max size": 20, "max levels": 4}),
+                                          ("Chebyshev", {"coarse: type": "Amesos-KLU"})])      # the reference's default coarse solver (precond_ml.h:55): explicit inverse of the coarsest operator
 def test_ml_standin_external_matrix(smoother, ml):
     """second API client's situation (fix_qeq_reax hands over a CSR matrix): 5-point operator, 6400 rows -> three levels"""
     A = lap2d(80, 0.002, 0.2); n = A.shape[0]; b = np.random.default_rng(0).standard_normal(n)
     ml = dict({"aggregation: threshold": 0.1}, **ml)
-    okw = oracle_params(smoother, **ml)
+    okw = oracle_params(smoother, **dict(ml))
     h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw))
     xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
     xj, infoj = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(precond=O.PREC_JACOBI))
     c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
     x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
-    ml_configure(c, True, smoother, **ml); c.set_initial_solution(isph.INIT_ZERO)
+    ml_configure(c, True, smoother, **dict(ml)); c.set_initial_solution(isph.INIT_ZERO)
     st = c.solve(True, "ext-ml"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates()
     assert hi["levels"] == h["levels"] >= 3 and list(hi["rows"]) == list(h["rows"]) and list(hi["nnz"][1:]) == list(h["nnz"][1:]), (hi, h)
     assert np.array_equal(agg, h["agg"])                                       # the same aggregates, numbered the same way
@@ -114,13 +116,13 @@ def test_ml_standin_aggregates_stay_inside_a_block():
 
 
 def test_ml_parameter_list_is_checked():
-    """precond_ml.h:44-58 sets symmetric Gauss-Seidel and Amesos-KLU: both are refused by name (not silently replaced)"""
+    """precond_ml.h:44-58 sets symmetric Gauss-Seidel: refused by name (not silently replaced); Amesos-KLU is provided (direct coarse solve)"""
     A = lap2d(20, 0.1); c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
     x = np.zeros(A.shape[0]); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(np.ones(A.shape[0]))
     c.precond_param("Precond Package", "ML"); c.precond_param("smoother: type", "symmetric Gauss-Seidel")
     with pytest.raises(isph.IsphError, match="smoother: type"):
         c.solve(True, "x")
-    c.precond_param("smoother: type", "Chebyshev"); c.precond_param("coarse: type", "Amesos-KLU")
+    c.precond_param("smoother: type", "Chebyshev"); c.precond_param("coarse: type", "Gauss-Seidel")
     with pytest.raises(isph.IsphError, match="coarse: type"):
         c.solve(True, "x")
     c.precond_param("coarse: type", "Chebyshev"); c.precond_param("aggregation: damping factor", 1.333)
