@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(VB) k_amg_rowlen(int n, const int *rp, int *le
 struct AmgLevel {
   int n = 0, nc = 0, nc_mine = 0, first = 0; long long nnz = 0; double lmax = 0.0;         // nc = coarse size (all ranks), first/nc_mine = this rank's aggregates (level 0)
   DevBuf<int> rp, ci, gid, agg, root_of, moff, mem; DevBuf<double> va, invdiag, xa, xb, b, w;
+  ~AmgLevel() { rp.release(); ci.release(); gid.release(); agg.release(); root_of.release(); moff.release(); mem.release(); va.release(); invdiag.release(); xa.release(); xb.release(); b.release(); w.release(); }
 };
 struct AmgData {
   std::vector<AmgLevel *> L; int nlev = 0; bool ready = false, direct = false; DevBuf<double> coarse_inv;
@@ -263,7 +264,12 @@ struct AmgData {
   DevBuf<char> tmp; DevBuf<int> ctr; DevBuf<long long> cnt2;
   DevBuf<double> t0, w0;                           // finest-level work vectors (length ld: the product needs the halo tail)
   std::map<std::string, double> setup_ms;
-  ~AmgData() { for (auto *l : L) delete l; }
+  ~AmgData() {
+    for (auto *l : L) delete l;
+    sg.release(); cnt.release(); state.release(); flag.release(); scan.release(); agg2.release(); skey.release(); skey2.release(); sval.release(); ccnt.release(); qcnt.release(); qj.release();
+    aggc.release(); rlen.release(); gbuf_i.release(); sw.release(); key.release(); m1.release(); tok.release(); d.release(); qv.release(); aggd.release(); gbuf_d.release(); red.release();
+    tmp.release(); ctr.release(); cnt2.release(); t0.release(); w0.release(); coarse_inv.release();
+  }
 };
 
 namespace {
@@ -417,7 +423,7 @@ static bool dense_inverse(int n, std::vector<double> &a, std::vector<double> &in
 }
 
 void amg_free(Ctx *c) { if (c->amg) c->amg->ready = false; }
-void amg_destroy(Ctx *c) { delete c->amg; c->amg = nullptr; }
+void amg_destroy(Ctx *c) { if (c->amg) { cudaSetDevice(c->device); delete c->amg; } c->amg = nullptr; }
 
 void amg_create(Ctx *c) {
   const PrecondParams &pp = c->pp;

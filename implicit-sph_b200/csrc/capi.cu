@@ -490,6 +490,7 @@ int isph_solver_set_block_end(isph_ctx *ctx) {
 int isph_solver_solve_block(isph_ctx *ctx, int use_prec, const char *label) {
   API_BEGIN(ctx) ISPH_REQUIRE(c->blk && c->blk->filled, "solveBlockProblem: createBlockMatrix / setBlock / setBlockEnd first");
   BlockSys &B = *c->blk; Ctx *k = reinterpret_cast<Ctx *>(B.child); const int n = B.n, d = B.dim;
+  k->stream = c->stream; k->own_stream = false;                    // the parent's stream may have been replaced since setBlockEnd (isph_set_stream)
   ISPH_REQUIRE(c->b_nvec == d && c->x_nvec == d && c->xs.p && c->bs.p, ">> SolverLin_Belos::solveBlockProblem, dimension of rhs does not match to the block matrix");   // solver_lin_belos.h:58-59
   ISPH_REQUIRE(!c->is_singular, ">> SolverLin_Belos::solveBlockProblem does not support singular problems");                                                    // :60-61
   ISPH_REQUIRE(!use_prec || (c->A.built && c->A.n == n), "solveBlockProblem: the preconditioner is built from the scalar matrix (prec->setMatrix): it must have the blocks' row map");

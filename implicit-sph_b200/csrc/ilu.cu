@@ -615,7 +615,7 @@ static void ilu_apply_launch(Ctx *c, const double *r, double *z) {
 void ilu_destroy(Ctx *c) {
   if (!c->ilu) return; IluData &I = *c->ilu;
   I.rp.release(); I.ci.release(); I.dpos.release(); I.order_l.release(); I.order_u.release(); I.lptr_l.release(); I.lptr_u.release(); I.cnt.release();
-  I.ov.release(); I.rext.release(); I.zext.release();
+  I.ov.release(); I.rext.release(); I.zext.release(); I.slot_ref.release();
   I.Lrp.release(); I.Lci.release(); I.Urp.release(); I.Uci.release(); I.plen.release(); I.Lfv.release(); I.Ufv.release(); I.Udinv.release();
   I.fv.release(); I.dinv.release(); I.y.release(); I.tmp.release(); I.rp0.release(); I.ci0.release(); I.fv0.release(); I.lev.release(); I.hist.release(); I.fault.release(); delete c->ilu; c->ilu = nullptr;
 }

@@ -204,3 +204,28 @@ def test_known_answer_poisson_boltzmann_table_with_the_ml_standin(N):
     err = np.sqrt(np.mean((psi - s[:nl]) ** 2))
     assert st["converged"] and st["newton_iters"] < 10 and h["levels"] >= 2, (st, h)
     assert abs(err - PB_TABLE[N]) <= 1e-10 * PB_TABLE[N], (err, PB_TABLE[N])
+
+
+def test_reference_benchmark_ml_parameter_file_chebyshev_variant():
+    """The parameter list of the reference's own scaling benchmark (bench-script/hopper/tgv/4096/ml.xml) with the smoother switched to the
+    Chebyshev lines that file keeps commented (:15-18) is accepted key by key and solves the singular pressure Poisson problem (coarse: type
+    Amesos-KLU replaced by the smoother, as PrecondWrapper_ML::setNullVector does) with the iteration count of the restatement."""
+    import harness
+    ml_xml = [("ML output", 10), ("max levels", 10), ("increasing or decreasing", "increasing"), ("aggregation: type", "Uncoupled"),
+              ("smoother: pre or post", "both"), ("smoother: type", "Chebyshev"), ("smoother: sweeps", 4), ("coarse: type", "Amesos-KLU")]
+    P, F, ref = _case_with_oracle("jitter3d"); cs = P["case"]; nl = P["nlocal"]
+    col = O.tags_to_local(ref["col"], P["tag"][:nl]); b = ref["b_poisson"].copy(); mask = np.ones(nl, dtype=np.int32)
+    prm = O.krylov_params(precond=O.PREC_AMG, amg_max_levels=10, amg_pre=4, amg_post=4, amg_coarse_direct=0, row_gid=P["tag"][:nl])
+    xo, info = O.krylov_solve(ref["rowptr"], col, ref["A_poisson"], b, params=prm, null_mask=mask, use_null=True)
+    c = harness.cuda_context(P, F)
+    c.compute_pre(); c.graph_build(); c.create_load(None, 1); c.ns_poisson(cs["dt"])
+    x = np.zeros(nl); c.create_solution(x, 1)
+    c.set_null_vector_mask(mask); c.set_matrix_is_singular(True); c.set_initial_solution(isph.INIT_ZERO)
+    c.solver_param("Solver Type", "Block GMRES"); c.precond_param("Precond Package", "ML")
+    for k, v in ml_xml:
+        c.precond_param(k, v)
+    st = c.solve(True, "Poisson"); c.close()
+    check(st, info, x, xo, sol_tol=1e-5)
+    with pytest.raises(isph.IsphError):                                        # ... and the Gauss-Seidel lines of the same file are refused by name
+        c2 = isph.Context(); c2.precond_param("smoother: type", "ML Gauss-Seidel"); A = lap2d(10, 0.1); c2.matrix_set_csr(A.indptr, A.indices, A.data)
+        c2.precond_param("Precond Package", "ML"); xx = np.zeros(100); c2.create_solution(xx, 1); c2.create_load(None, 1); c2.load_set(np.ones(100)); c2.solve(True, "x")
