@@ -888,6 +888,8 @@ void solver_solve(Ctx *c, bool use_prec, const char *label) {
   const bool is_cg = c->sp.solver_type == "Block CG";
   ISPH_REQUIRE(is_cg || c->sp.solver_type == "Block GMRES", "Solver Type must be \"Block GMRES\" or \"Block CG\" (Recycling GMRES is not implemented)");
   ISPH_REQUIRE(c->sp.block_size == 1, "Block Size must be 1");
+  ISPH_REQUIRE(!(is_cg && use_prec && !c->prec_parent && c->pp.type == "ML" && c->pp.ml_pre != c->pp.ml_post),
+               "Block CG needs a symmetric preconditioner: give the ML stand-in the same number of pre- and post-smoothing sweeps (smoother: sweeps)");
   c->prof_phases = getenv("ISPH_PROFILE") != nullptr;
   halo_recover(c);                                               // a peer wait that timed out in an earlier solve: re-arm the slots on all ranks
   std::string tname = std::string("solve") + (label ? label : "");

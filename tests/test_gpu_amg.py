@@ -229,3 +229,21 @@ def test_reference_benchmark_ml_parameter_file_chebyshev_variant():
     with pytest.raises(isph.IsphError):                                        # ... and the Gauss-Seidel lines of the same file are refused by name
         c2 = isph.Context(); c2.precond_param("smoother: type", "ML Gauss-Seidel"); A = lap2d(10, 0.1); c2.matrix_set_csr(A.indptr, A.indices, A.data)
         c2.precond_param("Precond Package", "ML"); xx = np.zeros(100); c2.create_solution(xx, 1); c2.create_load(None, 1); c2.load_set(np.ones(100)); c2.solve(True, "x")
+
+
+def test_ml_standin_under_block_cg_needs_a_symmetric_cycle():
+    """Block CG (solver_lin_belos.h:181-182) with the multilevel preconditioner: a V-cycle with equal pre- and post-smoothing is a symmetric
+    operator (Chebyshev polynomial in D^-1 A on both sides of a Galerkin correction) and PCG matches the restatement; the default asymmetric
+    cycle (1 + 2 sweeps, chosen for flexible GMRES) is refused under CG instead of silently breaking the recurrence."""
+    A = lap2d(64, 0.001); n = A.shape[0]; b = np.random.default_rng(4).standard_normal(n)
+    ml = {"aggregation: threshold": 0.1, "smoother: pre sweeps": 2, "smoother: post sweeps": 2, "coarse correction scale": 1.0}
+    xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(solver=O.SOLVER_CG, **oracle_params(**ml)))
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    ml_configure(c, **ml); c.solver_param("Solver Type", "Block CG"); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "cg-ml")
+    check(st, info, x, xo, sol_tol=1e-6)
+    c.precond_param("smoother: post sweeps", 3); c.set_initial_solution(isph.INIT_ZERO)
+    with pytest.raises(isph.IsphError, match="symmetric preconditioner"):
+        c.solve(True, "cg-ml")
+    c.close()
