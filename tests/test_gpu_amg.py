@@ -38,17 +38,19 @@ def oracle_params(smoother="Chebyshev", **ml):
 @pytest.mark.parametrize("smoother,ml", [("Chebyshev", {}), ("Jacobi", {"smoother: pre sweeps": 2, "smoother: post sweeps": 2}),
                                           ("Chebyshev", {"aggregation: threshold": 0.2, "coarse: max size": 20, "max levels": 4}),
                                           ("Chebyshev", {"coarse: type": "Amesos-KLU"})])      # the reference's default coarse solver (precond_ml.h:55): explicit inverse of the coarsest operator
-def test_ml_standin_external_matrix(smoother, ml):
-    """second API client's situation (fix_qeq_reax hands over a CSR matrix): 5-point operator, 6400 rows -> three levels"""
+@pytest.mark.parametrize("flex", [True, False])
+def test_ml_standin_external_matrix(smoother, ml, flex):
+    """second API client's situation (fix_qeq_reax hands over a CSR matrix): 5-point operator, 6400 rows -> three levels; flexible and
+    standard right-preconditioned GMRES (the V-cycle is a fixed linear operator, so both are legitimate)"""
     A = lap2d(80, 0.002, 0.2); n = A.shape[0]; b = np.random.default_rng(0).standard_normal(n)
     ml = dict({"aggregation: threshold": 0.1}, **ml)
-    okw = oracle_params(smoother, **dict(ml))
+    okw = oracle_params(smoother, **dict(ml)); okw["flexible"] = int(flex)
     h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw))
     xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
     xj, infoj = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(precond=O.PREC_JACOBI))
     c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
     x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
-    ml_configure(c, True, smoother, **dict(ml)); c.set_initial_solution(isph.INIT_ZERO)
+    ml_configure(c, flex, smoother, **dict(ml)); c.set_initial_solution(isph.INIT_ZERO)
     st = c.solve(True, "ext-ml"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates()
     assert hi["levels"] == h["levels"] >= 3 and list(hi["rows"]) == list(h["rows"]) and list(hi["nnz"][1:]) == list(h["nnz"][1:]), (hi, h)
     assert np.array_equal(agg, h["agg"])                                       # the same aggregates, numbered the same way
