@@ -137,10 +137,10 @@ template <class M, int KQ> __global__ void __launch_bounds__(128) k_amg_compress
 }
 // (2) the rows of an aggregate merged, one warp per coarse row: members in ascending row order, their Q entries in list order.  The set
 // of columns goes through a shared-memory hash, is sorted, and every sum is accumulated by the lane that owns its slot, in stream order.
-template <int HS, bool FILL> __global__ void __launch_bounds__(128) k_amg_merge(int nc, int n, const int *moff, const int *mem, const int *qcnt, const int *qj, const double *qv,
+template <int HS, int WPB, bool FILL> __global__ void __launch_bounds__(32 * WPB) k_amg_merge(int nc, int n, const int *moff, const int *mem, const int *qcnt, const int *qj, const double *qv,
                                                                                  int *ccnt, const int *crp, int *cci, double *cva, int *overflow) {
-  __shared__ int hk[4][HS]; __shared__ int lst[4][HS]; __shared__ double acc[FILL ? 4 : 1][FILL ? HS : 1]; __shared__ int cnts[4];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, I = blockIdx.x * 4 + w;
+  __shared__ int hk[WPB][HS]; __shared__ int lst[WPB][HS]; __shared__ double acc[FILL ? WPB : 1][FILL ? HS : 1]; __shared__ int cnts[WPB];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, I = blockIdx.x * WPB + w;
   if (I >= nc) return;
   int *H = hk[w], *Ls = lst[w];
   for (int i = lane; i < HS; i += 32) H[i] = -1;
@@ -393,13 +393,21 @@ template <class M> bool galerkin(Ctx *c, AmgData *D, AmgLevel *L, AmgLevel *Cn, 
     if (d2h(c, D->ctr.p + 1)) return false;
   }
   D->rlen.ensure(nc + 2); Cn->rp.ensure(nc + 2);
-  CUDA_CHECK(cudaMemsetAsync(D->rlen.p, 0, sizeof(int) * (nc + 2), c->stream));
-  k_amg_merge<512, false><<<tgrid(nc, 4), 128, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, D->rlen.p, nullptr, nullptr, nullptr, D->ctr.p + 1); LAUNCH(c);
-  if (d2h(c, D->ctr.p + 1)) return false;                                  // a row touches more aggregates than the kernels are sized for: stop coarsening here
+  // coarse rows of up to 384 columns: 4 warps per block, 512-slot tables; wider rows (dense small levels): one warp per block, 2048 slots
+  bool wide = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CUDA_CHECK(cudaMemsetAsync(D->rlen.p, 0, sizeof(int) * (nc + 2), c->stream)); CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
+    if (!wide) { k_amg_merge<512, 4, false><<<tgrid(nc, 4), 128, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, D->rlen.p, nullptr, nullptr, nullptr, D->ctr.p + 1); LAUNCH(c); }
+    else { k_amg_merge<2048, 1, false><<<tgrid(nc, 1), 32, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, D->rlen.p, nullptr, nullptr, nullptr, D->ctr.p + 1); LAUNCH(c); }
+    if (!d2h(c, D->ctr.p + 1)) break;
+    if (wide) return false;                                                // a coarse row with more than 1536 columns: stop coarsening here
+    wide = true;
+  }
   exclusive_scan(c, D, D->rlen.p, Cn->rp.p, nc + 1);
   const long long nnz = d2h(c, Cn->rp.p + nc);
   Cn->ci.ensure(nnz + 1); Cn->va.ensure(nnz + 1);
-  k_amg_merge<512, true><<<tgrid(nc, 4), 128, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, nullptr, Cn->rp.p, Cn->ci.p, Cn->va.p, D->ctr.p + 1); LAUNCH(c);
+  if (!wide) { k_amg_merge<512, 4, true><<<tgrid(nc, 4), 128, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, nullptr, Cn->rp.p, Cn->ci.p, Cn->va.p, D->ctr.p + 1); LAUNCH(c); }
+  else { k_amg_merge<2048, 1, true><<<tgrid(nc, 1), 32, 0, c->stream>>>(nc, n, L->moff.p, L->mem.p, D->qcnt.p, D->qj.p, D->qv.p, nullptr, Cn->rp.p, Cn->ci.p, Cn->va.p, D->ctr.p + 1); LAUNCH(c); }
   Cn->nnz = nnz;
   return true;
 }
@@ -494,7 +502,7 @@ void amg_create(Ctx *c) {
         double bad = ok ? 0.0 : 1.0; double *dv = D->red.p + 592 * 3 + 4; CUDA_CHECK(cudaMemcpyAsync(dv, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         halo_allreduce(c, dv, 1); ok = d2h(c, dv) == 0.0;
       }
-      if (!ok && c->rank == 0) fprintf(stderr, ">> isph_b200 ML stand-in: level %d is not coarsened further (a coarse row would hold more than %d columns); it becomes the coarsest level\n", lev, 384);
+      if (!ok && c->rank == 0) fprintf(stderr, ">> isph_b200 ML stand-in: level %d is not coarsened further (a coarse row would hold more than %d columns); it becomes the coarsest level\n", lev, 1536);
       if (ok) {
         Cn->gid.ensure(nc_all + 1);
         if (lev == 0 && c->nranks > 1) {

@@ -168,18 +168,21 @@ def test_solve_block_problem_matches_the_stacked_oracle(prec, name):
     c.close()
 
 
-def test_ml_standin_rows_that_reach_many_aggregates():
+@pytest.mark.parametrize("n,m,reach_min,cols_min", [(600, 40, 48, 0), (4000, 75, 48, 384)])
+def test_ml_standin_rows_that_reach_many_aggregates(n, m, reach_min, cols_min):
     """small aggregates under a wide stencil: only the two ring neighbours of a row are strong (aggregates of 3-5 rows) while every row has
-    ~80 weak entries spread over the whole matrix, so a row reaches > 48 aggregates — the wide variant of the row compression takes over;
-    hierarchy and iteration count still equal the restatement's"""
-    n = 600; rng = np.random.default_rng(7)
-    r = np.repeat(np.arange(n), 40); cidx = rng.integers(0, n, size=len(r)); keep = r != cidx
+    2m weak entries spread over the whole matrix, so a row reaches > 48 aggregates — the wide variant of the row compression takes over —
+    and (second case) a coarse row holds > 384 columns — the wide variant of the merge kernel; hierarchy and iteration count still equal
+    the restatement's"""
+    rng = np.random.default_rng(7)
+    r = np.repeat(np.arange(n), m); cidx = rng.integers(0, n, size=len(r)); keep = r != cidx
     W = sp.coo_matrix((-np.ones(keep.sum()), (r[keep], cidx[keep])), shape=(n, n)).tocsr(); W.data[:] = -1.0; W = W + W.T; W.data[:] = -1.0
     i = np.arange(n); R = sp.coo_matrix((-5.0 * np.ones(2 * n), (np.r_[i, i], np.r_[(i + 1) % n, (i - 1) % n])), shape=(n, n)).tocsr()
     off = sp.csr_matrix(W + R); A = sp.csr_matrix(off + sp.diags(-np.asarray(off.sum(1)).ravel() + 0.5)); A.sum_duplicates(); A.sort_indices()
     ml = {"aggregation: threshold": 0.03, "coarse: max size": 40}; okw = oracle_params(**ml)
-    h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw))
-    reach = max(len(set(h["agg"][A.indices[A.indptr[q]:A.indptr[q + 1]]])) for q in range(n)); assert reach > 48, reach
+    h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw), cap_rows=n, cap_nnz=n * n // 4)
+    reach = max(len(set(h["agg"][A.indices[A.indptr[q]:A.indptr[q + 1]]])) for q in range(n)); assert reach > reach_min, reach
+    assert np.diff(h["coarse"][0]).max() > cols_min
     b = rng.standard_normal(n); xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
     c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
     x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
@@ -249,3 +252,32 @@ def test_ml_standin_under_block_cg_needs_a_symmetric_cycle():
     with pytest.raises(isph.IsphError, match="symmetric preconditioner"):
         c.solve(True, "cg-ml")
     c.close()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_ml_standin_random_geometric_operators(seed):
+    """seeded sweep over random particle-like operators (kernel-weighted graph Laplacians of random point clouds in 2-D / 3-D with random
+    positive shifts, some identity rows, varying thresholds and coarse sizes): the device hierarchy equals the restatement's (aggregates,
+    level sizes) and the solves agree — corner cases of the aggregation (isolated rows, leftovers, tiny aggregates, early stop) included."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(1000 + seed); dim = 2 + seed % 2; n = int(rng.integers(300, 3000))
+    X = rng.random((n, dim)); rad = (6.0 if dim == 2 else 9.0) ** (1.0 / dim) * (1.0 / n) ** (1.0 / dim) * (1.3 + 0.5 * rng.random())
+    pairs = cKDTree(X).query_pairs(rad, output_type="ndarray"); d = np.linalg.norm(X[pairs[:, 0]] - X[pairs[:, 1]], axis=1)
+    w = (1.0 - d / rad) ** 3 + 1e-3
+    W = sp.coo_matrix((np.r_[w, w], (np.r_[pairs[:, 0], pairs[:, 1]], np.r_[pairs[:, 1], pairs[:, 0]])), shape=(n, n)).tocsr()
+    A = sp.lil_matrix(sp.diags(np.asarray(W.sum(1)).ravel() * (1.0 + 0.01 * rng.random(n)) + 1e-3) - W)
+    for r in rng.choice(n, size=n // 50, replace=False):                       # identity rows (solid particles): no strong connection
+        A.rows[r] = [int(r)]; A.data[r] = [1.0]
+    A = sp.csr_matrix(A); A.sort_indices()
+    ml = {"aggregation: threshold": float(rng.choice([0.0, 0.02, 0.1, 0.25])), "coarse: max size": int(rng.choice([10, 40, 128])), "max levels": int(rng.choice([2, 3, 5]))}
+    okw = oracle_params(**dict(ml)); b = rng.standard_normal(n)
+    h = O.amg_hierarchy(A.indptr, A.indices, A.data, O.krylov_params(**okw)); xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    ml_configure(c, **dict(ml)); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "fuzz"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates(); c.close()
+    assert hi["levels"] == h["levels"] and list(hi["rows"]) == list(h["rows"]) and list(hi["nnz"][1:]) == list(h["nnz"][1:]), (ml, hi, h)
+    assert np.array_equal(agg, h["agg"]), ml
+    assert st["converged"] == info["converged"] and abs(st["iters"] - info["iters"]) <= 2, (ml, st, info)
+    if info["converged"]:
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-5
