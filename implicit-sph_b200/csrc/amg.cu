@@ -382,15 +382,21 @@ void member_lists(Ctx *c, AmgData *D, AmgLevel *L) {
 
 // Galerkin operator of level `lev` -> local rows (nc_mine) with global coarse column ids, in D->rlen / Cn->ci / Cn->va (CSR by Cn->rp)
 template <class M> bool galerkin(Ctx *c, AmgData *D, AmgLevel *L, AmgLevel *Cn, M A, const int *aggc) {
-  const int n = L->n, nc = L->nc_mine; const int KQ = 48, KQ2 = 160;
+  const int n = L->n, nc = L->nc_mine; const int KQ = 48, KQ2 = 160, KQ3 = 512;
   D->qcnt.ensure(n); D->qj.ensure((size_t)n * KQ); D->qv.ensure((size_t)n * KQ); D->ctr.ensure(8);
   CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
   k_amg_compress<M, KQ><<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, aggc, L->agg.p, D->qcnt.p, D->qj.p, D->qv.p, D->ctr.p + 1); LAUNCH(c);
-  if (d2h(c, D->ctr.p + 1)) {                                             // a row reaches more than 48 aggregates (small aggregates under a wide stencil): the wide variant
+  if (d2h(c, D->ctr.p + 1)) {                                             // a row reaches more than 48 aggregates (small aggregates under a wide stencil): the wide variants
     D->qj.ensure((size_t)n * KQ2); D->qv.ensure((size_t)n * KQ2);
     CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
     k_amg_compress<M, KQ2><<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, aggc, L->agg.p, D->qcnt.p, D->qj.p, D->qv.p, D->ctr.p + 1); LAUNCH(c);
-    if (d2h(c, D->ctr.p + 1)) return false;
+    if (d2h(c, D->ctr.p + 1)) {
+      if ((size_t)n * KQ3 * 12 > ((size_t)16 << 30)) return false;        // more than 160 aggregates per row on a level too large to give every row 512 slots
+      D->qj.ensure((size_t)n * KQ3); D->qv.ensure((size_t)n * KQ3);
+      CUDA_CHECK(cudaMemsetAsync(D->ctr.p + 1, 0, sizeof(int), c->stream));
+      k_amg_compress<M, KQ3><<<tgrid(n, 128), 128, 0, c->stream>>>(A, n, aggc, L->agg.p, D->qcnt.p, D->qj.p, D->qv.p, D->ctr.p + 1); LAUNCH(c);
+      if (d2h(c, D->ctr.p + 1)) return false;
+    }
   }
   D->rlen.ensure(nc + 2); Cn->rp.ensure(nc + 2);
   // coarse rows of up to 384 columns: 4 warps per block, 512-slot tables; wider rows (dense small levels): one warp per block, 2048 slots
@@ -502,7 +508,7 @@ void amg_create(Ctx *c) {
         double bad = ok ? 0.0 : 1.0; double *dv = D->red.p + 592 * 3 + 4; CUDA_CHECK(cudaMemcpyAsync(dv, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         halo_allreduce(c, dv, 1); ok = d2h(c, dv) == 0.0;
       }
-      if (!ok && c->rank == 0) fprintf(stderr, ">> isph_b200 ML stand-in: level %d is not coarsened further (a coarse row would hold more than %d columns); it becomes the coarsest level\n", lev, 1536);
+      if (!ok && c->rank == 0) fprintf(stderr, ">> isph_b200 ML stand-in: level %d is not coarsened further (a row reaches more than 512 aggregates or a coarse row would hold more than %d columns); it becomes the coarsest level\n", lev, 1536);
       if (ok) {
         Cn->gid.ensure(nc_all + 1);
         if (lev == 0 && c->nranks > 1) {
