@@ -7,7 +7,7 @@ One *step* = what `PairISPH::compute` does per time step for the pressure Poisso
 reference does.  Metric: rows assembled-and-solved per second (whole job), with `ms_per_step` = the absolute Poisson
 step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM bandwidth inside the solve.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|p8m_ml|c2|c2_ml|c1|c3|c4|c4s|c5|c5_ml|c2j] [--n LATTICE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload p8m|p8m_ml|c2|c2_ml|c1|c3|c4|c4s|c4s_ml|c5|c5_ml|c2j] [--n LATTICE]
 
 Default workload = the configuration BASELINE.json's metric and target are quoted on: the 3-D 8M-particle (200^3) pressure
 Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  The line
@@ -60,6 +60,8 @@ WORKLOADS = {
                    desc="north_star problem (3-D 8M-particle pressure Poisson) with the reference's default preconditioner package: flexible GMRES(50) + the multilevel stand-in for ML (MIS aggregation, Chebyshev smoothers, V-cycle), fixed global size (strong scaling)"),
     "c2_ml": dict(dim=3, n=100, jitter=0.0, rs2=9, prec="ML", solver="Block GMRES",
                   desc="BASELINE configs[1] problem (1M particles) with flexible GMRES(50) + the multilevel stand-in for ML"),
+    "c4s_ml": dict(dim=3, n=200, jitter=0.04, rs2=12, prec="ML", solver="Block GMRES", anti=False, strong=True,
+                   desc="BASELINE configs[3] problem (8M particles, corrected Gc/Lc operators, jittered lattice) with GMRES(50) + the multilevel stand-in for ML instead of block-Jacobi ILU(0)"),
     "c5_ml": dict(dim=3, n=160, jitter=0.0, rs2=9, prec="ML", solver="Block GMRES", strong=True, system="pb",
                   desc="BASELINE configs[4] problem (4M-particle Poisson-Boltzmann Newton) with GMRES(50) + the multilevel stand-in for ML in the Jacobian solves"),
     # north_star target: fixed 8M-particle problem split over the GPUs (strong scaling)
