@@ -12,7 +12,8 @@ step time BASELINE.json asks for and `roofline` = the SpMV kernel's achieved HBM
 Default workload = the configuration BASELINE.json's metric and target are quoted on: the 3-D 8M-particle (200^3) pressure
 Poisson GMRES solve — it fits one B200 (17 GB), and the same global problem is split over N GPUs (strong scaling).  The line
 also carries, at every N, secondary blocks for BASELINE configs[2] (`configs2_c3`: 8M Helmholtz, 3 RHS, CG + Chebyshev),
-configs[3] (`configs3_c4`: 8M corrected-operator Poisson, GMRES + block-Jacobi ILU(0) on 4x4x4 bricks of 50^3) and configs[4]
+configs[3] (`configs3_c4`: 8M corrected-operator Poisson, GMRES + block-Jacobi ILU(0) on 4x4x4 bricks of 50^3; `configs3_c4_ml`: the same
+problem with the multilevel stand-in for ML), `p8m_ml` (the headline problem with the ML stand-in) and configs[4]
 (`configs4_c5`: 4M Poisson-Boltzmann Newton), at N=1 also configs[1] (`configs1_c2`, 1M particles), and at N>1 a `parity`
 block: the multi-GPU path checked against the CPU oracle on a small global problem before the timed region (the run fails on
 a mismatch).  `--impl reference` times the CPU path (oracle port, OpenMP over all host cores) on a bounded sample of the same
@@ -594,7 +595,7 @@ def main():
     # the other BASELINE configs beside the headline line: same code path, measured in the same run, at this GPU count
     if args.workload == "p8m" and not args.n and not args.no_secondary:
         sec_steps = max(1, min(args.steps, 3))
-        todo = ([("configs1_c2", "c2"), ("configs1_c2_ml", "c2_ml")] if world == 1 else []) + [("p8m_ml", "p8m_ml"), ("configs2_c3", "c3"), ("configs3_c4", "c4s"), ("configs4_c5", "c5")]
+        todo = ([("configs1_c2", "c2"), ("configs1_c2_ml", "c2_ml")] if world == 1 else []) + [("p8m_ml", "p8m_ml"), ("configs2_c3", "c3"), ("configs3_c4", "c4s"), ("configs3_c4_ml", "c4s_ml"), ("configs4_c5", "c5")]
         for key, wn in todo:
             sec = measure(args, wn, min(args.steps, 5) if wn == "c2" else sec_steps, isph, lat, torch, dist, rank, world, local_rank, fresh_id(), with_cpu=False, warmup=3)
             if rank != 0:
