@@ -281,3 +281,20 @@ def test_ml_standin_random_geometric_operators(seed):
     assert st["converged"] == info["converged"] and abs(st["iters"] - info["iters"]) <= 2, (ml, st, info)
     if info["converged"]:
         assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-5
+
+
+def test_ml_standin_device_matches_the_golden_fixture():
+    """the committed fixture of the restatement (tests/golden/amg_restatement.npz) reproduced by the device path alone, without running the
+    oracle: aggregates and level sizes exactly, one V-cycle to 1e-11, the iteration count exactly"""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    A, b, r = m.problem(); want = np.load(os.path.join(here, "golden", "amg_restatement.npz")); n = A.shape[0]
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    ml_configure(c, **{"aggregation: threshold": 0.1, "coarse: max size": 20}); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "golden"); hi = c.precond_ml_info(); agg = c.precond_ml_aggregates()
+    c.precond_create(); z = c.precond_apply(r); c.precond_free(); c.close()
+    assert np.array_equal(agg, want["agg"]) and list(hi["rows"]) == list(want["rows"]) and list(hi["nnz"][1:]) == list(want["nnz"][1:])
+    assert st["iters"] == int(want["iters"]) and np.abs(z - want["z"]).max() <= 1e-11 * np.abs(want["z"]).max()
+    assert np.linalg.norm(x - want["x"]) <= 1e-6 * np.linalg.norm(want["x"])

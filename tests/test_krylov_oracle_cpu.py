@@ -278,3 +278,14 @@ def test_block_problem_is_the_stacked_system_with_one_preconditioner_on_every_di
     x1, info1 = O.krylov_solve_block(dim, S, A0, b, params=O.krylov_params(precond=getattr(O, prec), amg_threshold=0.1, amg_max_coarse=20, max_iters=1))
     w = S @ z; alpha = (w @ b) / (w @ w)                                       # GMRES(1): x1 = alpha z minimises ||b - alpha A z||
     assert np.linalg.norm(x1 - alpha * z) <= 1e-12 * np.linalg.norm(x1)
+
+
+def test_ml_standin_restatement_matches_its_golden_fixture(oracle_mod):
+    """self-consistency pin (tests/golden/make_golden_amg.py): the discrete decisions are frozen exactly, the numbers to rounding"""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    got = m.compute(); want = np.load(os.path.join(here, "golden", "amg_restatement.npz"))
+    assert np.array_equal(got["agg"], want["agg"]) and np.array_equal(got["rows"], want["rows"]) and np.array_equal(got["nnz"], want["nnz"]) and int(got["iters"]) == int(want["iters"])
+    assert np.allclose(got["lmax"], want["lmax"], rtol=1e-12) and np.abs(got["z"] - want["z"]).max() <= 1e-12 * np.abs(want["z"]).max()
+    assert np.linalg.norm(got["x"] - want["x"]) <= 1e-9 * np.linalg.norm(want["x"])
