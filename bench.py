@@ -197,7 +197,7 @@ def cpu_step(O, P, F, dt, w, pin_iters=None):
     t1 = time.perf_counter()
     nl = P["nlocal"]
     colL = O.tags_to_local(col, P["tag"][:nl])
-    prec = {"point relaxation": O.PREC_JACOBI, "ILU": O.PREC_ILU0, "Chebyshev": O.PREC_CHEBYSHEV}[w["prec"]]
+    prec = {"point relaxation": O.PREC_JACOBI, "ILU": O.PREC_ILU0, "Chebyshev": O.PREC_CHEBYSHEV, "ML": O.PREC_AMG}[w["prec"]]
     kw = dict(tol=0.0, max_iters=int(pin_iters)) if pin_iters else {}
     x, info = O.krylov_solve(rp, colL, A, b, params=O.krylov_params(precond=prec, row_gid=P["tag"][:nl], **kw), null_mask=np.ones(nl, dtype=np.int32), use_null=True)
     t2 = time.perf_counter()
