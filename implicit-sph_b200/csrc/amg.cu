@@ -54,12 +54,19 @@ template <class M> __global__ void __launch_bounds__(128) k_amg_strength(M A, in
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
   long long base; int len, st; row_span(A, r, base, len, st);
   const double dr = d[r]; const int br = blk ? blk[r] : 0; int k = 0;
-  for (int e = 0; e < len; ++e) {
-    const int c = A.col[base + (long long)e * st]; if (c == r || c >= nown) continue;        // halo columns belong to another rank: never strong
-    if (blk && blk[c] != br) continue;
-    const double a = A.val[base + (long long)e * st];
+  auto visit = [&](int c, double a) {
+    if (c == r || c >= nown) return;                                 // halo columns belong to another rank: never strong
+    if (blk && blk[c] != br) return;
     if (a * a > theta2 * fabs(dr * d[c])) { sg[(size_t)k * n + r] = c; sw[(size_t)k * n + r] = (float)fabs(a); ++k; }
+  };
+  int e = 0;
+  for (; e + 4 <= len; e += 4) {                                     // four independent (column, value) loads in flight, visited in stored order
+    const long long q = base + (long long)e * st;
+    const int c0 = A.col[q], c1 = A.col[q + st], c2 = A.col[q + 2ll * st], c3 = A.col[q + 3ll * st];
+    const double a0 = A.val[q], a1 = A.val[q + st], a2 = A.val[q + 2ll * st], a3 = A.val[q + 3ll * st];
+    visit(c0, a0); visit(c1, a1); visit(c2, a2); visit(c3, a3);
   }
+  for (; e < len; ++e) visit(A.col[base + (long long)e * st], A.val[base + (long long)e * st]);
   cnt[r] = k;
 }
 
@@ -74,15 +81,25 @@ __global__ void __launch_bounds__(VB) k_amg_mis_init(int n, const int *gid, cons
 }
 __global__ void __launch_bounds__(VB) k_amg_mis_m1(int n, const int *sg, const int *cnt, const unsigned long long *tok, unsigned long long *m1) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
-  unsigned long long m = tok[r];
-  for (int k = 0; k < cnt[r]; ++k) { const unsigned long long t = tok[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
+  unsigned long long m = tok[r]; const int nk = cnt[r]; int k = 0;
+  for (; k + 4 <= nk; k += 4) {                                      // four neighbour tokens in flight
+    const int j0 = sg[(size_t)k * n + r], j1 = sg[(size_t)(k + 1) * n + r], j2 = sg[(size_t)(k + 2) * n + r], j3 = sg[(size_t)(k + 3) * n + r];
+    const unsigned long long t0 = tok[j0], t1 = tok[j1], t2 = tok[j2], t3 = tok[j3];
+    const unsigned long long a = t0 > t1 ? t0 : t1, b = t2 > t3 ? t2 : t3, c2 = a > b ? a : b; m = c2 > m ? c2 : m;
+  }
+  for (; k < nk; ++k) { const unsigned long long t = tok[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
   m1[r] = m;
 }
 __global__ void __launch_bounds__(VB) k_amg_mis_m2(int n, const int *sg, const int *cnt, const unsigned long long *key, int *state, unsigned long long *tok, const unsigned long long *m1, int *undecided) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= n) return;
   if (state[r] != 0) return;                                        // only a row's own thread writes its state / token; neighbours are read through m1 (snapshot)
-  unsigned long long m = m1[r];
-  for (int k = 0; k < cnt[r]; ++k) { const unsigned long long t = m1[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
+  unsigned long long m = m1[r]; const int nk = cnt[r]; int k = 0;
+  for (; k + 4 <= nk; k += 4) {
+    const int j0 = sg[(size_t)k * n + r], j1 = sg[(size_t)(k + 1) * n + r], j2 = sg[(size_t)(k + 2) * n + r], j3 = sg[(size_t)(k + 3) * n + r];
+    const unsigned long long t0 = m1[j0], t1 = m1[j1], t2 = m1[j2], t3 = m1[j3];
+    const unsigned long long a = t0 > t1 ? t0 : t1, b = t2 > t3 ? t2 : t3, c2 = a > b ? a : b; m = c2 > m ? c2 : m;
+  }
+  for (; k < nk; ++k) { const unsigned long long t = m1[sg[(size_t)k * n + r]]; m = t > m ? t : m; }
   if (m == ~0ULL) { state[r] = -1; tok[r] = 0ULL; } else if (m == key[r]) { state[r] = 1; tok[r] = ~0ULL; } else atomicAdd(undecided, 1);
 }
 __global__ void __launch_bounds__(VB) k_amg_flag(int n, const int *state, const int *agg, int what, int *flag) {
@@ -126,12 +143,20 @@ template <class M, int KQ> __global__ void __launch_bounds__(128) k_amg_compress
   // (summing runs of consecutive entries with the same aggregate in registers before touching the list was measured: 14.4 ms against 12.3 ms
   // for this loop on 8M rows — the extra divergence costs more than the saved local-memory traffic; not kept)
   int J[KQ]; double S[KQ]; int m = 0;
-  for (int e = 0; e < len; ++e) {
-    const int jc = aggc[A.col[base + (long long)e * st]]; if (jc < 0) continue;
-    const double a = A.val[base + (long long)e * st];
+  auto visit = [&](int jc, double a) {
+    if (jc < 0) return;
     int k = 0; for (; k < m; ++k) if (J[k] == jc) break;
     if (k < m) S[k] += a; else if (m < KQ) { J[m] = jc; S[m] = a; ++m; } else *overflow = 1;
+  };
+  int e = 0;
+  for (; e + 4 <= len; e += 4) {                                     // four (column -> aggregate) gathers in flight; the list is updated in stored order
+    const long long q = base + (long long)e * st;
+    const int c0 = A.col[q], c1 = A.col[q + st], c2 = A.col[q + 2ll * st], c3 = A.col[q + 3ll * st];
+    const double a0 = A.val[q], a1 = A.val[q + st], a2 = A.val[q + 2ll * st], a3 = A.val[q + 3ll * st];
+    const int j0 = aggc[c0], j1 = aggc[c1], j2 = aggc[c2], j3 = aggc[c3];
+    visit(j0, a0); visit(j1, a1); visit(j2, a2); visit(j3, a3);
   }
+  for (; e < len; ++e) visit(aggc[A.col[base + (long long)e * st]], A.val[base + (long long)e * st]);
   qcnt[r] = m;
   for (int k = 0; k < m; ++k) { qj[(size_t)k * n + r] = J[k]; qv[(size_t)k * n + r] = S[k]; }
 }
@@ -147,20 +172,24 @@ template <int HS, int WPB, bool FILL> __global__ void __launch_bounds__(32 * WPB
   if (lane == 0) cnts[w] = 0;
   __syncwarp();
   const int m0 = moff[I], m1 = moff[I + 1];
-  for (int mi = m0; mi < m1; ++mi) {
-    const int row = mem[mi], qc = qcnt[row];
-    for (int k = lane; k < qc; k += 32) {
-      const int J = qj[(size_t)k * n + row]; unsigned h = ((unsigned)J * 2654435761u) & (HS - 1); bool placed = false;
-      for (int probe = 0; probe < HS && !placed; ++probe) {
-        const int old = atomicCAS(&H[h], -1, J);
-        if (old == -1) { atomicAdd(&cnts[w], 1); placed = true; }
-        else if (old == J) placed = true;
-        else h = (h + 1) & (HS - 1);
+  // the column set: a lane per member (32 members' rows in flight at once; the order of insertion is irrelevant for a set)
+  for (int b = m0; b < m1; b += 32) {
+    const int my_row = b + lane < m1 ? mem[b + lane] : 0, my_qc = b + lane < m1 ? qcnt[my_row] : 0;
+    int qmax = my_qc; for (int o = 16; o > 0; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+    for (int k = 0; k < qmax; ++k) {
+      if (k < my_qc) {
+        const int J = qj[(size_t)k * n + my_row]; unsigned h = ((unsigned)J * 2654435761u) & (HS - 1); bool placed = false;
+        for (int probe = 0; probe < HS && !placed; ++probe) {
+          const int old = atomicCAS(&H[h], -1, J);
+          if (old == -1) { atomicAdd(&cnts[w], 1); placed = true; }
+          else if (old == J) placed = true;
+          else h = (h + 1) & (HS - 1);
+        }
+        if (!placed) atomicExch(&cnts[w], HS);                      // table full: reported as overflow below (never a silently dropped column)
       }
-      if (!placed) atomicExch(&cnts[w], HS);                        // table full: reported as overflow below (never a silently dropped column)
+      __syncwarp();
+      if (cnts[w] > HS * 3 / 4) { if (lane == 0) { *overflow = 1; if (!FILL) ccnt[I] = 0; } return; }
     }
-    __syncwarp();
-    if (cnts[w] > HS * 3 / 4) { if (lane == 0) { *overflow = 1; if (!FILL) ccnt[I] = 0; } return; }
   }
   const int nd = cnts[w];
   if (!FILL) { if (lane == 0) ccnt[I] = nd; return; }
@@ -177,13 +206,24 @@ template <int HS, int WPB, bool FILL> __global__ void __launch_bounds__(32 * WPB
   double *Ac = acc[w];
   for (int i = lane; i < nd; i += 32) Ac[i] = 0.0;
   __syncwarp();
-  for (int mi = m0; mi < m1; ++mi) {
-    const int row = mem[mi], qc = qcnt[row];
-    for (int k0 = 0; k0 < qc; k0 += 32) {
-      const int k = k0 + lane; int slot = -1; double v = 0.0;
-      if (k < qc) { const int J = qj[(size_t)k * n + row]; v = qv[(size_t)k * n + row]; int lo = 0, hi = nd - 1; while (lo < hi) { const int mid = (lo + hi) >> 1; if (Ls[mid] < J) lo = mid + 1; else hi = mid; } slot = lo; }
-      const int na = qc - k0 < 32 ? qc - k0 : 32;
-      for (int t = 0; t < na; ++t) { const int s = __shfl_sync(0xffffffffu, slot, t); const double vt = __shfl_sync(0xffffffffu, v, t); if ((s & 31) == lane) Ac[s] += vt; }
+  // the sums, members in ascending row order, entries of a member in list order: (row, length) of 32 members are fetched at once and the
+  // first 32 entries of the next member are loaded while the current one is accumulated (one memory latency per member instead of three)
+  for (int b = m0; b < m1; b += 32) {
+    const int nb = m1 - b < 32 ? m1 - b : 32;
+    const int my_row = lane < nb ? mem[b + lane] : 0, my_qc = lane < nb ? qcnt[my_row] : 0;
+    int row = __shfl_sync(0xffffffffu, my_row, 0), qc = __shfl_sync(0xffffffffu, my_qc, 0);
+    int J = 0; double v = 0.0; if (lane < qc) { J = qj[(size_t)lane * n + row]; v = qv[(size_t)lane * n + row]; }
+    for (int t = 0; t < nb; ++t) {
+      int rown = 0, qcn = 0, Jn = 0; double vn = 0.0;
+      if (t + 1 < nb) { rown = __shfl_sync(0xffffffffu, my_row, t + 1); qcn = __shfl_sync(0xffffffffu, my_qc, t + 1); if (lane < qcn) { Jn = qj[(size_t)lane * n + rown]; vn = qv[(size_t)lane * n + rown]; } }
+      for (int k0 = 0; k0 < qc; k0 += 32) {
+        const int k = k0 + lane; int slot = -1;
+        if (k0 > 0 && k < qc) { J = qj[(size_t)k * n + row]; v = qv[(size_t)k * n + row]; }
+        if (k < qc) { int lo = 0, hi = nd - 1; while (lo < hi) { const int mid = (lo + hi) >> 1; if (Ls[mid] < J) lo = mid + 1; else hi = mid; } slot = lo; }
+        const int na = qc - k0 < 32 ? qc - k0 : 32;
+        for (int u = 0; u < na; ++u) { const int sl = __shfl_sync(0xffffffffu, slot, u); const double vt = __shfl_sync(0xffffffffu, v, u); if ((sl & 31) == lane) Ac[sl] += vt; }
+      }
+      row = rown; qc = qcn; J = Jn; v = vn;
     }
   }
   __syncwarp();
