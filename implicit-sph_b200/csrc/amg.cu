@@ -640,15 +640,15 @@ double *vcycle_csr(Ctx *c, AmgData *D, int lev) {
     return smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_coarse_sweeps, pp.ml_coarse_alpha, jac, pp.ml_damping);
   }
   AmgLevel *Cn = D->L[lev + 1];
-  double *x = smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_level_sweeps, pp.ml_alpha, jac, pp.ml_damping);
+  double *x = smooth_csr(c, L, L->b.p, L->xa.p, L->xb.p, true, pp.ml_level_sweeps, pp.ml_level_alpha, jac, pp.ml_damping);
   double *other = x == L->xa.p ? L->xb.p : L->xa.p;
   const double *res = nullptr;
   if (pp.ml_level_sweeps > 0) { k_amg_csr<4><<<tgrid((long long)n * 8), VB, 0, c->stream>>>(view(L), n, x, L->b.p, nullptr, 0.0, 0.0, nullptr, other); LAUNCH(c); res = other; }
   // restriction of res (already r - A x): V = nullptr form with r := res
   k_amg_restrict<<<tgrid(L->nc), VB, 0, c->stream>>>(L->nc, 0, L->nc, L->moff.p, L->mem.p, res ? res : L->b.p, nullptr, Cn->b.p); LAUNCH(c);
   const double *ec = vcycle_csr(c, D, lev + 1);
-  k_amg_prolong<<<vgrid(n), VB, 0, c->stream>>>(n, L->agg.p, 0, ec, pp.ml_scale, x); LAUNCH(c);
-  return smooth_csr(c, L, L->b.p, x, other, false, pp.ml_level_sweeps, pp.ml_alpha, jac, pp.ml_damping);
+  k_amg_prolong<<<vgrid(n), VB, 0, c->stream>>>(n, L->agg.p, 0, ec, pp.ml_level_scale, x); LAUNCH(c);
+  return smooth_csr(c, L, L->b.p, x, other, false, pp.ml_level_sweeps, pp.ml_level_alpha, jac, pp.ml_damping);
 }
 
 }  // namespace

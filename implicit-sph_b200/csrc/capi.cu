@@ -418,6 +418,7 @@ int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v) {
   else if (k == "aggregation: threshold") { ISPH_REQUIRE(v >= 0.0, "aggregation: threshold >= 0"); c->pp.ml_threshold = v; }
   else if (k == "aggregation: damping factor") c->pp.ml_agg_damping = v;          // only 0 (non-smoothed aggregation) is provided: checked at create
   else if (k == "smoother: Chebyshev alpha") c->pp.ml_alpha = v; else if (k == "coarse: Chebyshev alpha") c->pp.ml_coarse_alpha = v;
+  else if (k == "smoother: Chebyshev alpha (coarse levels)") c->pp.ml_level_alpha = v; else if (k == "coarse correction scale (coarse levels)") c->pp.ml_level_scale = v;
   else if (k == "smoother: damping factor") c->pp.ml_damping = v; else if (k == "coarse correction scale") c->pp.ml_scale = v;
   else ISPH_REQUIRE(false, "unknown double preconditioner parameter: " + k);
   API_END

@@ -76,8 +76,8 @@ struct PrecondParams {             // names of precond_ifpack.h:28-48 + Ifpack's
   // "Precond Package" = ML: the multilevel stand-in of amg.cu; names = ML's parameter list (precond_ml.h:44-58), defaults chosen for the GPU
   // (Chebyshev instead of the sequential symmetric Gauss-Seidel, non-smoothed MIS aggregation)
   std::string ml_smoother = "Chebyshev", ml_coarse = "Chebyshev", ml_agg_type = "MIS";
-  int ml_max_levels = 5, ml_pre = 1, ml_post = 2, ml_level_sweeps = 3, ml_coarse_sweeps = 8, ml_eig_iters = 10, ml_max_coarse = 128;
-  double ml_threshold = 0.02, ml_agg_damping = 0.0, ml_alpha = 10.0, ml_coarse_alpha = 30.0, ml_scale = 2.0, ml_damping = 0.67;
+  int ml_max_levels = 5, ml_pre = 1, ml_post = 1, ml_level_sweeps = 3, ml_coarse_sweeps = 8, ml_eig_iters = 10, ml_max_coarse = 128;
+  double ml_threshold = 0.02, ml_agg_damping = 0.0, ml_alpha = 2.0, ml_level_alpha = 10.0, ml_coarse_alpha = 30.0, ml_scale = 2.5, ml_level_scale = 2.0, ml_damping = 0.67;   // alpha / scale: finest level; level_*: between the finest and the coarsest
 };
 
 struct Halo;      // halo.cu

@@ -215,10 +215,11 @@ int isph_solver_set_default_params(isph_ctx *ctx);                        /* set
  * "aggregation: threshold" (0.02; ML's criterion a_ij^2 > eps^2 |a_ii a_jj|), "aggregation: damping factor" (must be 0), "smoother: type"
  * ("Chebyshev" | "Jacobi"; "symmetric Gauss-Seidel", the value precond_ml.h:53 sets, is sequential within a rank and is refused),
  * "smoother: sweeps" (Chebyshev degree / Jacobi sweeps before and after the coarse correction), "smoother: pre or post", "smoother: Chebyshev
- * alpha" (10), "smoother: damping factor" (Jacobi, 0.67), "coarse: type" (= smoother: type, or "Amesos-KLU" = direct solve of the coarsest operator; replaced by the smoother for singular problems as
+ * alpha" (eigenvalue ratio on the finest level, 2), "smoother: damping factor" (Jacobi, 0.67), "coarse: type" (= smoother: type, or "Amesos-KLU" = direct solve of the coarsest operator; replaced by the smoother for singular problems as
  * PrecondWrapper_ML::setNullVector does, precond_ml.h:118-120), "coarse: sweeps" (8),
  * "coarse: Chebyshev alpha" (30), "coarse: max size" (128), "eigen-analysis: iterations" (10).  Extensions (not ML keys): "smoother: pre
- * sweeps" (1), "smoother: post sweeps" (2), "smoother: sweeps (coarse levels)" (3), "coarse correction scale" (2.0). */
+ * sweeps" (1), "smoother: post sweeps" (1), "smoother: sweeps (coarse levels)" (3), "smoother: Chebyshev alpha (coarse levels)" (10),
+ * "coarse correction scale" (2.5 on the finest level), "coarse correction scale (coarse levels)" (2.0). */
 int isph_precond_set_param_int(isph_ctx *ctx, const char *name, int v);
 int isph_precond_set_param_double(isph_ctx *ctx, const char *name, double v);
 int isph_precond_set_param_str(isph_ctx *ctx, const char *name, const char *v);

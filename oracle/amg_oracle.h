@@ -21,8 +21,8 @@
 namespace amg_oracle {
 
 struct Params {
-  int max_levels = 5, pre = 1, post = 2, level_sweeps = 3, coarse_sweeps = 8, eig_iters = 10, max_coarse = 128, smoother = 0;
-  double theta = 0.02, alpha = 10.0, coarse_alpha = 30.0, oc = 2.0, damping = 0.67;
+  int max_levels = 5, pre = 1, post = 1, level_sweeps = 3, coarse_sweeps = 8, eig_iters = 10, max_coarse = 128, smoother = 0;
+  double theta = 0.02, alpha = 2.0, level_alpha = 10.0, coarse_alpha = 30.0, oc = 2.5, level_oc = 2.0, damping = 0.67;    // alpha / oc: finest level; level_*: the levels between the finest and the coarsest
   int coarse_direct = 0;      // "coarse: type" = Amesos-KLU: dense inverse of the coarsest operator (non-singular problems only)
 };
 
@@ -210,12 +210,13 @@ struct Hierarchy {
     }
     const int pre = l == 0 ? P.pre : P.level_sweeps, post = l == 0 ? P.post : P.level_sweeps;
     Level &C = L[l + 1];
-    cheb(Lv, r, x, true, pre, P.alpha);
+    const double ratio = l == 0 ? P.alpha : P.level_alpha, oc = l == 0 ? P.oc : P.level_oc;
+    cheb(Lv, r, x, true, pre, ratio);
     if (pre > 0) spmv(Lv.A, x, Lv.t.data()); else for (int i = 0; i < n; ++i) Lv.t[i] = 0.0;
     for (int I = 0; I < Lv.nc; ++I) { double s = 0.0; for (int i : Lv.members[I]) s += r[i] - Lv.t[i]; C.b[I] = s; }
     vcycle(l + 1, C.b.data(), C.x.data());
-    for (int i = 0; i < n; ++i) if (Lv.agg[i] >= 0) x[i] += P.oc * C.x[Lv.agg[i]];
-    cheb(Lv, r, x, false, post, P.alpha);
+    for (int i = 0; i < n; ++i) if (Lv.agg[i] >= 0) x[i] += oc * C.x[Lv.agg[i]];
+    cheb(Lv, r, x, false, post, ratio);
   }
   void apply(const double *r, double *z) { vcycle(0, r, z); }
 };

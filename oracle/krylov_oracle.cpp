@@ -105,7 +105,7 @@ struct Precond {
     if (type == ORC_PREC_AMG) {                             // PrecondWrapper_ML::create, precond_ml.h:128-135 (stand-in: amg_oracle.h)
       amg_oracle::Params q; q.max_levels = p->amg_max_levels; q.theta = p->amg_threshold; q.smoother = p->amg_smoother; q.pre = p->amg_pre; q.post = p->amg_post;
       q.level_sweeps = p->amg_level_sweeps; q.coarse_sweeps = p->amg_coarse_sweeps; q.alpha = p->amg_alpha; q.coarse_alpha = p->amg_coarse_alpha;
-      q.eig_iters = p->amg_eig_iters; q.max_coarse = p->amg_max_coarse; q.oc = p->amg_scale; q.damping = p->amg_damping; q.coarse_direct = p->amg_coarse_direct;
+      q.eig_iters = p->amg_eig_iters; q.max_coarse = p->amg_max_coarse; q.oc = p->amg_scale; q.damping = p->amg_damping; q.coarse_direct = p->amg_coarse_direct; q.level_alpha = p->amg_level_alpha; q.level_oc = p->amg_level_scale;
       amg = new amg_oracle::Hierarchy(); amg->setup(n, A_.rp, A_.ci, A_.v, p->row_gid, block_of_row, q); lmax = amg->L[0].lmax; return;
     }
     if (type == ORC_PREC_JACOBI || type == ORC_PREC_CHEBYSHEV) {
@@ -244,7 +244,7 @@ void orc_krylov_default_params(orc_krylov_params *p) {
   amg_oracle::Params q;                                    // defaults of the multilevel stand-in (implicit-sph_b200/csrc/amg.cu)
   p->amg_max_levels = q.max_levels; p->amg_threshold = q.theta; p->amg_smoother = q.smoother; p->amg_pre = q.pre; p->amg_post = q.post; p->amg_level_sweeps = q.level_sweeps;
   p->amg_coarse_sweeps = q.coarse_sweeps; p->amg_alpha = q.alpha; p->amg_coarse_alpha = q.coarse_alpha; p->amg_eig_iters = q.eig_iters; p->amg_max_coarse = q.max_coarse;
-  p->amg_scale = q.oc; p->amg_damping = q.damping; p->amg_coarse_direct = 0;
+  p->amg_scale = q.oc; p->amg_damping = q.damping; p->amg_coarse_direct = 0; p->amg_level_alpha = q.level_alpha; p->amg_level_scale = q.level_oc;
 }
 
 }  // extern "C"

@@ -40,6 +40,8 @@ typedef struct {
   int amg_max_coarse;        /* "coarse: max size" */
   double amg_scale;          /* scaling of the coarse-grid correction */
   double amg_damping;        /* "smoother: damping factor" (Jacobi) */
+  double amg_level_alpha;    /* eigenvalue ratio on the levels between the finest and the coarsest (amg_alpha: finest level) */
+  double amg_level_scale;    /* coarse-correction scaling on those levels (amg_scale: finest level) */
   int amg_coarse_direct;     /* "coarse: type" = Amesos-KLU: dense inverse of the coarsest operator (used for non-singular problems; the caller clears it for singular ones as PrecondWrapper_ML::setNullVector does, precond_ml.h:118-120) */
 } orc_krylov_params;
 

@@ -224,7 +224,7 @@ class KrylovParams(C.Structure):
                 ("row_gid", _ip), ("ilu_fill", C.c_int), ("overlap", C.c_int),
                 ("amg_max_levels", C.c_int), ("amg_threshold", C.c_double), ("amg_smoother", C.c_int), ("amg_pre", C.c_int), ("amg_post", C.c_int),
                 ("amg_level_sweeps", C.c_int), ("amg_coarse_sweeps", C.c_int), ("amg_alpha", C.c_double), ("amg_coarse_alpha", C.c_double),
-                ("amg_eig_iters", C.c_int), ("amg_max_coarse", C.c_int), ("amg_scale", C.c_double), ("amg_damping", C.c_double), ("amg_coarse_direct", C.c_int)]
+                ("amg_eig_iters", C.c_int), ("amg_max_coarse", C.c_int), ("amg_scale", C.c_double), ("amg_damping", C.c_double), ("amg_level_alpha", C.c_double), ("amg_level_scale", C.c_double), ("amg_coarse_direct", C.c_int)]
 
 
 SOLVER_GMRES, SOLVER_CG = 0, 1

@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 
 ML = {"max levels": "amg_max_levels", "aggregation: threshold": "amg_threshold", "smoother: pre sweeps": "amg_pre", "smoother: post sweeps": "amg_post",
       "smoother: sweeps (coarse levels)": "amg_level_sweeps", "coarse: sweeps": "amg_coarse_sweeps", "coarse: max size": "amg_max_coarse",
-      "smoother: Chebyshev alpha": "amg_alpha", "coarse correction scale": "amg_scale", "eigen-analysis: iterations": "amg_eig_iters"}
+      "smoother: Chebyshev alpha": "amg_alpha", "coarse correction scale": "amg_scale", "eigen-analysis: iterations": "amg_eig_iters",
+      "smoother: Chebyshev alpha (coarse levels)": "amg_level_alpha", "coarse correction scale (coarse levels)": "amg_level_scale"}
 
 
 def ml_configure(c, flexible=True, smoother="Chebyshev", **ml):
@@ -37,7 +38,9 @@ def oracle_params(smoother="Chebyshev", **ml):
 
 @pytest.mark.parametrize("smoother,ml", [("Chebyshev", {}), ("Jacobi", {"smoother: pre sweeps": 2, "smoother: post sweeps": 2}),
                                           ("Chebyshev", {"aggregation: threshold": 0.2, "coarse: max size": 20, "max levels": 4}),
-                                          ("Chebyshev", {"coarse: type": "Amesos-KLU"})])      # the reference's default coarse solver (precond_ml.h:55): explicit inverse of the coarsest operator
+                                          ("Chebyshev", {"coarse: type": "Amesos-KLU"}),
+                                          ("Chebyshev", {"smoother: post sweeps": 2, "smoother: Chebyshev alpha": 10.0, "coarse correction scale": 2.0,
+                                                         "smoother: Chebyshev alpha (coarse levels)": 4.0, "coarse correction scale (coarse levels)": 1.5})])      # the reference's default coarse solver (precond_ml.h:55): explicit inverse of the coarsest operator
 @pytest.mark.parametrize("flex", [True, False])
 def test_ml_standin_external_matrix(smoother, ml, flex):
     """second API client's situation (fix_qeq_reax hands over a CSR matrix): 5-point operator, 6400 rows -> three levels; flexible and
