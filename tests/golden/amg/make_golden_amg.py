@@ -1,9 +1,9 @@
-"""Regenerates tests/golden/amg_restatement.npz: a self-consistency pin of the multilevel stand-in's sequential restatement
+"""Regenerates tests/golden/amg/amg_restatement.npz: a self-consistency pin of the multilevel stand-in's sequential restatement
 (oracle/amg_oracle.h).  NOT a reference pin — ML is not available (parity unpinned); the fixture freezes the algorithm's
 discrete decisions (aggregates, level sizes) and numbers (lambda_max, one V-cycle, iteration count) so that a later change to the
 restatement or to the device code (the GPU tests compare the two) cannot drift unnoticed.
 
-    python tests/golden/make_golden_amg.py
+    python tests/golden/amg/make_golden_amg.py
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import scipy.sparse as sp
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle as O  # noqa: E402
 
@@ -31,5 +31,5 @@ def compute():
 
 
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "amg_restatement.npz"), **compute())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "amg", "amg_restatement.npz"), **compute())
     print("written")

@@ -287,12 +287,12 @@ def test_ml_standin_random_geometric_operators(seed):
 
 
 def test_ml_standin_device_matches_the_golden_fixture():
-    """the committed fixture of the restatement (tests/golden/amg_restatement.npz) reproduced by the device path alone, without running the
+    """the committed fixture of the restatement (tests/golden/amg/amg_restatement.npz) reproduced by the device path alone, without running the
     oracle: aggregates and level sizes exactly, one V-cycle to 1e-11, the iteration count exactly"""
     import importlib.util, os
     here = os.path.dirname(os.path.abspath(__file__))
-    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
-    A, b, r = m.problem(); want = np.load(os.path.join(here, "golden", "amg_restatement.npz")); n = A.shape[0]
+    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "amg", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    A, b, r = m.problem(); want = np.load(os.path.join(here, "golden", "amg", "amg_restatement.npz")); n = A.shape[0]
     c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
     x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
     ml_configure(c, **{"aggregation: threshold": 0.1, "coarse: max size": 20}); c.set_initial_solution(isph.INIT_ZERO)

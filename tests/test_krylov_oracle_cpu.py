@@ -281,11 +281,11 @@ def test_block_problem_is_the_stacked_system_with_one_preconditioner_on_every_di
 
 
 def test_ml_standin_restatement_matches_its_golden_fixture(oracle_mod):
-    """self-consistency pin (tests/golden/make_golden_amg.py): the discrete decisions are frozen exactly, the numbers to rounding"""
+    """self-consistency pin (tests/golden/amg/make_golden_amg.py): the discrete decisions are frozen exactly, the numbers to rounding"""
     import importlib.util, os
     here = os.path.dirname(os.path.abspath(__file__))
-    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
-    got = m.compute(); want = np.load(os.path.join(here, "golden", "amg_restatement.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden_amg", os.path.join(here, "golden", "amg", "make_golden_amg.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    got = m.compute(); want = np.load(os.path.join(here, "golden", "amg", "amg_restatement.npz"))
     assert np.array_equal(got["agg"], want["agg"]) and np.array_equal(got["rows"], want["rows"]) and np.array_equal(got["nnz"], want["nnz"]) and int(got["iters"]) == int(want["iters"])
     assert np.allclose(got["lmax"], want["lmax"], rtol=1e-12) and np.abs(got["z"] - want["z"]).max() <= 1e-12 * np.abs(want["z"]).max()
     assert np.linalg.norm(got["x"] - want["x"]) <= 1e-9 * np.linalg.norm(want["x"])
