@@ -658,7 +658,7 @@ void amg_apply(Ctx *c, const double *r, double *z) {
   AmgData *D = c->amg; ISPH_REQUIRE(D && D->ready, "ML stand-in: preconditioner not created");
   const PrecondParams &pp = c->pp; AmgLevel *L = D->L[0]; const int n = L->n, ld = c->ld, g = vgrid(n); const bool jac = pp.ml_smoother == "Jacobi";
   double *t = D->t0.p, *W = D->w0.p; const double *inv = L->invdiag.p;
-  const Cheb k = cheb_consts(L->lmax, pp.ml_alpha);
+  const Cheb k = cheb_consts(L->lmax, D->nlev == 1 ? pp.ml_coarse_alpha : pp.ml_alpha);      // a hierarchy of one level: the finest level is the coarsest ("coarse: *" parameters)
   auto smooth = [&](bool zero, int degree) {
     if (degree <= 0) { if (zero) CUDA_CHECK(cudaMemsetAsync(z, 0, sizeof(double) * n, c->stream)); return; }
     if (jac) {

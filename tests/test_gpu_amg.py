@@ -301,3 +301,19 @@ def test_ml_standin_device_matches_the_golden_fixture():
     assert np.array_equal(agg, want["agg"]) and list(hi["rows"]) == list(want["rows"]) and list(hi["nnz"][1:]) == list(want["nnz"][1:])
     assert st["iters"] == int(want["iters"]) and np.abs(z - want["z"]).max() <= 1e-11 * np.abs(want["z"]).max()
     assert np.linalg.norm(x - want["x"]) <= 1e-6 * np.linalg.norm(want["x"])
+
+
+def test_ml_standin_with_one_level_is_the_coarse_solver():
+    """'max levels' 1: the hierarchy is the finest level alone and the preconditioner is the coarse solver on it ('coarse: sweeps' Chebyshev
+    steps over the 'coarse: Chebyshev alpha' interval) — the same on the device and in the restatement"""
+    A = lap2d(40, 0.05, 0.2); n = A.shape[0]; b = np.random.default_rng(2).standard_normal(n)
+    ml = {"max levels": 1}; okw = oracle_params(**ml)
+    xo, info = O.krylov_solve(A.indptr, A.indices, A.data, b, params=O.krylov_params(**okw))
+    c = isph.Context(); c.matrix_set_csr(A.indptr, A.indices, A.data)
+    x = np.zeros(n); c.create_solution(x, 1); c.create_load(None, 1); c.load_set(b)
+    ml_configure(c, **ml); c.set_initial_solution(isph.INIT_ZERO)
+    st = c.solve(True, "one-level"); hi = c.precond_ml_info()
+    r = np.random.default_rng(3).standard_normal(n); c.precond_create(); z = c.precond_apply(r); c.precond_free(); c.close()
+    zo, _ = O.precond_apply(A.indptr, A.indices, A.data, r, O.krylov_params(**okw))
+    assert hi["levels"] == 1 and np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max()
+    check(st, info, x, xo, sol_tol=1e-7)
