@@ -590,9 +590,10 @@ void amg_create(Ctx *c) {
     ++nlev;
   }
   D->nlev = nlev; D->direct = false;
-  if (coarse_direct && !c->is_singular && nlev > 1) {
+  if (coarse_direct && !c->is_singular && nlev > 1 && D->L[nlev - 1]->n > 1024 && c->rank == 0)
+    fprintf(stderr, ">> isph_b200 ML stand-in: the coarsest level has %d rows — too many for the direct coarse solve (coarse: type = Amesos-KLU); the smoother is used on it\n", D->L[nlev - 1]->n);
+  if (coarse_direct && !c->is_singular && nlev > 1 && D->L[nlev - 1]->n <= 1024) {
     AmgLevel *L = D->L[nlev - 1]; const int nc = L->n;
-    ISPH_REQUIRE(nc <= 1024, "ML stand-in: the coarsest level has " + std::to_string(nc) + " rows — too many for the direct coarse solve (raise max levels or use coarse: type = the smoother)");
     std::vector<int> rp(nc + 1), ci(L->nnz); std::vector<double> va(L->nnz), a((size_t)nc * nc, 0.0), inv;
     CUDA_CHECK(cudaMemcpyAsync(rp.data(), L->rp.p, sizeof(int) * (nc + 1), cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaMemcpyAsync(ci.data(), L->ci.p, sizeof(int) * L->nnz, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(va.data(), L->va.p, sizeof(double) * L->nnz, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream));

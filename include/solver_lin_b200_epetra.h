@@ -60,6 +60,20 @@ class PrecondWrapper_B200E {
   std::vector<std::pair<std::string, int> > _ints; std::vector<std::pair<std::string, double> > _dbls; std::vector<std::pair<std::string, std::string> > _strs;
 };
 
+// PrecondWrapper_ML(MPI_Comm) as USER-REAXC-T/fix_qeq_reax.cpp:551-552 constructs it: the multilevel stand-in of csrc/amg.cu with the default
+// list of precond_ml.h:44-58 except for the smoother (Chebyshev instead of symmetric Gauss-Seidel, see solver_lin_b200.h / isph_b200.h)
+class PrecondWrapper_ML_B200E : public PrecondWrapper_B200E {
+ public:
+  explicit PrecondWrapper_ML_B200E(MPI_Comm comm) : PrecondWrapper_B200E(comm) { setParameters(); }
+  virtual Teuchos::ParameterList *setParameters(Teuchos::ParameterList *param = NULL) {
+    (void)param; _ints.clear(); _dbls.clear(); _strs.clear();
+    set("Precond Package", "ML"); set("ML output", 10); set("max levels", 5); set("increasing or decreasing", "increasing"); set("aggregation: type", "Uncoupled");
+    set("smoother: type", "Chebyshev"); set("smoother: sweeps", 1); set("smoother: pre or post", "both"); set("coarse: type", "Amesos-KLU");
+    return NULL;
+  }
+  void setCoordinates(const int, double *, double *, double *) {}      // Zoltan repartitioning (precond_ml.h:65-99): nothing to repartition
+};
+
 class SolverLin_B200E {
  public:
   enum SolutionInitType { Random = ISPH_INIT_RANDOM, Zero = ISPH_INIT_ZERO, Value = ISPH_INIT_VALUE };     // solver_lin.h:25
@@ -141,7 +155,7 @@ class SolverLin_B200E {
 #ifdef ISPH_B200_REPLACE_TRILINOS_SOLVERS          // the switch a maintainer adds to USER-REAXC-T/lammps-trilinos.h
 typedef SolverLin_B200E SolverLin_Belos;
 typedef PrecondWrapper_B200E PrecondWrapper_Ifpack;
-typedef PrecondWrapper_B200E PrecondWrapper_ML;
+typedef PrecondWrapper_ML_B200E PrecondWrapper_ML;
 #endif
 
 }  // namespace LAMMPS_NS
