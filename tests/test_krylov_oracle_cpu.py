@@ -289,3 +289,49 @@ def test_ml_standin_restatement_matches_its_golden_fixture(oracle_mod):
     assert np.array_equal(got["agg"], want["agg"]) and np.array_equal(got["rows"], want["rows"]) and np.array_equal(got["nnz"], want["nnz"]) and int(got["iters"]) == int(want["iters"])
     assert np.allclose(got["lmax"], want["lmax"], rtol=1e-12) and np.abs(got["z"] - want["z"]).max() <= 1e-12 * np.abs(want["z"]).max()
     assert np.linalg.norm(got["x"] - want["x"]) <= 1e-9 * np.linalg.norm(want["x"])
+
+
+def test_ml_standin_two_level_cycle_against_an_independent_numpy_cycle(oracle_mod):
+    """One V-cycle of a two-level hierarchy with the direct coarse solve ('coarse: type' = Amesos-KLU), rebuilt independently in numpy from the
+    restatement's aggregates and eigenvalue estimate only: z = S_post(r, S_pre(r) + s P Ac^-1 P^T (r - A S_pre(r))) with Ifpack's Chebyshev
+    recurrence on D^-1 A over [lmax / alpha, 1.1 lmax] for S and Ac = P^T A P inverted densely."""
+    O = oracle_mod; A, rp, ci, v = _amg_case(30, 0.01); n = A.shape[0]; rng = np.random.default_rng(9); r = rng.standard_normal(n)
+    pre, post, alpha, scale = 2, 3, 4.0, 1.7
+    prm = O.krylov_params(precond=O.PREC_AMG, amg_threshold=0.1, amg_max_levels=2, amg_pre=pre, amg_post=post, amg_alpha=alpha, amg_scale=scale, amg_coarse_direct=1)
+    h = O.amg_hierarchy(rp, ci, v, prm); assert h["levels"] == 2
+    z, _ = O.precond_apply(rp, ci, v, r, prm)
+    agg = h["agg"]; nc = h["rows"][1]; lmax = h["lmax"][0]; Ad = A.toarray(); dinv = 1.0 / np.diag(Ad)
+    P = np.zeros((n, nc)); P[np.arange(n), agg] = 1.0
+
+    def cheb(x, zero, degree):
+        a, b = lmax / alpha, 1.1 * lmax; delta = 2.0 / (b - a); theta = 0.5 * (b + a); s1 = theta * delta
+        w = dinv * (r if zero else r - Ad @ x) / theta; x = w.copy() if zero else x + w; rho = 1.0 / s1
+        for _ in range(degree - 1):
+            rho1 = 1.0 / (2.0 * s1 - rho); w = rho1 * rho * w + 2.0 * rho1 * delta * dinv * (r - Ad @ x); x = x + w; rho = rho1
+        return x
+    x = cheb(None, True, pre)
+    x = x + scale * (P @ np.linalg.solve(P.T @ Ad @ P, P.T @ (r - Ad @ x)))
+    x = cheb(x, False, post)
+    assert np.abs(z - x).max() <= 1e-12 * np.abs(x).max()
+    # the eigenvalue estimate itself: 10 power iterations on D^-1 A from the hashed start vector (same generator as lattice._hash01)
+    import importlib
+    lat = importlib.import_module("implicit-sph_b200.lattice")
+    xv = 2.0 * lat._hash01(np.arange(n) + 1, 7) - 1.0; xv /= np.linalg.norm(xv); lam = 0.0
+    for _ in range(10):
+        yv = dinv * (Ad @ xv); lam = (yv @ xv) / (xv @ xv); xv = yv / np.linalg.norm(yv)
+    assert abs(lam - lmax) <= 1e-12 * lmax
+
+
+def test_ml_standin_aggregates_are_connected_and_compact(oracle_mod):
+    """rebuilt independently with scipy: the strength graph from ML's criterion a_ij^2 > eps^2 |a_ii a_jj|; a row is left out of every
+    aggregate exactly when it has no strong connection; every aggregate has a member (its founder) from which all its members are reached
+    within three hops of that graph (root, its neighbours, two rounds of joins) — aggregates are connected and compact, never scattered"""
+    O = oracle_mod; A, rp, ci, v = _amg_case(28, 0.004); n = A.shape[0]; eps = 0.1
+    h = O.amg_hierarchy(rp, ci, v, O.krylov_params(precond=O.PREC_AMG, amg_threshold=eps, amg_max_coarse=10)); agg = h["agg"]; nc = h["rows"][1]
+    d = np.abs(A.diagonal()); C = A.tocoo(); m = (C.row != C.col) & (C.data ** 2 > eps * eps * d[C.row] * d[C.col])
+    S = sp.csr_matrix((np.ones(m.sum()), (C.row[m], C.col[m])), shape=(n, n)); S3 = sp.csr_matrix(S + S @ S + S @ S @ S).toarray() != 0
+    assert np.array_equal(np.asarray(S.sum(1)).ravel() == 0, agg < 0)
+    for a in range(nc):
+        mem = np.nonzero(agg == a)[0]
+        assert any(all(S3[r, q] or q == r for q in mem) for r in mem), a
+    assert 3 <= n / nc <= 13                                                        # 5-point graph: a root takes its distance <= 2 neighbourhood (13 rows) at most
