@@ -507,6 +507,7 @@ int isph_solver_solve_block(isph_ctx *ctx, int use_prec, const char *label) {
                                 CUDA_CHECK(cudaMemcpyAsync(k->bs.p + (size_t)q * n, c->bs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); }
   k->prec_parent = use_prec ? c : nullptr; k->prec_dim = d; k->launches = 0;
   solver_solve(k, use_prec != 0, label);                          // Belos on the product space: the same GMRES / CG on the stacked vectors
+  if (use_prec && c->prec_kind == 3) ISPH_REQUIRE(!ilu_fault(c), "ILU(0): a dependency wait timed out or a factor entry is not a number (zero pivot?)");
   for (int q = 0; q < d; ++q) CUDA_CHECK(cudaMemcpyAsync(c->xs.p + (size_t)q * ld, k->xs.p + (size_t)q * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
   if (c->x_host) for (int q = 0; q < d; ++q) CUDA_CHECK(cudaMemcpyAsync(c->x_host + (size_t)q * c->x_lda, c->xs.p + (size_t)q * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
